@@ -1,0 +1,244 @@
+"""Mint golden vectors from the REAL reference (normflows 1.7.3 at /root/reference).
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Writes tests/golden/<case>.npz, each holding:
+    spec (json string), sd__<key> (state_dict arrays), x, [y], and for fp64 & fp32:
+    log_prob, z, kld, per-layer log_det (ld__<i>) in the density direction, and
+    fwd_z / fwd_ld (forward_and_log_det of the latent = sampling direction).
+The reference ships no golden vectors, so these files are what
+pins the oracle (oracle/nf_oracle.py) and the CUDA path to the reference.
+torch version used is recorded in each file.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, "/root/reference")
+import normflows as nf  # noqa: E402  (the reference)
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def perturb(model, sigma, seed):
+    """Move weights off identity-init (final layer weight 0 hides every bug)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in model.parameters():
+            p.add_(sigma * torch.randn(p.shape, generator=g, dtype=p.dtype))
+
+
+def dump(name, model, spec, x, y=None, sampling=True, extra=None):
+    out = {"spec": json.dumps(spec), "torch_version": torch.__version__,
+           "x": x.numpy().astype(np.float64)}
+    if y is not None:
+        out["y"] = y.numpy()
+    for k, v in model.state_dict().items():
+        out["sd__" + k] = v.detach().numpy()  # float32 params are stored exactly; .double() models are casts of these
+    for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        m = model.to(dt)
+        xx = x.to(dt)
+        with torch.no_grad():
+            if spec["kind"] == "MultiscaleFlow":
+                lp = m.log_prob(xx, y)
+                out[f"log_prob_{tag}"] = lp.numpy()
+                out[f"kld_{tag}"] = m.forward_kld(xx, y).numpy()
+                continue
+            lp = m.log_prob(xx)
+            out[f"log_prob_{tag}"] = lp.numpy()
+            out[f"kld_{tag}"] = m.forward_kld(xx).numpy()
+            z = xx
+            for i in range(len(m.flows) - 1, -1, -1):
+                z, ld = m.flows[i].inverse(z)
+                out[f"ld_{tag}__{i}"] = (ld * torch.ones(len(xx), dtype=dt)).numpy()
+                out[f"zl_{tag}__{i}"] = z.numpy()
+            out[f"z_{tag}"] = z.numpy()
+            if sampling:
+                fz, fld = m.forward_and_log_det(z)
+                out[f"fwd_x_{tag}"] = fz.numpy()
+                out[f"fwd_ld_{tag}"] = fld.numpy()
+    model.to(torch.float32)
+    if extra:
+        out.update(extra)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, {k: v.shape for k, v in out.items() if k.startswith(("log_prob", "kld"))})
+
+
+def nsf(kind, d, layers, hidden, blocks, seed, sigma, tail_bound=3.0, bins=8, lu_identity=True):
+    torch.manual_seed(seed)
+    flows, spec = [], []
+    for i in range(layers):
+        if kind == "ar":
+            flows += [nf.flows.AutoregressiveRationalQuadraticSpline(d, blocks, hidden, num_bins=bins,
+                                                                      tail_bound=tail_bound)]
+            spec += [{"type": "AutoregressiveRationalQuadraticSpline", "num_input_channels": d,
+                      "num_blocks": blocks, "num_hidden_channels": hidden, "num_bins": bins,
+                      "tail_bound": tail_bound}]
+        else:
+            flows += [nf.flows.CoupledRationalQuadraticSpline(d, blocks, hidden, num_bins=bins,
+                                                               tail_bound=tail_bound,
+                                                               reverse_mask=bool(i % 2))]
+            spec += [{"type": "CoupledRationalQuadraticSpline", "num_input_channels": d,
+                      "num_blocks": blocks, "num_hidden_channels": hidden, "num_bins": bins,
+                      "tail_bound": tail_bound, "reverse_mask": bool(i % 2)}]
+        flows += [nf.flows.LULinearPermute(d, identity_init=lu_identity)]
+        spec += [{"type": "LULinearPermute", "num_channels": d}]
+    q0 = nf.distributions.DiagGaussian(d, trainable=False)
+    model = nf.NormalizingFlow(q0, flows)
+    perturb(model, sigma, seed + 1)
+    return model, {"kind": "NormalizingFlow", "q0": {"type": "DiagGaussian", "shape": [d]},
+                   "flows": spec}
+
+
+def case_spline_edges():
+    """Raw spline calls incl. the edge cases of SURVEY 8c.4 (x = +-B exactly, just outside,
+    interior-knot hits, |x| >> B, NaN)."""
+    from normflows.utils import splines
+    torch.manual_seed(7)
+    n, k, b = 64, 8, 3.0
+    out = {"torch_version": torch.__version__}
+    for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        g = torch.Generator().manual_seed(11)
+        uw = torch.randn(n, k, generator=g, dtype=torch.float64).to(dt)
+        uh = torch.randn(n, k, generator=g, dtype=torch.float64).to(dt)
+        ud = torch.randn(n, k - 1, generator=g, dtype=torch.float64).to(dt)
+        x = (torch.randn(n, generator=g, dtype=torch.float64) * 2).to(dt)
+        x[0], x[1], x[2], x[3] = b, -b, 3.0000002, -3.0000002
+        x[4], x[5], x[6] = 100.0, -1e6, float("nan")
+        # interior knot hits: compute knots exactly as the reference does
+        w = torch.softmax(uw, -1)
+        w = 1e-3 + (1 - 1e-3 * k) * w
+        cw = torch.nn.functional.pad(torch.cumsum(w, -1), (1, 0)) * (2 * b) - b
+        for j in range(1, 8):
+            x[7 + j] = cw[7 + j, j]
+        for inv in (False, True):
+            y, lad = splines.unconstrained_rational_quadratic_spline(
+                x.clone(), uw.clone(), uh.clone(), ud.clone(), inverse=inv, tails="linear",
+                tail_bound=b)
+            out[f"y_{tag}_{int(inv)}"] = y.numpy()
+            out[f"lad_{tag}_{int(inv)}"] = lad.numpy()
+        out[f"x_{tag}"], out[f"uw_{tag}"], out[f"uh_{tag}"], out[f"ud_{tag}"] = \
+            x.numpy(), uw.numpy(), uh.numpy(), ud.numpy()
+    np.savez_compressed(os.path.join(HERE, "spline_edges.npz"), **out)
+    print("wrote spline_edges")
+
+
+def case_realnvp():
+    """BASELINE config 1 shape: 8 x [MaskedAffineFlow(MLP[2,4,2] x2), ActNorm(2)] (examples/real_nvp.ipynb)."""
+    torch.manual_seed(3)
+    flows, spec = [], []
+    b = torch.tensor([1.0, 0.0])
+    for i in range(8):
+        s = nf.nets.MLP([2, 4, 2], init_zeros=True)
+        t = nf.nets.MLP([2, 4, 2], init_zeros=True)
+        flows += [nf.flows.MaskedAffineFlow(b if i % 2 == 0 else 1 - b, t, s)]
+        spec += [{"type": "MaskedAffineFlow"}]
+        flows += [nf.flows.ActNorm(2)]
+        spec += [{"type": "ActNorm"}]
+    model = nf.NormalizingFlow(nf.distributions.DiagGaussian(2), flows)
+    x = nf.distributions.TwoMoons().sample(256)
+    with torch.no_grad():
+        model.log_prob(x)  # ActNorm data-dependent init happens here (flows/normalization.py:33-38)
+    perturb(model, 0.2, 4)
+    dump("realnvp2d", model, {"kind": "NormalizingFlow", "q0": {"type": "DiagGaussian", "shape": [2]},
+                              "flows": spec}, x)
+
+
+def case_affine_block():
+    """README Real NVP: AffineCouplingBlock(MLP[1,64,64,2]) + Permute(2, 'swap')."""
+    torch.manual_seed(5)
+    flows, spec = [], []
+    for i in range(4):
+        pm = nf.nets.MLP([1, 64, 64, 2], init_zeros=True)
+        flows += [nf.flows.AffineCouplingBlock(pm)]
+        spec += [{"type": "AffineCouplingBlock", "net": "mlp", "scale_map": "exp", "split_mode": "channel"}]
+        flows += [nf.flows.Permute(2, mode="swap")]
+        spec += [{"type": "Permute", "mode": "swap"}]
+    model = nf.NormalizingFlow(nf.distributions.DiagGaussian(2), flows)
+    perturb(model, 0.1, 6)
+    x = torch.randn(128, 2, generator=torch.Generator().manual_seed(8))
+    dump("affine_block2d", model, {"kind": "NormalizingFlow", "q0": {"type": "DiagGaussian", "shape": [2]},
+                                   "flows": spec}, x)
+    # 6-D variant with shuffle permute and odd split sizes
+    torch.manual_seed(9)
+    flows, spec = [], []
+    for i in range(3):
+        pm = nf.nets.MLP([3, 32, 32, 6], init_zeros=False)
+        mode = "channel" if i % 2 == 0 else "channel_inv"
+        flows += [nf.flows.AffineCouplingBlock(pm, scale_map=["exp", "sigmoid", "sigmoid_inv"][i],
+                                               split_mode=mode)]
+        spec += [{"type": "AffineCouplingBlock", "net": "mlp",
+                  "scale_map": ["exp", "sigmoid", "sigmoid_inv"][i], "split_mode": mode}]
+        flows += [nf.flows.Permute(6, mode="shuffle")]
+        spec += [{"type": "Permute", "mode": "shuffle"}]
+    model = nf.NormalizingFlow(nf.distributions.DiagGaussian(6), flows)
+    perturb(model, 0.05, 10)
+    x = torch.randn(96, 6, generator=torch.Generator().manual_seed(12))
+    dump("affine_block6d", model, {"kind": "NormalizingFlow", "q0": {"type": "DiagGaussian", "shape": [6]},
+                                   "flows": spec}, x)
+
+
+def case_glow():
+    """examples/glow.ipynb cell 2 at reduced size: L=2, K=2, hidden 32, 3x8x8, 10 classes."""
+    torch.manual_seed(13)
+    L, K, hidden, shape, ncls = 2, 2, 32, (3, 8, 8), 10
+    q0, merges, flows, levels = [], [], [], []
+    for i in range(L):
+        flows_, lv = [], []
+        for j in range(K):
+            c = shape[0] * 2 ** (L + 1 - i)
+            flows_ += [nf.flows.GlowBlock(c, hidden, split_mode="channel", scale=True)]
+            lv += [{"type": "GlowBlock", "channels": c, "hidden_channels": hidden}]
+        flows_ += [nf.flows.Squeeze()]
+        lv += [{"type": "Squeeze"}]
+        flows += [flows_]
+        levels += [lv]
+        if i > 0:
+            merges += [nf.flows.Merge()]
+            ls = (shape[0] * 2 ** (L - i), shape[1] // 2 ** (L - i), shape[2] // 2 ** (L - i))
+        else:
+            ls = (shape[0] * 2 ** (L + 1), shape[1] // 2 ** L, shape[2] // 2 ** L)
+        q0 += [nf.distributions.ClassCondDiagGaussian(ls, ncls)]
+    model = nf.MultiscaleFlow(q0, flows, merges)
+    g = torch.Generator().manual_seed(14)
+    x = torch.rand(16, *shape, generator=g)
+    y = torch.randint(ncls, (16,), generator=g)
+    with torch.no_grad():
+        model.log_prob(x, y)  # ActNorm init
+    perturb(model, 0.03, 15)
+    dump("glow_small", model, {"kind": "MultiscaleFlow", "levels": levels, "class_cond": True,
+                               "num_classes": ncls}, x, y)
+    # ActNorm data-dependent init statistics, on their own
+    an = nf.flows.ActNorm((6, 1, 1))
+    xx = torch.randn(8, 6, 4, 4, generator=g).double() * 2 + 0.5
+    an = an.double()
+    with torch.no_grad():
+        zz, ld = an.inverse(xx)
+    np.savez_compressed(os.path.join(HERE, "actnorm_init.npz"), x=xx.numpy(), s=an.s.detach().numpy(),
+                        t=an.t.detach().numpy(), z=zz.numpy(), ld=ld.numpy())
+    print("wrote actnorm_init")
+
+
+def main():
+    case_spline_edges()
+    # the survey's sanity anchors are re-derived by tests from these files
+    for kind in ("ar", "coupled"):
+        m, spec = nsf(kind, 64, 2, 256, 2, seed=0, sigma=0.05)
+        x = torch.randn(48, 64, generator=torch.Generator().manual_seed(1234)) * 1.5
+        dump(f"nsf_{kind}_d64_h256_l2", m, spec, x, sampling=(kind == "coupled"))
+        m, spec = nsf(kind, 5, 3, 128, 2, seed=20, sigma=0.1, lu_identity=False)
+        x = torch.randn(64, 5, generator=torch.Generator().manual_seed(21)) * 1.5
+        dump(f"nsf_{kind}_d5_h128_l3", m, spec, x)
+        m, spec = nsf(kind, 2, 2, 32, 1, seed=30, sigma=0.2, tail_bound=2.0, bins=4, lu_identity=False)
+        x = torch.randn(64, 2, generator=torch.Generator().manual_seed(31)) * 1.5
+        dump(f"nsf_{kind}_d2_h32_l2_k4", m, spec, x)
+    case_realnvp()
+    case_affine_block()
+    case_glow()
+
+
+if __name__ == "__main__":
+    main()
