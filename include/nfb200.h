@@ -1,0 +1,180 @@
+/* nfb200.h -- C ABI of libnfb200.so: the B200-native coupling-stack hot path of normflows.
+ *
+ * The reference (normflows 1.7.3, pure Python/PyTorch) has no FFI; its seam for this path is the
+ * `Flow` protocol `forward(z)/inverse(z) -> (z', log_det[B])` (normflows/flows/base.py:13-24) driven
+ * by `NormalizingFlow.forward_kld / log_prob / inverse_and_log_det / forward_and_log_det`
+ * (normflows/core.py:40-102,182-197).  This header is what a binding for that seam calls: plain
+ * pointers and sizes, no torch types.  All tensors are fp32, row-major, contiguous.
+ *
+ *   - "dev" pointers are CUDA device pointers on the current device; `stream` is a cudaStream_t
+ *     passed as void* (NULL = default stream).  Nothing here synchronises unless its name ends in
+ *     `_host`; those take HOST pointers and include the host<->device copies (pinned or pageable).
+ *   - Parameter descriptors carry the layer's parameters EXACTLY as the reference stores them in
+ *     `state_dict()` (same shapes, nn.Linear [out,in] layout).  Packing for the kernels (mask
+ *     pre-multiply, bf16 hi/lo split, swizzle, LU assembly) happens inside `nfb_flow_finalize` /
+ *     `nfb_flow_repack`; the descriptor pointers must stay valid and are re-read on repack.
+ *   - Every function returns 0 on success; on failure a non-zero code and `nfb_last_error()`
+ *     holds a message (thread-local).  Argument errors mirror the reference's ValueErrors.
+ *   - direction: NFB_INVERSE is the reference's `.inverse()` (density pass, x -> z);
+ *     NFB_FORWARD is `.forward()` (sampling pass, z -> x).
+ *
+ * There is no CPU implementation behind this ABI: without a CUDA device every compute entry point
+ * fails with NFB_ERR_CUDA.
+ */
+#ifndef NFB200_H
+#define NFB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built -fvisibility=hidden; these are its exports */
+#endif
+
+#define NFB_ABI_VERSION 1
+#define NFB_INVERSE 0
+#define NFB_FORWARD 1
+
+typedef struct nfb_flow nfb_flow_t;
+
+/* ---- library ---- */
+int nfb_abi_version(void);
+const char* nfb_last_error(void);
+/* sm count / compute capability of the current device */
+int nfb_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- stand-alone operators (device pointers) ---- */
+
+/* utils/splines.py:16-97 `unconstrained_rational_quadratic_spline(tails="linear")`.
+ * x,y: [rows, feats]; params: [rows, feats*(3*num_bins-1)] laid out per feature as
+ * [widths(K) | heights(K) | derivatives(K-1)] (neural_spline/coupling.py:157-160,:330-332).
+ * wh_scale multiplies the width/height logits (1/sqrt(hidden) in the coupling layer).
+ * log_det: [rows]; += sum over features when `accumulate`, else overwritten.  May be NULL. */
+int nfb_rqs_spline(const float* x_dev, const float* params_dev, float* y_dev, float* log_det_dev,
+                   int64_t rows, int32_t feats, int32_t num_bins, float tail_bound, float wh_scale,
+                   int32_t inverse, int32_t accumulate, void* stream);
+
+/* distributions/base.py:94-103 DiagGaussian.log_prob: log_q[r] (+)= log N(z_r; loc, exp(log_scale)) */
+int nfb_diag_gaussian_log_prob(const float* z_dev, const float* loc_dev, const float* log_scale_dev,
+                               float* log_q_dev, int64_t rows, int32_t dim, int32_t accumulate,
+                               void* stream);
+
+/* ---- layer parameter descriptors (device pointers into the caller's parameters) ---- */
+
+/* A residual conditioner: nets/resnet.py:53-104 ResidualNet (mask pointers NULL) or
+ * nets/made.py:217-304 MADE with residual blocks (mask pointers = the `mask` buffers).
+ * blocks: 2*num_blocks entries, ordered blocks.0.linear_layers.0, blocks.0.linear_layers.1, ... */
+typedef struct {
+    int32_t in_features, hidden_features, out_features, num_blocks;
+    const float* w_initial; const float* b_initial; const float* m_initial;
+    const float* const* w_blocks; const float* const* b_blocks; const float* const* m_blocks;
+    const float* w_final; const float* b_final; const float* m_final;
+} nfb_resnet_desc_t;
+
+/* flows/neural_spline/wrapper.py:186-244 AutoregressiveRationalQuadraticSpline */
+typedef struct {
+    int32_t features, num_bins;
+    float tail_bound;
+    nfb_resnet_desc_t net; /* mprqat.autoregressive_net.* */
+} nfb_ar_rqs_desc_t;
+
+/* flows/neural_spline/wrapper.py:14-85 CoupledRationalQuadraticSpline */
+typedef struct {
+    int32_t features, num_bins, num_identity, num_transform;
+    float tail_bound;
+    const int64_t* identity_features;  /* prqct.identity_features  (device, int64 as in state_dict) */
+    const int64_t* transform_features; /* prqct.transform_features */
+    nfb_resnet_desc_t net;             /* prqct.transform_net.* */
+    const float* uncond_widths;        /* prqct.unconditional_transform.unnormalized_widths  [n_id,K]   */
+    const float* uncond_heights;       /*                               unnormalized_heights [n_id,K]   */
+    const float* uncond_derivatives;   /*                               unnormalized_derivatives [n_id,K-1] */
+} nfb_coupled_rqs_desc_t;
+
+/* flows/mixing.py:535-563 LULinearPermute */
+typedef struct {
+    int32_t features;
+    const int64_t* permutation;   /* permutation._permutation [features] (device, int64) */
+    const float* lower_entries;   /* linear.lower_entries  [n(n-1)/2] */
+    const float* upper_entries;   /* linear.upper_entries  [n(n-1)/2] */
+    const float* unconstrained_upper_diag; /* [n] */
+    const float* bias;            /* linear.bias [n] */
+    float eps;                    /* _LULinear eps (1e-3) */
+} nfb_lu_desc_t;
+
+/* nets/mlp.py:5-58 MLP (Linear / LeakyReLU stack, last layer linear) */
+typedef struct {
+    int32_t num_layers;           /* number of Linear layers, <= 6; 0 = net absent */
+    int32_t sizes[7];             /* sizes[0]=in ... sizes[num_layers]=out */
+    const float* w[6];
+    const float* b[6];
+    float leaky;
+} nfb_mlp_desc_t;
+
+/* flows/affine/coupling.py:174-229 MaskedAffineFlow */
+typedef struct { int32_t features; const float* b; nfb_mlp_desc_t s; nfb_mlp_desc_t t; } nfb_masked_affine_desc_t;
+
+/* flows/affine/coupling.py:232-267 AffineCouplingBlock with an MLP param_map */
+typedef struct {
+    int32_t features;
+    int32_t scale;       /* bool */
+    int32_t scale_map;   /* 0 exp, 1 sigmoid, 2 sigmoid_inv */
+    int32_t split_mode;  /* 0 channel, 1 channel_inv */
+    nfb_mlp_desc_t param_map;
+} nfb_affine_coupling_desc_t;
+
+/* flows/affine/coupling.py:9-54 AffineConstFlow; flows/normalization.py:7-39 ActNorm after init */
+typedef struct { int32_t features; const float* s; const float* t; } nfb_affine_const_desc_t;
+
+/* flows/mixing.py:9-54 Permute: forward z[:, perm], inverse z[:, inv_perm] (host int32 arrays) */
+typedef struct { int32_t features; const int32_t* perm; const int32_t* inv_perm; } nfb_permute_desc_t;
+
+/* ---- flow object: an ordered list of layers + base density, packed for the device ---- */
+int nfb_flow_create(nfb_flow_t** out, int32_t features);
+int nfb_flow_destroy(nfb_flow_t* f);
+int nfb_flow_add_ar_rqs(nfb_flow_t* f, const nfb_ar_rqs_desc_t* d);
+int nfb_flow_add_coupled_rqs(nfb_flow_t* f, const nfb_coupled_rqs_desc_t* d);
+int nfb_flow_add_lu_linear_permute(nfb_flow_t* f, const nfb_lu_desc_t* d);
+int nfb_flow_add_masked_affine(nfb_flow_t* f, const nfb_masked_affine_desc_t* d);
+int nfb_flow_add_affine_coupling(nfb_flow_t* f, const nfb_affine_coupling_desc_t* d);
+int nfb_flow_add_affine_const(nfb_flow_t* f, const nfb_affine_const_desc_t* d);
+int nfb_flow_add_permute(nfb_flow_t* f, const nfb_permute_desc_t* d);
+/* q0 = DiagGaussian(features): loc/log_scale [features] (distributions/base.py:71-76) */
+int nfb_flow_set_base_diag_gaussian(nfb_flow_t* f, const float* loc_dev, const float* log_scale_dev);
+/* pack parameters; `use_tensor_cores`=0 forces the plain-fp32 kernels for every layer (A/B parity) */
+int nfb_flow_finalize(nfb_flow_t* f, int32_t use_tensor_cores, void* stream);
+/* re-read the descriptor pointers after a parameter update (optimizer step / load_state_dict) */
+int nfb_flow_repack(nfb_flow_t* f, void* stream);
+int nfb_flow_num_layers(const nfb_flow_t* f);
+/* how many CUDA kernels the last pass launched (bench.py reports it as gpu_launches) */
+int64_t nfb_flow_last_launch_count(const nfb_flow_t* f);
+/* 1 if layer `index` runs on the fused tcgen05 kernel in the density direction */
+int nfb_flow_layer_is_fused(const nfb_flow_t* f, int32_t index);
+
+/* flows/base.py:13-24: apply ONE layer.  log_det_dev [rows]: overwritten (accumulate=0) or += . */
+int nfb_flow_layer_apply(nfb_flow_t* f, int32_t index, int32_t direction, const float* z_in_dev,
+                         float* z_out_dev, float* log_det_dev, int64_t rows, int32_t accumulate,
+                         void* stream);
+/* core.py:70-85 inverse_and_log_det (direction=NFB_INVERSE, layers last-to-first) and
+ * core.py:40-55 forward_and_log_det (NFB_FORWARD).  z_out may alias z_in. */
+int nfb_flow_transform(nfb_flow_t* f, int32_t direction, const float* z_in_dev, float* z_out_dev,
+                       float* log_det_dev, int64_t rows, void* stream);
+/* core.py:182-197 log_prob: log_q[r] = sum log_det + q0.log_prob(z) */
+int nfb_flow_log_prob(nfb_flow_t* f, const float* x_dev, float* log_q_dev, int64_t rows, void* stream);
+/* core.py:87-102 forward_kld: *loss_dev = -mean(log_q); *sum_dev (optional, double) = sum(log_q),
+ * the per-rank partial a data-parallel caller all-reduces. */
+int nfb_flow_forward_kld(nfb_flow_t* f, const float* x_dev, int64_t rows, float* loss_dev,
+                         double* sum_dev, void* stream);
+
+/* ---- host-buffer entry points (what a non-CUDA caller binds; copies are inside) ---- */
+int nfb_flow_log_prob_host(nfb_flow_t* f, const float* x_host, float* log_q_host, int64_t rows);
+int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, float* loss_host);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFB200_H */

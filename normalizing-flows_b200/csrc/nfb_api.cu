@@ -1,0 +1,1020 @@
+// nfb_api.cu -- the extern "C" surface declared in include/nfb200.h.
+//
+// A `nfb_flow` is the packed, device-resident image of `NormalizingFlow(q0, flows)`
+// (normflows/core.py:9-25): the ordered layer list, each layer's parameters re-laid-out for the
+// kernels, and the execution plan for the density pass (core.py:98-100 walks the layers
+// last-to-first calling `.inverse`) and the sampling pass (core.py:52-54).
+//
+// Execution plan ("groups"):
+//   FUSED  : [LULinearPermute +] neural-spline block on the tcgen05 kernel (nfb_fused_rqs.cu)
+//   AFFINE : a maximal run of low-dimensional affine-family layers in one kernel (nfb_affine.cu)
+//   SINGLE : any other layer through the generic fp32 kernels (nfb_kernels.cu)
+#include <cstdarg>
+#include <cstring>
+#include <cmath>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/nfb200.h"
+#include "nfb_kernels.h"
+
+static thread_local std::string g_err;
+void nfb_set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+namespace {
+using namespace nfb;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    int reserve(size_t n) {
+        if (n <= bytes) return NFB_OK;
+        release();
+        NFB_CUDA(cudaMalloc(&p, n ? n : 16));
+        bytes = n;
+        return NFB_OK;
+    }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+    template <typename T> int upload(const std::vector<T>& v) {
+        int rc = reserve(v.size() * sizeof(T));
+        if (rc) return rc;
+        if (!v.empty()) NFB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return NFB_OK;
+    }
+};
+
+template <typename T>
+int download(const T* dev, size_t n, std::vector<T>& out) {
+    out.resize(n);
+    if (n) NFB_CUDA(cudaMemcpy(out.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost));
+    return NFB_OK;
+}
+
+#define NFB_TRY(expr) do { int rc__ = (expr); if (rc__) return rc__; } while (0)
+
+enum LayerKind { L_AR_RQS, L_COUPLED_RQS, L_LU, L_MASKED_AFFINE, L_AFFINE_COUPLING, L_AFFINE_CONST, L_PERMUTE };
+
+struct NetDesc {  // deep copy of nfb_resnet_desc_t
+    int in = 0, H = 0, out = 0, nb = 0;
+    const float *w0 = nullptr, *b0 = nullptr, *m0 = nullptr, *wf = nullptr, *bf = nullptr, *mf = nullptr;
+    std::vector<const float*> wb, bb, mb;
+};
+
+struct NetPack {  // generic path: effective (mask-multiplied) fp32 weights
+    std::vector<DevBuf> owned;
+    const float* w0 = nullptr;
+    const float* wf = nullptr;
+    std::vector<const float*> wb;
+};
+
+struct FusedPack {
+    bool ok = false;
+    int D = 0, H = 0, n_hidden = 0, T = 0, n_chunks = 0, n_id = 0, n_steps = 0;
+    float tail = 3.f;
+    size_t rqs_bytes = 0;
+    std::vector<FusedStep> steps_host;
+    DevBuf wstream, steps, bias_h, bias_f, in_idx, tr_idx, id_idx, uncond;
+    struct Gemm { DevBuf src_row, src_col, row_scale; const float* W; const float* M; int src_cols, n_pad, k_pad, rpr; size_t off; };
+    std::vector<Gemm> gemms;
+    // LU + this block as one launch (built when the next layer in list order is an LU)
+    bool pair_ok = false;
+    int pair_steps = 0;
+    DevBuf pair_wstream, pair_steps_dev, lu_src_row, lu_src_col, bias_lu;
+};
+
+struct Layer {
+    LayerKind kind;
+    int D = 0, K = 8;
+    float tail = 3.f;
+    // rqs
+    NetDesc net;
+    NetPack pack;
+    FusedPack fused;
+    float wh_scale = 1.f;
+    int n_id = 0, n_tr = 0;
+    const int64_t *id64 = nullptr, *tr64 = nullptr;
+    DevBuf id_idx, tr_idx;  // int32 on device
+    const float *uw = nullptr, *uh = nullptr, *ud = nullptr;
+    DevBuf uncond;          // [n_id][3K-1]
+    // lu
+    nfb_lu_desc_t lu{};
+    DevBuf lu_Wd, lu_Ws, lu_bs, lu_logdet, lu_perm, lu_tmp;
+    std::vector<int> perm_host;
+    // affine family
+    AffineOp op{};
+    std::vector<int> perm_fwd, perm_inv;
+    DevBuf perm_fwd_dev, perm_inv_dev;
+};
+
+enum GroupKind { G_FUSED_PAIR, G_FUSED, G_AFFINE, G_SINGLE };
+struct Group { GroupKind kind; int first, last; DevBuf ops; };
+
+}  // namespace
+
+struct nfb_flow {
+    int D = 0;
+    bool finalized = false;
+    bool use_tc = true;
+    int sm_count = 148;
+    std::vector<std::unique_ptr<Layer>> layers;
+    std::vector<Group> groups;
+    const float* base_loc = nullptr;
+    const float* base_log_scale = nullptr;
+    // workspaces
+    DevBuf zA, zB, logq, hA, hB, hT, params, E, scratch_sum, loss, err, ar_tmp, pair_tmp, host_x, zfinal;
+    long long launches = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// generic conditioner
+// ------------------------------------------------------------------------------------------
+int copy_net(const nfb_resnet_desc_t& d, NetDesc& n) {
+    NFB_CHECK(d.in_features > 0 && d.hidden_features > 0 && d.out_features > 0 && d.num_blocks >= 0,
+              NFB_ERR_ARG, "resnet desc: bad sizes");
+    NFB_CHECK(d.w_initial && d.b_initial && d.w_final && d.b_final, NFB_ERR_ARG, "resnet desc: null weights");
+    n.in = d.in_features; n.H = d.hidden_features; n.out = d.out_features; n.nb = d.num_blocks;
+    n.w0 = d.w_initial; n.b0 = d.b_initial; n.m0 = d.m_initial;
+    n.wf = d.w_final; n.bf = d.b_final; n.mf = d.m_final;
+    for (int i = 0; i < 2 * n.nb; ++i) {
+        NFB_CHECK(d.w_blocks && d.b_blocks && d.w_blocks[i] && d.b_blocks[i], NFB_ERR_ARG, "resnet desc: null block weights");
+        n.wb.push_back(d.w_blocks[i]);
+        n.bb.push_back(d.b_blocks[i]);
+        n.mb.push_back(d.m_blocks ? d.m_blocks[i] : nullptr);
+    }
+    return NFB_OK;
+}
+
+int pack_net_generic(const NetDesc& n, NetPack& p, cudaStream_t st) {
+    p.owned.clear(); p.wb.clear();
+    auto eff = [&](const float* w, const float* m, size_t cnt, const float** out) -> int {
+        if (!m) { *out = w; return NFB_OK; }
+        DevBuf b;
+        NFB_TRY(b.reserve(cnt * sizeof(float)));
+        NFB_TRY(launch_mask_mul(w, m, b.as<float>(), (long long)cnt, st));
+        *out = b.as<float>();
+        p.owned.push_back(std::move(b));
+        return NFB_OK;
+    };
+    NFB_TRY(eff(n.w0, n.m0, (size_t)n.H * n.in, &p.w0));
+    for (int i = 0; i < 2 * n.nb; ++i) {
+        const float* w;
+        NFB_TRY(eff(n.wb[i], n.mb[i], (size_t)n.H * n.H, &w));
+        p.wb.push_back(w);
+    }
+    NFB_TRY(eff(n.wf, n.mf, (size_t)n.out * n.H, &p.wf));
+    return NFB_OK;
+}
+
+// params[rows, out] = net(X[:, xidx])
+int run_net_generic(nfb_flow* f, const NetDesc& n, const NetPack& p, const float* X, int ldx,
+                    const int* xidx, long long rows, float* params, cudaStream_t st) {
+    NFB_TRY(f->hA.reserve((size_t)rows * n.H * 4));
+    NFB_TRY(f->hB.reserve((size_t)rows * n.H * 4));
+    NFB_TRY(f->hT.reserve((size_t)rows * n.H * 4));
+    float* h = f->hA.as<float>();
+    float* h2 = f->hB.as<float>();
+    float* t = f->hT.as<float>();
+    NFB_TRY(launch_linear(X, ldx, xidx, p.w0, n.b0, nullptr, 0, h, n.H, rows, n.H, n.in, 0, 0, 0.f, st));
+    f->launches++;
+    for (int b = 0; b < n.nb; ++b) {  // nets/resnet.py:37-50 / nets/made.py:199-214
+        NFB_TRY(launch_linear(h, n.H, nullptr, p.wb[2 * b], n.bb[2 * b], nullptr, 0, t, n.H, rows, n.H, n.H, 1, 0, 0.f, st));
+        NFB_TRY(launch_linear(t, n.H, nullptr, p.wb[2 * b + 1], n.bb[2 * b + 1], h, n.H, h2, n.H, rows, n.H, n.H, 1, 0, 0.f, st));
+        f->launches += 2;
+        std::swap(h, h2);
+    }
+    NFB_TRY(launch_linear(h, n.H, nullptr, p.wf, n.bf, nullptr, 0, params, n.out, rows, n.out, n.H, 0, 0, 0.f, st));
+    f->launches++;
+    return NFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused pack
+// ------------------------------------------------------------------------------------------
+uint16_t make_ctl(int col, int first, int wait, int signal) {
+    return (uint16_t)((col & 511) | ((first & 1) << 9) | ((wait & 7) << 10) | ((signal & 7) << 13));
+}
+int chunk_col_host(int i) { return (i & 1) * 96 + (i >> 1) * 256; }
+
+int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
+    FusedPack& F = L.fused;
+    F.ok = false; F.pair_ok = false;
+    const NetDesc& n = L.net;
+    const bool ar = (L.kind == L_AR_RQS);
+    const int T = ar ? L.D : L.n_tr;
+    if (!f->use_tc) return NFB_OK;
+    if (L.K != 8 || L.D > 64 || n.H % 64 != 0 || n.H > 256 || n.in > 64 || T > 64 || T < 1) return NFB_OK;
+    if (n.out != T * 23) return NFB_OK;
+    const int H = n.H, n_hidden = 1 + 2 * n.nb, n_chunks = (T + 3) / 4;
+    const int rpr = (H <= 128) ? H : (H == 192 ? 96 : 128);
+    const int kcs_h = H / 64;
+    // ---- step table ----
+    std::vector<FusedStep> steps;
+    auto add = [&](int rows, int a0, int a1, int a2, int col, int first, int wait, int signal) {
+        FusedStep s;
+        s.bytes16 = (uint16_t)(rows * 8);
+        s.n8 = (uint8_t)(rows / 8);
+        s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
+        s.ctl = make_ctl(col, first, wait, signal);
+        steps.push_back(s);
+    };
+    for (int ph = 0; ph < n_hidden; ++ph) {
+        const int region = (ph & 1) ? 256 : 0;
+        const bool accum_onto = (ph > 0 && (ph & 1) == 0);  // second GEMM of a residual block: h += ...
+        const int kcs = (ph == 0) ? 1 : kcs_h;
+        const int nrb = H / rpr;
+        for (int rb = 0; rb < nrb; ++rb)
+            for (int kc = 0; kc < kcs; ++kc) {
+                const bool very_first = (rb == 0 && kc == 0);
+                const bool very_last = (rb == nrb - 1 && kc == kcs - 1);
+                add(rpr, kc, 4 + kc, 0xFF, region + rb * rpr, (kc == 0 && !accum_onto) ? 1 : 0, very_first ? 1 : 0, 0);
+                add(rpr, kc, 0xFF, 0xFF, region + rb * rpr, 0, 0, very_last ? 1 : 0);
+            }
+    }
+    for (int c = 0; c < n_chunks; ++c) {
+        const int b = c & 3;
+        for (int kc = 0; kc < kcs_h; ++kc) {
+            const int wait = (kc == 0) ? (c == 0 ? 6 : 2 + b) : 0;
+            add(96, kc, 4 + kc, 0xFF, chunk_col_host(b), kc == 0 ? 1 : 0, wait, 0);
+            add(96, kc, 0xFF, 0xFF, chunk_col_host(b), 0, 0, (kc == kcs_h - 1) ? 2 + b : 0);
+        }
+    }
+    if (steps.size() + 3 > 256) return NFB_OK;  // step table would not fit in shared memory
+    F.steps_host = steps;
+    F.n_steps = (int)steps.size();
+    F.D = L.D; F.H = H; F.n_hidden = n_hidden; F.T = T; F.n_chunks = n_chunks; F.tail = L.tail;
+    F.n_id = ar ? 0 : L.n_id;
+    size_t total = 0;
+    for (auto& s : steps) total += (size_t)s.bytes16 * 16;
+    F.rqs_bytes = total;
+    NFB_TRY(F.wstream.reserve(total));
+    NFB_TRY(F.steps.upload(steps));
+
+    // ---- GEMM source tables ----
+    F.gemms.clear();
+    auto add_gemm = [&](const float* W, const float* M, int src_rows, int src_cols, int n_pad, int k_pad,
+                        int rpr_, const std::vector<int>& sr, const std::vector<int>& sc,
+                        const std::vector<float>& rs, size_t off) -> int {
+        FusedPack::Gemm g;
+        g.W = W; g.M = M; g.src_cols = src_cols; g.n_pad = n_pad; g.k_pad = k_pad; g.rpr = rpr_; g.off = off;
+        (void)src_rows;
+        NFB_TRY(g.src_row.upload(sr));
+        NFB_TRY(g.src_col.upload(sc));
+        if (!rs.empty()) NFB_TRY(g.row_scale.upload(rs));
+        F.gemms.push_back(std::move(g));
+        return NFB_OK;
+    };
+    size_t off = 0;
+    {
+        std::vector<int> sr(H), sc(64);
+        for (int i = 0; i < H; ++i) sr[i] = i;
+        for (int k = 0; k < 64; ++k) sc[k] = k < n.in ? k : -1;
+        NFB_TRY(add_gemm(n.w0, n.m0, H, n.in, H, 64, rpr, sr, sc, {}, off));
+        off += (size_t)H * 64 * 2 * 2;
+    }
+    for (int i = 0; i < 2 * n.nb; ++i) {
+        std::vector<int> sr(H), sc(H);
+        for (int j = 0; j < H; ++j) sr[j] = sc[j] = j;
+        NFB_TRY(add_gemm(n.wb[i], n.mb[i], H, H, H, H, rpr, sr, sc, {}, off));
+        off += (size_t)H * H * 2 * 2;
+    }
+    std::vector<int> fr(n_chunks * 96);
+    std::vector<float> fs(n_chunks * 96);
+    {
+        std::vector<int> sc(H);
+        for (int j = 0; j < H; ++j) sc[j] = j;
+        for (int i = 0; i < n_chunks * 96; ++i) {
+            const int t = 4 * (i / 96) + (i % 96) / 24, q = (i % 96) % 24;
+            fr[i] = (t < T && q < 23) ? t * 23 + q : -1;
+            fs[i] = (q < 16) ? L.wh_scale : 1.f;
+        }
+        NFB_TRY(add_gemm(n.wf, n.mf, n.out, H, n_chunks * 96, H, 96, fr, sc, fs, off));
+        off += (size_t)n_chunks * 96 * H * 2 * 2;
+    }
+    NFB_CHECK(off == total, NFB_ERR_STATE, "fused pack: stream size mismatch %zu vs %zu", off, total);
+
+    // ---- index lists ----
+    std::vector<int> in_idx(64, -1), tr_idx(T);
+    if (ar) {
+        for (int k = 0; k < L.D; ++k) in_idx[k] = k;
+        for (int t = 0; t < T; ++t) tr_idx[t] = t;
+    } else {
+        std::vector<int64_t> id64, tr64;
+        NFB_TRY(download(L.id64, (size_t)L.n_id, id64));
+        NFB_TRY(download(L.tr64, (size_t)L.n_tr, tr64));
+        for (int k = 0; k < L.n_id; ++k) in_idx[k] = (int)id64[k];
+        for (int t = 0; t < T; ++t) tr_idx[t] = (int)tr64[t];
+        std::vector<int> idv(L.n_id);
+        for (int k = 0; k < L.n_id; ++k) idv[k] = (int)id64[k];
+        NFB_TRY(F.id_idx.upload(idv));
+    }
+    NFB_TRY(F.in_idx.upload(in_idx));
+    NFB_TRY(F.tr_idx.upload(tr_idx));
+    F.ok = true;
+    (void)st;
+    return NFB_OK;
+}
+
+// (re)pack the weights/biases of a fused block from the live parameters
+int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
+    FusedPack& F = L.fused;
+    if (!F.ok) return NFB_OK;
+    const NetDesc& n = L.net;
+    size_t emax = 0;
+    for (auto& g : F.gemms) emax = std::max(emax, (size_t)g.n_pad * g.k_pad);
+    NFB_TRY(f->E.reserve(emax * sizeof(float)));
+    for (auto& g : F.gemms) {
+        NFB_TRY(launch_build_effective(g.W, g.M, g.src_cols, g.src_row.as<int>(), g.src_col.as<int>(),
+                                       g.row_scale.p ? g.row_scale.as<float>() : nullptr, f->E.as<float>(),
+                                       g.n_pad, g.k_pad, st));
+        NFB_TRY(launch_swizzle_split(f->E.as<float>(), g.n_pad, g.k_pad, g.rpr, 2,
+                                     F.wstream.as<uint8_t>() + g.off, st));
+    }
+    // biases (tiny; synchronous download is fine at pack time)
+    NFB_CUDA(cudaStreamSynchronize(st));
+    const int H = n.H;
+    std::vector<float> bh((size_t)F.n_hidden * 256, 0.f), b0, tmp;
+    NFB_TRY(download(n.b0, (size_t)H, b0));
+    std::vector<float> cum = b0;
+    for (int j = 0; j < H; ++j) bh[j] = b0[j];
+    for (int b = 0; b < n.nb; ++b) {
+        NFB_TRY(download(n.bb[2 * b], (size_t)H, tmp));
+        for (int j = 0; j < H; ++j) bh[(size_t)(1 + 2 * b) * 256 + j] = tmp[j];
+        NFB_TRY(download(n.bb[2 * b + 1], (size_t)H, tmp));
+        for (int j = 0; j < H; ++j) { cum[j] += tmp[j]; bh[(size_t)(2 + 2 * b) * 256 + j] = cum[j]; }
+    }
+    NFB_TRY(F.bias_h.upload(bh));
+    std::vector<float> bfin, bf((size_t)F.n_chunks * 96, 0.f);
+    NFB_TRY(download(n.bf, (size_t)n.out, bfin));
+    for (int i = 0; i < F.n_chunks * 96; ++i) {
+        const int t = 4 * (i / 96) + (i % 96) / 24, q = (i % 96) % 24;
+        if (t < F.T && q < 23) bf[i] = bfin[t * 23 + q] * ((q < 16) ? L.wh_scale : 1.f);
+    }
+    NFB_TRY(F.bias_f.upload(bf));
+    if (L.kind == L_COUPLED_RQS) {
+        std::vector<float> w, h, d, tab((size_t)L.n_id * 23);
+        NFB_TRY(download(L.uw, (size_t)L.n_id * 8, w));
+        NFB_TRY(download(L.uh, (size_t)L.n_id * 8, h));
+        NFB_TRY(download(L.ud, (size_t)L.n_id * 7, d));
+        for (int i = 0; i < L.n_id; ++i) {
+            for (int k = 0; k < 8; ++k) { tab[i * 23 + k] = w[i * 8 + k]; tab[i * 23 + 8 + k] = h[i * 8 + k]; }
+            for (int k = 0; k < 7; ++k) tab[i * 23 + 16 + k] = d[i * 7 + k];
+        }
+        NFB_TRY(F.uncond.upload(tab));
+    }
+    return NFB_OK;
+}
+
+// LU layer pack (generic + the pieces the fused pair needs)
+int repack_lu(nfb_flow* f, Layer& L, cudaStream_t st) {
+    const int n = L.D;
+    NFB_TRY(L.lu_Wd.reserve((size_t)n * n * 4));
+    NFB_TRY(L.lu_Ws.reserve((size_t)n * n * 4));
+    NFB_TRY(L.lu_logdet.reserve(4));
+    NFB_TRY(launch_lu_pack(L.lu.lower_entries, L.lu.upper_entries, L.lu.unconstrained_upper_diag,
+                           L.lu.eps, n, L.lu_Wd.as<float>(), L.lu_Ws.as<float>(),
+                           L.lu_logdet.as<float>(), st));
+    // sampling direction: x = (z - b) Winv^T = z Winv^T + bs with bs = -Winv b (tiny; host side)
+    NFB_CUDA(cudaStreamSynchronize(st));
+    std::vector<float> winv, b, bs(n);
+    NFB_TRY(download(L.lu_Ws.as<float>(), (size_t)n * n, winv));
+    NFB_TRY(download(L.lu.bias, (size_t)n, b));
+    for (int i = 0; i < n; ++i) {
+        double acc = 0.0;
+        for (int k = 0; k < n; ++k) acc += (double)winv[(size_t)i * n + k] * b[k];
+        bs[i] = (float)(-acc);
+    }
+    NFB_TRY(L.lu_bs.upload(bs));
+    (void)f;
+    return NFB_OK;
+}
+
+int build_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
+    FusedPack& F = R.fused;
+    F.pair_ok = false;
+    if (!F.ok || U.D != R.D || U.D > 64) return NFB_OK;
+    if (F.n_steps + 3 > 256) return NFB_OK;
+    std::vector<FusedStep> steps;
+    auto mk = [&](int a0, int a1, int a2, int first, int wait, int signal) {
+        FusedStep s;
+        s.bytes16 = 64 * 8; s.n8 = 8; s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
+        s.ctl = make_ctl(256, first, wait, signal);
+        steps.push_back(s);
+    };
+    mk(0, 4, 1, 1, 1, 0);        // W_h x {A_h, A_m, A_l}
+    mk(0, 4, 0xFF, 0, 0, 0);     // W_m x {A_h, A_m}
+    mk(0, 0xFF, 0xFF, 0, 0, 1);  // W_l x {A_h}
+    steps.insert(steps.end(), F.steps_host.begin(), F.steps_host.end());
+    F.pair_steps = (int)steps.size();
+    NFB_TRY(F.pair_steps_dev.upload(steps));
+    NFB_TRY(F.pair_wstream.reserve(3 * 8192 + F.rqs_bytes));
+    std::vector<int> sr(64), sc(64, -1);
+    for (int i = 0; i < 64; ++i) sr[i] = i < U.D ? i : -1;
+    for (int j = 0; j < U.D; ++j) sc[U.perm_host[j]] = j;  // E[i, perm[j]] = W[i, j]
+    NFB_TRY(F.lu_src_row.upload(sr));
+    NFB_TRY(F.lu_src_col.upload(sc));
+    F.pair_ok = true;
+    (void)f; (void)st;
+    return NFB_OK;
+}
+
+int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
+    FusedPack& F = R.fused;
+    if (!F.pair_ok) return NFB_OK;
+    NFB_TRY(f->E.reserve(64 * 64 * 4));
+    NFB_TRY(launch_build_effective(U.lu_Wd.as<float>(), nullptr, U.D, F.lu_src_row.as<int>(),
+                                   F.lu_src_col.as<int>(), nullptr, f->E.as<float>(), 64, 64, st));
+    NFB_TRY(launch_swizzle_split(f->E.as<float>(), 64, 64, 64, 3, F.pair_wstream.as<uint8_t>(), st));
+    NFB_CUDA(cudaMemcpyAsync(F.pair_wstream.as<uint8_t>() + 3 * 8192, F.wstream.p, F.rqs_bytes,
+                             cudaMemcpyDeviceToDevice, st));
+    std::vector<float> b, bl(64, 0.f);
+    NFB_CUDA(cudaStreamSynchronize(st));
+    NFB_TRY(download(U.lu.bias, (size_t)U.D, b));
+    for (int i = 0; i < U.D; ++i) bl[i] = b[i];
+    NFB_TRY(F.bias_lu.upload(bl));
+    return NFB_OK;
+}
+
+int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float* zout, float* logq,
+                       long long rows, int accumulate, cudaStream_t st) {
+    FusedPack& F = R.fused;
+    FusedParams p{};
+    p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows;
+    p.D = F.D; p.H = F.H; p.n_hidden = F.n_hidden; p.has_lu = U ? 1 : 0; p.T = F.T;
+    p.n_chunks = F.n_chunks; p.n_id = F.n_id; p.accumulate = accumulate; p.tail = F.tail;
+    p.n_steps = U ? F.pair_steps : F.n_steps;
+    p.wstream = U ? F.pair_wstream.as<uint8_t>() : F.wstream.as<uint8_t>();
+    p.steps = U ? F.pair_steps_dev.as<FusedStep>() : F.steps.as<FusedStep>();
+    p.bias_lu = U ? F.bias_lu.as<float>() : nullptr;
+    p.bias_h = F.bias_h.as<float>();
+    p.bias_f = F.bias_f.as<float>();
+    p.in_idx = F.in_idx.as<int>();
+    p.tr_idx = F.tr_idx.as<int>();
+    p.id_idx = F.id_idx.as<int>();
+    p.uncond = F.uncond.as<float>();
+    p.lu_logdet = U ? U->lu_logdet.as<float>() : nullptr;
+    p.err = f->err.as<int>();
+    NFB_TRY(launch_fused_rqs(p, f->sm_count, st));
+    f->launches++;
+    return NFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// per-layer generic application.  zin != zout.  logdet: [rows], accumulate semantic.
+// ------------------------------------------------------------------------------------------
+int zero_if(nfb_flow* f, float* logdet, long long rows, int accumulate, cudaStream_t st) {
+    if (logdet && !accumulate) { NFB_TRY(launch_fill(logdet, rows, 0.f, st)); f->launches++; }
+    return NFB_OK;
+}
+
+int apply_layer_generic(nfb_flow* f, Layer& L, int direction, const float* zin, float* zout,
+                        float* logdet, long long rows, int accumulate, cudaStream_t st) {
+    const int D = L.D;
+    switch (L.kind) {
+    case L_AR_RQS: {
+        const int P = 3 * L.K - 1;
+        NFB_TRY(f->params.reserve((size_t)rows * D * P * 4));
+        NFB_TRY(zero_if(f, logdet, rows, accumulate, st));
+        if (direction == NFB_INVERSE) {  // affine/autoregressive.py:24-27: one MADE pass
+            NFB_TRY(run_net_generic(f, L.net, L.pack, zin, D, nullptr, rows, f->params.as<float>(), st));
+            NFB_TRY(launch_rqs_rows(zin, f->params.as<float>(), zout, logdet, rows, D, D, nullptr, L.K,
+                                    L.tail, 1.f, 0, st));
+            f->launches++;
+        } else {  // affine/autoregressive.py:29-38: D MADE passes, spline inverse
+            NFB_TRY(f->ar_tmp.reserve((size_t)rows * D * 4));
+            float* out = f->ar_tmp.as<float>();
+            NFB_TRY(launch_fill(out, rows * D, 0.f, st));
+            f->launches++;
+            for (int i = 0; i < D; ++i) {
+                NFB_TRY(run_net_generic(f, L.net, L.pack, out, D, nullptr, rows, f->params.as<float>(), st));
+                const bool last = (i == D - 1);
+                NFB_TRY(launch_rqs_rows(zin, f->params.as<float>(), last ? zout : out, last ? logdet : nullptr,
+                                        rows, D, D, nullptr, L.K, L.tail, 1.f, 1, st));
+                f->launches++;
+            }
+        }
+        return NFB_OK;
+    }
+    case L_COUPLED_RQS: {
+        const int P = 3 * L.K - 1;
+        NFB_TRY(f->params.reserve((size_t)rows * L.n_tr * P * 4));
+        NFB_TRY(zero_if(f, logdet, rows, accumulate, st));
+        if (direction == NFB_INVERSE) {  // Coupling.forward, neural_spline/coupling.py:71-98
+            NFB_TRY(run_net_generic(f, L.net, L.pack, zin, D, L.id_idx.as<int>(), rows, f->params.as<float>(), st));
+            NFB_TRY(launch_rqs_rows(zin, f->params.as<float>(), zout, logdet, rows, L.n_tr, D,
+                                    L.tr_idx.as<int>(), L.K, L.tail, L.wh_scale, 0, st));
+            NFB_TRY(launch_rqs_shared(zin, L.uncond.as<float>(), zout, logdet, rows, L.n_id, D,
+                                      L.id_idx.as<int>(), L.K, L.tail, 0, st));
+            f->launches += 2;
+        } else {  // Coupling.inverse, :100-128: unconditional inverse first, net sees its output
+            NFB_TRY(launch_rqs_shared(zin, L.uncond.as<float>(), zout, logdet, rows, L.n_id, D,
+                                      L.id_idx.as<int>(), L.K, L.tail, 1, st));
+            NFB_TRY(run_net_generic(f, L.net, L.pack, zout, D, L.id_idx.as<int>(), rows, f->params.as<float>(), st));
+            NFB_TRY(launch_rqs_rows(zin, f->params.as<float>(), zout, logdet, rows, L.n_tr, D,
+                                    L.tr_idx.as<int>(), L.K, L.tail, L.wh_scale, 1, st));
+            f->launches += 2;
+        }
+        return NFB_OK;
+    }
+    case L_LU: {
+        if (direction == NFB_INVERSE) {  // mixing.py:560-563 -> :414-434
+            NFB_TRY(launch_linear(zin, D, L.lu_perm.as<int>(), L.lu_Wd.as<float>(), L.lu.bias, nullptr, 0,
+                                  zout, D, rows, D, D, 0, 0, 0.f, st));
+        } else {  // mixing.py:555-558 -> :436-473 : (z - b) (LU)^-T, then inverse permutation
+            NFB_TRY(f->hT.reserve((size_t)rows * D * 4));
+            // t = z W^-T - (W^-1 b) == (z - b) W^-T ; bias term applied via a second tiny pass below
+            NFB_TRY(launch_linear(zin, D, nullptr, L.lu_Ws.as<float>(), L.lu_bs.as<float>(), nullptr, 0,
+                                  f->hT.as<float>(), D, rows, D, D, 0, 0, 0.f, st));
+            NFB_TRY(launch_gather_cols(f->hT.as<float>(), zout, L.lu_tmp.as<int>(), rows, D, 1, st));
+            f->launches++;
+        }
+        f->launches++;
+        if (logdet) {
+            NFB_TRY(zero_if(f, logdet, rows, accumulate, st));
+            NFB_TRY(launch_add_scalar(logdet, rows, L.lu_logdet.as<float>(), direction == NFB_INVERSE ? 1.f : -1.f, st));
+            f->launches++;
+        }
+        return NFB_OK;
+    }
+    default:
+        break;
+    }
+    nfb_set_error("apply_layer_generic: layer kind %d not handled here", (int)L.kind);
+    return NFB_ERR_STATE;
+}
+
+bool is_affine_kind(const Layer& L) {
+    return L.kind == L_MASKED_AFFINE || L.kind == L_AFFINE_COUPLING || L.kind == L_AFFINE_CONST ||
+           L.kind == L_PERMUTE;
+}
+
+int copy_mlp(const nfb_mlp_desc_t& d, AffMlp& m, float* slope) {
+    NFB_CHECK(d.num_layers >= 0 && d.num_layers <= kAffMaxLayers, NFB_ERR_UNSUPPORTED, "MLP: %d layers > %d", d.num_layers, kAffMaxLayers);
+    m.n_layers = d.num_layers;
+    for (int i = 0; i <= d.num_layers; ++i) {
+        NFB_CHECK(d.sizes[i] >= 1 && d.sizes[i] <= kAffMaxW, NFB_ERR_UNSUPPORTED, "MLP: layer width %d > %d", d.sizes[i], kAffMaxW);
+        m.sizes[i] = d.sizes[i];
+    }
+    for (int i = 0; i < d.num_layers; ++i) {
+        NFB_CHECK(d.w[i] && d.b[i], NFB_ERR_ARG, "MLP: null weight");
+        m.w[i] = d.w[i]; m.b[i] = d.b[i];
+    }
+    if (d.num_layers) *slope = d.leaky;
+    return NFB_OK;
+}
+
+cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+int ensure_ws(nfb_flow* f, long long rows) {
+    NFB_TRY(f->zA.reserve((size_t)rows * f->D * 4));
+    NFB_TRY(f->zB.reserve((size_t)rows * f->D * 4));
+    NFB_TRY(f->logq.reserve((size_t)rows * 4));
+    NFB_TRY(f->scratch_sum.reserve(1024 * 8));
+    NFB_TRY(f->loss.reserve(16));
+    return NFB_OK;
+}
+
+// Apply execution group g.  in/out must differ.  logdet accumulates (+=) -- caller zeroes first.
+int run_group(nfb_flow* f, Group& g, int direction, const float* zin, float* zout, float* logdet,
+              long long rows, cudaStream_t st) {
+    switch (g.kind) {
+    case G_FUSED_PAIR:
+        if (direction == NFB_INVERSE)
+            return launch_fused_layer(f, *f->layers[g.first], f->layers[g.last].get(), zin, zout, logdet, rows, 1, st);
+        break;
+    case G_FUSED:
+        if (direction == NFB_INVERSE)
+            return launch_fused_layer(f, *f->layers[g.first], nullptr, zin, zout, logdet, rows, 1, st);
+        break;
+    case G_AFFINE:
+        NFB_TRY(launch_affine_stack(g.ops.p, g.last - g.first + 1, zin, zout, logdet, rows, f->D, 1, direction, st));
+        f->launches++;
+        return NFB_OK;
+    case G_SINGLE:
+        return apply_layer_generic(f, *f->layers[g.first], direction, zin, zout, logdet, rows, 1, st);
+    }
+    // fused groups in the sampling direction: generic kernels, layer by layer
+    if (g.first == g.last)
+        return apply_layer_generic(f, *f->layers[g.first], direction, zin, zout, logdet, rows, 1, st);
+    // pair = [spline block (first), LU (last)] in list order; forward applies first then last
+    NFB_TRY(f->pair_tmp.reserve((size_t)rows * f->D * 4));
+    NFB_TRY(apply_layer_generic(f, *f->layers[g.first], direction, zin, f->pair_tmp.as<float>(), logdet, rows, 1, st));
+    return apply_layer_generic(f, *f->layers[g.last], direction, f->pair_tmp.as<float>(), zout, logdet, rows, 1, st);
+}
+
+}  // namespace
+
+// ==========================================================================================
+// extern "C"
+// ==========================================================================================
+extern "C" {
+
+int nfb_abi_version(void) { return NFB_ABI_VERSION; }
+const char* nfb_last_error(void) { return g_err.c_str(); }
+
+int nfb_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    NFB_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    NFB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return NFB_OK;
+}
+
+int nfb_rqs_spline(const float* x, const float* params, float* y, float* log_det, int64_t rows,
+                   int32_t feats, int32_t num_bins, float tail_bound, float wh_scale, int32_t inverse,
+                   int32_t accumulate, void* stream) {
+    NFB_CHECK(x && params && y, NFB_ERR_ARG, "nfb_rqs_spline: null pointer");
+    NFB_CHECK(rows >= 0 && feats >= 0, NFB_ERR_ARG, "nfb_rqs_spline: negative size");
+    if (log_det && !accumulate) NFB_TRY(launch_fill(log_det, rows, 0.f, S(stream)));
+    return launch_rqs_rows(x, params, y, log_det, rows, feats, feats, nullptr, num_bins, tail_bound,
+                           wh_scale, inverse, S(stream));
+}
+
+int nfb_diag_gaussian_log_prob(const float* z, const float* loc, const float* log_scale, float* log_q,
+                               int64_t rows, int32_t dim, int32_t accumulate, void* stream) {
+    NFB_CHECK(z && loc && log_scale && log_q, NFB_ERR_ARG, "nfb_diag_gaussian_log_prob: null pointer");
+    return launch_diag_gauss(z, loc, log_scale, log_q, rows, dim, accumulate, S(stream));
+}
+
+int nfb_flow_create(nfb_flow_t** out, int32_t features) {
+    NFB_CHECK(out, NFB_ERR_ARG, "nfb_flow_create: null out");
+    NFB_CHECK(features >= 1, NFB_ERR_ARG, "nfb_flow_create: features must be >= 1");
+    int n = 0;
+    NFB_CUDA(cudaGetDeviceCount(&n));
+    NFB_CHECK(n > 0, NFB_ERR_CUDA, "nfb_flow_create: no CUDA device (this library has no CPU path)");
+    nfb_flow* f = new nfb_flow();
+    f->D = features;
+    int sm = 148;
+    if (nfb_device_info(&sm, nullptr, nullptr) == NFB_OK) f->sm_count = sm;
+    int rc = f->err.reserve(16);
+    if (rc) { delete f; return rc; }
+    cudaMemset(f->err.p, 0, 16);
+    *out = f;
+    return NFB_OK;
+}
+
+int nfb_flow_destroy(nfb_flow_t* f) {
+    delete f;
+    return NFB_OK;
+}
+
+#define NFB_NEW_LAYER(kind_)                                                             \
+    NFB_CHECK(f && d, NFB_ERR_ARG, "null argument");                                     \
+    NFB_CHECK(!f->finalized, NFB_ERR_STATE, "flow already finalized");                   \
+    NFB_CHECK(d->features == f->D, NFB_ERR_ARG, "Expected features = %d, got %d.", f->D, d->features); \
+    std::unique_ptr<Layer> L(new Layer());                                               \
+    L->kind = kind_;                                                                     \
+    L->D = f->D
+
+int nfb_flow_add_ar_rqs(nfb_flow_t* f, const nfb_ar_rqs_desc_t* d) {
+    NFB_NEW_LAYER(L_AR_RQS);
+    L->K = d->num_bins; L->tail = d->tail_bound; L->wh_scale = 1.f;  // MADE has no hidden_features attr
+    NFB_CHECK(L->K >= 1 && L->K <= 32, NFB_ERR_ARG, "num_bins out of range");
+    NFB_CHECK(kMinBinWidth * L->K <= 1.0f, NFB_ERR_ARG, "Minimal bin width too large for the number of bins");
+    NFB_TRY(copy_net(d->net, L->net));
+    NFB_CHECK(L->net.in == f->D && L->net.out == f->D * (3 * L->K - 1), NFB_ERR_ARG, "AR net shape mismatch");
+    L->n_tr = f->D;
+    f->layers.push_back(std::move(L));
+    return NFB_OK;
+}
+
+int nfb_flow_add_coupled_rqs(nfb_flow_t* f, const nfb_coupled_rqs_desc_t* d) {
+    NFB_NEW_LAYER(L_COUPLED_RQS);
+    L->K = d->num_bins; L->tail = d->tail_bound;
+    NFB_CHECK(L->K >= 1 && L->K <= 32, NFB_ERR_ARG, "num_bins out of range");
+    NFB_CHECK(kMinBinWidth * L->K <= 1.0f, NFB_ERR_ARG, "Minimal bin width too large for the number of bins");
+    NFB_CHECK(d->num_identity + d->num_transform == f->D && d->num_identity > 0 && d->num_transform > 0,
+              NFB_ERR_ARG, "coupled: identity + transform features must cover the input");
+    NFB_CHECK(d->identity_features && d->transform_features && d->uncond_widths && d->uncond_heights && d->uncond_derivatives,
+              NFB_ERR_ARG, "coupled: null pointer");
+    NFB_TRY(copy_net(d->net, L->net));
+    NFB_CHECK(L->net.in == d->num_identity && L->net.out == d->num_transform * (3 * L->K - 1), NFB_ERR_ARG, "coupled net shape mismatch");
+    L->wh_scale = 1.0f / sqrtf((float)L->net.H);  // neural_spline/coupling.py:334-336
+    L->n_id = d->num_identity; L->n_tr = d->num_transform;
+    L->id64 = d->identity_features; L->tr64 = d->transform_features;
+    L->uw = d->uncond_widths; L->uh = d->uncond_heights; L->ud = d->uncond_derivatives;
+    f->layers.push_back(std::move(L));
+    return NFB_OK;
+}
+
+int nfb_flow_add_lu_linear_permute(nfb_flow_t* f, const nfb_lu_desc_t* d) {
+    NFB_NEW_LAYER(L_LU);
+    NFB_CHECK(d->permutation && d->lower_entries && d->upper_entries && d->unconstrained_upper_diag && d->bias,
+              NFB_ERR_ARG, "LULinearPermute: null pointer");
+    NFB_CHECK(f->D <= 64, NFB_ERR_UNSUPPORTED, "LULinearPermute: features %d > 64", f->D);
+    L->lu = *d;
+    f->layers.push_back(std::move(L));
+    return NFB_OK;
+}
+
+int nfb_flow_add_masked_affine(nfb_flow_t* f, const nfb_masked_affine_desc_t* d) {
+    NFB_NEW_LAYER(L_MASKED_AFFINE);
+    NFB_CHECK(f->D <= kAffMaxD, NFB_ERR_UNSUPPORTED, "MaskedAffineFlow: features %d > %d", f->D, kAffMaxD);
+    NFB_CHECK(d->b, NFB_ERR_ARG, "MaskedAffineFlow: null mask");
+    L->op.type = kOpMasked; L->op.p0 = d->b; L->op.slope = 0.f;
+    NFB_TRY(copy_mlp(d->s, L->op.s, &L->op.slope));
+    NFB_TRY(copy_mlp(d->t, L->op.t, &L->op.slope));
+    if (d->s.num_layers) NFB_CHECK(d->s.sizes[0] == f->D && d->s.sizes[d->s.num_layers] == f->D, NFB_ERR_ARG, "s-net must map D -> D");
+    if (d->t.num_layers) NFB_CHECK(d->t.sizes[0] == f->D && d->t.sizes[d->t.num_layers] == f->D, NFB_ERR_ARG, "t-net must map D -> D");
+    f->layers.push_back(std::move(L));
+    return NFB_OK;
+}
+
+int nfb_flow_add_affine_coupling(nfb_flow_t* f, const nfb_affine_coupling_desc_t* d) {
+    NFB_NEW_LAYER(L_AFFINE_COUPLING);
+    NFB_CHECK(f->D <= kAffMaxD, NFB_ERR_UNSUPPORTED, "AffineCouplingBlock: features %d > %d", f->D, kAffMaxD);
+    NFB_CHECK(d->scale_map >= 0 && d->scale_map <= 2, NFB_ERR_UNSUPPORTED, "This scale map is not implemented.");
+    NFB_CHECK(d->split_mode == 0 || d->split_mode == 1, NFB_ERR_UNSUPPORTED, "split mode is not implemented.");
+    L->op.type = kOpCoupling;
+    L->op.flags = (d->scale ? 1 : 0) | (d->scale_map << 1) | (d->split_mode << 3);
+    NFB_TRY(copy_mlp(d->param_map, L->op.s, &L->op.slope));
+    const int h = (f->D + 1) / 2;
+    const int n1 = d->split_mode ? f->D - h : h, n2 = f->D - n1;
+    NFB_CHECK(d->param_map.num_layers >= 1 && d->param_map.sizes[0] == n1 &&
+              d->param_map.sizes[d->param_map.num_layers] == (d->scale ? 2 : 1) * n2,
+              NFB_ERR_ARG, "param_map must map %d -> %d", n1, (d->scale ? 2 : 1) * n2);
+    f->layers.push_back(std::move(L));
+    return NFB_OK;
+}
+
+int nfb_flow_add_affine_const(nfb_flow_t* f, const nfb_affine_const_desc_t* d) {
+    NFB_NEW_LAYER(L_AFFINE_CONST);
+    NFB_CHECK(f->D <= kAffMaxD, NFB_ERR_UNSUPPORTED, "AffineConstFlow: features %d > %d", f->D, kAffMaxD);
+    NFB_CHECK(d->s && d->t, NFB_ERR_ARG, "AffineConstFlow: null s/t");
+    L->op.type = kOpConst; L->op.p0 = d->s; L->op.p1 = d->t;
+    f->layers.push_back(std::move(L));
+    return NFB_OK;
+}
+
+int nfb_flow_add_permute(nfb_flow_t* f, const nfb_permute_desc_t* d) {
+    NFB_NEW_LAYER(L_PERMUTE);
+    NFB_CHECK(f->D <= kAffMaxD, NFB_ERR_UNSUPPORTED, "Permute: features %d > %d", f->D, kAffMaxD);
+    NFB_CHECK(d->perm && d->inv_perm, NFB_ERR_ARG, "Permute: null index list");
+    L->perm_fwd.assign(d->perm, d->perm + f->D);
+    L->perm_inv.assign(d->inv_perm, d->inv_perm + f->D);
+    for (int j = 0; j < f->D; ++j)
+        NFB_CHECK(L->perm_fwd[j] >= 0 && L->perm_fwd[j] < f->D && L->perm_inv[j] >= 0 && L->perm_inv[j] < f->D,
+                  NFB_ERR_ARG, "Permute: index out of range");
+    NFB_TRY(L->perm_fwd_dev.upload(L->perm_fwd));
+    NFB_TRY(L->perm_inv_dev.upload(L->perm_inv));
+    L->op.type = kOpPermute; L->op.fwd_idx = L->perm_fwd_dev.as<int>(); L->op.inv_idx = L->perm_inv_dev.as<int>();
+    f->layers.push_back(std::move(L));
+    return NFB_OK;
+}
+
+int nfb_flow_set_base_diag_gaussian(nfb_flow_t* f, const float* loc, const float* log_scale) {
+    NFB_CHECK(f && loc && log_scale, NFB_ERR_ARG, "null argument");
+    f->base_loc = loc; f->base_log_scale = log_scale;
+    return NFB_OK;
+}
+
+int nfb_flow_repack(nfb_flow_t* f, void* stream) {
+    NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "nfb_flow_repack: flow not finalized");
+    cudaStream_t st = S(stream);
+    for (auto& Lp : f->layers) {
+        Layer& L = *Lp;
+        if (L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) {
+            NFB_TRY(pack_net_generic(L.net, L.pack, st));
+            if (L.kind == L_COUPLED_RQS) {
+                const int P = 3 * L.K - 1, K = L.K;
+                std::vector<float> w, h, d, tab((size_t)L.n_id * P);
+                NFB_CUDA(cudaStreamSynchronize(st));
+                NFB_TRY(download(L.uw, (size_t)L.n_id * K, w));
+                NFB_TRY(download(L.uh, (size_t)L.n_id * K, h));
+                NFB_TRY(download(L.ud, (size_t)L.n_id * (K - 1), d));
+                for (int i = 0; i < L.n_id; ++i) {
+                    for (int k = 0; k < K; ++k) { tab[i * P + k] = w[i * K + k]; tab[i * P + K + k] = h[i * K + k]; }
+                    for (int k = 0; k < K - 1; ++k) tab[i * P + 2 * K + k] = d[i * (K - 1) + k];
+                }
+                NFB_TRY(L.uncond.upload(tab));
+            }
+            NFB_TRY(repack_fused(f, L, st));
+        } else if (L.kind == L_LU) {
+            NFB_TRY(repack_lu(f, L, st));
+        }
+    }
+    for (auto& g : f->groups)
+        if (g.kind == G_FUSED_PAIR) NFB_TRY(repack_pair(f, *f->layers[g.first], *f->layers[g.last], st));
+    NFB_CUDA(cudaStreamSynchronize(st));
+    return NFB_OK;
+}
+
+int nfb_flow_finalize(nfb_flow_t* f, int32_t use_tensor_cores, void* stream) {
+    NFB_CHECK(f, NFB_ERR_ARG, "null flow");
+    NFB_CHECK(!f->finalized, NFB_ERR_STATE, "flow already finalized");
+    cudaStream_t st = S(stream);
+    f->use_tc = use_tensor_cores != 0;
+    int major = 0;
+    NFB_TRY(nfb_device_info(nullptr, &major, nullptr));
+    if (major != 10) f->use_tc = false;  // tcgen05 exists on sm_100 only; the fp32 kernels still run
+    const int n = (int)f->layers.size();
+    // per-layer static prep
+    for (auto& Lp : f->layers) {
+        Layer& L = *Lp;
+        if (L.kind == L_COUPLED_RQS) {
+            std::vector<int64_t> id64, tr64;
+            NFB_TRY(download(L.id64, (size_t)L.n_id, id64));
+            NFB_TRY(download(L.tr64, (size_t)L.n_tr, tr64));
+            std::vector<int> a(id64.begin(), id64.end()), b(tr64.begin(), tr64.end());
+            for (int v : a) NFB_CHECK(v >= 0 && v < L.D, NFB_ERR_ARG, "identity feature index out of range");
+            for (int v : b) NFB_CHECK(v >= 0 && v < L.D, NFB_ERR_ARG, "transform feature index out of range");
+            NFB_TRY(L.id_idx.upload(a));
+            NFB_TRY(L.tr_idx.upload(b));
+        }
+        if (L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) NFB_TRY(build_fused(f, L, st));
+        if (L.kind == L_LU) {
+            std::vector<int64_t> p64;
+            NFB_TRY(download(L.lu.permutation, (size_t)L.D, p64));
+            L.perm_host.assign(p64.begin(), p64.end());
+            std::vector<int> inv(L.D);
+            for (int j = 0; j < L.D; ++j) {
+                NFB_CHECK(L.perm_host[j] >= 0 && L.perm_host[j] < L.D, NFB_ERR_ARG, "permutation out of range");
+                inv[L.perm_host[j]] = j;
+            }
+            NFB_TRY(L.lu_perm.upload(L.perm_host));
+            NFB_TRY(L.lu_tmp.upload(inv));
+        }
+    }
+    // execution groups (list order)
+    f->groups.clear();
+    for (int i = 0; i < n;) {
+        Layer& L = *f->layers[i];
+        if ((L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) && L.fused.ok) {
+            if (i + 1 < n && f->layers[i + 1]->kind == L_LU) {
+                NFB_TRY(build_pair(f, L, *f->layers[i + 1], st));
+                if (L.fused.pair_ok) {
+                    Group g; g.kind = G_FUSED_PAIR; g.first = i; g.last = i + 1;
+                    f->groups.push_back(std::move(g));
+                    i += 2;
+                    continue;
+                }
+            }
+            Group g; g.kind = G_FUSED; g.first = g.last = i;
+            f->groups.push_back(std::move(g));
+            ++i;
+        } else if (is_affine_kind(L)) {
+            int j = i;
+            while (j + 1 < n && is_affine_kind(*f->layers[j + 1])) ++j;
+            Group g; g.kind = G_AFFINE; g.first = i; g.last = j;
+            std::vector<AffineOp> ops;
+            for (int k = i; k <= j; ++k) ops.push_back(f->layers[k]->op);
+            NFB_TRY(g.ops.upload(ops));
+            f->groups.push_back(std::move(g));
+            i = j + 1;
+        } else {
+            Group g; g.kind = G_SINGLE; g.first = g.last = i;
+            f->groups.push_back(std::move(g));
+            ++i;
+        }
+    }
+    f->finalized = true;
+    return nfb_flow_repack(f, stream);
+}
+
+int nfb_flow_num_layers(const nfb_flow_t* f) { return f ? (int)f->layers.size() : 0; }
+int64_t nfb_flow_last_launch_count(const nfb_flow_t* f) { return f ? f->launches : 0; }
+int nfb_flow_layer_is_fused(const nfb_flow_t* f, int32_t index) {
+    if (!f || index < 0 || index >= (int)f->layers.size()) return 0;
+    for (auto& g : f->groups)
+        if ((g.kind == G_FUSED || g.kind == G_FUSED_PAIR) && index >= g.first && index <= g.last) return 1;
+    return 0;
+}
+
+int nfb_flow_layer_apply(nfb_flow_t* f, int32_t index, int32_t direction, const float* z_in, float* z_out,
+                         float* log_det, int64_t rows, int32_t accumulate, void* stream) {
+    NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "flow not finalized");
+    NFB_CHECK(index >= 0 && index < (int)f->layers.size(), NFB_ERR_ARG, "layer index out of range");
+    NFB_CHECK(z_in && z_out, NFB_ERR_ARG, "null pointer");
+    NFB_CHECK(direction == NFB_INVERSE || direction == NFB_FORWARD, NFB_ERR_ARG, "bad direction");
+    cudaStream_t st = S(stream);
+    if (rows == 0) return NFB_OK;
+    Layer& L = *f->layers[index];
+    float* out = z_out;
+    if (z_in == z_out) {
+        NFB_TRY(f->zA.reserve((size_t)rows * f->D * 4));
+        out = f->zA.as<float>();
+    }
+    if (log_det && !accumulate) NFB_TRY(launch_fill(log_det, rows, 0.f, st));
+    int rc;
+    if (is_affine_kind(L)) {
+        DevBuf ops;
+        std::vector<AffineOp> v{L.op};
+        NFB_TRY(ops.upload(v));
+        rc = launch_affine_stack(ops.p, 1, z_in, out, log_det, rows, f->D, 1, direction, st);
+        NFB_CUDA(cudaStreamSynchronize(st));  // ops buffer is freed on return
+    } else if ((L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) && L.fused.ok && direction == NFB_INVERSE) {
+        if (!log_det) { NFB_TRY(f->logq.reserve((size_t)rows * 4)); }
+        rc = launch_fused_layer(f, L, nullptr, z_in, out, log_det ? log_det : f->logq.as<float>(), rows, 1, st);
+    } else {
+        rc = apply_layer_generic(f, L, direction, z_in, out, log_det, rows, 1, st);
+    }
+    if (rc) return rc;
+    if (out != z_out) NFB_CUDA(cudaMemcpyAsync(z_out, out, (size_t)rows * f->D * 4, cudaMemcpyDeviceToDevice, st));
+    return NFB_OK;
+}
+
+int nfb_flow_transform(nfb_flow_t* f, int32_t direction, const float* z_in, float* z_out, float* log_det,
+                       int64_t rows, void* stream) {
+    NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "flow not finalized");
+    NFB_CHECK(z_in && z_out, NFB_ERR_ARG, "null pointer");
+    NFB_CHECK(direction == NFB_INVERSE || direction == NFB_FORWARD, NFB_ERR_ARG, "bad direction");
+    cudaStream_t st = S(stream);
+    f->launches = 0;
+    if (rows == 0) return NFB_OK;
+    NFB_TRY(ensure_ws(f, rows));
+    float* ld = log_det ? log_det : f->logq.as<float>();
+    NFB_TRY(launch_fill(ld, rows, 0.f, st));
+    f->launches++;
+    const int ng = (int)f->groups.size();
+    const float* cur = z_in;
+    float* bufs[2] = {f->zA.as<float>(), f->zB.as<float>()};
+    int flip = 0;
+    for (int k = 0; k < ng; ++k) {
+        Group& g = f->groups[direction == NFB_FORWARD ? k : ng - 1 - k];
+        float* out = (k == ng - 1 && z_out != z_in) ? z_out : bufs[flip];
+        NFB_TRY(run_group(f, g, direction, cur, out, ld, rows, st));
+        cur = out;
+        flip ^= 1;
+    }
+    if (cur != z_out) NFB_CUDA(cudaMemcpyAsync(z_out, cur, (size_t)rows * f->D * 4, cudaMemcpyDeviceToDevice, st));
+    return NFB_OK;
+}
+
+int nfb_flow_log_prob(nfb_flow_t* f, const float* x, float* log_q, int64_t rows, void* stream) {
+    NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "flow not finalized");
+    NFB_CHECK(f->base_loc && f->base_log_scale, NFB_ERR_STATE, "no base distribution set");
+    NFB_CHECK(x && log_q, NFB_ERR_ARG, "null pointer");
+    if (rows == 0) return NFB_OK;
+    NFB_TRY(ensure_ws(f, rows));
+    NFB_TRY(f->zfinal.reserve((size_t)rows * f->D * 4));
+    float* z = f->zfinal.as<float>();
+    NFB_TRY(nfb_flow_transform(f, NFB_INVERSE, x, z, log_q, rows, stream));
+    NFB_TRY(launch_diag_gauss(z, f->base_loc, f->base_log_scale, log_q, rows, f->D, 1, S(stream)));
+    f->launches++;
+    return NFB_OK;
+}
+
+int nfb_flow_forward_kld(nfb_flow_t* f, const float* x, int64_t rows, float* loss, double* sum, void* stream) {
+    NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "flow not finalized");
+    NFB_CHECK(x && (loss || sum), NFB_ERR_ARG, "null pointer");
+    NFB_CHECK(rows > 0, NFB_ERR_ARG, "forward_kld needs at least one row");
+    NFB_TRY(ensure_ws(f, rows));
+    NFB_TRY(f->loss.reserve(16 + (size_t)rows * 4));
+    float* logq = reinterpret_cast<float*>(static_cast<char*>(f->loss.p) + 16);
+    NFB_TRY(nfb_flow_log_prob(f, x, logq, rows, stream));
+    NFB_TRY(launch_sum(logq, rows, -1.0 / (double)rows, f->scratch_sum.as<double>(), loss, sum, S(stream)));
+    f->launches += 2;
+    return NFB_OK;
+}
+
+int nfb_flow_log_prob_host(nfb_flow_t* f, const float* x_host, float* log_q_host, int64_t rows) {
+    NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "flow not finalized");
+    NFB_CHECK(x_host && log_q_host, NFB_ERR_ARG, "null pointer");
+    if (rows == 0) return NFB_OK;
+    NFB_TRY(f->host_x.reserve((size_t)rows * f->D * 4 + (size_t)rows * 4));
+    float* xd = f->host_x.as<float>();
+    float* lq = xd + (size_t)rows * f->D;
+    NFB_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)rows * f->D * 4, cudaMemcpyHostToDevice, 0));
+    NFB_TRY(nfb_flow_log_prob(f, xd, lq, rows, nullptr));
+    NFB_CUDA(cudaMemcpyAsync(log_q_host, lq, (size_t)rows * 4, cudaMemcpyDeviceToHost, 0));
+    NFB_CUDA(cudaStreamSynchronize(0));
+    return NFB_OK;
+}
+
+int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, float* loss_host) {
+    NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "flow not finalized");
+    NFB_CHECK(x_host && loss_host, NFB_ERR_ARG, "null pointer");
+    NFB_CHECK(rows > 0, NFB_ERR_ARG, "forward_kld needs at least one row");
+    NFB_TRY(f->host_x.reserve((size_t)rows * f->D * 4));
+    NFB_TRY(f->loss.reserve(16 + (size_t)rows * 4));
+    float* xd = f->host_x.as<float>();
+    NFB_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)rows * f->D * 4, cudaMemcpyHostToDevice, 0));
+    NFB_TRY(nfb_flow_forward_kld(f, xd, rows, f->loss.as<float>(), nullptr, nullptr));
+    NFB_CUDA(cudaMemcpyAsync(loss_host, f->loss.p, 4, cudaMemcpyDeviceToHost, 0));
+    NFB_CUDA(cudaStreamSynchronize(0));
+    return NFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+// nfb_common.cuh -- shared device helpers for the normflows-b200 kernels (sm_100a only).
+// PTX wrappers for mbarrier / bulk-copy (TMA) / tcgen05 + error plumbing for the C-ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define NFB_OK 0
+#define NFB_ERR_CUDA 1
+#define NFB_ERR_ARG 2
+#define NFB_ERR_UNSUPPORTED 3
+#define NFB_ERR_STATE 4
+
+void nfb_set_error(const char* fmt, ...);
+
+#define NFB_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            nfb_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call,                  \
+                          cudaGetErrorString(e__));                                      \
+            return NFB_ERR_CUDA;                                                         \
+        }                                                                                \
+    } while (0)
+
+#define NFB_CHECK(cond, code, ...)                                                       \
+    do {                                                                                 \
+        if (!(cond)) {                                                                   \
+            nfb_set_error(__VA_ARGS__);                                                  \
+            return (code);                                                               \
+        }                                                                                \
+    } while (0)
+
+#define NFB_LAUNCH_CHECK() NFB_CUDA(cudaGetLastError())
+
+namespace nfb {
+
+constexpr float kMinBinWidth = 1e-3f;    // utils/splines.py:6
+constexpr float kMinBinHeight = 1e-3f;   // utils/splines.py:7
+constexpr float kMinDerivative = 1e-3f;  // utils/splines.py:8
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ----------------------------------------------------------------------------------------
+// mbarrier
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must never hang the GPU box.  On timeout the kernel records
+// the barrier id in *err and traps; the host sees a launch failure instead of a dead device.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err, int tag) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s
+            if (err) atomicExch(err, tag);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------
+// TMA: 1-D bulk copy global -> shared with mbarrier completion (SASS: UBLKCP)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes,
+                                         uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ----------------------------------------------------------------------------------------
+// tcgen05 / TMEM
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]; kind::f16 covers bf16 inputs with fp32 accumulate.
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrives when all tcgen05.mma issued so far by this thread have completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+
+// K-major, SWIZZLE_128B canonical tile: rows of 128 B (64 bf16), 8-row groups 1024 B apart.
+// desc: [0,14) addr>>4 | [16,30) LBO>>4 (=1, ignored for swizzled K-major) | [32,46) SBO>>4 (=64)
+//       | [46,48) version=1 (sm_100) | [61,64) layout=2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
+           (2ull << 61);
+}
+// instruction descriptor: c=f32 (bit4), a=bf16 (bit7), b=bf16 (bit10), K-major A and B,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
+#define NFB_TMEM_LD8(addr, v)                                                            \
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];" \
+                 : "=r"((v)[0]), "=r"((v)[1]), "=r"((v)[2]), "=r"((v)[3]), "=r"((v)[4]),   \
+                   "=r"((v)[5]), "=r"((v)[6]), "=r"((v)[7])                                \
+                 : "r"(addr))
+#define NFB_TMEM_LD16(addr, v)                                                           \
+    asm volatile(                                                                        \
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "                                        \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"                \
+        : "=r"((v)[0]), "=r"((v)[1]), "=r"((v)[2]), "=r"((v)[3]), "=r"((v)[4]), "=r"((v)[5]), \
+          "=r"((v)[6]), "=r"((v)[7]), "=r"((v)[8]), "=r"((v)[9]), "=r"((v)[10]), "=r"((v)[11]), \
+          "=r"((v)[12]), "=r"((v)[13]), "=r"((v)[14]), "=r"((v)[15])                     \
+        : "r"(addr))
+#define NFB_TMEM_LD32(addr, v)                                                           \
+    asm volatile(                                                                        \
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                        \
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"                        \
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"       \
+        : "=r"((v)[0]), "=r"((v)[1]), "=r"((v)[2]), "=r"((v)[3]), "=r"((v)[4]), "=r"((v)[5]), \
+          "=r"((v)[6]), "=r"((v)[7]), "=r"((v)[8]), "=r"((v)[9]), "=r"((v)[10]), "=r"((v)[11]), \
+          "=r"((v)[12]), "=r"((v)[13]), "=r"((v)[14]), "=r"((v)[15]), "=r"((v)[16]),      \
+          "=r"((v)[17]), "=r"((v)[18]), "=r"((v)[19]), "=r"((v)[20]), "=r"((v)[21]),      \
+          "=r"((v)[22]), "=r"((v)[23]), "=r"((v)[24]), "=r"((v)[25]), "=r"((v)[26]),      \
+          "=r"((v)[27]), "=r"((v)[28]), "=r"((v)[29]), "=r"((v)[30]), "=r"((v)[31])       \
+        : "r"(addr))
+
+// ----------------------------------------------------------------------------------------
+// bf16 split helpers: v ~= hi + lo (+ lo2), each term a bf16 (round-to-nearest-even)
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+    uint32_t r;  // cvt.rn.bf16x2.f32 d, a, b: a -> upper half, b -> lower half
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ float bf16_round(float v) {
+    return __bfloat162float(__float2bfloat16_rn(v));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace nfb

@@ -1,0 +1,452 @@
+// nfb_fused_rqs.cu -- one fused sm_100a kernel per neural-spline coupling block.
+//
+// Per 128-row tile, without leaving the SM:
+//   [LULinearPermute.inverse  (flows/mixing.py:560-563)]      x  = z[:,perm] (LU)^T + b
+//   conditioner  MADE (nets/made.py:296-304) or ResidualNet (nets/resnet.py:92-104)
+//   RQ spline    (utils/splines.py:16-219) on every transformed feature
+//   [unconditional CDF spline on the identity features (neural_spline/coupling.py:221-253)]
+//   log_q += sum_j logabsdet_j (+ LU logabsdet)                 (core.py:98-100)
+// z is read once and written once per block; the [B, T*(3K-1)] parameter tensor the reference
+// materialises never exists.
+//
+// Tensor-core numerics: every GEMM runs as split-bf16 on tcgen05 (fp32 accumulate in TMEM):
+//   a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo     (conditioner layers; ~2^-17 relative per product)
+//   6-term 3-way split for the LU linear map that transforms z itself (~2^-24).
+// Plain bf16/tf32 fail the rtol 1e-4 log_prob bar; this is why.
+//
+// Structure (320 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0   weight producer: 1-D bulk TMA (cp.async.bulk -> UBLKCP) of pre-swizzled bf16 records
+//            from the packed weight stream (L2 resident) into a 4 x 16 KB ring.
+//   warp 1   MMA issuer: walks the same step table, one elected lane issues tcgen05.mma
+//            (M=128, N=64/96/128, K=16) and commits to mbarriers; owns the 512-column TMEM alloc.
+//   warps 2-9 epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias/ReLU, bf16 hi/lo split back
+//            into the swizzled A-operand tiles; final layer arrives in 96-column chunks
+//            (4 features x 24) through a 4-deep TMEM ring and is consumed by the spline evaluator
+//            while the tensor core produces the next chunk.
+// The residual stream h lives in TMEM columns [0,256) and is updated by accumulating the second
+// GEMM of each residual block straight onto it (h += W2 relu(...)); biases are pre-summed on the
+// host side of the packer.  Shared memory: A operand 128 KB (hi|lo x K=256), weight ring 64 KB,
+// x/y tile 32 KB (XOR-swizzled, conflict-free column access).
+#include "nfb_kernels.h"
+#include "nfb_spline.cuh"
+
+namespace nfb {
+
+constexpr int kFusedThreads = 320;
+constexpr uint32_t kTileA = 16384;    // one [128 x 64] bf16 SW128 tile
+constexpr uint32_t kSlotBytes = 16384;
+constexpr int kSlots = 4;
+constexpr uint32_t kOffA = 0;
+constexpr uint32_t kOffW = 131072;
+constexpr uint32_t kOffX = kOffW + kSlots * kSlotBytes;  // 196608
+constexpr uint32_t kOffSteps = kOffX + 32768;            // 229376
+constexpr uint32_t kMaxSteps = 256;
+constexpr uint32_t kOffBars = kOffSteps + kMaxSteps * 8;  // 231424
+constexpr uint32_t kNumBars = 18;
+constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;  // 231568
+constexpr uint32_t kOffLd = kOffTmemPtr + 16;              // 231584
+constexpr uint32_t kFusedSmem = kOffLd + 128 * 4;          // 232096 <= 232448
+static_assert(kFusedSmem <= 232448, "shared memory budget");
+
+// barrier indices
+constexpr int kBarWFull = 0, kBarWEmpty = 4, kBarAReady = 8, kBarAccFull = 9, kBarCFull = 10,
+              kBarCEmpty = 14;
+// TMEM column of final-layer chunk buffer i
+__device__ __forceinline__ uint32_t chunk_col(int i) { return (i & 1) * 96 + (i >> 1) * 256; }
+
+__device__ __forceinline__ uint32_t xs_index(int r, int c) { return r * 64 + (c ^ (r & 31)); }
+
+// A-operand tile address of element chunk (row r, 16-byte chunk c8 in 0..7) inside a SW128 tile
+__device__ __forceinline__ uint32_t a_chunk_off(int r, int c8) {
+    return (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4);
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c,
+                                             uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
+                 : "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {  // the 256 epilogue threads only
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+
+// split 8 consecutive fp32 values into bf16 hi / lo (/ lo2) chunks and store them at the same
+// chunk offset of up to three A tiles.
+template <int NSPLIT>
+__device__ __forceinline__ void split_store8(const float* v, uint32_t t0, uint32_t t1, uint32_t t2,
+                                             uint32_t off) {
+    uint32_t h[4], m[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float a = v[2 * i], b = v[2 * i + 1];
+        h[i] = pack_bf16x2(a, b);
+        const float ra = a - __uint_as_float(h[i] << 16);
+        const float rb = b - __uint_as_float(h[i] & 0xffff0000u);
+        m[i] = pack_bf16x2(ra, rb);
+        if (NSPLIT == 3) {
+            const float sa = ra - __uint_as_float(m[i] << 16);
+            const float sb = rb - __uint_as_float(m[i] & 0xffff0000u);
+            l[i] = pack_bf16x2(sa, sb);
+        }
+    }
+    st_shared_v4(t0 + off, h[0], h[1], h[2], h[3]);
+    st_shared_v4(t1 + off, m[0], m[1], m[2], m[3]);
+    if (NSPLIT == 3) st_shared_v4(t2 + off, l[0], l[1], l[2], l[3]);
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const FusedParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* xs = reinterpret_cast<float*>(smem + kOffX);
+    FusedStep* steps = reinterpret_cast<FusedStep*>(smem + kOffSteps);
+    const uint32_t bars = sbase + kOffBars;
+    float* ldsum = reinterpret_cast<float*>(smem + kOffLd);
+    auto bar = [bars](int i) { return bars + 8u * i; };
+
+    if ((sbase & 1023u) != 0) {
+        if (threadIdx.x == 0 && p.err) atomicExch(p.err, 900);
+        return;
+    }
+    for (int i = threadIdx.x; i < p.n_steps; i += kFusedThreads) steps[i] = p.steps[i];
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kSlots; ++i) {
+            mbar_init(bar(kBarWFull + i), 1);
+            mbar_init(bar(kBarWEmpty + i), 1);
+            mbar_init(bar(kBarCFull + i), 1);
+            mbar_init(bar(kBarCEmpty + i), 8);
+        }
+        mbar_init(bar(kBarAReady), 8);
+        mbar_init(bar(kBarAccFull), 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(sbase + kOffTmemPtr, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+
+    const long long n_tiles = (p.rows + 127) / 128;
+
+    if (warp == 0) {
+        // ------------------------------ weight producer -----------------------------------
+        if (lane == 0) {
+            uint32_t slot = 0, par = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const uint8_t* src = p.wstream;
+                for (int s = 0; s < p.n_steps; ++s) {
+                    const uint32_t bytes = (uint32_t)steps[s].bytes16 << 4;
+                    mbar_wait(bar(kBarWEmpty + slot), par ^ 1, p.err, 100 + slot);
+                    mbar_expect_tx(bar(kBarWFull + slot), bytes);
+                    bulk_g2s(sbase + kOffW + slot * kSlotBytes, src, bytes, bar(kBarWFull + slot));
+                    src += bytes;
+                    if (++slot == kSlots) { slot = 0; par ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ----------------------------------------
+        if (lane == 0) {
+            uint32_t slot = 0, wpar = 0, apar = 0, cebits = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int s = 0; s < p.n_steps; ++s) {
+                    const FusedStep st = steps[s];
+                    const uint32_t ctl = st.ctl;
+                    const uint32_t col = ctl & 511u, first = (ctl >> 9) & 1u;
+                    const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
+                    if (wcode == 1 || wcode == 6) {
+                        mbar_wait(bar(kBarAReady), apar, p.err, 200);
+                        apar ^= 1;
+                    }
+                    if (wcode >= 2) {
+                        const uint32_t i = wcode == 6 ? 0u : wcode - 2;
+                        mbar_wait(bar(kBarCEmpty + i), ((cebits >> i) & 1u) ^ 1u, p.err, 210 + i);
+                        cebits ^= 1u << i;
+                    }
+                    mbar_wait(bar(kBarWFull + slot), wpar, p.err, 220 + slot);
+                    tc_fence_after();
+                    const uint32_t n = (uint32_t)st.n8 << 3;
+                    const uint32_t idesc = umma_idesc_bf16(128, n);
+                    const uint32_t bsm = sbase + kOffW + slot * kSlotBytes;
+                    const uint8_t at[3] = {st.a0, st.a1, st.a2};
+                    uint32_t accum = first ? 0u : 1u;
+#pragma unroll
+                    for (int ai = 0; ai < 3; ++ai) {
+                        if (at[ai] == 0xFF) continue;
+                        const uint32_t asm_ = sbase + kOffA + at[ai] * kTileA;
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            umma_bf16(tmem + col, umma_desc_sw128(asm_ + ks * 32),
+                                      umma_desc_sw128(bsm + ks * 32), idesc, accum);
+                            accum = 1u;
+                        }
+                    }
+                    umma_commit(bar(kBarWEmpty + slot));
+                    if (scode == 1) umma_commit(bar(kBarAccFull));
+                    else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
+                    if (++slot == kSlots) { slot = 0; wpar ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ------------------------------ epilogue warps ------------------------------------
+        const int et = threadIdx.x - 64;       // 0..255
+        const int q = warp & 3;                // TMEM lane quadrant this warp may touch
+        const int wh = (warp - 2) >> 2;        // column half
+        const int r = q * 32 + lane;           // tile row owned by this thread
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+        const uint32_t aA = sbase + kOffA;
+        uint32_t afpar = 0, cfbits = 0;
+        const int D = p.D, H = p.H;
+
+        auto build_a = [&](bool lu_stage) {
+            // A[:, k] for k in [wh*32, wh*32+32): lu_stage -> 3-way split of xs[:, k] (k < D);
+            // otherwise 2-way split of the conditioner input xs[:, in_idx[k]].
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = wh * 32 + g * 8 + j;
+                    int c = lu_stage ? (k < D ? k : -1) : p.in_idx[k];
+                    v[j] = c >= 0 ? xs[xs_index(r, c)] : 0.f;
+                }
+                const uint32_t off = a_chunk_off(r, wh * 4 + g);
+                if (lu_stage) split_store8<3>(v, aA, aA + 4 * kTileA, aA + 1 * kTileA, off);
+                else split_store8<2>(v, aA, aA + 4 * kTileA, 0, off);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(kBarAReady));
+        };
+
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long row0 = tile * 128;
+            // ---- load z tile -> xs (coalesced global, swizzled shared) ----
+            for (int i = et; i < 128 * D; i += 256) {
+                const int rr = i / D, cc = i - rr * D;
+                const long long gr = row0 + rr;
+                xs[xs_index(rr, cc)] = gr < p.rows ? __ldg(p.zin + gr * D + cc) : 0.f;
+            }
+            epi_bar_sync();
+            float ladsum = 0.f;
+            if (p.has_lu) {
+                build_a(true);
+                mbar_wait(bar(kBarAccFull), afpar, p.err, 300);
+                afpar ^= 1;
+                tc_fence_after();
+                // x' = acc + b  (64 columns at TMEM col 256; this thread: 32 of them)
+                uint32_t acc[32];
+                NFB_TMEM_LD32(tlane + 256 + wh * 32, acc);
+                tc_wait_ld();
+                epi_bar_sync();  // every thread has built A from the old xs before it is overwritten
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int c = wh * 32 + j;
+                    if (c < D) xs[xs_index(r, c)] = __uint_as_float(acc[j]) + __ldg(p.bias_lu + c);
+                }
+                epi_bar_sync();
+            }
+            build_a(false);
+
+            // ---- unconditional spline on the identity features (coupled layer only); runs while
+            //      the tensor core is busy with the first GEMMs.  The conditioner input was taken
+            //      from the raw values above (Coupling.forward, neural_spline/coupling.py:80-92).
+            if (p.n_id > 0) {
+                const int per = (p.n_id + 1) / 2;
+                for (int i = wh * per; i < min(p.n_id, (wh + 1) * per); ++i) {
+                    const int c = p.id_idx[i];
+                    const float* tb = p.uncond + i * 23;
+                    auto acc = [tb](int k) { return __ldg(tb + k); };
+                    float y, l;
+                    rqs_eval<8, false>(xs[xs_index(r, c)], acc, p.tail, 1.0f, y, l);
+                    xs[xs_index(r, c)] = y;
+                    ladsum += l;
+                }
+            }
+
+            // ---- hidden layers ----
+            for (int ph = 0; ph < p.n_hidden; ++ph) {
+                mbar_wait(bar(kBarAccFull), afpar, p.err, 310 + ph);
+                afpar ^= 1;
+                tc_fence_after();
+                const uint32_t region = (ph & 1) ? 256u : 0u;
+                const bool relu = ph + 1 < p.n_hidden;
+                const float* bias = p.bias_h + ph * 256;
+                const int half = H >> 1;
+                for (int g = 0; g < half; g += 32) {
+                    const int c0 = wh * half + g;
+                    uint32_t acc[32];
+                    NFB_TMEM_LD32(tlane + region + c0, acc);
+                    float4 b4[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+                    tc_wait_ld();
+                    const float* bf = reinterpret_cast<const float*>(b4);
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float t = __uint_as_float(acc[j]) + bf[j];
+                        v[j] = relu ? fmaxf(t, 0.f) : t;
+                    }
+                    const int kc = c0 >> 6;
+                    const uint32_t thi = aA + kc * kTileA, tlo = aA + (4 + kc) * kTileA;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        split_store8<2>(v + 8 * j, thi, tlo, 0, a_chunk_off(r, ((c0 & 63) >> 3) + j));
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(kBarAReady));
+            }
+
+            // ---- final layer chunks -> spline ----
+            for (int c = 0; c < p.n_chunks; ++c) {
+                const int b = c & 3;
+                const int t0 = c * 4 + wh * 2;  // first transformed-feature slot of this thread
+                float4 bb[12];
+#pragma unroll
+                for (int j = 0; j < 12; ++j)
+                    bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias_f + t0 * 24) + j);
+                mbar_wait(bar(kBarCFull + b), (cfbits >> b) & 1u, p.err, 400 + b);
+                cfbits ^= 1u << b;
+                tc_fence_after();
+                uint32_t pr[48];
+                const uint32_t ta = tlane + chunk_col(b) + wh * 48;
+                NFB_TMEM_LD16(ta, pr);
+                NFB_TMEM_LD16(ta + 16, pr + 16);
+                NFB_TMEM_LD16(ta + 32, pr + 32);
+                tc_wait_ld();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
+                const float* bf = reinterpret_cast<const float*>(bb);
+#pragma unroll
+                for (int f = 0; f < 2; ++f) {
+                    const int t = t0 + f;
+                    if (t < p.T) {
+                        float pv[24];
+#pragma unroll
+                        for (int j = 0; j < 24; ++j) pv[j] = __uint_as_float(pr[f * 24 + j]) + bf[f * 24 + j];
+                        auto acc = [&pv](int k) { return pv[k]; };
+                        const int col = p.tr_idx[t];
+                        float y, l;
+                        rqs_eval<8, false>(xs[xs_index(r, col)], acc, p.tail, 1.0f, y, l);
+                        xs[xs_index(r, col)] = y;
+                        ladsum += l;
+                    }
+                }
+            }
+
+            // ---- log-det reduction across the two column halves, then store ----
+            if (wh == 1) ldsum[r] = ladsum;
+            epi_bar_sync();
+            if (wh == 0) {
+                const long long gr = row0 + r;
+                if (gr < p.rows) {
+                    float tot = ladsum + ldsum[r] + (p.lu_logdet ? __ldg(p.lu_logdet) : 0.f);
+                    p.logq[gr] = p.accumulate ? p.logq[gr] + tot : tot;
+                }
+            }
+            for (int i = et; i < 128 * D; i += 256) {
+                const int rr = i / D, cc = i - rr * D;
+                const long long gr = row0 + rr;
+                if (gr < p.rows) p.zout[gr * D + cc] = xs[xs_index(rr, cc)];
+            }
+            epi_bar_sync();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st) {
+    static bool attr_done = false;
+    if (!attr_done) {
+        NFB_CUDA(cudaFuncSetAttribute(fused_rqs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kFusedSmem));
+        attr_done = true;
+    }
+    NFB_CHECK(p.n_steps <= (int)kMaxSteps, NFB_ERR_UNSUPPORTED, "fused rqs: %d steps > %d", p.n_steps,
+              kMaxSteps);
+    const long long n_tiles = (p.rows + 127) / 128;
+    if (n_tiles == 0) return NFB_OK;
+    const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
+    fused_rqs_kernel<<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// -----------------------------------------------------------------------------------------
+// packing: fp32 effective matrix [n_pad x k_pad] -> stream of swizzled bf16 split records
+// record order: for row-block rb: for kc: for split s: [rows_per_rec x 64] tile
+// -----------------------------------------------------------------------------------------
+// stage 1: E[i,j] = scale[i] * W[src_row[i], src_col[j]] * (mask ? mask[...] : 1), zero if index < 0
+__global__ void build_effective_kernel(const float* __restrict__ W, const float* __restrict__ M,
+                                       int src_cols, const int* __restrict__ src_row,
+                                       const int* __restrict__ src_col,
+                                       const float* __restrict__ row_scale, float* __restrict__ E,
+                                       int n_pad, int k_pad) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_pad * k_pad) return;
+    const int i = idx / k_pad, j = idx - i * k_pad;
+    const int sr = src_row[i], sc = src_col[j];
+    float v = 0.f;
+    if (sr >= 0 && sc >= 0) {
+        const long long o = (long long)sr * src_cols + sc;
+        v = W[o];
+        if (M) v *= M[o];
+        if (row_scale) v *= row_scale[i];
+    }
+    E[idx] = v;
+}
+// stage 2
+__global__ void swizzle_split_kernel(const float* __restrict__ E, int n_pad, int k_pad,
+                                     int rows_per_rec, int nsplit, uint8_t* __restrict__ out) {
+    const int kcs = k_pad / 64;
+    const long long total = (long long)n_pad * k_pad;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int i = (int)(idx / k_pad), j = (int)(idx - (long long)i * k_pad);
+    const int rb = i / rows_per_rec, rr = i - rb * rows_per_rec;
+    const int kc = j >> 6, kk = j & 63;
+    const float v = E[idx];
+    const size_t rec_bytes = (size_t)rows_per_rec * 128;
+    const size_t in_rec = (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + (((kk >> 3) ^ (rr & 7)) << 4) +
+                          (kk & 7) * 2;
+    float rem = v;
+    for (int s = 0; s < nsplit; ++s) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(rem);
+        rem -= __bfloat162float(h);
+        const size_t rec = ((size_t)rb * kcs + kc) * nsplit + s;
+        *reinterpret_cast<__nv_bfloat16*>(out + rec * rec_bytes + in_rec) = h;
+    }
+}
+
+int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
+                           const int* src_col, const float* row_scale, float* E, int n_pad,
+                           int k_pad, cudaStream_t st) {
+    const int n = n_pad * k_pad;
+    build_effective_kernel<<<(n + 255) / 256, 256, 0, st>>>(W, M, src_cols, src_row, src_col,
+                                                            row_scale, E, n_pad, k_pad);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit,
+                         uint8_t* out, cudaStream_t st) {
+    NFB_CHECK(n_pad % rows_per_rec == 0 && k_pad % 64 == 0 && rows_per_rec % 8 == 0, NFB_ERR_ARG,
+              "swizzle_split: bad shape %d x %d / %d", n_pad, k_pad, rows_per_rec);
+    const long long n = (long long)n_pad * k_pad;
+    swizzle_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, n_pad, k_pad, rows_per_rec,
+                                                                      nsplit, out);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+}  // namespace nfb

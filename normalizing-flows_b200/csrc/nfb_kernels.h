@@ -1,0 +1,94 @@
+// nfb_kernels.h -- internal launch interface between the C-ABI layer (nfb_api.cu) and the kernels.
+#pragma once
+#include "nfb_common.cuh"
+
+namespace nfb {
+
+// ---- generic kernels (nfb_kernels.cu) ----
+int launch_rqs_rows(const float* zin, const float* params, float* zout, float* logdet,
+                    long long rows, int feats, int ld, const int* fidx, int K, float tail,
+                    float wh_scale, int inverse, cudaStream_t st);
+int launch_rqs_shared(const float* zin, const float* table, float* zout, float* logdet,
+                      long long rows, int feats, int ld, const int* fidx, int K, float tail,
+                      int inverse, cudaStream_t st);
+int launch_linear(const float* X, int ldx, const int* xidx, const float* W, const float* bias,
+                  const float* R, int ldr, float* Y, int ldy, long long M, int N, int K, int act_in,
+                  int act_out, float slope, cudaStream_t st);
+int launch_mask_mul(const float* w, const float* m, float* out, long long n, cudaStream_t st);
+int launch_lu_pack(const float* lower_e, const float* upper_e, const float* udiag, float eps, int n,
+                   float* W, float* Winv, float* logabsdet, cudaStream_t st);
+int launch_add_scalar(float* v, long long n, const float* c, float sign, cudaStream_t st);
+int launch_fill(float* v, long long n, float c, cudaStream_t st);
+int launch_gather_cols(const float* in, float* out, const int* idx, long long rows, int d,
+                       long long inner, cudaStream_t st);
+int launch_diag_gauss(const float* z, const float* loc, const float* log_scale, float* logq,
+                      long long rows, int d, int accumulate, cudaStream_t st);
+int launch_sum(const float* v, long long n, double scale, double* scratch, float* out,
+               double* out_sum, cudaStream_t st);
+
+// ---- small-dimension affine stack (nfb_affine.cu) ----
+constexpr int kAffMaxD = 16;
+constexpr int kAffMaxW = 128;  // widest MLP layer supported
+constexpr int kAffMaxLayers = 6;
+
+struct AffMlp {
+    int n_layers;                  // number of Linear layers (0 = absent)
+    int sizes[kAffMaxLayers + 1];  // sizes[0] = in, sizes[n_layers] = out
+    const float* w[kAffMaxLayers];
+    const float* b[kAffMaxLayers];
+};
+enum { kOpMasked = 0, kOpConst = 1, kOpCoupling = 2, kOpPermute = 3 };
+struct AffineOp {
+    int type;
+    int flags;      // coupling: bit0 scale, bits1-2 scale_map (0 exp,1 sigmoid,2 sigmoid_inv), bit3 channel_inv
+    float slope;    // LeakyReLU slope of the MLPs
+    int pad_;
+    AffMlp s;       // masked: s-net ; coupling: param_map
+    AffMlp t;       // masked: t-net
+    const float* p0;  // masked: b[D] ; const: s[D]
+    const float* p1;  // const: t[D]
+    const int* fwd_idx;  // permute: forward index list
+    const int* inv_idx;  // permute: inverse index list
+};
+
+size_t affine_op_size();
+int launch_affine_stack(const void* ops_dev, int n_ops, const float* zin, float* zout, float* logq,
+                        long long rows, int d, int accumulate, int direction, cudaStream_t st);
+
+// ---- fused tcgen05 neural-spline block (nfb_fused_rqs.cu) ----
+struct __align__(8) FusedStep {
+    uint16_t bytes16;    // weight record size / 16
+    uint8_t n8;          // MMA N / 8
+    uint8_t a0, a1, a2;  // A-operand tiles to multiply this record with (0xFF = none)
+    uint16_t ctl;        // [0,9) TMEM column | [9] first (overwrite) | [10,13) wait | [13,16) signal
+};
+// wait codes : 0 none, 1 a_ready, 2+i chunk_empty[i] (i<4), 6 a_ready + chunk_empty[0]
+// signal codes: 0 none, 1 acc_full, 2+i chunk_full[i]
+
+struct FusedParams {
+    const float* zin;
+    float* zout;
+    float* logq;
+    long long rows;
+    int D, H, n_hidden, has_lu, T, n_chunks, n_id, n_steps, accumulate;
+    float tail;
+    const uint8_t* wstream;
+    const FusedStep* steps;
+    const float* bias_lu;    // [64]
+    const float* bias_h;     // [n_hidden][256], residual biases pre-summed
+    const float* bias_f;     // [n_chunks*4*24]
+    const int* in_idx;       // [64] conditioner input column per k (-1 = zero pad)
+    const int* tr_idx;       // [T]
+    const int* id_idx;       // [n_id]
+    const float* uncond;     // [n_id][23]
+    const float* lu_logdet;  // device scalar or null
+    int* err;
+};
+int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st);
+int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
+                           const int* src_col, const float* row_scale, float* E, int n_pad,
+                           int k_pad, cudaStream_t st);
+int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit,
+                         uint8_t* out, cudaStream_t st);
+
+}  // namespace nfb

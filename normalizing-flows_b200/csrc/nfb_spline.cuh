@@ -1,0 +1,217 @@
+// nfb_spline.cuh -- monotone rational-quadratic spline, one element per call.
+//
+// Mask-free restatement of normflows/utils/splines.py:16-219 (`unconstrained_rational_
+// quadratic_spline` with tails="linear" -> `rational_quadratic_spline`):
+//   * outside [-B,B] (or NaN): identity, logabsdet 0                       (:28,:40-41)
+//   * widths/heights: softmax -> min size 1e-3 -> cumsum -> scale to [-B,B],
+//     end knots pinned exactly, bin sizes re-derived as knot differences    (:126-152)
+//   * bin = (#knots <= x) - 1 with +1e-6 on the last knot only, so x == +B is
+//     inside the last bin and an interior-knot hit goes to the right bin    (:11-13,:154-157)
+//   * derivatives 1e-3 + softplus(.), boundary derivative from the constant
+//     log(exp(1-1e-3)-1)                                                    (:35-38,:138)
+//   * forward: :200-219   inverse (quadratic root 2c/(-b-sqrt(b^2-4ac))): :172-198
+// Differences that are deliberate (and covered by the stated fp32 tolerance):
+//   softplus is evaluated only for the two selected knot derivatives instead of all K+1;
+//   the scan keeps running knots instead of materialising [K+1] arrays and gathering.
+#pragma once
+#include "nfb_common.cuh"
+
+namespace nfb {
+
+// MUFU approximations on the device.  The __host__ bodies exist only so that tests/native can
+// compile this header for the CPU and check the arithmetic against the golden vectors without a
+// GPU; no product code calls them on the host.
+__host__ __device__ __forceinline__ float fast_ex2(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return exp2f(x);
+#endif
+}
+__host__ __device__ __forceinline__ float fast_lg2(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return log2f(x);
+#endif
+}
+__host__ __device__ __forceinline__ float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
+
+// F.softplus(beta=1, threshold=20).  log1p(e) by series for small e: 1+e would round away
+// up to 6e-8 absolute, which matters when the derivative sits at its 1e-3 floor.
+__host__ __device__ __forceinline__ float softplus_f(float u) {
+    if (u > 20.f) return u;
+    float e = fast_ex2(u * kLog2e);
+    if (e < 0.03f) return e * (1.f - e * (0.5f - e * (0.33333334f - 0.25f * e)));
+    return kLn2 * fast_lg2(1.f + e);
+}
+
+// The unnormalised boundary derivative, as the reference computes it in fp32 (:36).
+#define NFB_BOUNDARY_UD 0.5397424f /* float32(log(exp(1 - 1e-3) - 1)) = 0.5397424172... */
+
+// Param accessor: P(i) returns the i-th of the 3K-1 raw parameters [w(K) | h(K) | d(K-1)] of this
+// element.  `wh_scale` multiplies the w and h logits (1/sqrt(hidden) in the coupling layer,
+// neural_spline/coupling.py:334-336; 1 in the autoregressive layer and the unconditional CDF).
+template <int K, bool INVERSE, typename P>
+__host__ __device__ __forceinline__ void rqs_eval(float x, P p, float tail, float wh_scale, float& y,
+                                         float& lad) {
+    const bool inside = (x >= -tail) && (x <= tail);
+    const float s2 = wh_scale * kLog2e;
+    float ew[K], eh[K];
+    float mw = -3.0e38f, mh = -3.0e38f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        ew[i] = p(i) * s2;
+        eh[i] = p(K + i) * s2;
+        mw = fmaxf(mw, ew[i]);
+        mh = fmaxf(mh, eh[i]);
+    }
+    float sw = 0.f, sh = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        ew[i] = fast_ex2(ew[i] - mw);
+        eh[i] = fast_ex2(eh[i] - mh);
+        sw += ew[i];
+        sh += eh[i];
+    }
+    const float kw = (1.f - kMinBinWidth * K) * fast_rcp(sw);
+    const float kh = (1.f - kMinBinHeight * K) * fast_rcp(sh);
+    const float two_b = 2.f * tail;
+
+    float cumw = 0.f, cumh = 0.f;
+    float left = -tail, bottom = -tail;
+    float in_cw = -tail, in_w = 1.f, in_ch = -tail, in_h = 1.f;
+    float ud0 = NFB_BOUNDARY_UD, ud1 = NFB_BOUNDARY_UD;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        cumw += kMinBinWidth + kw * ew[i];
+        cumh += kMinBinHeight + kh * eh[i];
+        const float right = (i == K - 1) ? tail : (two_b * cumw - tail);
+        const float top = (i == K - 1) ? tail : (two_b * cumh - tail);
+        const bool ge = INVERSE ? (x >= bottom) : (x >= left);  // knot i <= x ?
+        if (ge) {
+            in_cw = left;
+            in_w = right - left;
+            in_ch = bottom;
+            in_h = top - bottom;
+            ud0 = (i == 0) ? NFB_BOUNDARY_UD : p(2 * K + i - 1);
+            ud1 = (i == K - 1) ? NFB_BOUNDARY_UD : p(2 * K + i);
+        }
+        left = right;
+        bottom = top;
+    }
+    const float d0 = kMinDerivative + softplus_f(ud0);
+    const float d1 = kMinDerivative + softplus_f(ud1);
+    const float rw = fast_rcp(in_w);
+    const float delta = in_h * rw;
+    const float s = d0 + d1 - 2.f * delta;
+    float out, theta, tomt, den;
+    if (INVERSE) {
+        const float t = x - in_ch;
+        const float a = t * s + in_h * (delta - d0);
+        const float b = in_h * d0 - t * s;
+        const float c = -delta * t;
+        const float disc = fmaxf(b * b - 4.f * a * c, 0.f);
+        theta = (2.f * c) / (-b - sqrtf(disc));
+        out = theta * in_w + in_cw;
+        tomt = theta * (1.f - theta);
+        den = delta + s * tomt;
+    } else {
+        theta = (x - in_cw) * rw;
+        tomt = theta * (1.f - theta);
+        den = delta + s * tomt;
+        const float num = in_h * (delta * theta * theta + d0 * tomt);
+        out = in_ch + num * fast_rcp(den);
+    }
+    const float omt = 1.f - theta;
+    const float dnum = delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * omt * omt);
+    float l = kLn2 * (fast_lg2(dnum) - 2.f * fast_lg2(den));
+    if (INVERSE) l = -l;
+    y = inside ? out : x;
+    lad = inside ? l : 0.f;
+}
+
+// Runtime-K version (K <= 32) reading parameters through the accessor twice; used by the
+// generic kernels for bin counts other than 8.
+template <bool INVERSE, typename P>
+__host__ __device__ __forceinline__ void rqs_eval_dyn(int K, float x, P p, float tail, float wh_scale,
+                                             float& y, float& lad) {
+    const bool inside = (x >= -tail) && (x <= tail);
+    const float s2 = wh_scale * kLog2e;
+    float mw = -3.0e38f, mh = -3.0e38f;
+    for (int i = 0; i < K; ++i) {
+        mw = fmaxf(mw, p(i) * s2);
+        mh = fmaxf(mh, p(K + i) * s2);
+    }
+    float sw = 0.f, sh = 0.f;
+    for (int i = 0; i < K; ++i) {
+        sw += fast_ex2(p(i) * s2 - mw);
+        sh += fast_ex2(p(K + i) * s2 - mh);
+    }
+    const float kw = (1.f - kMinBinWidth * K) * fast_rcp(sw);
+    const float kh = (1.f - kMinBinHeight * K) * fast_rcp(sh);
+    const float two_b = 2.f * tail;
+    float cumw = 0.f, cumh = 0.f, left = -tail, bottom = -tail;
+    float in_cw = -tail, in_w = 1.f, in_ch = -tail, in_h = 1.f;
+    float ud0 = NFB_BOUNDARY_UD, ud1 = NFB_BOUNDARY_UD;
+    for (int i = 0; i < K; ++i) {
+        cumw += kMinBinWidth + kw * fast_ex2(p(i) * s2 - mw);
+        cumh += kMinBinHeight + kh * fast_ex2(p(K + i) * s2 - mh);
+        const float right = (i == K - 1) ? tail : (two_b * cumw - tail);
+        const float top = (i == K - 1) ? tail : (two_b * cumh - tail);
+        const bool ge = INVERSE ? (x >= bottom) : (x >= left);
+        if (ge) {
+            in_cw = left;
+            in_w = right - left;
+            in_ch = bottom;
+            in_h = top - bottom;
+            ud0 = (i == 0) ? NFB_BOUNDARY_UD : p(2 * K + i - 1);
+            ud1 = (i == K - 1) ? NFB_BOUNDARY_UD : p(2 * K + i);
+        }
+        left = right;
+        bottom = top;
+    }
+    const float d0 = kMinDerivative + softplus_f(ud0);
+    const float d1 = kMinDerivative + softplus_f(ud1);
+    const float rw = fast_rcp(in_w);
+    const float delta = in_h * rw;
+    const float s = d0 + d1 - 2.f * delta;
+    float out, theta, tomt, den;
+    if (INVERSE) {
+        const float t = x - in_ch;
+        const float a = t * s + in_h * (delta - d0);
+        const float b = in_h * d0 - t * s;
+        const float c = -delta * t;
+        const float disc = fmaxf(b * b - 4.f * a * c, 0.f);
+        theta = (2.f * c) / (-b - sqrtf(disc));
+        out = theta * in_w + in_cw;
+        tomt = theta * (1.f - theta);
+        den = delta + s * tomt;
+    } else {
+        theta = (x - in_cw) * rw;
+        tomt = theta * (1.f - theta);
+        den = delta + s * tomt;
+        const float num = in_h * (delta * theta * theta + d0 * tomt);
+        out = in_ch + num * fast_rcp(den);
+    }
+    const float omt = 1.f - theta;
+    const float dnum = delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * omt * omt);
+    float l = kLn2 * (fast_lg2(dnum) - 2.f * fast_lg2(den));
+    if (INVERSE) l = -l;
+    y = inside ? out : x;
+    lad = inside ? l : 0.f;
+}
+
+}  // namespace nfb

@@ -1,0 +1,206 @@
+"""Host-side glue between the nn.Module shims and the C ABI (include/nfb200.h).
+
+`FlowHandle` owns one `nfb_flow_t`: the packed device image of an ordered list of layers (plus an
+optional DiagGaussian base).  It re-reads the parameters when they change (optimizer step,
+load_state_dict, .to()) by comparing (data_ptr, _version) signatures -- the same idea as the
+reference's cache invalidation in `_Linear.train()` (normflows/flows/mixing.py:328-332)."""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def require_cuda_f32(t, what="input"):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{what} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what} is on {t.device}: normflows-b200 runs the transform stack as sm_100a CUDA kernels "
+            "only; there is no CPU/eager fallback. Move the model and data to a CUDA device.")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{what} has dtype {t.dtype}; the CUDA path computes in float32 only")
+    return t.contiguous()
+
+
+class FlowHandle:
+    def __init__(self, layers, base=None, use_tensor_cores=True):
+        self.layers = list(layers)
+        self.base = base
+        self.use_tc = bool(use_tensor_cores)
+        self._h = None
+        self._sig_ptr = None
+        self._sig_ver = None
+        self._features = None
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if self._h is not None:
+            L.lib().nfb_flow_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _tensors(self):
+        ts = []
+        for layer in self.layers:
+            ts.extend(layer._native_tensors())
+        if self.base is not None:
+            ts.extend([self.base.loc, self.base.log_scale])
+        return ts
+
+    def ensure(self, features, device):
+        ts = self._tensors()
+        for t in ts:
+            if t.device != device:
+                raise RuntimeError(f"parameter on {t.device} but input on {device}: call model.to(device)")
+            if t.dtype.is_floating_point and t.dtype != torch.float32:
+                raise RuntimeError(f"parameter dtype {t.dtype}: the CUDA path computes in float32 only")
+            if not t.is_contiguous():
+                raise RuntimeError("non-contiguous parameter")
+        sig_ptr = tuple(t.data_ptr() for t in ts) + (features, device.index)
+        sig_ver = tuple(t._version for t in ts)
+        lib = L.lib()
+        with torch.cuda.device(device):
+            if self._h is None or sig_ptr != self._sig_ptr:
+                self.close()
+                h = C.c_void_p()
+                L.check(lib.nfb_flow_create(C.byref(h), features))
+                self._h = h
+                try:
+                    for layer in self.layers:
+                        layer._native_add(self._h, features)
+                    if self.base is not None:
+                        L.check(lib.nfb_flow_set_base_diag_gaussian(
+                            self._h, L.ptr(self.base.loc), L.ptr(self.base.log_scale)))
+                    L.check(lib.nfb_flow_finalize(self._h, int(self.use_tc), L.stream_ptr()))
+                except Exception:
+                    self.close()
+                    raise
+                self._sig_ptr, self._sig_ver, self._features = sig_ptr, sig_ver, features
+            elif sig_ver != self._sig_ver:
+                L.check(lib.nfb_flow_repack(self._h, L.stream_ptr()))
+                self._sig_ver = sig_ver
+        return self._h
+
+    # -- operations -------------------------------------------------------------------------
+    def _prep(self, z):
+        z = require_cuda_f32(z)
+        if z.dim() != 2:
+            raise ValueError("Inputs must be a 2D tensor [batch, features] on the CUDA path.")
+        return z, self.ensure(z.shape[1], z.device)
+
+    def layer_apply(self, index, direction, z):
+        z, h = self._prep(z)
+        out = torch.empty_like(z)
+        ld = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            L.check(L.lib().nfb_flow_layer_apply(h, index, direction, L.ptr(z), L.ptr(out), L.ptr(ld),
+                                                 z.shape[0], 0, L.stream_ptr()))
+        return out, ld
+
+    def transform(self, direction, z):
+        z, h = self._prep(z)
+        out = torch.empty_like(z)
+        ld = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            L.check(L.lib().nfb_flow_transform(h, direction, L.ptr(z), L.ptr(out), L.ptr(ld), z.shape[0],
+                                               L.stream_ptr()))
+        return out, ld
+
+    def log_prob(self, x):
+        x, h = self._prep(x)
+        lq = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nfb_flow_log_prob(h, L.ptr(x), L.ptr(lq), x.shape[0], L.stream_ptr()))
+        return lq
+
+    def forward_kld(self, x, want_sum=False):
+        x, h = self._prep(x)
+        loss = torch.empty((), dtype=torch.float32, device=x.device)
+        s = torch.empty((), dtype=torch.float64, device=x.device) if want_sum else None
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nfb_flow_forward_kld(h, L.ptr(x), x.shape[0], L.ptr(loss), L.ptr(s),
+                                                 L.stream_ptr()))
+        return (loss, s) if want_sum else loss
+
+    def forward_kld_host(self, x_host, device):
+        """x_host: pinned (or pageable) CPU float32 tensor [B, D]; H2D + D2H copies are inside the call."""
+        if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 2:
+            raise ValueError("forward_kld_host expects a CPU float32 [batch, features] tensor")
+        x_host = x_host.contiguous()
+        h = self.ensure(x_host.shape[1], device)
+        out = C.c_float()
+        with torch.cuda.device(device):
+            L.check(L.lib().nfb_flow_forward_kld_host(h, C.c_void_p(x_host.data_ptr()), x_host.shape[0],
+                                                      C.byref(out)))
+        return out.value
+
+    def log_prob_host(self, x_host, device):
+        if x_host.is_cuda or x_host.dtype != torch.float32 or x_host.dim() != 2:
+            raise ValueError("log_prob_host expects a CPU float32 [batch, features] tensor")
+        x_host = x_host.contiguous()
+        h = self.ensure(x_host.shape[1], device)
+        out = torch.empty(x_host.shape[0], dtype=torch.float32)
+        with torch.cuda.device(device):
+            L.check(L.lib().nfb_flow_log_prob_host(h, C.c_void_p(x_host.data_ptr()), C.c_void_p(out.data_ptr()),
+                                                   x_host.shape[0]))
+        return out
+
+    def launch_count(self):
+        return int(L.lib().nfb_flow_last_launch_count(self._h)) if self._h is not None else 0
+
+    def fused_layers(self):
+        if self._h is None:
+            return []
+        return [i for i in range(len(self.layers)) if L.lib().nfb_flow_layer_is_fused(self._h, i)]
+
+
+def resnet_desc(net, masked):
+    """Fill an nfb_resnet_desc_t from a ResidualNet / MADE shim; returns (desc, keepalive)."""
+    nb = len(net.blocks)
+    VP = C.c_void_p
+    wb = (VP * max(1, 2 * nb))()
+    bb = (VP * max(1, 2 * nb))()
+    mb = (VP * max(1, 2 * nb))()
+    for i, blk in enumerate(net.blocks):
+        for j in range(2):
+            lin = blk.linear_layers[j]
+            wb[2 * i + j] = lin.weight.data_ptr()
+            bb[2 * i + j] = lin.bias.data_ptr()
+            mb[2 * i + j] = lin.mask.data_ptr() if masked else None
+    d = L.ResnetDesc()
+    d.in_features = net.initial_layer.in_features
+    d.hidden_features = net.initial_layer.out_features
+    d.out_features = net.final_layer.out_features
+    d.num_blocks = nb
+    d.w_initial, d.b_initial = net.initial_layer.weight.data_ptr(), net.initial_layer.bias.data_ptr()
+    d.m_initial = net.initial_layer.mask.data_ptr() if masked else None
+    d.w_blocks = C.cast(wb, C.POINTER(VP))
+    d.b_blocks = C.cast(bb, C.POINTER(VP))
+    d.m_blocks = C.cast(mb, C.POINTER(VP)) if masked else None
+    d.w_final, d.b_final = net.final_layer.weight.data_ptr(), net.final_layer.bias.data_ptr()
+    d.m_final = net.final_layer.mask.data_ptr() if masked else None
+    return d, (wb, bb, mb)
+
+
+def mlp_desc(mlp):
+    d = L.MlpDesc()
+    if mlp is None:
+        d.num_layers = 0
+        return d
+    lins = mlp.linear_layers()
+    if len(lins) > 6:
+        raise NotImplementedError("MLP with more than 6 Linear layers is not supported by the CUDA path")
+    d.num_layers = len(lins)
+    d.sizes[0] = lins[0].in_features
+    for i, lin in enumerate(lins):
+        d.sizes[i + 1] = lin.out_features
+        d.w[i] = lin.weight.data_ptr()
+        d.b[i] = lin.bias.data_ptr()
+    d.leaky = float(mlp.leaky)
+    return d

@@ -1,0 +1,111 @@
+"""NormalizingFlow driver (reference: normflows/core.py:9-213).
+
+Same public surface: forward, forward_and_log_det, inverse, inverse_and_log_det, forward_kld, sample,
+log_prob, save, load.  Where the reference loops over layers in Python and accumulates `log_q` with a
+tiny kernel per layer (core.py:96-102), this class hands the whole stack to one `nfb_flow` so that
+log-det accumulation happens in kernel epilogues and adjacent layers fuse
+([LULinearPermute + spline block] -> one tcgen05 kernel).  If any layer is not a `NativeFlow`, it
+falls back to the reference's per-layer loop over whatever the layers implement."""
+import torch
+from torch import nn
+
+from . import _lib as L
+from ._native import FlowHandle
+from .distributions.base import DiagGaussian
+from .flows.base import NativeFlow
+
+
+class NormalizingFlow(nn.Module):
+    def __init__(self, q0, flows, p=None):
+        super().__init__()
+        self.q0 = q0
+        self.flows = nn.ModuleList(flows)
+        self.p = p
+
+    # -- native stack -------------------------------------------------------------------------
+    def _stack(self):
+        if not all(isinstance(f, NativeFlow) for f in self.flows):
+            return None
+        h = self.__dict__.get("_nfb_stack")
+        base = self.q0 if isinstance(self.q0, DiagGaussian) and self.q0.temperature is None \
+            and self.q0.n_dim == 1 else None
+        layers = list(self.flows)
+        if (h is None or h.layers != layers or h.base is not base
+                or h.use_tc != NativeFlow.use_tensor_cores):
+            for f in layers:  # data-dependent inits must have happened before packing
+                pass
+            h = FlowHandle(layers, base, NativeFlow.use_tensor_cores)
+            self.__dict__["_nfb_stack"] = h
+        return h
+
+    def _needs_eager_init(self):
+        from .flows.affine import ActNorm
+        return any(isinstance(f, ActNorm) and not f._done() for f in self.flows)
+
+    # -- reference API ------------------------------------------------------------------------
+    def forward(self, z):
+        z, _ = self.forward_and_log_det(z)
+        return z
+
+    def forward_and_log_det(self, z):
+        h = self._stack()
+        if h is not None and z.dim() == 2 and not self._needs_eager_init():
+            return h.transform(L.NFB_FORWARD, z)
+        log_det = torch.zeros(len(z), device=z.device)
+        for flow in self.flows:
+            z, ld = flow(z)
+            log_det = log_det + ld
+        return z, log_det
+
+    def inverse(self, x):
+        z, _ = self.inverse_and_log_det(x)
+        return z
+
+    def inverse_and_log_det(self, x):
+        h = self._stack()
+        if h is not None and x.dim() == 2 and not self._needs_eager_init():
+            return h.transform(L.NFB_INVERSE, x)
+        log_det = torch.zeros(len(x), device=x.device)
+        for i in range(len(self.flows) - 1, -1, -1):
+            x, ld = self.flows[i].inverse(x)
+            log_det = log_det + ld
+        return x, log_det
+
+    def log_prob(self, x):
+        h = self._stack()
+        if h is not None and h.base is not None and x.dim() == 2 and not self._needs_eager_init():
+            return h.log_prob(x)
+        z, log_q = self.inverse_and_log_det(x)
+        return log_q + self.q0.log_prob(z)
+
+    def forward_kld(self, x):
+        h = self._stack()
+        if h is not None and h.base is not None and x.dim() == 2 and not self._needs_eager_init():
+            return h.forward_kld(x)
+        return -torch.mean(self.log_prob(x))
+
+    def sample(self, num_samples=1):
+        z, log_q = self.q0(num_samples)
+        x, log_det = self.forward_and_log_det(z)
+        return x, log_q - log_det
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path))
+
+    # -- host-buffer entry points (C ABI `_host` functions) -------------------------------------
+    def forward_kld_host(self, x_host, device=None):
+        h = self._stack()
+        if h is None or h.base is None:
+            raise NotImplementedError("forward_kld_host needs an all-native stack with a DiagGaussian base")
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        return h.forward_kld_host(x_host, device)
+
+    def log_prob_host(self, x_host, device=None):
+        h = self._stack()
+        if h is None or h.base is None:
+            raise NotImplementedError("log_prob_host needs an all-native stack with a DiagGaussian base")
+        device = torch.device(device) if device is not None else next(self.parameters()).device
+        return h.log_prob_host(x_host, device)

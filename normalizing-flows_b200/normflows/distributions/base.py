@@ -1,0 +1,57 @@
+"""Base distributions: only what the density pass ends in (reference:
+normflows/distributions/base.py:8-49 BaseDistribution, :53-103 DiagGaussian)."""
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .._native import require_cuda_f32
+
+
+class BaseDistribution(nn.Module):
+    def forward(self, num_samples=1):
+        raise NotImplementedError
+
+    def log_prob(self, z):
+        raise NotImplementedError
+
+    def sample(self, num_samples=1, **kwargs):
+        z, _ = self.forward(num_samples, **kwargs)
+        return z
+
+
+class DiagGaussian(BaseDistribution):
+    def __init__(self, shape, trainable=True):
+        super().__init__()
+        if isinstance(shape, int):
+            shape = (shape,)
+        shape = tuple(shape)
+        self.shape, self.n_dim, self.d = shape, len(shape), int(np.prod(shape))
+        if trainable:
+            self.loc = nn.Parameter(torch.zeros(1, *shape))
+            self.log_scale = nn.Parameter(torch.zeros(1, *shape))
+        else:
+            self.register_buffer("loc", torch.zeros(1, *shape))
+            self.register_buffer("log_scale", torch.zeros(1, *shape))
+        self.temperature = None
+
+    def _log_scale(self):
+        return self.log_scale if self.temperature is None else self.log_scale + np.log(self.temperature)
+
+    def forward(self, num_samples=1, context=None):
+        # sampling from the base is off the hot path (core.py:167-180): plain torch RNG
+        eps = torch.randn((num_samples,) + self.shape, dtype=self.loc.dtype, device=self.loc.device)
+        ls = self._log_scale()
+        z = self.loc + torch.exp(ls) * eps
+        log_p = -0.5 * self.d * np.log(2 * np.pi) - torch.sum(ls + 0.5 * eps ** 2,
+                                                              list(range(1, self.n_dim + 1)))
+        return z, log_p
+
+    def log_prob(self, z, context=None):
+        z = require_cuda_f32(z)
+        ls = self._log_scale().contiguous()
+        out = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        with torch.cuda.device(z.device):
+            L.check(L.lib().nfb_diag_gaussian_log_prob(L.ptr(z), L.ptr(self.loc), L.ptr(ls), L.ptr(out),
+                                                       z.shape[0], self.d, 0, L.stream_ptr()))
+        return out

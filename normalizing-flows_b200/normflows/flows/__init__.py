@@ -1,0 +1,5 @@
+from .base import Flow, NativeFlow, Reverse, Composite, zero_log_det_like_z
+from .neural_spline import AutoregressiveRationalQuadraticSpline, CoupledRationalQuadraticSpline
+from .mixing import LULinearPermute, Permute
+from .affine import (AffineConstFlow, ActNorm, MaskedAffineFlow, AffineCouplingBlock, AffineCoupling,
+                     Split, Merge)

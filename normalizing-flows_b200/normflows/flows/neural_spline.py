@@ -1,0 +1,141 @@
+"""Neural spline flow layers (reference: normflows/flows/neural_spline/wrapper.py:14-85,186-244,
+coupling.py:16-362, autoregressive.py:17-134, flows/affine/autoregressive.py:10-47).
+
+Module trees mirror the reference so `state_dict()` keys match:
+  AutoregressiveRationalQuadraticSpline.mprqat.autoregressive_net.{initial_layer,blocks,final_layer}
+  CoupledRationalQuadraticSpline.prqct.{identity_features,transform_features,transform_net,
+                                        unconditional_transform.unnormalized_*}
+NOTE the wrappers swap directions (wrapper.py:79-85,238-244): `inverse()` is the density direction
+(one conditioner pass), `forward()` is sampling (D passes for the autoregressive layer)."""
+import ctypes as C
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .._native import resnet_desc
+from ..nets.made import MADE
+from ..nets.resnet import ResidualNet
+from .base import NativeFlow
+
+_BOUNDARY = float(np.log(np.exp(1 - 1e-3) - 1))  # utils/splines.py:36 with min_derivative 1e-3
+
+
+def _check_bins(num_bins):
+    if 1e-3 * num_bins > 1.0:
+        raise ValueError("Minimal bin width too large for the number of bins")
+
+
+class _ARTransform(nn.Module):
+    """Holds `autoregressive_net` under the reference's attribute name (`mprqat`)."""
+
+    def __init__(self, features, hidden_features, num_bins, num_blocks, permute_mask, activation,
+                 dropout_probability, init_identity):
+        super().__init__()
+        self.autoregressive_net = MADE(features, hidden_features, None, num_blocks,
+                                       output_multiplier=3 * num_bins - 1, use_residual_blocks=True,
+                                       random_mask=False, permute_mask=permute_mask, activation=activation,
+                                       dropout_probability=dropout_probability, use_batch_norm=False)
+        if init_identity:
+            nn.init.constant_(self.autoregressive_net.final_layer.weight, 0.0)
+            nn.init.constant_(self.autoregressive_net.final_layer.bias, _BOUNDARY)
+
+
+class AutoregressiveRationalQuadraticSpline(NativeFlow):
+    def __init__(self, num_input_channels, num_blocks, num_hidden_channels, num_context_channels=None,
+                 num_bins=8, tail_bound=3, activation=nn.ReLU, dropout_probability=0.0,
+                 permute_mask=False, init_identity=True):
+        super().__init__()
+        if num_context_channels is not None:
+            raise NotImplementedError("context channels are not on the CUDA path yet")
+        if torch.is_tensor(tail_bound):
+            raise NotImplementedError("per-feature tail bounds are not on the CUDA path")
+        _check_bins(num_bins)
+        self.features, self.num_bins, self.tail_bound = num_input_channels, num_bins, float(tail_bound)
+        self.mprqat = _ARTransform(num_input_channels, num_hidden_channels, num_bins, num_blocks,
+                                   permute_mask, activation(), dropout_probability, init_identity)
+
+    def _native_tensors(self):
+        net = self.mprqat.autoregressive_net
+        return list(net.parameters()) + [b for n, b in net.named_buffers() if n.endswith("mask")]
+
+    def _native_add(self, handle, features):
+        if features != self.features:
+            raise ValueError("Expected features = {}, got {}.".format(self.features, features))
+        d = L.ArRqsDesc()
+        d.features, d.num_bins, d.tail_bound = self.features, self.num_bins, self.tail_bound
+        d.net, keep = resnet_desc(self.mprqat.autoregressive_net, masked=True)
+        L.check(L.lib().nfb_flow_add_ar_rqs(handle, C.byref(d)))
+        del keep
+
+
+class _UnconditionalCDF(nn.Module):
+    def __init__(self, features, num_bins):
+        super().__init__()
+        self.unnormalized_widths = nn.Parameter(torch.zeros(features, num_bins))
+        self.unnormalized_heights = nn.Parameter(torch.zeros(features, num_bins))
+        self.unnormalized_derivatives = nn.Parameter(_BOUNDARY * torch.ones(features, num_bins - 1))
+
+
+class _CoupledTransform(nn.Module):
+    """`prqct`: feature index buffers, the conditioner and the unconditional transform."""
+
+    def __init__(self, features, hidden_features, num_blocks, num_bins, reverse_mask, activation,
+                 dropout_probability, init_identity):
+        super().__init__()
+        idx = torch.arange(features)
+        start = 0 if reverse_mask else 1  # utils/masks.py:14-16 with even=reverse_mask
+        transform = (idx % 2 == start % 2) if features > 1 else idx == start
+        mask = torch.zeros(features, dtype=torch.bool)
+        mask[start::2] = True
+        self.register_buffer("identity_features", idx[~mask])
+        self.register_buffer("transform_features", idx[mask])
+        n_id, n_tr = int((~mask).sum()), int(mask.sum())
+        if n_id == 0 or n_tr == 0:
+            raise ValueError("Mask can't be empty.")
+        self.transform_net = ResidualNet(n_id, n_tr * (3 * num_bins - 1), hidden_features, None, num_blocks,
+                                         activation, dropout_probability, False)
+        if init_identity:
+            nn.init.constant_(self.transform_net.final_layer.weight, 0.0)
+            nn.init.constant_(self.transform_net.final_layer.bias, _BOUNDARY)
+        self.unconditional_transform = _UnconditionalCDF(n_id, num_bins)
+        del transform
+
+
+class CoupledRationalQuadraticSpline(NativeFlow):
+    def __init__(self, num_input_channels, num_blocks, num_hidden_channels, num_context_channels=None,
+                 num_bins=8, tails="linear", tail_bound=3.0, activation=nn.ReLU, dropout_probability=0.0,
+                 reverse_mask=False, init_identity=True):
+        super().__init__()
+        if num_context_channels is not None:
+            raise NotImplementedError("context channels are not on the CUDA path yet")
+        if tails != "linear":
+            raise NotImplementedError("only tails='linear' is on the CUDA path")
+        if torch.is_tensor(tail_bound):
+            raise NotImplementedError("per-feature tail bounds are not on the CUDA path")
+        _check_bins(num_bins)
+        self.features, self.num_bins, self.tail_bound = num_input_channels, num_bins, float(tail_bound)
+        self.prqct = _CoupledTransform(num_input_channels, num_hidden_channels, num_blocks, num_bins,
+                                       reverse_mask, activation(), dropout_probability, init_identity)
+
+    def _native_tensors(self):
+        p = self.prqct
+        return list(p.parameters()) + [p.identity_features, p.transform_features]
+
+    def _native_add(self, handle, features):
+        if features != self.features:
+            raise ValueError("Expected features = {}, got {}.".format(self.features, features))
+        p = self.prqct
+        d = L.CoupledRqsDesc()
+        d.features, d.num_bins, d.tail_bound = self.features, self.num_bins, self.tail_bound
+        d.num_identity, d.num_transform = len(p.identity_features), len(p.transform_features)
+        d.identity_features = p.identity_features.data_ptr()
+        d.transform_features = p.transform_features.data_ptr()
+        d.net, keep = resnet_desc(p.transform_net, masked=False)
+        u = p.unconditional_transform
+        d.uncond_widths = u.unnormalized_widths.data_ptr()
+        d.uncond_heights = u.unnormalized_heights.data_ptr()
+        d.uncond_derivatives = u.unnormalized_derivatives.data_ptr()
+        L.check(L.lib().nfb_flow_add_coupled_rqs(handle, C.byref(d)))
+        del keep

@@ -1,0 +1,198 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Everything goes through the C ABI.
+
+Stated tolerance (BASELINE.json north_star): per-sample `log_prob` rtol <= 1e-4 against the reference
+(fp64 golden / fp64 oracle), with atol 1e-3 for |log_prob| < 10; scalar forward_kld rel 2e-5;
+per-layer z atol 2e-4, per-layer log_det atol 2e-3 (fp32 conditioning of single spline elements, see
+tests/test_spline_host.py).  The golden vectors were minted from the real reference
+(tests/golden/make_golden.py); the oracle (oracle/nf_oracle.py) is pinned to them on CPU."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from helpers import annotate_spec, build_model, rel_err
+from oracle import nf_oracle as O
+
+import normflows as nf
+from normflows.flows.base import NativeFlow
+
+pytestmark = pytest.mark.gpu
+
+CASES = ["nsf_ar_d64_h256_l2", "nsf_ar_d5_h128_l3", "nsf_ar_d2_h32_l2_k4", "nsf_coupled_d64_h256_l2",
+         "nsf_coupled_d5_h128_l3", "nsf_coupled_d2_h32_l2_k4", "realnvp2d", "affine_block2d", "affine_block6d"]
+RTOL, ATOL = 1e-4, 1e-3
+
+
+def cuda(a):
+    return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+
+
+@pytest.fixture(autouse=True)
+def _tc_default():
+    NativeFlow.use_tensor_cores = True
+    yield
+    NativeFlow.use_tensor_cores = True
+
+
+@pytest.mark.parametrize("use_tc", [True, False])
+@pytest.mark.parametrize("name", CASES)
+def test_log_prob_and_kld_match_reference(name, use_tc):
+    NativeFlow.use_tensor_cores = use_tc
+    spec, sd, a = load_golden(name)
+    model = build_model(annotate_spec(spec, sd), sd).cuda()
+    x = cuda(a["x"])
+    lp = model.log_prob(x).cpu().numpy()
+    np.testing.assert_allclose(lp, a["log_prob_f64"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(lp, a["log_prob_f32"], rtol=RTOL, atol=ATOL)
+    kld = float(model.forward_kld(x))
+    assert kld == pytest.approx(float(a["kld_f64"]), rel=2e-5)
+    if use_tc and "d64" in name:
+        assert model._stack().fused_layers() == list(range(len(model.flows))), "flagship shape must run fused"
+
+
+@pytest.mark.parametrize("use_tc", [True, False])
+@pytest.mark.parametrize("name", CASES)
+def test_per_layer_inverse_matches_reference(name, use_tc):
+    NativeFlow.use_tensor_cores = use_tc
+    spec, sd, a = load_golden(name)
+    model = build_model(annotate_spec(spec, sd), sd).cuda()
+    n = len(model.flows)
+    for i in range(n - 1, -1, -1):
+        zin = a["x"] if i == n - 1 else a[f"zl_f64__{i + 1}"]
+        z, ld = model.flows[i].inverse(cuda(zin))
+        assert z.dtype == torch.float32 and ld.shape == (zin.shape[0],)
+        np.testing.assert_allclose(z.cpu().numpy(), a[f"zl_f64__{i}"], rtol=1e-4, atol=2e-4, err_msg=f"layer {i}")
+        np.testing.assert_allclose(ld.cpu().numpy(), a[f"ld_f64__{i}"], rtol=1e-4, atol=2e-3, err_msg=f"layer {i}")
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c != "nsf_ar_d64_h256_l2"])
+def test_sampling_direction_matches_reference(name):
+    spec, sd, a = load_golden(name)
+    model = build_model(annotate_spec(spec, sd), sd).cuda()
+    xr, ld = model.forward_and_log_det(cuda(a["z_f64"]))
+    np.testing.assert_allclose(xr.cpu().numpy(), a["fwd_x_f64"], rtol=2e-4, atol=5e-4)
+    np.testing.assert_allclose(ld.cpu().numpy(), a["fwd_ld_f64"], rtol=2e-4, atol=5e-3)
+
+
+def test_inverse_and_log_det_and_round_trip_ar64():
+    spec, sd, a = load_golden("nsf_ar_d64_h256_l2")
+    model = build_model(spec, sd).cuda()
+    z, ld = model.inverse_and_log_det(cuda(a["x"]))
+    np.testing.assert_allclose(z.cpu().numpy(), a["z_f64"], rtol=1e-4, atol=2e-4)
+    # sampling direction of the autoregressive layer = D sequential MADE passes
+    xr, ld2 = model.forward_and_log_det(z)
+    np.testing.assert_allclose(xr.cpu().numpy(), a["x"], rtol=1e-3, atol=2e-3)
+    np.testing.assert_allclose((ld + ld2).cpu().numpy(), 0, atol=2e-2)
+
+
+def _random_model(kind, d=64, layers=4, hidden=256, seed=0, sigma=0.05):
+    torch.manual_seed(seed)
+    fl = []
+    for i in range(layers):
+        if kind == "ar":
+            fl.append(nf.flows.AutoregressiveRationalQuadraticSpline(d, 2, hidden))
+        else:
+            fl.append(nf.flows.CoupledRationalQuadraticSpline(d, 2, hidden, reverse_mask=bool(i % 2)))
+        fl.append(nf.flows.LULinearPermute(d))
+    m = nf.NormalizingFlow(nf.distributions.DiagGaussian(d, trainable=False), fl)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(sigma * torch.randn(p.shape, generator=g))
+    return m
+
+
+def _oracle_of(model, spec_kind, d, layers, hidden):
+    sd = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    flows = []
+    for i in range(layers):
+        flows.append({"type": "AutoregressiveRationalQuadraticSpline" if spec_kind == "ar"
+                      else "CoupledRationalQuadraticSpline", "num_bins": 8, "tail_bound": 3.0})
+        flows.append({"type": "LULinearPermute"})
+    return {"kind": "NormalizingFlow", "q0": {"shape": [d]}, "flows": flows}, sd
+
+
+@pytest.mark.parametrize("kind", ["ar", "coupled"])
+def test_full_batch_properties(kind):
+    """BASELINE batch size (65 536 + a ragged tail): fused kernel vs plain-fp32 kernels on every row,
+    a row subset vs the fp64 oracle, run-to-run determinism, and ragged/tiny batches."""
+    d, layers, hidden = 64, 4, 256
+    model = _random_model(kind, d, layers, hidden).cuda()
+    spec, sd = _oracle_of(model, kind, d, layers, hidden)
+    B = 65536 + 77
+    x = torch.randn(B, d, generator=torch.Generator().manual_seed(1234)) * 1.5
+    xc = x.cuda()
+    lp = model.log_prob(xc)
+    lp2 = model.log_prob(xc)
+    assert torch.equal(lp, lp2), "fused path must be deterministic"
+    NativeFlow.use_tensor_cores = False
+    lp_fp32 = model.log_prob(xc)
+    NativeFlow.use_tensor_cores = True
+    assert rel_err(lp.cpu().numpy(), lp_fp32.cpu().numpy()) < RTOL
+    idx = np.r_[0:96, 65500:B]
+    ref = O.log_prob(spec, sd, x.numpy()[idx].astype(np.float64))
+    np.testing.assert_allclose(lp.cpu().numpy()[idx], ref, rtol=RTOL, atol=ATOL)
+    for b in (1, 127, 128, 129, 300):
+        np.testing.assert_allclose(model.log_prob(xc[:b]).cpu().numpy(), lp.cpu().numpy()[:b], rtol=1e-6, atol=1e-5)
+    assert model.log_prob(xc[:0]).shape == (0,)
+    assert float(model.forward_kld(xc)) == pytest.approx(-float(lp.double().mean()), rel=1e-6)
+
+
+def test_edge_inputs_through_fused_kernel():
+    """x exactly at +-B, just outside, far outside and NaN through the fused block."""
+    spec, sd, a = load_golden("nsf_ar_d64_h256_l2")
+    model = build_model(spec, sd).cuda()
+    x = a["x"].copy()
+    x[0, :4] = [3.0, -3.0, 3.0000002, -3.0000002]
+    x[1, :3] = [100.0, -1e6, 0.0]
+    layer = model.flows[2]
+    z, ld = layer.inverse(cuda(x))
+    zo, ldo = O.ar_rqs(x.astype(np.float64), O._cast(sd, np.float64), "flows.2.", spec["flows"][2], "inverse")
+    np.testing.assert_allclose(z.cpu().numpy(), zo, rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(ld.cpu().numpy(), ldo, rtol=1e-4, atol=2e-3)
+    assert z[0, 2].item() == np.float32(3.0000002) and z[1, 0].item() == 100.0 and z[1, 1].item() == -1e6
+    xn = cuda(x)
+    xn[5, 7] = float("nan")
+    zn, ldn = layer.inverse(xn)
+    assert torch.isnan(zn[5, 7]) and torch.isfinite(zn[4]).all()
+
+
+def test_standalone_spline_kernel_edges():
+    import ctypes as C
+    from normflows import _lib as L
+    f = np.load("tests/golden/spline_edges.npz")
+    x = cuda(f["x_f32"].reshape(-1, 1))
+    params = cuda(np.concatenate([f["uw_f32"], f["uh_f32"], f["ud_f32"]], axis=1))
+    for inv in (0, 1):
+        y, ld = torch.empty_like(x), torch.empty(x.shape[0], device="cuda")
+        L.check(L.lib().nfb_rqs_spline(L.ptr(x), L.ptr(params), L.ptr(y), L.ptr(ld), x.shape[0], 1, 8,
+                                       C.c_float(3.0), C.c_float(1.0), inv, 0, None))
+        np.testing.assert_allclose(y.cpu().numpy()[:, 0], f[f"y_f64_{inv}"], rtol=1e-5, atol=2e-5, equal_nan=True)
+        np.testing.assert_allclose(ld.cpu().numpy(), f[f"lad_f64_{inv}"], rtol=1e-4, atol=5e-4, equal_nan=True)
+
+
+def test_host_entry_points_and_repack():
+    spec, sd, a = load_golden("nsf_coupled_d64_h256_l2")
+    model = build_model(spec, sd).cuda()
+    xh = torch.from_numpy(a["x"].astype(np.float32)).pin_memory()
+    lp_host = model.log_prob_host(xh)
+    np.testing.assert_allclose(lp_host.numpy(), a["log_prob_f64"], rtol=RTOL, atol=ATOL)
+    assert model.forward_kld_host(xh) == pytest.approx(float(a["kld_f64"]), rel=2e-5)
+    # parameter update -> packed weights must follow (cache invalidation by tensor version)
+    with torch.no_grad():
+        model.flows[0].prqct.transform_net.final_layer.bias.add_(0.1)
+    sd2 = {k: v.detach().cpu().numpy() for k, v in model.state_dict().items()}
+    ref = O.log_prob(spec, sd2, a["x"].astype(np.float64))
+    np.testing.assert_allclose(model.log_prob(cuda(a["x"])).cpu().numpy(), ref, rtol=RTOL, atol=ATOL)
+
+
+def test_actnorm_data_dependent_init():
+    f = np.load("tests/golden/actnorm_init.npz")
+    an = nf.flows.ActNorm(6).cuda()
+    x = f["x"][:, :, 0, 0]  # [8, 6] slice as a 2-D batch
+    z, ld = an.inverse(cuda(x))
+    s, t = O.actnorm_init(x.astype(np.float64), (1, 6), "inverse")
+    np.testing.assert_allclose(an.s.detach().cpu().numpy(), s, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(an.t.detach().cpu().numpy(), t, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(z.cpu().numpy(), (x - t) * np.exp(-s), rtol=1e-4, atol=1e-5)
+    assert float(an.data_dep_init_done) == 1.0

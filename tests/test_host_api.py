@@ -1,0 +1,100 @@
+"""CPU-side checks of the drop-in boundary: module trees / state_dict keys identical to the
+reference's (taken from the golden fixtures, which hold the reference `state_dict()`), MADE masks
+bit-identical, C-ABI library loads and exports every symbol the header declares, and the product
+path refuses to run without CUDA (no silent fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+from helpers import annotate_spec, build_model
+
+import normflows as nf
+from normflows import _lib
+
+CASES = ["nsf_ar_d64_h256_l2", "nsf_ar_d5_h128_l3", "nsf_ar_d2_h32_l2_k4", "nsf_coupled_d64_h256_l2",
+         "nsf_coupled_d5_h128_l3", "nsf_coupled_d2_h32_l2_k4", "realnvp2d", "affine_block2d", "affine_block6d"]
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_state_dict_keys_and_shapes_match_reference(name):
+    spec, sd, _ = load_golden(name)
+    model = build_model(annotate_spec(spec, sd))
+    ours = model.state_dict()
+    assert set(ours.keys()) == set(sd.keys())
+    for k, v in sd.items():
+        assert tuple(ours[k].shape) == tuple(v.shape), k
+    # loading the reference checkpoint verbatim works (strict)
+    build_model(spec, sd)
+
+
+def test_made_masks_and_degrees_bit_identical():
+    for name in ("nsf_ar_d64_h256_l2", "nsf_ar_d5_h128_l3", "nsf_ar_d2_h32_l2_k4"):
+        spec, sd, _ = load_golden(name)
+        model = build_model(spec)  # fresh construction, masks computed by OUR MaskedLinear
+        for k, v in model.state_dict().items():
+            if k.endswith(".mask") or k.endswith(".degrees"):
+                np.testing.assert_array_equal(v.numpy(), sd[k], err_msg=k)
+
+
+def test_coupled_feature_split_matches_reference():
+    spec, sd, _ = load_golden("nsf_coupled_d5_h128_l3")
+    model = build_model(spec)
+    for k, v in model.state_dict().items():
+        if k.endswith("identity_features") or k.endswith("transform_features"):
+            np.testing.assert_array_equal(v.numpy(), sd[k], err_msg=k)
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "nfb200.h")).read()
+    declared = set(re.findall(r"\b(nfb_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = _lib.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.nfb_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    spec, sd, a = load_golden("nsf_ar_d2_h32_l2_k4")
+    model = build_model(spec, sd)
+    x = torch.from_numpy(a["x"].astype(np.float32))
+    with pytest.raises(RuntimeError, match="no CPU/eager fallback"):
+        model.log_prob(x)
+    with pytest.raises(RuntimeError, match="no CPU/eager fallback"):
+        model.flows[0].inverse(x)
+    if not torch.cuda.is_available():
+        import ctypes as C
+        h = C.c_void_p()
+        assert _lib.lib().nfb_flow_create(C.byref(h), 4) != 0  # no device -> loud failure
+        assert b"CUDA" in _lib.lib().nfb_last_error() or b"cuda" in _lib.lib().nfb_last_error()
+
+
+def test_constructor_errors_mirror_reference():
+    with pytest.raises(ValueError, match="Minimal bin width too large"):
+        nf.flows.AutoregressiveRationalQuadraticSpline(4, 1, 16, num_bins=2000)
+    with pytest.raises(NotImplementedError):
+        nf.flows.AffineCouplingBlock(nf.nets.MLP([1, 4, 2]), scale_map="tanh")
+    with pytest.raises(NotImplementedError):
+        nf.flows.Permute(4, mode="rotate")
+
+
+def test_permute_index_lists():
+    p = nf.flows.Permute(5, mode="swap")
+    f, i = p._index_lists()
+    z = np.arange(5)
+    assert list(z[f]) == [2, 3, 4, 0, 1]      # cat(z[2:], z[:2])   (mixing.py:34-37)
+    assert list(z[f][i]) == [0, 1, 2, 3, 4]   # inverse undoes it   (mixing.py:47-50)
+
+
+def test_shard_rows_cover():
+    from normflows.parallel import shard_rows
+    for n in (0, 1, 7, 64, 65536 + 3):
+        for w in (1, 2, 3, 8):
+            spans = [shard_rows(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))

@@ -1,0 +1,74 @@
+"""The spline arithmetic the kernels use (csrc/nfb_spline.cuh), compiled for the host by
+tests/native, against the reference's golden vectors -- catches formula bugs without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+SO = os.path.join(ROOT, "tests", "native", "_spline_host_check.so")
+
+
+@pytest.fixture(scope="module")
+def hostlib():
+    src = os.path.join(ROOT, "tests", "native", "spline_host_check.cu")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(ROOT, "normalizing-flows_b200/csrc/nfb_spline.cuh"))):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", SO, src])
+    return C.CDLL(SO)
+
+
+def run(lib, x, uw, uh, ud, K, tail, inverse, templated):
+    n = x.shape[0]
+    params = np.ascontiguousarray(np.concatenate([uw, uh, ud], axis=1).astype(np.float32))
+    x = np.ascontiguousarray(x.astype(np.float32))
+    y, lad = np.empty(n, np.float32), np.empty(n, np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.spline_host_check(vp(x), vp(params), n, K, C.c_float(tail), C.c_float(1.0), int(inverse),
+                          int(templated), vp(y), vp(lad))
+    return y, lad
+
+
+@pytest.mark.parametrize("templated", [0, 1])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_spline_formula_vs_reference_golden(hostlib, templated, inverse):
+    f = np.load(os.path.join(ROOT, "tests/golden/spline_edges.npz"))
+    y, lad = run(hostlib, f["x_f32"], f["uw_f32"], f["uh_f32"], f["ud_f32"], 8, 3.0, inverse, templated)
+    yr, lr = f[f"y_f64_{inverse}"], f[f"lad_f64_{inverse}"]
+    # knot-hit rows 8..14: see tests/test_oracle_golden.py for why the atol is loose there
+    np.testing.assert_allclose(y, yr, rtol=1e-5, atol=2e-5, equal_nan=True)
+    np.testing.assert_allclose(lad, lr, rtol=1e-4, atol=5e-4, equal_nan=True)
+    # exact edge semantics
+    x = f["x_f32"]
+    assert y[2] == x[2] and lad[2] == 0 and y[3] == x[3] and lad[3] == 0   # just outside +-B: identity
+    assert y[4] == 100.0 and y[5] == -1e6 and np.isnan(y[6]) and lad[6] == 0
+    assert abs(y[0] - 3.0) < 1e-5 and abs(y[1] + 3.0) < 1e-5 and abs(lad[0]) < 1e-5
+
+
+def test_spline_random_vs_oracle(hostlib):
+    from oracle import nf_oracle as O
+    rng = np.random.default_rng(0)
+    for K in (4, 8, 10):
+        n = 4000
+        uw, uh = rng.normal(size=(n, K)) * 2, rng.normal(size=(n, K)) * 2
+        ud = rng.normal(size=(n, K - 1)) * 2
+        x = rng.normal(size=n) * 2.2
+        for inv in (0, 1):
+            y, lad = run(hostlib, x, uw, uh, ud, K, 3.0, inv, 1)
+            yo, lo = O.unconstrained_rqs(x.astype(np.float32).astype(np.float64), uw.astype(np.float32).astype(np.float64),
+                                         uh.astype(np.float32).astype(np.float64), ud.astype(np.float32).astype(np.float64),
+                                         inverse=bool(inv), tail_bound=3.0)
+            # fp32 conditioning: where the spline is very steep/flat a 1-ulp change of theta moves y by
+            # ~1e-4; the reference's own fp32 path has the same spread.  Bound the bulk and the tail.
+            err = np.abs(y - yo)
+            assert np.mean(err < 3e-5) > 0.998 and err.max() < 1e-3
+            # same story for logabsdet: compare with what the reference's own fp32 arithmetic
+            # (the oracle run in float32) loses against fp64 on the same inputs
+            f32 = lambda a: a.astype(np.float32)
+            _, l32 = O.unconstrained_rqs(f32(x), f32(uw), f32(uh), f32(ud), inverse=bool(inv), tail_bound=3.0)
+            e_ours, e_ref32 = np.abs(lad - lo), np.abs(l32 - lo)
+            assert np.mean(e_ours) < 2e-5
+            assert e_ours.max() < max(4 * e_ref32.max(), 1e-3)

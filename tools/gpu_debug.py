@@ -1,0 +1,102 @@
+"""Stage-by-stage GPU bring-up diagnostics (not a test; prints numbers).  usage: gpu_debug.py <mode>"""
+import os, sys, time, traceback
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "normalizing-flows_b200"), os.path.join(ROOT, "tests")]
+import numpy as np
+import torch
+import normflows as nf
+from normflows.flows.base import NativeFlow
+from conftest import load_golden
+from helpers import annotate_spec, build_model
+from oracle import nf_oracle as O
+
+mode = sys.argv[1] if len(sys.argv) > 1 else "generic"
+cuda = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).cuda()
+CASES = ["nsf_ar_d2_h32_l2_k4", "nsf_coupled_d2_h32_l2_k4", "nsf_ar_d5_h128_l3", "nsf_coupled_d5_h128_l3",
+         "nsf_ar_d64_h256_l2", "nsf_coupled_d64_h256_l2", "realnvp2d", "affine_block2d", "affine_block6d"]
+
+
+def report(tag, got, ref):
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    d = np.abs(got - ref)
+    print(f"  {tag:34s} max_abs={np.nanmax(d):.3e} max_rel={np.nanmax(d / (np.abs(ref) + 1e-3)):.3e} "
+          f"nan={int(np.isnan(got).sum())}", flush=True)
+
+
+def per_layer(model, a, n):
+    for i in range(n - 1, -1, -1):
+        zin = a["x"] if i == n - 1 else a[f"zl_f64__{i + 1}"]
+        z, ld = model.flows[i].inverse(cuda(zin))
+        torch.cuda.synchronize()
+        report(f"layer {i} z ({type(model.flows[i]).__name__[:12]})", z.cpu().numpy(), a[f"zl_f64__{i}"])
+        report(f"layer {i} log_det", ld.cpu().numpy(), a[f"ld_f64__{i}"])
+
+
+def run_cases(use_tc, cases):
+    NativeFlow.use_tensor_cores = use_tc
+    for name in cases:
+        print(f"== {name} use_tc={use_tc}", flush=True)
+        try:
+            spec, sd, a = load_golden(name)
+            model = build_model(annotate_spec(spec, sd), sd).cuda()
+            per_layer(model, a, len(model.flows))
+            lp = model.log_prob(cuda(a["x"]))
+            torch.cuda.synchronize()
+            print("  fused layers:", model._stack().fused_layers(), "launches:", model._stack().launch_count())
+            report("log_prob (stack)", lp.cpu().numpy(), a["log_prob_f64"])
+            print("  kld", float(model.forward_kld(cuda(a["x"]))), "ref", float(a["kld_f64"]))
+            if "fwd_x_f64" in a:
+                xr, ld = model.forward_and_log_det(cuda(a["z_f64"]))
+                report("sampling x", xr.cpu().numpy(), a["fwd_x_f64"])
+                report("sampling log_det", ld.cpu().numpy(), a["fwd_ld_f64"])
+        except Exception:
+            traceback.print_exc()
+            print("  !! failed", flush=True)
+
+
+def rand_model(kind, layers, d=64, hidden=256):
+    torch.manual_seed(0)
+    fl = []
+    for i in range(layers):
+        fl.append(nf.flows.AutoregressiveRationalQuadraticSpline(d, 2, hidden) if kind == "ar"
+                  else nf.flows.CoupledRationalQuadraticSpline(d, 2, hidden, reverse_mask=bool(i % 2)))
+        fl.append(nf.flows.LULinearPermute(d))
+    m = nf.NormalizingFlow(nf.distributions.DiagGaussian(d, trainable=False), fl)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    return m.cuda()
+
+
+def timeit(fn, n=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i in range(n):
+        fn()
+        ev[i + 1].record()
+    torch.cuda.synchronize()
+    return sorted(ev[i].elapsed_time(ev[i + 1]) for i in range(n))[n // 2]
+
+
+if mode == "generic":
+    run_cases(False, CASES)
+elif mode == "fused":
+    run_cases(True, ["nsf_ar_d64_h256_l2", "nsf_coupled_d64_h256_l2", "nsf_ar_d5_h128_l3"])
+elif mode == "time":
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+    layers = int(sys.argv[3]) if len(sys.argv) > 3 else 32
+    for kind in ("ar", "coupled"):
+        m = rand_model(kind, layers)
+        x = (torch.randn(B, 64) * 1.5).cuda()
+        for tc in (True, False):
+            NativeFlow.use_tensor_cores = tc
+            try:
+                ms = timeit(lambda: m.forward_kld(x), n=5 if tc else 2, warm=2 if tc else 1)
+                print(f"time {kind} B={B} L={layers} use_tc={tc}: {ms:.2f} ms/pass  {B / ms * 1e3:.3e} samples/s "
+                      f"launches={m._stack().launch_count()}", flush=True)
+            except Exception:
+                traceback.print_exc()
+print("done", mode, flush=True)
