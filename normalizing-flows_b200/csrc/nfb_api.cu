@@ -87,11 +87,12 @@ struct NetPack {  // generic path: effective (mask-multiplied) fp32 weights
 
 struct FusedPack {
     bool ok = false;
-    int D = 0, H = 0, n_hidden = 0, T = 0, n_chunks = 0, n_id = 0, n_steps = 0;
+    int D = 0, H = 0, n_hidden = 0, T = 0, F = 0, n_chunks = 0, n_id = 0, n_steps = 0;
     float tail = 3.f;
     size_t rqs_bytes = 0;
     std::vector<FusedStep> steps_host;
-    DevBuf wstream, steps, bias_h, bias_f, in_idx, tr_idx, id_idx, uncond;
+    DevBuf wstream, steps, bias_h, bias_f, uncond;
+    std::vector<int> in_idx, tr_idx, id_idx;
     struct Gemm { DevBuf src_row, src_col, row_scale; const float* W; const float* M; int src_cols, n_pad, k_pad, rpr; size_t off; };
     std::vector<Gemm> gemms;
     // LU + this block as one launch (built when the next layer in list order is an LU)
@@ -139,7 +140,7 @@ struct nfb_flow {
     const float* base_loc = nullptr;
     const float* base_log_scale = nullptr;
     // workspaces
-    DevBuf zA, zB, logq, hA, hB, hT, params, E, scratch_sum, loss, err, ar_tmp, pair_tmp, host_x, zfinal;
+    DevBuf zA, zB, logq, hA, hB, hT, params, E, scratch_sum, loss, err, ar_tmp, pair_tmp, host_x, zfinal, prof;
     long long launches = 0;
 };
 
@@ -213,7 +214,7 @@ int run_net_generic(nfb_flow* f, const NetDesc& n, const NetPack& p, const float
 uint16_t make_ctl(int col, int first, int wait, int signal) {
     return (uint16_t)((col & 511) | ((first & 1) << 9) | ((wait & 7) << 10) | ((signal & 7) << 13));
 }
-int chunk_col_host(int i) { return (i & 1) * 96 + (i >> 1) * 256; }
+int chunk_col_host(int i) { return i * 256; }
 
 int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     FusedPack& F = L.fused;
@@ -224,8 +225,22 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     if (!f->use_tc) return NFB_OK;
     if (L.K != 8 || L.D > 64 || n.H % 64 != 0 || n.H > 256 || n.in > 64 || T > 64 || T < 1) return NFB_OK;
     if (n.out != T * 23) return NFB_OK;
-    const int H = n.H, n_hidden = 1 + 2 * n.nb, n_chunks = (T + 3) / 4;
-    const int rpr = (H <= 128) ? H : (H == 192 ? 96 : 128);
+    const int H = n.H, n_hidden = 1 + 2 * n.nb;
+    // final layer: F features (x24 columns) per MMA chunk.  One record = one [N x 64] bf16 tile <= 32 KB,
+    // so N = 24 F <= 240; large N keeps the per-record issue bubble (~330 cycles) hidden behind
+    // 120-cycle MMAs (measured: tools/ring_bench.cu).
+    int fpc = 2;
+    {   // even features-per-chunk <= 10 that wastes the fewest padded feature slots (ties: larger N)
+        int best = 1 << 30;
+        for (int c = 2; c <= 10; c += 2) {
+            const int slots = (T + c - 1) / c * c;
+            if (slots <= best && !(slots == best && c < fpc)) { best = slots; fpc = c; }
+            if (c >= T + (T & 1)) break;
+        }
+        // T = 64: 10 -> 70 slots beats 8 -> 64 because 120-cycle MMAs hide the per-record bubble
+        if (T > 40 && fpc < 10) fpc = 10;
+    }
+    const int n_chunks = (T + fpc - 1) / fpc;
     const int kcs_h = H / 64;
     // ---- step table ----
     std::vector<FusedStep> steps;
@@ -241,27 +256,23 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         const int region = (ph & 1) ? 256 : 0;
         const bool accum_onto = (ph > 0 && (ph & 1) == 0);  // second GEMM of a residual block: h += ...
         const int kcs = (ph == 0) ? 1 : kcs_h;
-        const int nrb = H / rpr;
-        for (int rb = 0; rb < nrb; ++rb)
-            for (int kc = 0; kc < kcs; ++kc) {
-                const bool very_first = (rb == 0 && kc == 0);
-                const bool very_last = (rb == nrb - 1 && kc == kcs - 1);
-                add(rpr, kc, 4 + kc, 0xFF, region + rb * rpr, (kc == 0 && !accum_onto) ? 1 : 0, very_first ? 1 : 0, 0);
-                add(rpr, kc, 0xFF, 0xFF, region + rb * rpr, 0, 0, very_last ? 1 : 0);
-            }
+        for (int kc = 0; kc < kcs; ++kc) {
+            add(H, kc, 4 + kc, 0xFF, region, (kc == 0 && !accum_onto) ? 1 : 0, kc == 0 ? 1 : 0, 0);
+            add(H, kc, 0xFF, 0xFF, region, 0, 0, (kc == kcs - 1) ? 1 : 0);
+        }
     }
     for (int c = 0; c < n_chunks; ++c) {
-        const int b = c & 3;
+        const int b = c & 1;  // two TMEM chunk buffers (columns 0.. and 256..)
         for (int kc = 0; kc < kcs_h; ++kc) {
             const int wait = (kc == 0) ? (c == 0 ? 6 : 2 + b) : 0;
-            add(96, kc, 4 + kc, 0xFF, chunk_col_host(b), kc == 0 ? 1 : 0, wait, 0);
-            add(96, kc, 0xFF, 0xFF, chunk_col_host(b), 0, 0, (kc == kcs_h - 1) ? 2 + b : 0);
+            add(fpc * 24, kc, 4 + kc, 0xFF, chunk_col_host(b), kc == 0 ? 1 : 0, wait, 0);
+            add(fpc * 24, kc, 0xFF, 0xFF, chunk_col_host(b), 0, 0, (kc == kcs_h - 1) ? 2 + b : 0);
         }
     }
     if (steps.size() + 3 > 256) return NFB_OK;  // step table would not fit in shared memory
     F.steps_host = steps;
     F.n_steps = (int)steps.size();
-    F.D = L.D; F.H = H; F.n_hidden = n_hidden; F.T = T; F.n_chunks = n_chunks; F.tail = L.tail;
+    F.D = L.D; F.H = H; F.n_hidden = n_hidden; F.T = T; F.F = fpc; F.n_chunks = n_chunks; F.tail = L.tail;
     F.n_id = ar ? 0 : L.n_id;
     size_t total = 0;
     for (auto& s : steps) total += (size_t)s.bytes16 * 16;
@@ -288,27 +299,28 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         std::vector<int> sr(H), sc(64);
         for (int i = 0; i < H; ++i) sr[i] = i;
         for (int k = 0; k < 64; ++k) sc[k] = k < n.in ? k : -1;
-        NFB_TRY(add_gemm(n.w0, n.m0, H, n.in, H, 64, rpr, sr, sc, {}, off));
+        NFB_TRY(add_gemm(n.w0, n.m0, H, n.in, H, 64, H, sr, sc, {}, off));
         off += (size_t)H * 64 * 2 * 2;
     }
     for (int i = 0; i < 2 * n.nb; ++i) {
         std::vector<int> sr(H), sc(H);
         for (int j = 0; j < H; ++j) sr[j] = sc[j] = j;
-        NFB_TRY(add_gemm(n.wb[i], n.mb[i], H, H, H, H, rpr, sr, sc, {}, off));
+        NFB_TRY(add_gemm(n.wb[i], n.mb[i], H, H, H, H, H, sr, sc, {}, off));
         off += (size_t)H * H * 2 * 2;
     }
-    std::vector<int> fr(n_chunks * 96);
-    std::vector<float> fs(n_chunks * 96);
+    const int crow = fpc * 24;  // rows (MMA N) per final-layer chunk
+    std::vector<int> fr(n_chunks * crow);
+    std::vector<float> fs(n_chunks * crow);
     {
         std::vector<int> sc(H);
         for (int j = 0; j < H; ++j) sc[j] = j;
-        for (int i = 0; i < n_chunks * 96; ++i) {
-            const int t = 4 * (i / 96) + (i % 96) / 24, q = (i % 96) % 24;
+        for (int i = 0; i < n_chunks * crow; ++i) {
+            const int t = fpc * (i / crow) + (i % crow) / 24, q = (i % crow) % 24;
             fr[i] = (t < T && q < 23) ? t * 23 + q : -1;
             fs[i] = (q < 16) ? L.wh_scale : 1.f;
         }
-        NFB_TRY(add_gemm(n.wf, n.mf, n.out, H, n_chunks * 96, H, 96, fr, sc, fs, off));
-        off += (size_t)n_chunks * 96 * H * 2 * 2;
+        NFB_TRY(add_gemm(n.wf, n.mf, n.out, H, n_chunks * crow, H, crow, fr, sc, fs, off));
+        off += (size_t)n_chunks * crow * H * 2 * 2;
     }
     NFB_CHECK(off == total, NFB_ERR_STATE, "fused pack: stream size mismatch %zu vs %zu", off, total);
 
@@ -323,12 +335,11 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         NFB_TRY(download(L.tr64, (size_t)L.n_tr, tr64));
         for (int k = 0; k < L.n_id; ++k) in_idx[k] = (int)id64[k];
         for (int t = 0; t < T; ++t) tr_idx[t] = (int)tr64[t];
-        std::vector<int> idv(L.n_id);
-        for (int k = 0; k < L.n_id; ++k) idv[k] = (int)id64[k];
-        NFB_TRY(F.id_idx.upload(idv));
+        F.id_idx.assign(L.n_id, 0);
+        for (int k = 0; k < L.n_id; ++k) F.id_idx[k] = (int)id64[k];
     }
-    NFB_TRY(F.in_idx.upload(in_idx));
-    NFB_TRY(F.tr_idx.upload(tr_idx));
+    F.in_idx = in_idx;
+    F.tr_idx = tr_idx;
     F.ok = true;
     (void)st;
     return NFB_OK;
@@ -363,10 +374,11 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         for (int j = 0; j < H; ++j) { cum[j] += tmp[j]; bh[(size_t)(2 + 2 * b) * 256 + j] = cum[j]; }
     }
     NFB_TRY(F.bias_h.upload(bh));
-    std::vector<float> bfin, bf((size_t)F.n_chunks * 96, 0.f);
+    const int crow = F.F * 24;
+    std::vector<float> bfin, bf((size_t)(F.n_chunks + 1) * crow, 0.f);  // +1 chunk: the bias prefetch runs one chunk ahead
     NFB_TRY(download(n.bf, (size_t)n.out, bfin));
-    for (int i = 0; i < F.n_chunks * 96; ++i) {
-        const int t = 4 * (i / 96) + (i % 96) / 24, q = (i % 96) % 24;
+    for (int i = 0; i < F.n_chunks * crow; ++i) {
+        const int t = F.F * (i / crow) + (i % crow) / 24, q = (i % crow) % 24;
         if (t < F.T && q < 23) bf[i] = bfin[t * 23 + q] * ((q < 16) ? L.wh_scale : 1.f);
     }
     NFB_TRY(F.bias_f.upload(bf));
@@ -459,7 +471,7 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
     FusedPack& F = R.fused;
     FusedParams p{};
     p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows;
-    p.D = F.D; p.H = F.H; p.n_hidden = F.n_hidden; p.has_lu = U ? 1 : 0; p.T = F.T;
+    p.D = F.D; p.H = F.H; p.n_hidden = F.n_hidden; p.has_lu = U ? 1 : 0; p.T = F.T; p.F = F.F;
     p.n_chunks = F.n_chunks; p.n_id = F.n_id; p.accumulate = accumulate; p.tail = F.tail;
     p.n_steps = U ? F.pair_steps : F.n_steps;
     p.wstream = U ? F.pair_wstream.as<uint8_t>() : F.wstream.as<uint8_t>();
@@ -467,12 +479,15 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
     p.bias_lu = U ? F.bias_lu.as<float>() : nullptr;
     p.bias_h = F.bias_h.as<float>();
     p.bias_f = F.bias_f.as<float>();
-    p.in_idx = F.in_idx.as<int>();
-    p.tr_idx = F.tr_idx.as<int>();
-    p.id_idx = F.id_idx.as<int>();
+    for (int k = 0; k < 64; ++k) {
+        p.in_idx[k] = (signed char)(k < (int)F.in_idx.size() ? F.in_idx[k] : -1);
+        p.tr_idx[k] = (unsigned char)(k < (int)F.tr_idx.size() ? F.tr_idx[k] : 0);
+        p.id_idx[k] = (unsigned char)(k < (int)F.id_idx.size() ? F.id_idx[k] : 0);
+    }
     p.uncond = F.uncond.as<float>();
     p.lu_logdet = U ? U->lu_logdet.as<float>() : nullptr;
     p.err = f->err.as<int>();
+    p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
     NFB_TRY(launch_fused_rqs(p, f->sm_count, st));
     f->launches++;
     return NFB_OK;
@@ -1014,6 +1029,14 @@ int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, 
     NFB_TRY(nfb_flow_forward_kld(f, xd, rows, f->loss.as<float>(), nullptr, nullptr));
     NFB_CUDA(cudaMemcpyAsync(loss_host, f->loss.p, 4, cudaMemcpyDeviceToHost, 0));
     NFB_CUDA(cudaStreamSynchronize(0));
+    return NFB_OK;
+}
+
+/* debug-only (not part of the ABI header): phase timestamps of CTA 0's first tile */
+__attribute__((visibility("default"))) int nfb_debug_profile(nfb_flow_t* f, int enable, long long* out128) {
+    if (!f) return NFB_ERR_ARG;
+    if (enable) { NFB_TRY(f->prof.reserve(128 * 8)); NFB_CUDA(cudaMemset(f->prof.p, 0, 128 * 8)); return NFB_OK; }
+    if (f->prof.p && out128) NFB_CUDA(cudaMemcpy(out128, f->prof.p, 128 * 8, cudaMemcpyDeviceToHost));
     return NFB_OK;
 }
 

@@ -46,6 +46,20 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// One lane of a fully-converged warp.  Issuing tcgen05.mma / cp.async.bulk under this predicate
+// (instead of `lane == 0`) lets ptxas keep the operands in uniform registers; with a plain lane test
+// it wraps every UTCHMMA in an ELECT/BRA.U.ANY waterfall loop (~17 dependent instructions per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+        "elect.sync %%rx|%%px, %1;\n\t"
+        "@%%px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred)
+        : "r"(0xffffffffu));
+    return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
@@ -135,6 +149,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// Same, with the A operand read from tensor memory (128 lanes x 8 columns of packed bf16 pairs per
+// K=16 step) -- no shared-memory traffic for A.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                             uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() {
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+#define NFB_TMEM_ST16(addr, v)                                                           \
+    asm volatile(                                                                        \
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "                                  \
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"                      \
+        ::"r"(addr), "r"((v)[0]), "r"((v)[1]), "r"((v)[2]), "r"((v)[3]), "r"((v)[4]),    \
+          "r"((v)[5]), "r"((v)[6]), "r"((v)[7]), "r"((v)[8]), "r"((v)[9]), "r"((v)[10]), \
+          "r"((v)[11]), "r"((v)[12]), "r"((v)[13]), "r"((v)[14]), "r"((v)[15])           \
+        : "memory")
 // mbarrier arrives when all tcgen05.mma issued so far by this thread have completed
 // (implies tcgen05.fence::before_thread_sync).
 __device__ __forceinline__ void umma_commit(uint32_t bar) {

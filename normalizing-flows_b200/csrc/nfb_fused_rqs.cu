@@ -34,8 +34,8 @@ namespace nfb {
 
 constexpr int kFusedThreads = 320;
 constexpr uint32_t kTileA = 16384;    // one [128 x 64] bf16 SW128 tile
-constexpr uint32_t kSlotBytes = 16384;
-constexpr int kSlots = 4;
+constexpr uint32_t kSlotBytes = 32768;  // one record = up to [256 rows x 64 K] bf16
+constexpr int kSlots = 2;
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffW = 131072;
 constexpr uint32_t kOffX = kOffW + kSlots * kSlotBytes;  // 196608
@@ -52,7 +52,9 @@ static_assert(kFusedSmem <= 232448, "shared memory budget");
 constexpr int kBarWFull = 0, kBarWEmpty = 4, kBarAReady = 8, kBarAccFull = 9, kBarCFull = 10,
               kBarCEmpty = 14;
 // TMEM column of final-layer chunk buffer i
-__device__ __forceinline__ uint32_t chunk_col(int i) { return (i & 1) * 96 + (i >> 1) * 256; }
+// (both accumulator regions are dead once the last hidden epilogue has run: one buffer in each)
+__device__ __forceinline__ uint32_t chunk_col(int i) { return (uint32_t)i * 256u; }
+constexpr uint32_t kTmemAHi = 256;  // TS-mode A operand base (kept for experiments; unused by the table)
 
 __device__ __forceinline__ uint32_t xs_index(int r, int c) { return r * 64 + (c ^ (r & 31)); }
 
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     }
     for (int i = threadIdx.x; i < p.n_steps; i += kFusedThreads) steps[i] = p.steps[i];
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kSlots; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(bar(kBarWFull + i), 1);
             mbar_init(bar(kBarWEmpty + i), 1);
             mbar_init(bar(kBarCFull + i), 1);
@@ -133,62 +135,79 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 
     if (warp == 0) {
         // ------------------------------ weight producer -----------------------------------
-        if (lane == 0) {
-            uint32_t slot = 0, par = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const uint8_t* src = p.wstream;
-                for (int s = 0; s < p.n_steps; ++s) {
-                    const uint32_t bytes = (uint32_t)steps[s].bytes16 << 4;
-                    mbar_wait(bar(kBarWEmpty + slot), par ^ 1, p.err, 100 + slot);
+        // whole warp walks the table (warp-uniform control flow); one elected lane issues the copy
+        uint32_t slot = 0, par = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint8_t* src = p.wstream;
+            for (int s = 0; s < p.n_steps; ++s) {
+                const uint32_t bytes = (uint32_t)steps[s].bytes16 << 4;
+                mbar_wait(bar(kBarWEmpty + slot), par ^ 1, p.err, 100 + slot);
+                if (elect_one_sync()) {
                     mbar_expect_tx(bar(kBarWFull + slot), bytes);
                     bulk_g2s(sbase + kOffW + slot * kSlotBytes, src, bytes, bar(kBarWFull + slot));
-                    src += bytes;
-                    if (++slot == kSlots) { slot = 0; par ^= 1; }
                 }
+                __syncwarp();
+                src += bytes;
+                if (++slot == kSlots) { slot = 0; par ^= 1; }
             }
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ----------------------------------------
-        if (lane == 0) {
-            uint32_t slot = 0, wpar = 0, apar = 0, cebits = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int s = 0; s < p.n_steps; ++s) {
-                    const FusedStep st = steps[s];
-                    const uint32_t ctl = st.ctl;
-                    const uint32_t col = ctl & 511u, first = (ctl >> 9) & 1u;
-                    const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
-                    if (wcode == 1 || wcode == 6) {
-                        mbar_wait(bar(kBarAReady), apar, p.err, 200);
-                        apar ^= 1;
-                    }
-                    if (wcode >= 2) {
-                        const uint32_t i = wcode == 6 ? 0u : wcode - 2;
-                        mbar_wait(bar(kBarCEmpty + i), ((cebits >> i) & 1u) ^ 1u, p.err, 210 + i);
-                        cebits ^= 1u << i;
-                    }
-                    mbar_wait(bar(kBarWFull + slot), wpar, p.err, 220 + slot);
-                    tc_fence_after();
-                    const uint32_t n = (uint32_t)st.n8 << 3;
-                    const uint32_t idesc = umma_idesc_bf16(128, n);
-                    const uint32_t bsm = sbase + kOffW + slot * kSlotBytes;
-                    const uint8_t at[3] = {st.a0, st.a1, st.a2};
-                    uint32_t accum = first ? 0u : 1u;
-#pragma unroll
-                    for (int ai = 0; ai < 3; ++ai) {
-                        if (at[ai] == 0xFF) continue;
-                        const uint32_t asm_ = sbase + kOffA + at[ai] * kTileA;
-#pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) {
-                            umma_bf16(tmem + col, umma_desc_sw128(asm_ + ks * 32),
-                                      umma_desc_sw128(bsm + ks * 32), idesc, accum);
-                            accum = 1u;
+        // Warp-uniform loop; the MMAs of one weight record are issued by one elected lane from
+        // descriptors that differ only by an add on the 14-bit address field (16-byte units).
+        uint32_t slot = 0, wpar = 0, apar = 0, cebits = 0;
+        const uint64_t adesc0 = umma_desc_sw128(sbase + kOffA);
+        const uint64_t bdesc0 = umma_desc_sw128(sbase + kOffW);
+        constexpr uint32_t kIdesc0 = umma_idesc_bf16(128, 0);
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            FusedStep st = steps[0];
+            for (int s = 0; s < p.n_steps; ++s) {
+                const FusedStep nxt = steps[s + 1 < p.n_steps ? s + 1 : 0];  // prefetch (LDS latency)
+                const uint32_t ctl = st.ctl;
+                const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
+                if (wcode == 1 || wcode == 6) {
+                    mbar_wait(bar(kBarAReady), apar, p.err, 200);
+                    apar ^= 1;
+                }
+                if (wcode >= 2) {
+                    const uint32_t i = wcode == 6 ? 0u : wcode - 2;
+                    mbar_wait(bar(kBarCEmpty + i), ((cebits >> i) & 1u) ^ 1u, p.err, 210 + i);
+                    cebits ^= 1u << i;
+                }
+                mbar_wait(bar(kBarWFull + slot), wpar, p.err, 220 + slot);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t d = tmem + (ctl & 511u);
+                    const uint32_t idesc = kIdesc0 | ((uint32_t)st.n8 << 17);
+                    const uint64_t bd = bdesc0 + (uint64_t)(slot * (kSlotBytes >> 4));
+                    uint32_t accum = ((ctl >> 9) & 1u) ^ 1u;
+                    // A code: 0..7 = shared-memory tile; 0x80|t = tensor memory (final layer), t = split*4+kc
+                    auto issue4 = [&](uint32_t code) {
+                        if (code & 0x80u) {
+                            const uint32_t at = tmem + kTmemAHi + (code & 7u) * 32u;
+                            umma_bf16_ts(d, at, bd, idesc, accum);
+                            umma_bf16_ts(d, at + 8, bd + 2, idesc, 1u);
+                            umma_bf16_ts(d, at + 16, bd + 4, idesc, 1u);
+                            umma_bf16_ts(d, at + 24, bd + 6, idesc, 1u);
+                        } else {
+                            const uint64_t ad = adesc0 + (uint64_t)(code * (kTileA >> 4));
+                            umma_bf16(d, ad, bd, idesc, accum);
+                            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
                         }
-                    }
+                        accum = 1u;
+                    };
+                    issue4(st.a0);
+                    if (st.a1 != 0xFF) issue4(st.a1);
+                    if (st.a2 != 0xFF) issue4(st.a2);
                     umma_commit(bar(kBarWEmpty + slot));
                     if (scode == 1) umma_commit(bar(kBarAccFull));
                     else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
-                    if (++slot == kSlots) { slot = 0; wpar ^= 1; }
                 }
+                __syncwarp();
+                if (++slot == kSlots) { slot = 0; wpar ^= 1; }
+                st = nxt;
             }
         }
     } else {
@@ -201,6 +220,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const uint32_t aA = sbase + kOffA;
         uint32_t afpar = 0, cfbits = 0;
         const int D = p.D, H = p.H;
+        long long* prof = (p.prof && blockIdx.x == 0 && et == 0) ? p.prof : nullptr;
+        int pi = 0;
+#define NFB_STAMP() do { if (prof && pi < 126) prof[pi++] = clock64(); } while (0)
 
         auto build_a = [&](bool lu_stage) {
             // A[:, k] for k in [wh*32, wh*32+32): lu_stage -> 3-way split of xs[:, k] (k < D);
@@ -226,17 +248,41 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long row0 = tile * 128;
+            if (tile != blockIdx.x) prof = nullptr;
+            NFB_STAMP();  // [0] tile start
             // ---- load z tile -> xs (coalesced global, swizzled shared) ----
-            for (int i = et; i < 128 * D; i += 256) {
-                const int rr = i / D, cc = i - rr * D;
-                const long long gr = row0 + rr;
-                xs[xs_index(rr, cc)] = gr < p.rows ? __ldg(p.zin + gr * D + cc) : 0.f;
+            if (D == 64) {
+                float4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i4 = et + k * 256, rr = i4 >> 4;
+                    const long long gr = row0 + rr;
+                    v[k] = gr < p.rows ? __ldg(reinterpret_cast<const float4*>(p.zin + gr * 64) + (i4 & 15))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i4 = et + k * 256, rr = i4 >> 4, c0 = (i4 & 15) * 4;
+                    xs[xs_index(rr, c0)] = v[k].x;
+                    xs[xs_index(rr, c0 + 1)] = v[k].y;
+                    xs[xs_index(rr, c0 + 2)] = v[k].z;
+                    xs[xs_index(rr, c0 + 3)] = v[k].w;
+                }
+            } else {
+                for (int i = et; i < 128 * D; i += 256) {
+                    const int rr = i / D, cc = i - rr * D;
+                    const long long gr = row0 + rr;
+                    xs[xs_index(rr, cc)] = gr < p.rows ? __ldg(p.zin + gr * D + cc) : 0.f;
+                }
             }
             epi_bar_sync();
+            NFB_STAMP();  // [1] load done
             float ladsum = 0.f;
             if (p.has_lu) {
                 build_a(true);
+                NFB_STAMP();  // build_a(lu) done
                 mbar_wait(bar(kBarAccFull), afpar, p.err, 300);
+                NFB_STAMP();  // LU gemm done
                 afpar ^= 1;
                 tc_fence_after();
                 // x' = acc + b  (64 columns at TMEM col 256; this thread: 32 of them)
@@ -252,6 +298,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 epi_bar_sync();
             }
             build_a(false);
+            NFB_STAMP();  // net input A built
 
             // ---- unconditional spline on the identity features (coupled layer only); runs while
             //      the tensor core is busy with the first GEMMs.  The conditioner input was taken
@@ -274,17 +321,26 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 mbar_wait(bar(kBarAccFull), afpar, p.err, 310 + ph);
                 afpar ^= 1;
                 tc_fence_after();
+                NFB_STAMP();  // hidden gemm ph done
                 const uint32_t region = (ph & 1) ? 256u : 0u;
                 const bool relu = ph + 1 < p.n_hidden;
                 const float* bias = p.bias_h + ph * 256;
                 const int half = H >> 1;
+                float4 bnext[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) bnext[j] = __ldg(reinterpret_cast<const float4*>(bias + wh * half) + j);
                 for (int g = 0; g < half; g += 32) {
                     const int c0 = wh * half + g;
                     uint32_t acc[32];
                     NFB_TMEM_LD32(tlane + region + c0, acc);
                     float4 b4[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(bias + c0) + j);
+                    for (int j = 0; j < 8; ++j) b4[j] = bnext[j];
+                    if (g + 32 < half) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            bnext[j] = __ldg(reinterpret_cast<const float4*>(bias + c0 + 32) + j);
+                    }
                     tc_wait_ld();
                     const float* bf = reinterpret_cast<const float*>(b4);
                     float v[32];
@@ -303,36 +359,48 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(kBarAReady));
+                NFB_STAMP();  // hidden epilogue ph done
             }
 
             // ---- final layer chunks -> spline ----
-            for (int c = 0; c < p.n_chunks; ++c) {
-                const int b = c & 3;
-                const int t0 = c * 4 + wh * 2;  // first transformed-feature slot of this thread
-                float4 bb[12];
+            // chunk = F features x 24 columns (N = 24 F <= 240); this thread: F/2 of them, one at a time
+            const int fh = p.F >> 1;
+            float4 bfn[6];
 #pragma unroll
-                for (int j = 0; j < 12; ++j)
-                    bb[j] = __ldg(reinterpret_cast<const float4*>(p.bias_f + t0 * 24) + j);
+            for (int j = 0; j < 6; ++j) bfn[j] = __ldg(reinterpret_cast<const float4*>(p.bias_f + wh * fh * 24) + j);
+            for (int c = 0; c < p.n_chunks; ++c) {
+                const int b = c & 1;
+                const int t0 = c * p.F + wh * fh;  // first transformed-feature slot of this thread
                 mbar_wait(bar(kBarCFull + b), (cfbits >> b) & 1u, p.err, 400 + b);
                 cfbits ^= 1u << b;
                 tc_fence_after();
-                uint32_t pr[48];
-                const uint32_t ta = tlane + chunk_col(b) + wh * 48;
-                NFB_TMEM_LD16(ta, pr);
-                NFB_TMEM_LD16(ta + 16, pr + 16);
-                NFB_TMEM_LD16(ta + 32, pr + 32);
-                tc_wait_ld();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
-                const float* bf = reinterpret_cast<const float*>(bb);
-#pragma unroll
-                for (int f = 0; f < 2; ++f) {
+                NFB_STAMP();  // chunk c available
+                const uint32_t ta = tlane + chunk_col(b) + wh * fh * 24;
+                for (int f = 0; f < fh; ++f) {
                     const int t = t0 + f;
+                    uint32_t pr[24];
+                    NFB_TMEM_LD16(ta + f * 24, pr);
+                    NFB_TMEM_LD8(ta + f * 24 + 16, pr + 16);
+                    float4 bb[6];
+#pragma unroll
+                    for (int j = 0; j < 6; ++j) bb[j] = bfn[j];
+                    {   // prefetch the next feature's bias (next chunk's first feature at the end)
+                        const int tn = (f + 1 < fh) ? t + 1 : t0 + p.F;
+#pragma unroll
+                        for (int j = 0; j < 6; ++j)
+                            bfn[j] = __ldg(reinterpret_cast<const float4*>(p.bias_f + tn * 24) + j);
+                    }
+                    tc_wait_ld();
+                    if (f == fh - 1) {  // all of this thread's columns are in registers: free the buffer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
+                    }
                     if (t < p.T) {
+                        const float* bf = reinterpret_cast<const float*>(bb);
                         float pv[24];
 #pragma unroll
-                        for (int j = 0; j < 24; ++j) pv[j] = __uint_as_float(pr[f * 24 + j]) + bf[f * 24 + j];
+                        for (int j = 0; j < 24; ++j) pv[j] = __uint_as_float(pr[j]) + bf[j];
                         auto acc = [&pv](int k) { return pv[k]; };
                         const int col = p.tr_idx[t];
                         float y, l;
@@ -341,8 +409,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         ladsum += l;
                     }
                 }
+                NFB_STAMP();  // chunk c consumed
             }
 
+            NFB_STAMP();  // last spline done
             // ---- log-det reduction across the two column halves, then store ----
             if (wh == 1) ldsum[r] = ladsum;
             epi_bar_sync();
@@ -353,12 +423,25 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     p.logq[gr] = p.accumulate ? p.logq[gr] + tot : tot;
                 }
             }
-            for (int i = et; i < 128 * D; i += 256) {
-                const int rr = i / D, cc = i - rr * D;
-                const long long gr = row0 + rr;
-                if (gr < p.rows) p.zout[gr * D + cc] = xs[xs_index(rr, cc)];
+            if (D == 64) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const int i4 = et + k * 256, rr = i4 >> 4, c0 = (i4 & 15) * 4;
+                    const long long gr = row0 + rr;
+                    const float4 v = make_float4(xs[xs_index(rr, c0)], xs[xs_index(rr, c0 + 1)],
+                                                 xs[xs_index(rr, c0 + 2)], xs[xs_index(rr, c0 + 3)]);
+                    if (gr < p.rows) *(reinterpret_cast<float4*>(p.zout + gr * 64) + (i4 & 15)) = v;
+                }
+            } else {
+                for (int i = et; i < 128 * D; i += 256) {
+                    const int rr = i / D, cc = i - rr * D;
+                    const long long gr = row0 + rr;
+                    if (gr < p.rows) p.zout[gr * D + cc] = xs[xs_index(rr, cc)];
+                }
             }
             epi_bar_sync();
+            NFB_STAMP();  // tile stored
+            if (prof) prof[127] = pi;
         }
     }
     tc_fence_before();

@@ -70,19 +70,21 @@ struct FusedParams {
     float* zout;
     float* logq;
     long long rows;
-    int D, H, n_hidden, has_lu, T, n_chunks, n_id, n_steps, accumulate;
+    int D, H, n_hidden, has_lu, T, F, n_chunks, n_id, n_steps, accumulate;  // F = features per final-layer chunk
     float tail;
     const uint8_t* wstream;
     const FusedStep* steps;
     const float* bias_lu;    // [64]
     const float* bias_h;     // [n_hidden][256], residual biases pre-summed
-    const float* bias_f;     // [n_chunks*4*24]
-    const int* in_idx;       // [64] conditioner input column per k (-1 = zero pad)
-    const int* tr_idx;       // [T]
-    const int* id_idx;       // [n_id]
+    const float* bias_f;     // [n_chunks*F*24]
+    // feature index tables live in the kernel parameter (constant) bank: no L2 round trip per use
+    signed char in_idx[64];    // conditioner input column per k (-1 = zero pad)
+    unsigned char tr_idx[64];  // transformed feature columns
+    unsigned char id_idx[64];  // identity feature columns (coupled layer)
     const float* uncond;     // [n_id][23]
     const float* lu_logdet;  // device scalar or null
     int* err;
+    long long* prof;         // optional [128] clock64 stamps (debug)
 };
 int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st);
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,

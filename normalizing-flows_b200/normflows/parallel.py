@@ -17,7 +17,7 @@ def all_reduce_kld(local_sum, local_count, group=None):
     """-(sum_r local_sum_r) / (sum_r local_count_r) with ONE collective on a 2-element fp64 tensor.
     local_sum: 0-dim tensor (sum of log_q over the local shard)."""
     buf = torch.stack([local_sum.to(torch.float64).reshape(()),
-                       torch.tensor(float(local_count), dtype=torch.float64, device=local_sum.device)])
+                       torch.full((), float(local_count), dtype=torch.float64, device=local_sum.device)])
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return -(buf[0] / buf[1])

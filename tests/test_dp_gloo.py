@@ -1,0 +1,47 @@
+"""Multi-process (world_size 2, gloo, CPU) test of the data-parallel host logic: row sharding and the
+single all-reduce of (sum log_q, count).  Per-rank log_q comes from the oracle (allowed in tests)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, load_golden
+
+
+def _worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "normalizing-flows_b200"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from conftest import load_golden as lg
+    from normflows.parallel import all_reduce_kld, shard_rows
+    from oracle import nf_oracle as O
+    spec, sd, a = lg("nsf_coupled_d5_h128_l3")
+    x = a["x"].astype(np.float64)
+    lo, hi = shard_rows(x.shape[0], rank, world)
+    lp = O.log_prob(spec, sd, x[lo:hi])
+    kld = all_reduce_kld(torch.tensor(lp.sum()), hi - lo)
+    q.put((rank, float(kld), lo, hi))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_forward_kld_all_reduce_matches_single_process(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    _, _, a = load_golden("nsf_coupled_d5_h128_l3")
+    for _, kld, _, _ in res:
+        assert kld == pytest.approx(float(a["kld_f64"]), rel=1e-6)  # golden kld accumulates in fp32
+    spans = sorted((lo, hi) for _, _, lo, hi in res)
+    assert spans[0][0] == 0 and spans[-1][1] == a["x"].shape[0]

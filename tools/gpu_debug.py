@@ -100,3 +100,24 @@ elif mode == "time":
             except Exception:
                 traceback.print_exc()
 print("done", mode, flush=True)
+
+if mode == "prof":
+    import ctypes as C
+    from normflows import _lib as L
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+    for kind in ("ar", "coupled"):
+        m = rand_model(kind, 2)
+        x = (torch.randn(B, 64) * 1.5).cuda()
+        m.forward_kld(x); torch.cuda.synchronize()
+        h = m._stack()._h
+        lib = L.lib()
+        lib.nfb_debug_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        lib.nfb_debug_profile(h, 1, None)
+        m.forward_kld(x); torch.cuda.synchronize()
+        buf = (C.c_longlong * 128)()
+        lib.nfb_debug_profile(h, 0, buf)
+        n = buf[127]
+        t = [buf[i] - buf[0] for i in range(n)]
+        print(f"prof {kind}: {n} stamps (cycles since tile start; deltas)")
+        print("  abs  :", t)
+        print("  delta:", [t[i] - t[i - 1] for i in range(1, n)])
