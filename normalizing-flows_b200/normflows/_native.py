@@ -98,6 +98,8 @@ class FlowHandle:
         z, h = self._prep(z)
         out = torch.empty_like(z)
         ld = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        if z.shape[0] == 0:
+            return out, ld
         with torch.cuda.device(z.device):
             L.check(L.lib().nfb_flow_layer_apply(h, index, direction, L.ptr(z), L.ptr(out), L.ptr(ld),
                                                  z.shape[0], 0, L.stream_ptr()))
@@ -107,6 +109,8 @@ class FlowHandle:
         z, h = self._prep(z)
         out = torch.empty_like(z)
         ld = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        if z.shape[0] == 0:
+            return out, ld
         with torch.cuda.device(z.device):
             L.check(L.lib().nfb_flow_transform(h, direction, L.ptr(z), L.ptr(out), L.ptr(ld), z.shape[0],
                                                L.stream_ptr()))
@@ -115,6 +119,8 @@ class FlowHandle:
     def log_prob(self, x):
         x, h = self._prep(x)
         lq = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+        if x.shape[0] == 0:
+            return lq
         with torch.cuda.device(x.device):
             L.check(L.lib().nfb_flow_log_prob(h, L.ptr(x), L.ptr(lq), x.shape[0], L.stream_ptr()))
         return lq
