@@ -91,7 +91,8 @@ struct FusedPack {
     float tail = 3.f;
     size_t rqs_bytes = 0;
     std::vector<FusedStep> steps_host;
-    DevBuf wstream, steps, bias_h, bias_f, uncond;
+    DevBuf wstream, steps, uncond;
+    std::vector<float> bias_h, bias_f;
     std::vector<int> in_idx, tr_idx, id_idx;
     struct Gemm { DevBuf src_row, src_col, row_scale; const float* W; const float* M; int src_cols, n_pad, k_pad, rpr; size_t off; };
     std::vector<Gemm> gemms;
@@ -257,19 +258,21 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         const bool accum_onto = (ph > 0 && (ph & 1) == 0);  // second GEMM of a residual block: h += ...
         const int kcs = (ph == 0) ? 1 : kcs_h;
         for (int kc = 0; kc < kcs; ++kc) {
-            add(H, kc, 4 + kc, 0xFF, region, (kc == 0 && !accum_onto) ? 1 : 0, kc == 0 ? 1 : 0, 0);
+            add(H, kc, 4 + kc, 0xFF, region, (kc == 0 && !accum_onto) ? 1 : 0, 1, 0);
             add(H, kc, 0xFF, 0xFF, region, 0, 0, (kc == kcs - 1) ? 1 : 0);
         }
     }
     for (int c = 0; c < n_chunks; ++c) {
-        const int b = c & 1;  // two TMEM chunk buffers (columns 0.. and 256..)
+        const int b = (c + 1) & 1;  // two TMEM chunk buffers (columns 0.. and 256..); chunk 0 uses the second
         for (int kc = 0; kc < kcs_h; ++kc) {
-            const int wait = (kc == 0) ? (c == 0 ? 6 : 2 + b) : 0;
+            // chunk 0 is the first reader of each A K-chunk (wait a_ready[kc]); kc==0 also waits for the buffer
+            const int wait = (kc == 0) ? (c == 0 ? 6 : 2 + b) : (c == 0 ? 1 : 0);
             add(fpc * 24, kc, 4 + kc, 0xFF, chunk_col_host(b), kc == 0 ? 1 : 0, wait, 0);
             add(fpc * 24, kc, 0xFF, 0xFF, chunk_col_host(b), 0, 0, (kc == kcs_h - 1) ? 2 + b : 0);
         }
     }
     if (steps.size() + 3 > 256) return NFB_OK;  // step table would not fit in shared memory
+    if (n_hidden > 7 || n_chunks * fpc > 72) return NFB_OK;  // bias tables in the kernel parameter bank
     F.steps_host = steps;
     F.n_steps = (int)steps.size();
     F.D = L.D; F.H = H; F.n_hidden = n_hidden; F.T = T; F.F = fpc; F.n_chunks = n_chunks; F.tail = L.tail;
@@ -373,7 +376,7 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         NFB_TRY(download(n.bb[2 * b + 1], (size_t)H, tmp));
         for (int j = 0; j < H; ++j) { cum[j] += tmp[j]; bh[(size_t)(2 + 2 * b) * 256 + j] = cum[j]; }
     }
-    NFB_TRY(F.bias_h.upload(bh));
+    F.bias_h = bh;
     const int crow = F.F * 24;
     std::vector<float> bfin, bf((size_t)(F.n_chunks + 1) * crow, 0.f);  // +1 chunk: the bias prefetch runs one chunk ahead
     NFB_TRY(download(n.bf, (size_t)n.out, bfin));
@@ -381,7 +384,7 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         const int t = F.F * (i / crow) + (i % crow) / 24, q = (i % crow) % 24;
         if (t < F.T && q < 23) bf[i] = bfin[t * 23 + q] * ((q < 16) ? L.wh_scale : 1.f);
     }
-    NFB_TRY(F.bias_f.upload(bf));
+    F.bias_f = bf;
     if (L.kind == L_COUPLED_RQS) {
         std::vector<float> w, h, d, tab((size_t)L.n_id * 23);
         NFB_TRY(download(L.uw, (size_t)L.n_id * 8, w));
@@ -477,8 +480,10 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
     p.wstream = U ? F.pair_wstream.as<uint8_t>() : F.wstream.as<uint8_t>();
     p.steps = U ? F.pair_steps_dev.as<FusedStep>() : F.steps.as<FusedStep>();
     p.bias_lu = U ? F.bias_lu.as<float>() : nullptr;
-    p.bias_h = F.bias_h.as<float>();
-    p.bias_f = F.bias_f.as<float>();
+    memset(p.bias_h, 0, sizeof(p.bias_h));
+    memset(p.bias_f, 0, sizeof(p.bias_f));
+    memcpy(p.bias_h, F.bias_h.data(), std::min(sizeof(p.bias_h), F.bias_h.size() * sizeof(float)));
+    memcpy(p.bias_f, F.bias_f.data(), std::min(sizeof(p.bias_f), F.bias_f.size() * sizeof(float)));
     for (int k = 0; k < 64; ++k) {
         p.in_idx[k] = (signed char)(k < (int)F.in_idx.size() ? F.in_idx[k] : -1);
         p.tr_idx[k] = (unsigned char)(k < (int)F.tr_idx.size() ? F.tr_idx[k] : 0);

@@ -62,7 +62,7 @@ struct __align__(8) FusedStep {
     uint8_t a0, a1, a2;  // A-operand tiles to multiply this record with (0xFF = none)
     uint16_t ctl;        // [0,9) TMEM column | [9] first (overwrite) | [10,13) wait | [13,16) signal
 };
-// wait codes : 0 none, 1 a_ready, 2+i chunk_empty[i] (i<4), 6 a_ready + chunk_empty[0]
+// wait codes : 0 none, 1 a_ready[kc], 2+i chunk_empty[i], 6 a_ready[kc] + chunk_empty[1]  (kc = a0 & 3)
 // signal codes: 0 none, 1 acc_full, 2+i chunk_full[i]
 
 struct FusedParams {
@@ -75,8 +75,6 @@ struct FusedParams {
     const uint8_t* wstream;
     const FusedStep* steps;
     const float* bias_lu;    // [64]
-    const float* bias_h;     // [n_hidden][256], residual biases pre-summed
-    const float* bias_f;     // [n_chunks*F*24]
     // feature index tables live in the kernel parameter (constant) bank: no L2 round trip per use
     signed char in_idx[64];    // conditioner input column per k (-1 = zero pad)
     unsigned char tr_idx[64];  // transformed feature columns
@@ -85,6 +83,10 @@ struct FusedParams {
     const float* lu_logdet;  // device scalar or null
     int* err;
     long long* prof;         // optional [128] clock64 stamps (debug)
+    // Biases ride in the kernel parameter (constant) bank: every thread of a warp reads the same element,
+    // so LDC broadcasts replace L2 round trips (L1 is ~1 KB with 227 KB of shared memory in use).
+    float bias_h[7 * 256];   // [n_hidden <= 7][256], residual biases pre-summed along the stream
+    float bias_f[72 * 24];   // [n_chunks*F <= 72][24] final-layer bias in chunk/column order
 };
 int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st);
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,

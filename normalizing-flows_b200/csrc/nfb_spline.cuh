@@ -51,11 +51,14 @@ __host__ __device__ __forceinline__ float fast_rcp(float x) {
 
 // F.softplus(beta=1, threshold=20).  log1p(e) by series for small e: 1+e would round away
 // up to 6e-8 absolute, which matters when the derivative sits at its 1e-3 floor.
+// Branch-free (selects only) so that two independent spline evaluations inlined back to back stay in
+// one basic block and ptxas can interleave them.
 __host__ __device__ __forceinline__ float softplus_f(float u) {
-    if (u > 20.f) return u;
-    float e = fast_ex2(u * kLog2e);
-    if (e < 0.03f) return e * (1.f - e * (0.5f - e * (0.33333334f - 0.25f * e)));
-    return kLn2 * fast_lg2(1.f + e);
+    const float e = fast_ex2(fminf(u, 20.f) * kLog2e);
+    const float series = e * (1.f - e * (0.5f - e * (0.33333334f - 0.25f * e)));
+    const float lg = kLn2 * fast_lg2(1.f + e);
+    const float sp = e < 0.03f ? series : lg;
+    return u > 20.f ? u : sp;
 }
 
 // The unnormalised boundary derivative, as the reference computes it in fp32 (:36).
