@@ -9,6 +9,7 @@
 //   FUSED  : [LULinearPermute +] neural-spline block on the tcgen05 kernel (nfb_fused_rqs.cu)
 //   AFFINE : a maximal run of low-dimensional affine-family layers in one kernel (nfb_affine.cu)
 //   SINGLE : any other layer through the generic fp32 kernels (nfb_kernels.cu)
+#include <algorithm>
 #include <cstdarg>
 #include <cstring>
 #include <cmath>
@@ -94,7 +95,9 @@ struct FusedPack {
     DevBuf wstream, steps, uncond;
     std::vector<float> bias_h, bias_f;
     std::vector<int> in_idx, tr_idx, id_idx;
-    struct Gemm { DevBuf src_row, src_col, row_scale; const float* W; const float* M; int src_cols, n_pad, k_pad, rpr; size_t off; };
+    struct Rec { int row0, nrows, kc; size_t off_hi, off_lo; };
+    struct Gemm { DevBuf src_row, src_col, row_scale; const float* W; const float* M; int src_cols, n_pad, k_pad; std::vector<Rec> recs; };
+    std::vector<int> hperm;  // sorted-by-degree order of the hidden units (identity for unmasked nets)
     std::vector<Gemm> gemms;
     // LU + this block as one launch (built when the next layer in list order is an LU)
     bool pair_ok = false;
@@ -243,89 +246,137 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     }
     const int n_chunks = (T + fpc - 1) / fpc;
     const int kcs_h = H / 64;
-    // ---- step table ----
-    std::vector<FusedStep> steps;
-    auto add = [&](int rows, int a0, int a1, int a2, int col, int first, int wait, int signal) {
-        FusedStep s;
-        s.bytes16 = (uint16_t)(rows * 8);
-        s.n8 = (uint8_t)(rows / 8);
-        s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
-        s.ctl = make_ctl(col, first, wait, signal);
-        steps.push_back(s);
-    };
-    for (int ph = 0; ph < n_hidden; ++ph) {
-        const int region = (ph & 1) ? 256 : 0;
-        const bool accum_onto = (ph > 0 && (ph & 1) == 0);  // second GEMM of a residual block: h += ...
-        const int kcs = (ph == 0) ? 1 : kcs_h;
-        for (int kc = 0; kc < kcs; ++kc) {
-            add(H, kc, 4 + kc, 0xFF, region, (kc == 0 && !accum_onto) ? 1 : 0, 1, 0);
-            add(H, kc, 0xFF, 0xFF, region, 0, 0, (kc == kcs - 1) ? 1 : 0);
-        }
-    }
-    for (int c = 0; c < n_chunks; ++c) {
-        const int b = (c + 1) & 1;  // two TMEM chunk buffers (columns 0.. and 256..); chunk 0 uses the second
-        for (int kc = 0; kc < kcs_h; ++kc) {
-            // chunk 0 is the first reader of each A K-chunk (wait a_ready[kc]); kc==0 also waits for the buffer
-            const int wait = (kc == 0) ? (c == 0 ? 6 : 2 + b) : (c == 0 ? 1 : 0);
-            add(fpc * 24, kc, 4 + kc, 0xFF, chunk_col_host(b), kc == 0 ? 1 : 0, wait, 0);
-            add(fpc * 24, kc, 0xFF, 0xFF, chunk_col_host(b), 0, 0, (kc == kcs_h - 1) ? 2 + b : 0);
-        }
-    }
-    if (steps.size() + 3 > 256) return NFB_OK;  // step table would not fit in shared memory
+    const int crow = fpc * 24;  // rows (MMA N) per final-layer chunk
     if (n_hidden > 7 || n_chunks * fpc > 72) return NFB_OK;  // bias tables in the kernel parameter bank
-    F.steps_host = steps;
-    F.n_steps = (int)steps.size();
-    F.D = L.D; F.H = H; F.n_hidden = n_hidden; F.T = T; F.F = fpc; F.n_chunks = n_chunks; F.tail = L.tail;
-    F.n_id = ar ? 0 : L.n_id;
-    size_t total = 0;
-    for (auto& s : steps) total += (size_t)s.bytes16 * 16;
-    F.rqs_bytes = total;
-    NFB_TRY(F.wstream.reserve(total));
-    NFB_TRY(F.steps.upload(steps));
 
-    // ---- GEMM source tables ----
+    // ---- MADE masks: sort hidden units by degree so that every masked matrix is block-triangular, and
+    //      find the all-zero [rows x 64-column] blocks to drop (nets/made.py:57-76 degree rules) ----
+    const bool masked = n.m0 != nullptr;
+    std::vector<int> perm(H);
+    for (int i = 0; i < H; ++i) perm[i] = i;
+    std::vector<float> m_init, m_hid, m_fin;
+    if (masked) {
+        NFB_TRY(download(n.m0, (size_t)H * n.in, m_init));
+        std::vector<int> deg(H, 0);  // row sum of the input mask = number of inputs a unit may see = its degree
+        for (int i = 0; i < H; ++i) for (int j = 0; j < n.in; ++j) deg[i] += m_init[(size_t)i * n.in + j] != 0.f;
+        std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) { return deg[x] < deg[y]; });
+        if (n.nb > 0) NFB_TRY(download(n.mb[0], (size_t)H * H, m_hid));  // all hidden masks share the structure
+        NFB_TRY(download(n.mf, (size_t)n.out * H, m_fin));
+    }
+    F.hperm = perm;
+    // first row (multiple of 16, in sorted order) of a hidden GEMM that has a non-zero in K-chunk kc
+    auto hidden_row0 = [&](int kc) -> int {
+        if (!masked || m_hid.empty()) return 0;
+        for (int i = 0; i < H; ++i)
+            for (int k = kc * 64; k < kc * 64 + 64; ++k)
+                if (m_hid[(size_t)perm[i] * H + perm[k]] != 0.f) return i & ~15;
+        return H;  // no row uses this K-chunk at all
+    };
+    // does chunk c of the final layer have a non-zero in K-chunk kc?
+    auto final_needs = [&](int c, int kc) -> bool {
+        if (!masked) return true;
+        for (int i = 0; i < crow; ++i) {
+            const int t = fpc * c + i / 24, q = i % 24;
+            if (t >= T || q >= 23) continue;
+            for (int k = kc * 64; k < kc * 64 + 64; ++k)
+                if (m_fin[(size_t)(t * 23 + q) * H + perm[k]] != 0.f) return true;
+        }
+        return false;
+    };
+
+    // ---- GEMM source tables (effective matrices are built in sorted hidden order) ----
     F.gemms.clear();
-    auto add_gemm = [&](const float* W, const float* M, int src_rows, int src_cols, int n_pad, int k_pad,
-                        int rpr_, const std::vector<int>& sr, const std::vector<int>& sc,
-                        const std::vector<float>& rs, size_t off) -> int {
+    auto add_gemm = [&](const float* W, const float* M, int src_cols, int n_pad, int k_pad,
+                        const std::vector<int>& sr, const std::vector<int>& sc,
+                        const std::vector<float>& rs) -> int {
         FusedPack::Gemm g;
-        g.W = W; g.M = M; g.src_cols = src_cols; g.n_pad = n_pad; g.k_pad = k_pad; g.rpr = rpr_; g.off = off;
-        (void)src_rows;
+        g.W = W; g.M = M; g.src_cols = src_cols; g.n_pad = n_pad; g.k_pad = k_pad;
         NFB_TRY(g.src_row.upload(sr));
         NFB_TRY(g.src_col.upload(sc));
         if (!rs.empty()) NFB_TRY(g.row_scale.upload(rs));
         F.gemms.push_back(std::move(g));
         return NFB_OK;
     };
-    size_t off = 0;
     {
-        std::vector<int> sr(H), sc(64);
-        for (int i = 0; i < H; ++i) sr[i] = i;
+        std::vector<int> sc(64);
         for (int k = 0; k < 64; ++k) sc[k] = k < n.in ? k : -1;
-        NFB_TRY(add_gemm(n.w0, n.m0, H, n.in, H, 64, H, sr, sc, {}, off));
-        off += (size_t)H * 64 * 2 * 2;
+        NFB_TRY(add_gemm(n.w0, n.m0, n.in, H, 64, perm, sc, {}));
     }
-    for (int i = 0; i < 2 * n.nb; ++i) {
-        std::vector<int> sr(H), sc(H);
-        for (int j = 0; j < H; ++j) sr[j] = sc[j] = j;
-        NFB_TRY(add_gemm(n.wb[i], n.mb[i], H, H, H, H, H, sr, sc, {}, off));
-        off += (size_t)H * H * 2 * 2;
-    }
-    const int crow = fpc * 24;  // rows (MMA N) per final-layer chunk
-    std::vector<int> fr(n_chunks * crow);
-    std::vector<float> fs(n_chunks * crow);
+    for (int i = 0; i < 2 * n.nb; ++i) NFB_TRY(add_gemm(n.wb[i], n.mb[i], H, H, H, perm, perm, {}));
     {
-        std::vector<int> sc(H);
-        for (int j = 0; j < H; ++j) sc[j] = j;
+        std::vector<int> fr(n_chunks * crow);
+        std::vector<float> fs(n_chunks * crow);
         for (int i = 0; i < n_chunks * crow; ++i) {
             const int t = fpc * (i / crow) + (i % crow) / 24, q = (i % crow) % 24;
             fr[i] = (t < T && q < 23) ? t * 23 + q : -1;
             fs[i] = (q < 16) ? L.wh_scale : 1.f;
         }
-        NFB_TRY(add_gemm(n.wf, n.mf, n.out, H, n_chunks * crow, H, crow, fr, sc, fs, off));
-        off += (size_t)n_chunks * crow * H * 2 * 2;
+        NFB_TRY(add_gemm(n.wf, n.mf, H, n_chunks * crow, H, fr, perm, fs));
     }
-    NFB_CHECK(off == total, NFB_ERR_STATE, "fused pack: stream size mismatch %zu vs %zu", off, total);
+
+    // ---- step table + record list (same order) ----
+    std::vector<FusedStep> steps;
+    size_t off = 0;
+    auto add = [&](FusedPack::Gemm& g, int row0, int nrows, int kc, int col, int first, int wait_hi,
+                   int signal_lo) {
+        FusedStep s;
+        s.bytes16 = (uint16_t)(nrows * 8);
+        s.n8 = (uint8_t)(nrows / 8);
+        s.a0 = (uint8_t)kc; s.a1 = (uint8_t)(4 + kc); s.a2 = 0xFF;
+        s.ctl = make_ctl(col, first, wait_hi, 0);
+        steps.push_back(s);  // W_hi x {A_hi, A_lo}
+        s.a1 = 0xFF;
+        s.ctl = make_ctl(col, 0, 0, signal_lo);
+        steps.push_back(s);  // W_lo x {A_hi}
+        FusedPack::Rec r{row0, nrows, kc, off, off + (size_t)nrows * 128};
+        off += (size_t)nrows * 256;
+        g.recs.push_back(r);
+    };
+    for (int ph = 0; ph < n_hidden; ++ph) {
+        const int region = (ph & 1) ? 256 : 0;
+        const bool accum_onto = (ph > 0 && (ph & 1) == 0);  // second GEMM of a residual block: h += ...
+        const int kcs = (ph == 0) ? 1 : kcs_h;
+        FusedPack::Gemm& g = F.gemms[ph];
+        int last = 0;
+        for (int kc = 0; kc < kcs; ++kc) if (ph == 0 || hidden_row0(kc) < H) last = kc;
+        for (int kc = 0; kc < kcs; ++kc) {
+            const int r0 = (ph == 0 || kc == 0) ? 0 : hidden_row0(kc);
+            if (r0 >= H) continue;
+            // every hi record is the first reader of A K-chunk kc in this phase: wait a_ready[kc]
+            add(g, r0, H - r0, kc, region + r0, (kc == 0 && !accum_onto) ? 1 : 0, 1, kc == last ? 1 : 0);
+        }
+    }
+    {
+        FusedPack::Gemm& g = F.gemms[n_hidden];
+        bool a_waited[4] = {false, false, false, false};
+        for (int c = 0; c < n_chunks; ++c) {
+            const int b = (c + 1) & 1;  // two TMEM chunk buffers (columns 0.. and 256..); chunk 0 uses the second
+            std::vector<int> need;
+            for (int kc = 0; kc < kcs_h; ++kc)
+                if (kc == 0 || c == n_chunks - 1 || final_needs(c, kc)) need.push_back(kc);
+            // (the last chunk reads every K-chunk so that each a_ready[kc] of the last hidden epilogue
+            //  is consumed exactly once per tile, keeping the barrier phases in step)
+            for (size_t j = 0; j < need.size(); ++j) {
+                const int kc = need[j];
+                int wait = 0;
+                if (j == 0) wait = (c == 0) ? 6 : 2 + b;           // chunk buffer free (+ a_ready[0] for chunk 0)
+                else if (!a_waited[kc]) wait = 1;                     // first reader of this A K-chunk
+                if (j == 0 && c > 0 && !a_waited[kc]) return NFB_OK;  // cannot encode both waits: keep generic path
+                a_waited[kc] = true;
+                add(g, c * crow, crow, kc, chunk_col_host(b), j == 0 ? 1 : 0, wait,
+                    j + 1 == need.size() ? 2 + b : 0);
+            }
+        }
+    }
+    if (steps.size() + 3 > 256) return NFB_OK;  // step table would not fit in shared memory
+    F.steps_host = steps;
+    F.n_steps = (int)steps.size();
+    F.D = L.D; F.H = H; F.n_hidden = n_hidden; F.T = T; F.F = fpc; F.n_chunks = n_chunks; F.tail = L.tail;
+    F.n_id = ar ? 0 : L.n_id;
+    const size_t total = off;
+    F.rqs_bytes = total;
+    NFB_TRY(F.wstream.reserve(total));
+    NFB_TRY(F.steps.upload(steps));
 
     // ---- index lists ----
     std::vector<int> in_idx(64, -1), tr_idx(T);
@@ -360,21 +411,24 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         NFB_TRY(launch_build_effective(g.W, g.M, g.src_cols, g.src_row.as<int>(), g.src_col.as<int>(),
                                        g.row_scale.p ? g.row_scale.as<float>() : nullptr, f->E.as<float>(),
                                        g.n_pad, g.k_pad, st));
-        NFB_TRY(launch_swizzle_split(f->E.as<float>(), g.n_pad, g.k_pad, g.rpr, 2,
-                                     F.wstream.as<uint8_t>() + g.off, st));
+        for (auto& r : g.recs)
+            NFB_TRY(launch_pack_record(f->E.as<float>(), g.k_pad, r.row0, r.nrows, r.kc,
+                                       F.wstream.as<uint8_t>() + r.off_hi, F.wstream.as<uint8_t>() + r.off_lo, st));
     }
     // biases (tiny; synchronous download is fine at pack time)
     NFB_CUDA(cudaStreamSynchronize(st));
     const int H = n.H;
     std::vector<float> bh((size_t)F.n_hidden * 256, 0.f), b0, tmp;
     NFB_TRY(download(n.b0, (size_t)H, b0));
+    const std::vector<int>& hp = F.hperm;  // bias index i <-> original hidden unit hp[i]
     std::vector<float> cum = b0;
-    for (int j = 0; j < H; ++j) bh[j] = b0[j];
+    for (int j = 0; j < H; ++j) bh[j] = b0[hp[j]];
     for (int b = 0; b < n.nb; ++b) {
         NFB_TRY(download(n.bb[2 * b], (size_t)H, tmp));
-        for (int j = 0; j < H; ++j) bh[(size_t)(1 + 2 * b) * 256 + j] = tmp[j];
+        for (int j = 0; j < H; ++j) bh[(size_t)(1 + 2 * b) * 256 + j] = tmp[hp[j]];
         NFB_TRY(download(n.bb[2 * b + 1], (size_t)H, tmp));
-        for (int j = 0; j < H; ++j) { cum[j] += tmp[j]; bh[(size_t)(2 + 2 * b) * 256 + j] = cum[j]; }
+        for (int j = 0; j < H; ++j) cum[j] += tmp[j];
+        for (int j = 0; j < H; ++j) bh[(size_t)(2 + 2 * b) * 256 + j] = cum[hp[j]];
     }
     F.bias_h = bh;
     const int crow = F.F * 24;

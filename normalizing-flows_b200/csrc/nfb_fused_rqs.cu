@@ -508,6 +508,26 @@ __global__ void swizzle_split_kernel(const float* __restrict__ E, int n_pad, int
     }
 }
 
+// one record: rows [row0, row0+nrows) x K-chunk kc of E -> hi and lo swizzled tiles (nrows*128 B each)
+__global__ void pack_record_kernel(const float* __restrict__ E, int k_pad, int row0, int nrows, int kc,
+                                   uint8_t* __restrict__ out_hi, uint8_t* __restrict__ out_lo) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= nrows * 64) return;
+    const int rr = idx >> 6, kk = idx & 63;
+    const float v = E[(size_t)(row0 + rr) * k_pad + kc * 64 + kk];
+    const size_t off = (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + (((kk >> 3) ^ (rr & 7)) << 4) + (kk & 7) * 2;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    *reinterpret_cast<__nv_bfloat16*>(out_hi + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(out_lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, uint8_t* out_hi,
+                       uint8_t* out_lo, cudaStream_t st) {
+    NFB_CHECK(nrows > 0 && nrows % 8 == 0, NFB_ERR_ARG, "pack_record: bad row count %d", nrows);
+    pack_record_kernel<<<(nrows * 64 + 255) / 256, 256, 0, st>>>(E, k_pad, row0, nrows, kc, out_hi, out_lo);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
                            const int* src_col, const float* row_scale, float* E, int n_pad,
                            int k_pad, cudaStream_t st) {

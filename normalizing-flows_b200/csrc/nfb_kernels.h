@@ -92,6 +92,8 @@ int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st);
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
                            const int* src_col, const float* row_scale, float* E, int n_pad,
                            int k_pad, cudaStream_t st);
+int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, uint8_t* out_hi,
+                       uint8_t* out_lo, cudaStream_t st);
 int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit,
                          uint8_t* out, cudaStream_t st);
 
