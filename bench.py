@@ -157,7 +157,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH, help="rows per GPU (weak scaling)")
@@ -179,6 +179,13 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        # NCCL sets channels up lazily over the first collectives (hundreds of ms when the GPU is busy):
+        # keep that out of the warm-up/timed steps
+        t = torch.ones(2, dtype=torch.float64, device=dev)
+        for _ in range(20):
+            dist.all_reduce(t)
+        torch.cuda.synchronize()
+        dist.barrier()
     warmup = max(3, args.warmup)
     steps = max(1, args.steps)
     B = args.batch
@@ -189,11 +196,18 @@ def main():
     xs_host = [(torch.randn(B, D, generator=g) * 1.5).pin_memory() for _ in range(2)]
     xs = [(torch.randn(B, D, generator=g) * 1.5).to(dev) for _ in range(nbuf)]
 
+    dp_mode = os.environ.get("NFB_BENCH_DP", "async")  # async | sync | none(debug: no collective)
+
     def step(i):
-        return forward_kld_dp(model, xs[i % nbuf])
+        if dp_mode == "none":
+            return model.forward_kld(xs[i % nbuf])
+        return forward_kld_dp(model, xs[i % nbuf], async_op=(dp_mode == "async"))
+
+    def value_of(l):
+        return l.result() if hasattr(l, "result") else l
 
     for i in range(warmup):
-        loss = step(i)
+        loss = value_of(step(i))
     stack = model._stack()
     launches_per_step = stack.launch_count()
     fused = stack.fused_layers()
@@ -206,8 +220,11 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
+    t_host0 = time.perf_counter()
     for i in range(steps):
         loss = step(i)
+    loss = value_of(loss)  # stream-waits for the last collective; every step's loss was reduced on device
+    host_enqueue_ms = (time.perf_counter() - t_host0) * 1e3 / steps  # CPU time to enqueue one step
     ev1.record()
     torch.cuda.synchronize()
     elapsed_ms = ev0.elapsed_time(ev1)
@@ -290,12 +307,13 @@ def main():
             "config": {"workload": f"{'Autoregressive' if KIND == 'ar' else 'Coupled'} RQ-NSF d={D}, {LAYERS} x "
                                    f"[spline block(2 blocks, hidden {HIDDEN}, {BINS} bins) + LULinearPermute], "
                                    f"batch {B}/GPU, forward_kld (BASELINE.json configs[1])",
-                       "global_batch": world * B, "parallelism": f"dp{world}",
+                       "global_batch": world * B, "parallelism": f"dp{world}", "dp_collective": dp_mode,
                        "l2_policy": f"{nbuf} rotating input batches ({nbuf * B * D * 4 >> 20} MiB > L2)",
                        "loss": loss_val},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / steps * 1e3, "loss": e2e_loss,
                     "api": "nfb_flow_forward_kld_host (pinned host batch)"},
+            "host_enqueue_ms_per_step": host_enqueue_ms,
             "gpu_launches": launches_per_step * steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks, "roofline": roof}
     if not args.no_cpu_baseline:

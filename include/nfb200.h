@@ -162,8 +162,9 @@ int nfb_flow_transform(nfb_flow_t* f, int32_t direction, const float* z_in_dev, 
                        float* log_det_dev, int64_t rows, void* stream);
 /* core.py:182-197 log_prob: log_q[r] = sum log_det + q0.log_prob(z) */
 int nfb_flow_log_prob(nfb_flow_t* f, const float* x_dev, float* log_q_dev, int64_t rows, void* stream);
-/* core.py:87-102 forward_kld: *loss_dev = -mean(log_q); *sum_dev (optional, double) = sum(log_q),
- * the per-rank partial a data-parallel caller all-reduces. */
+/* core.py:87-102 forward_kld: *loss_dev = -mean(log_q).  sum_dev (optional, double[2]) receives
+ * {sum(log_q), rows}: the per-rank partial a data-parallel caller all-reduces (one collective, 16 bytes),
+ * written by the same reduction kernel so the caller adds no device work of its own. */
 int nfb_flow_forward_kld(nfb_flow_t* f, const float* x_dev, int64_t rows, float* loss_dev,
                          double* sum_dev, void* stream);
 

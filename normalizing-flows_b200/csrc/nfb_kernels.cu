@@ -426,12 +426,12 @@ sum_stage1_kernel(const float* __restrict__ v, long long n, double* __restrict__
         partial[blockIdx.x] = t;
     }
 }
-__global__ void sum_stage2_kernel(const double* __restrict__ partial, int np, double scale,
+__global__ void sum_stage2_kernel(const double* __restrict__ partial, int np, double scale, long long n,
                                   float* __restrict__ out, double* __restrict__ out_sum) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double t = 0.0;
         for (int i = 0; i < np; ++i) t += partial[i];
-        if (out_sum) *out_sum = t;
+        if (out_sum) { out_sum[0] = t; out_sum[1] = (double)n; }  // [sum, count]: the all-reduce operand
         if (out) *out = (float)(t * scale);
     }
 }
@@ -440,7 +440,7 @@ int launch_sum(const float* v, long long n, double scale, double* scratch /*>=10
     int nb = (int)min((long long)592, (n + 255) / 256);
     if (nb < 1) nb = 1;
     sum_stage1_kernel<<<nb, 256, 0, st>>>(v, n, scratch);
-    sum_stage2_kernel<<<1, 32, 0, st>>>(scratch, nb, scale, out, out_sum);
+    sum_stage2_kernel<<<1, 32, 0, st>>>(scratch, nb, scale, n, out, out_sum);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

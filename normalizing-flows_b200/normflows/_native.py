@@ -125,10 +125,16 @@ class FlowHandle:
             L.check(L.lib().nfb_flow_log_prob(h, L.ptr(x), L.ptr(lq), x.shape[0], L.stream_ptr()))
         return lq
 
-    def forward_kld(self, x, want_sum=False):
+    def forward_kld(self, x, want_sum=False, sum_out=None):
+        """-mean(log_q) as a 0-dim fp32 tensor; optionally also sum(log_q) (fp64) -- either returned
+        (want_sum) or written into the caller's 1-element fp64 tensor `sum_out` (data-parallel callers)."""
         x, h = self._prep(x)
         loss = torch.empty((), dtype=torch.float32, device=x.device)
-        s = torch.empty((), dtype=torch.float64, device=x.device) if want_sum else None
+        s = sum_out if sum_out is not None else (
+            torch.empty(2, dtype=torch.float64, device=x.device) if want_sum else None)
+        if s is not None and (s.dtype != torch.float64 or s.device != x.device or s.numel() < 2
+                              or not s.is_contiguous()):
+            raise ValueError("sum_out must be a contiguous float64 tensor [sum, rows] on the input's device")
         with torch.cuda.device(x.device):
             L.check(L.lib().nfb_flow_forward_kld(h, L.ptr(x), x.shape[0], L.ptr(loss), L.ptr(s),
                                                  L.stream_ptr()))

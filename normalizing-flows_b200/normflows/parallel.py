@@ -23,11 +23,51 @@ def all_reduce_kld(local_sum, local_count, group=None):
     return -(buf[0] / buf[1])
 
 
-def forward_kld_dp(model, x_local, group=None):
-    """Global forward KL over all ranks' shards: each rank runs the fused stack on its rows, then one
-    NCCL all-reduce of the partial sums."""
+class _PendingLoss:
+    """Result of an asynchronous data-parallel forward_kld: `.result()` makes the current stream wait for
+    the collective and returns the 0-dim fp32 loss."""
+
+    def __init__(self, buf, work):
+        self._buf, self._work, self._val = buf, work, None
+
+    def result(self):
+        if self._val is None:
+            if self._work is not None:
+                self._work.wait()
+            self._val = (-(self._buf[0] / self._buf[1])).to(torch.float32)
+        return self._val
+
+
+def forward_kld_dp(model, x_local, group=None, async_op=False):
+    """Global forward KL over all ranks' shards: each rank runs the fused stack on its rows; the reduction
+    kernel writes the rank's sum(log_q) straight into a 2-element fp64 buffer [sum, count] which is the
+    operand of the ONE NCCL all-reduce.  No other device work, no host sync.
+
+    async_op=True returns a handle instead of the tensor: the compute stream does not wait for the
+    collective, so the next step's kernels are not serialised behind a 16-byte all-reduce (the buffers
+    rotate through a ring of 8, the oldest is waited on before reuse)."""
     h = model._stack()
     if h is None or h.base is None:
         raise NotImplementedError("forward_kld_dp needs an all-native stack with a DiagGaussian base")
-    _, s = h.forward_kld(x_local, want_sum=True)
-    return all_reduce_kld(s, x_local.shape[0], group).to(torch.float32)
+    ring = model.__dict__.get("_nfb_dp_ring")
+    if ring is None or ring["bufs"][0].device != x_local.device:
+        ring = {"bufs": [torch.zeros(2, dtype=torch.float64, device=x_local.device) for _ in range(8)],
+                "pending": [None] * 8, "i": 0}
+        model.__dict__["_nfb_dp_ring"] = ring
+    i = ring["i"]
+    ring["i"] = (i + 1) % 8
+    if ring["pending"][i] is not None:
+        ring["pending"][i].result()
+        ring["pending"][i] = None
+    buf = ring["bufs"][i]
+    h.forward_kld(x_local, sum_out=buf)  # the reduction kernel writes [sum(log_q), rows]
+    work = None
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if not async_op:
+            work = None
+    pend = _PendingLoss(buf, work)
+    if async_op:
+        ring["pending"][i] = pend
+        return pend
+    return pend.result()

@@ -121,3 +121,23 @@ if mode == "prof":
         print(f"prof {kind}: {n} stamps (cycles since tile start; deltas)")
         print("  abs  :", t)
         print("  delta:", [t[i] - t[i - 1] for i in range(1, n)])
+
+if mode == "spline":
+    import ctypes as C
+    from normflows import _lib as L
+    B, T, K = 65536, 64, 8
+    P = 3 * K - 1
+    x = (torch.randn(B, T) * 1.5).cuda()
+    params = [torch.randn(B, T * P, device="cuda") for _ in range(2)]  # 2 x 386 MB > L2
+    y = torch.empty_like(x)
+    ld = torch.zeros(B, device="cuda")
+    lib = L.lib()
+    for inv in (0, 1):
+        def run(i=[0]):
+            i[0] += 1
+            L.check(lib.nfb_rqs_spline(L.ptr(x), L.ptr(params[i[0] % 2]), L.ptr(y), L.ptr(ld), B, T, K,
+                                       C.c_float(3.0), C.c_float(1.0), inv, 1, None))
+        ms = timeit(run, n=11, warm=3)
+        byt = B * T * (P * 4 + 8) + B * 8
+        print(f"spline standalone inverse={inv}: {ms*1e3:.1f} us  {byt/ms/1e6:.1f} GB/s  "
+              f"frac of 6580 = {byt/ms/1e6/6580.3:.3f}", flush=True)
