@@ -61,6 +61,41 @@ int nfb_diag_gaussian_log_prob(const float* z_dev, const float* loc_dev, const f
                                float* log_q_dev, int64_t rows, int32_t dim, int32_t accumulate,
                                void* stream);
 
+/* ---- image-shaped (NCHW) operators of the Glow block, density direction (device pointers) ---- */
+
+/* nets/cnn.py:33-61 one layer of ConvNet2d: y = act(conv2d(x[:, c0:c0+cin], w[cout,cin,k,k], stride 1, pad k/2) + b);
+ * x is a channel slice of an NCHW tensor with `x_channels` channels; leaky < 0 means no activation,
+ * otherwise LeakyReLU(leaky) (0 = ReLU).  y: [B, cout, H, W]. */
+int nfb_conv2d(const float* x_dev, int32_t x_channels, int32_t c0, const float* w_dev, const float* b_dev,
+               float* y_dev, int64_t batch, int32_t cin, int32_t height, int32_t width, int32_t cout,
+               int32_t ksize, float leaky, void* stream);
+/* flows/normalization.py:31-39 ActNorm.inverse followed by flows/mixing.py:123-133 Invertible1x1Conv.inverse
+ * (LU parameterisation :88-104) folded into one 1x1 convolution: w_out[C,C], b_out[C] for nfb_conv2d, and
+ * *logdet_out = H*W*(sum log_S - sum s), the per-sample log|det| of both layers. */
+int nfb_glow_fold_actnorm_conv1x1(const float* P, const float* L, const float* U, const float* sign_S,
+                                  const float* log_S, const float* s, const float* t, int32_t channels,
+                                  int32_t hw, float* w_out, float* b_out, float* logdet_out, void* stream);
+/* flows/affine/coupling.py:113-171 AffineCoupling on images, in place on the z2 channels of z [B,C,H,W];
+ * param = conditioner output [B, (scale?2:1)*n2, H, W] with shift/scale interleaved (:152-153).
+ * scale_map 0 exp / 1 sigmoid / 2 sigmoid_inv; split_mode 0 channel / 1 channel_inv (reshape.py:27-31).
+ * log_det[b] (+)= sum of log-scale terms + *logdet_const (may be NULL). */
+int nfb_affine_coupling_image(float* z_dev, const float* param_dev, float* log_det_dev,
+                              const float* logdet_const_dev, int64_t batch, int32_t channels, int32_t hw,
+                              int32_t scale, int32_t scale_map, int32_t split_mode, int32_t direction,
+                              int32_t accumulate, void* stream);
+/* flows/reshape.py:114-128 Squeeze; (channels,height,width) describe the high-resolution side;
+ * NFB_INVERSE: [B,C,H,W] -> [B,4C,H/2,W/2], NFB_FORWARD the reverse. */
+int nfb_squeeze(const float* in_dev, float* out_dev, int64_t batch, int32_t channels, int32_t height,
+                int32_t width, int32_t direction, void* stream);
+/* flows/reshape.py:27-31 channel chunk made contiguous: out[b,j,:] = in[b,c0+j,:] */
+int nfb_copy_channels(const float* in_dev, float* out_dev, int64_t batch, int32_t channels, int32_t c0,
+                      int32_t n, int32_t hw, void* stream);
+/* distributions/base.py:327-344 ClassCondDiagGaussian.log_prob with integer labels y[B] (int64);
+ * loc/log_scale: [dim, num_classes] (the reference's (*shape, num_classes) flattened). */
+int nfb_class_cond_diag_gaussian_log_prob(const float* z_dev, const int64_t* y_dev, const float* loc_dev,
+                                          const float* log_scale_dev, float* log_q_dev, int64_t batch,
+                                          int32_t dim, int32_t num_classes, int32_t accumulate, void* stream);
+
 /* ---- layer parameter descriptors (device pointers into the caller's parameters) ---- */
 
 /* A residual conditioner: nets/resnet.py:53-104 ResidualNet (mask pointers NULL) or

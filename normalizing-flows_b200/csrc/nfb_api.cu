@@ -732,6 +732,46 @@ int nfb_diag_gaussian_log_prob(const float* z, const float* loc, const float* lo
     return launch_diag_gauss(z, loc, log_scale, log_q, rows, dim, accumulate, S(stream));
 }
 
+int nfb_conv2d(const float* x, int32_t x_channels, int32_t c0, const float* w, const float* b, float* y,
+               int64_t batch, int32_t cin, int32_t height, int32_t width, int32_t cout, int32_t ksize,
+               float leaky, void* stream) {
+    NFB_CHECK(x && w && y, NFB_ERR_ARG, "nfb_conv2d: null pointer");
+    return launch_conv2d(x, x_channels, c0, w, b, y, batch, cin, height, width, cout, ksize, leaky, S(stream));
+}
+int nfb_glow_fold_actnorm_conv1x1(const float* P, const float* L, const float* U, const float* sign_S,
+                                  const float* log_S, const float* s, const float* t, int32_t channels,
+                                  int32_t hw, float* w_out, float* b_out, float* logdet_out, void* stream) {
+    NFB_CHECK(P && L && U && sign_S && log_S && s && t && w_out && b_out && logdet_out, NFB_ERR_ARG,
+              "nfb_glow_fold_actnorm_conv1x1: null pointer");
+    return launch_glow_fold(P, L, U, sign_S, log_S, s, t, channels, hw, w_out, b_out, logdet_out, S(stream));
+}
+int nfb_affine_coupling_image(float* z, const float* param, float* log_det, const float* logdet_const,
+                              int64_t batch, int32_t channels, int32_t hw, int32_t scale, int32_t scale_map,
+                              int32_t split_mode, int32_t direction, int32_t accumulate, void* stream) {
+    NFB_CHECK(z && param, NFB_ERR_ARG, "nfb_affine_coupling_image: null pointer");
+    NFB_CHECK(scale_map >= 0 && scale_map <= 2, NFB_ERR_UNSUPPORTED, "This scale map is not implemented.");
+    NFB_CHECK(split_mode == 0 || split_mode == 1, NFB_ERR_UNSUPPORTED, "split mode is not implemented.");
+    return launch_coupling_image(z, param, log_det, logdet_const, batch, channels, hw, scale, scale_map,
+                                 split_mode, direction, accumulate, S(stream));
+}
+int nfb_squeeze(const float* in, float* out, int64_t batch, int32_t channels, int32_t height, int32_t width,
+                int32_t direction, void* stream) {
+    NFB_CHECK(in && out, NFB_ERR_ARG, "nfb_squeeze: null pointer");
+    return launch_squeeze(in, out, batch, channels, height, width, direction, S(stream));
+}
+int nfb_copy_channels(const float* in, float* out, int64_t batch, int32_t channels, int32_t c0, int32_t n,
+                      int32_t hw, void* stream) {
+    NFB_CHECK(in && out, NFB_ERR_ARG, "nfb_copy_channels: null pointer");
+    return launch_copy_channels(in, out, batch, channels, c0, n, hw, S(stream));
+}
+int nfb_class_cond_diag_gaussian_log_prob(const float* z, const int64_t* y, const float* loc,
+                                          const float* log_scale, float* log_q, int64_t batch, int32_t dim,
+                                          int32_t num_classes, int32_t accumulate, void* stream) {
+    NFB_CHECK(z && y && loc && log_scale && log_q, NFB_ERR_ARG, "nfb_class_cond_diag_gaussian_log_prob: null pointer");
+    return launch_class_cond_gauss(z, reinterpret_cast<const long long*>(y), loc, log_scale, log_q, batch, dim,
+                                   num_classes, accumulate, S(stream));
+}
+
 int nfb_flow_create(nfb_flow_t** out, int32_t features) {
     NFB_CHECK(out, NFB_ERR_ARG, "nfb_flow_create: null out");
     NFB_CHECK(features >= 1, NFB_ERR_ARG, "nfb_flow_create: features must be >= 1");

@@ -1,0 +1,273 @@
+// nfb_glow.cu -- image-shaped (NCHW) pieces of the Glow block, density direction:
+//   GlowBlock.inverse = ActNorm.inverse -> Invertible1x1Conv.inverse -> AffineCouplingBlock.inverse
+//   (flows/affine/glow.py:79-84; normalization.py:31-39; mixing.py:123-133; coupling.py:149-171,262-267)
+// ActNorm and the 1x1 convolution are both per-pixel affine maps over channels, so they are folded into ONE
+// 1x1 convolution W' = (P L U) diag(exp(-s)), b' = -W' t at pack time (`glow_fold_kernel`) and run through
+// the same implicit-GEMM kernel as the ConvNet2d conditioner (nets/cnn.py:33-61: 3x3 -> 1x1 -> 3x3 with
+// LeakyReLU).  The coupling epilogue applies shift/scale (interleaved channels, coupling.py:152-160) and
+// reduces log|det| per sample.  Plain fp32 FFMA tiles for now (parity first); the tcgen05 implicit-GEMM
+// version is future work.
+#include "nfb_kernels.h"
+
+namespace nfb {
+
+// y[b,n,h,w] = act( sum_{c,kh,kw} w[n,c,kh,kw] * x[b, c0+c, h+kh-p, w+kw-p] + bias[n] ),  stride 1, pad k/2.
+// Implicit GEMM: M = B*H*W pixels, N = Cout, K = Cin*k*k; 64x64 tile, 4x4 per thread.
+__global__ void __launch_bounds__(256)
+conv2d_kernel(const float* __restrict__ x, int ctot, int c0, const float* __restrict__ w,
+              const float* __restrict__ bias, float* __restrict__ y, long long B, int cin, int H, int W,
+              int cout, int ks, float leaky) {
+    __shared__ float As[16][64 + 1];
+    __shared__ float Bs[16][64 + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const long long M = B * H * W;
+    const int K = cin * ks * ks, pad = ks >> 1, HW = H * W, kk2 = ks * ks;
+    const long long m0 = (long long)blockIdx.x * 64;
+    const int n0 = blockIdx.y * 64;
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += 16) {
+        for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+            const int r = i & 63, k = i >> 6;  // r fastest: consecutive threads -> consecutive pixels
+            const long long m = m0 + r;
+            const int kk = k0 + k;
+            float a = 0.f, b = 0.f;
+            if (kk < K) {
+                if (m < M) {
+                    const int c = kk / kk2, rem = kk - c * kk2, kh = rem / ks, kw = rem - kh * ks;
+                    const long long bi = m / HW;
+                    const int pix = (int)(m - bi * HW), h = pix / W, ww = pix - h * W;
+                    const int hh = h + kh - pad, w2 = ww + kw - pad;
+                    if (hh >= 0 && hh < H && w2 >= 0 && w2 < W)
+                        a = x[((bi * ctot + c0 + c) * H + hh) * W + w2];
+                }
+                if (n0 + r < cout) b = w[(long long)(n0 + r) * K + kk];
+            }
+            As[k][r] = a;
+            Bs[k][r] = b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a[i] = As[k][ty * 4 + i];
+                b[i] = Bs[k][tx * 4 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        const long long bi = m / HW;
+        const int pix = (int)(m - bi * HW);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + tx * 4 + j;
+            if (n >= cout) continue;
+            float v = acc[i][j] + (bias ? bias[n] : 0.f);
+            if (leaky >= 0.f) v = v >= 0.f ? v : v * leaky;
+            y[(bi * cout + n) * HW + pix] = v;
+        }
+    }
+}
+
+int launch_conv2d(const float* x, int ctot, int c0, const float* w, const float* bias, float* y, long long B,
+                  int cin, int H, int W, int cout, int ks, float leaky, cudaStream_t st) {
+    NFB_CHECK(ks == 1 || ks == 3 || ks == 5, NFB_ERR_UNSUPPORTED, "conv2d: kernel size %d", ks);
+    NFB_CHECK(c0 >= 0 && c0 + cin <= ctot, NFB_ERR_ARG, "conv2d: channel slice out of range");
+    const long long M = B * H * W;
+    if (M == 0 || cout == 0) return NFB_OK;
+    dim3 grid((unsigned)((M + 63) / 64), (unsigned)((cout + 63) / 64));
+    conv2d_kernel<<<grid, 256, 0, st>>>(x, ctot, c0, w, bias, y, B, cin, H, W, cout, ks, leaky);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// W = P (tril(L,-1)+I) (triu(U,1) + diag(sign_S exp(log_S)))      (mixing.py:88-104, density direction)
+// w_out[o,c] = W[o,c] exp(-s[c]);  b_out[o] = -sum_c w_out[o,c] t[c]   (ActNorm.inverse folded in)
+// logdet = HW * (sum log_S - sum s)                                  (mixing.py:125,132; coupling.py:47-54)
+__global__ void glow_fold_kernel(const float* __restrict__ P, const float* __restrict__ L,
+                                 const float* __restrict__ U, const float* __restrict__ sign_S,
+                                 const float* __restrict__ log_S, const float* __restrict__ s,
+                                 const float* __restrict__ t, int C, int HW, float* __restrict__ w_out,
+                                 float* __restrict__ b_out, float* __restrict__ logdet) {
+    extern __shared__ float sh[];
+    float* LU = sh;          // C*C : L' U'
+    float* Wm = sh + C * C;  // C*C : P L' U'
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+        const int r = i / C, c = i % C;
+        float acc = 0.f;
+        for (int k = 0; k < C; ++k) {
+            const float l = (k < r) ? L[r * C + k] : (k == r ? 1.f : 0.f);
+            const float u = (c > k) ? U[k * C + c] : (c == k ? sign_S[k] * expf(log_S[k]) : 0.f);
+            acc = fmaf(l, u, acc);
+        }
+        LU[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+        const int r = i / C, c = i % C;
+        float acc = 0.f;
+        for (int k = 0; k < C; ++k) acc = fmaf(P[r * C + k], LU[k * C + c], acc);
+        Wm[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) w_out[i] = Wm[i] * expf(-s[i % C]);
+    for (int o = threadIdx.x; o < C; o += blockDim.x) {
+        float acc = 0.f;
+        for (int c = 0; c < C; ++c) acc = fmaf(Wm[o * C + c] * expf(-s[c]), t[c], acc);
+        b_out[o] = -acc;
+    }
+    if (threadIdx.x == 0) {
+        float a = 0.f;
+        for (int c = 0; c < C; ++c) a += log_S[c] - s[c];
+        *logdet = a * (float)HW;
+    }
+}
+int launch_glow_fold(const float* P, const float* L, const float* U, const float* sign_S, const float* log_S,
+                     const float* s, const float* t, int C, int HW, float* w_out, float* b_out, float* logdet,
+                     cudaStream_t st) {
+    NFB_CHECK(C >= 1 && C <= 128, NFB_ERR_UNSUPPORTED, "Invertible1x1Conv: channels %d > 128", C);
+    const size_t smem = (size_t)2 * C * C * sizeof(float);
+    NFB_CUDA(cudaFuncSetAttribute(glow_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    glow_fold_kernel<<<1, 256, smem, st>>>(P, L, U, sign_S, log_S, s, t, C, HW, w_out, b_out, logdet);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// AffineCoupling on images, in place on the z2 channels of z [B,C,H,W]; param [B, (scale?2:1)*n2, H, W].
+// One block per sample; log_det[b] (+)= sum log-scale terms + *logdet_const.
+__global__ void __launch_bounds__(256)
+coupling_image_kernel(float* __restrict__ z, const float* __restrict__ param, float* __restrict__ logdet,
+                      const float* __restrict__ logdet_const, int C, int HW, int scale, int smap, int inv_split,
+                      int direction, int accumulate) {
+    const long long b = blockIdx.x;
+    const int h = (C + 1) / 2;
+    const int o2 = inv_split ? 0 : h, n2 = inv_split ? h : C - h;  // channel_inv: z2 is the FIRST chunk
+    const int np = scale ? 2 : 1;
+    float ld = 0.f;
+    for (int i = threadIdx.x; i < n2 * HW; i += 256) {
+        const int c = i / HW, pix = i - c * HW;
+        float& v = z[(b * C + o2 + c) * HW + pix];
+        if (!scale) {
+            const float pm = param[(b * n2 + c) * HW + pix];
+            v = direction ? v + pm : v - pm;
+            continue;
+        }
+        const float shift = param[(b * np * n2 + 2 * c) * HW + pix];
+        const float sc = param[(b * np * n2 + 2 * c + 1) * HW + pix];
+        if (smap == 0) {
+            if (direction) { v = v * expf(sc) + shift; ld += sc; }
+            else { v = (v - shift) * expf(-sc); ld -= sc; }
+        } else {
+            const float sg = 1.f / (1.f + expf(-(sc + 2.f)));
+            const float lsg = logf(sg);
+            const bool div = (smap == 1) == (direction != 0);
+            if (direction) v = div ? v / sg + shift : v * sg + shift;
+            else v = div ? (v - shift) / sg : (v - shift) * sg;
+            ld += div ? -lsg : lsg;
+        }
+    }
+    __shared__ float red[8];
+    ld = warp_sum(ld);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ld;
+    __syncthreads();
+    if (threadIdx.x == 0 && logdet) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        if (logdet_const) t += *logdet_const;
+        logdet[b] = accumulate ? logdet[b] + t : t;
+    }
+}
+int launch_coupling_image(float* z, const float* param, float* logdet, const float* logdet_const, long long B,
+                          int C, int HW, int scale, int smap, int inv_split, int direction, int accumulate,
+                          cudaStream_t st) {
+    if (B == 0) return NFB_OK;
+    coupling_image_kernel<<<(unsigned)B, 256, 0, st>>>(z, param, logdet, logdet_const, C, HW, scale, smap,
+                                                       inv_split, direction, accumulate);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// Squeeze (flows/reshape.py:114-128).  direction 0 = inverse: [B,C,H,W] -> [B,4C,H/2,W/2]; 1 = forward.
+__global__ void squeeze_kernel(const float* __restrict__ in, float* __restrict__ out, long long B, int C, int H,
+                               int W, int direction) {
+    // (C,H,W) always describe the LARGE-resolution side: big[b,c,2h2+i,2w2+j] <-> small[b,4c+2i+j,h2,w2]
+    const long long n = B * C * H * W;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const int w = (int)(idx % W), h = (int)((idx / W) % H), c = (int)((idx / ((long long)W * H)) % C);
+    const long long b = idx / ((long long)W * H * C);
+    const int h2 = h >> 1, i = h & 1, w2 = w >> 1, j = w & 1;
+    const long long sidx = ((b * (4 * C) + 4 * c + 2 * i + j) * (H / 2) + h2) * (W / 2) + w2;
+    if (direction == 0) out[sidx] = in[idx];
+    else out[idx] = in[sidx];
+}
+int launch_squeeze(const float* in, float* out, long long B, int C, int H, int W, int direction, cudaStream_t st) {
+    NFB_CHECK(H % 2 == 0 && W % 2 == 0, NFB_ERR_ARG, "squeeze: H and W must be even");
+    const long long n = B * C * H * W;
+    if (n == 0) return NFB_OK;
+    squeeze_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, B, C, H, W, direction);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// out[b, j, :] = in[b, c0 + j, :]   (channel chunk of an NCHW tensor made contiguous; Split/Merge, reshape.py:27-31)
+__global__ void copy_channels_kernel(const float* __restrict__ in, float* __restrict__ out, long long B, int C,
+                                     int c0, int n, int HW) {
+    const long long total = B * n * HW;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long b = idx / ((long long)n * HW);
+    const long long rem = idx - b * n * HW;
+    out[idx] = in[(b * C + c0) * HW + rem];
+}
+int launch_copy_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st) {
+    NFB_CHECK(c0 >= 0 && n >= 0 && c0 + n <= C, NFB_ERR_ARG, "copy_channels: slice out of range");
+    const long long total = B * n * HW;
+    if (total == 0) return NFB_OK;
+    copy_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, C, c0, n, HW);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// ClassCondDiagGaussian.log_prob (distributions/base.py:327-344): loc/log_scale [dim, num_classes], y[b] int64.
+__global__ void __launch_bounds__(256)
+class_cond_gauss_kernel(const float* __restrict__ z, const long long* __restrict__ y,
+                        const float* __restrict__ loc, const float* __restrict__ log_scale,
+                        float* __restrict__ logq, int dim, int ncls, int accumulate) {
+    const long long b = blockIdx.x;
+    const int cls = (int)y[b];
+    float s = 0.f;
+    for (int i = threadIdx.x; i < dim; i += 256) {
+        const float ls = log_scale[(long long)i * ncls + cls];
+        const float t = (z[b * dim + i] - loc[(long long)i * ncls + cls]) / expf(ls);
+        s += ls + 0.5f * t * t;
+    }
+    __shared__ float red[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        const float lp = -0.5f * (float)dim * 1.8378770664093453f - t;
+        logq[b] = accumulate ? logq[b] + lp : lp;
+    }
+}
+int launch_class_cond_gauss(const float* z, const long long* y, const float* loc, const float* log_scale,
+                            float* logq, long long B, int dim, int ncls, int accumulate, cudaStream_t st) {
+    if (B == 0) return NFB_OK;
+    class_cond_gauss_kernel<<<(unsigned)B, 256, 0, st>>>(z, y, loc, log_scale, logq, dim, ncls, accumulate);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+}  // namespace nfb

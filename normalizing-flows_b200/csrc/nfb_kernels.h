@@ -26,6 +26,20 @@ int launch_diag_gauss(const float* z, const float* loc, const float* log_scale, 
 int launch_sum(const float* v, long long n, double scale, double* scratch, float* out,
                double* out_sum, cudaStream_t st);
 
+// ---- image-shaped Glow pieces (nfb_glow.cu) ----
+int launch_conv2d(const float* x, int ctot, int c0, const float* w, const float* bias, float* y, long long B,
+                  int cin, int H, int W, int cout, int ks, float leaky, cudaStream_t st);
+int launch_glow_fold(const float* P, const float* L, const float* U, const float* sign_S, const float* log_S,
+                     const float* s, const float* t, int C, int HW, float* w_out, float* b_out, float* logdet,
+                     cudaStream_t st);
+int launch_coupling_image(float* z, const float* param, float* logdet, const float* logdet_const, long long B,
+                          int C, int HW, int scale, int smap, int inv_split, int direction, int accumulate,
+                          cudaStream_t st);
+int launch_squeeze(const float* in, float* out, long long B, int C, int H, int W, int direction, cudaStream_t st);
+int launch_copy_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st);
+int launch_class_cond_gauss(const float* z, const long long* y, const float* loc, const float* log_scale,
+                            float* logq, long long B, int dim, int ncls, int accumulate, cudaStream_t st);
+
 // ---- small-dimension affine stack (nfb_affine.cu) ----
 constexpr int kAffMaxD = 16;
 constexpr int kAffMaxW = 128;  // widest MLP layer supported

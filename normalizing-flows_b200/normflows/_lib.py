@@ -73,6 +73,12 @@ SYMBOLS = {
     "nfb_device_info": (C.c_int, [_I32P, _I32P, _I32P]),
     "nfb_rqs_spline": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _F, _F, _I32, _I32, _VP]),
     "nfb_diag_gaussian_log_prob": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP]),
+    "nfb_conv2d": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _F, _VP]),
+    "nfb_glow_fold_actnorm_conv1x1": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
+    "nfb_affine_coupling_image": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
+    "nfb_squeeze": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _I32, _I32, _VP]),
+    "nfb_copy_channels": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _I32, _I32, _VP]),
+    "nfb_class_cond_diag_gaussian_log_prob": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _VP]),
     "nfb_flow_create": (C.c_int, [C.POINTER(_VP), _I32]),
     "nfb_flow_destroy": (C.c_int, [_VP]),
     "nfb_flow_add_ar_rqs": (C.c_int, [_VP, C.POINTER(ArRqsDesc)]),

@@ -109,3 +109,46 @@ class NormalizingFlow(nn.Module):
             raise NotImplementedError("log_prob_host needs an all-native stack with a DiagGaussian base")
         device = torch.device(device) if device is not None else next(self.parameters()).device
         return h.log_prob_host(x_host, device)
+
+
+class MultiscaleFlow(nn.Module):
+    """Multiscale (Glow) driver (reference: core.py:455-653); density pass only on the CUDA path."""
+
+    def __init__(self, q0, flows, merges, transform=None, class_cond=True):
+        super().__init__()
+        if transform is not None:
+            raise NotImplementedError("input transforms are out of scope of the CUDA path")
+        self.q0 = nn.ModuleList(q0)
+        self.num_levels = len(self.q0)
+        self.flows = nn.ModuleList([nn.ModuleList(f) for f in flows])
+        self.merges = nn.ModuleList(merges)
+        self.transform = transform
+        self.class_cond = class_cond
+
+    def log_prob(self, x, y=None):
+        """core.py:588-616: levels last-to-first; each flow's `.inverse`; channel split between levels."""
+        from .flows.glow import split_channels
+        log_q = 0
+        z = x
+        for i in range(len(self.q0) - 1, -1, -1):
+            for j in range(len(self.flows[i]) - 1, -1, -1):
+                z, log_det = self.flows[i][j].inverse(z)
+                log_q = log_q + log_det
+            if i > 0:
+                z, z_ = split_channels(z, getattr(self.merges[i - 1], "mode", "channel"))
+            else:
+                z_ = z
+            log_q = log_q + (self.q0[i].log_prob(z_, y) if self.class_cond else self.q0[i].log_prob(z_))
+        return log_q
+
+    def forward_kld(self, x, y=None):
+        return -torch.mean(self.log_prob(x, y))
+
+    def forward(self, x, y=None):
+        return -self.log_prob(x, y)
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path))

@@ -1,2 +1,2 @@
-from .base import BaseDistribution, DiagGaussian
+from .base import BaseDistribution, DiagGaussian, ClassCondDiagGaussian
 from .target import TwoMoons

@@ -55,3 +55,33 @@ class DiagGaussian(BaseDistribution):
             L.check(L.lib().nfb_diag_gaussian_log_prob(L.ptr(z), L.ptr(self.loc), L.ptr(ls), L.ptr(out),
                                                        z.shape[0], self.d, 0, L.stream_ptr()))
         return out
+
+
+class ClassCondDiagGaussian(BaseDistribution):
+    """Class-conditional diagonal Gaussian (reference: distributions/base.py:281-344); `log_prob(z, y)` with
+    integer labels runs in csrc/nfb_glow.cu."""
+
+    def __init__(self, shape, num_classes):
+        super().__init__()
+        if isinstance(shape, int):
+            shape = (shape,)
+        shape = tuple(shape)
+        self.shape, self.n_dim, self.d, self.num_classes = shape, len(shape), int(np.prod(shape)), num_classes
+        self.loc = nn.Parameter(torch.zeros(*shape, num_classes))
+        self.log_scale = nn.Parameter(torch.zeros(*shape, num_classes))
+        self.temperature = None
+
+    def log_prob(self, z, y):
+        z = require_cuda_f32(z)
+        if y.dim() != 1:
+            y = torch.argmax(y, dim=1)  # one-hot rows (base.py:336-337 accepts both)
+        y = y.to(device=z.device, dtype=torch.int64).contiguous()
+        if self.temperature is not None:
+            raise NotImplementedError("temperature annealing is off the density path")
+        out = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        if z.shape[0]:
+            with torch.cuda.device(z.device):
+                L.check(L.lib().nfb_class_cond_diag_gaussian_log_prob(
+                    L.ptr(z), L.ptr(y), L.ptr(self.loc), L.ptr(self.log_scale), L.ptr(out), z.shape[0], self.d,
+                    self.num_classes, 0, L.stream_ptr()))
+        return out

@@ -3,3 +3,4 @@ from .neural_spline import AutoregressiveRationalQuadraticSpline, CoupledRationa
 from .mixing import LULinearPermute, Permute
 from .affine import (AffineConstFlow, ActNorm, MaskedAffineFlow, AffineCouplingBlock, AffineCoupling,
                      Split, Merge)
+from .glow import GlowBlock, Invertible1x1Conv, Squeeze, ImageMerge

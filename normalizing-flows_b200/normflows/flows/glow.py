@@ -1,0 +1,142 @@
+"""Glow building blocks on NCHW tensors (reference: normflows/flows/affine/glow.py:11-84,
+flows/mixing.py:57-133 Invertible1x1Conv, flows/reshape.py:9-128 Split/Merge/Squeeze).
+
+Density direction (`inverse`) runs on the CUDA path: ActNorm.inverse and Invertible1x1Conv.inverse are folded
+into one 1x1 convolution, the ConvNet2d conditioner and the coupling epilogue are kernels in
+csrc/nfb_glow.cu.  The sampling direction of these image layers is not on the CUDA path yet."""
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib as L
+from .._native import require_cuda_f32
+from ..nets.cnn import ConvNet2d
+from .affine import ActNorm, AffineCoupling, Merge, Split
+from .base import Flow
+
+_MAPS = {"exp": 0, "sigmoid": 1, "sigmoid_inv": 2}
+
+
+class Invertible1x1Conv(Flow):
+    """Parameter container; same parameters/buffers as the reference (mixing.py:63-86)."""
+
+    def __init__(self, num_channels, use_lu=False):
+        super().__init__()
+        if not use_lu:
+            raise NotImplementedError("Invertible1x1Conv(use_lu=False) is not on the CUDA path")
+        self.num_channels, self.use_lu = num_channels, use_lu
+        Q, _ = torch.linalg.qr(torch.randn(num_channels, num_channels))
+        P, Lm, U = torch.linalg.lu(Q)
+        self.register_buffer("P", P)
+        self.L = nn.Parameter(Lm)
+        S = U.diag()
+        self.register_buffer("sign_S", torch.sign(S))
+        self.log_S = nn.Parameter(torch.log(torch.abs(S)))
+        self.U = nn.Parameter(torch.triu(U, diagonal=1))
+        self.register_buffer("eye", torch.diag(torch.ones(num_channels)))
+
+
+class Squeeze(Flow):
+    def _run(self, z, direction):
+        z = require_cuda_f32(z)
+        B, C, H, W = z.shape
+        if direction == L.NFB_INVERSE:
+            out = torch.empty(B, 4 * C, H // 2, W // 2, device=z.device, dtype=z.dtype)
+            big = (C, H, W)
+        else:
+            out = torch.empty(B, C // 4, 2 * H, 2 * W, device=z.device, dtype=z.dtype)
+            big = (C // 4, 2 * H, 2 * W)
+        if z.numel():
+            with torch.cuda.device(z.device):
+                L.check(L.lib().nfb_squeeze(L.ptr(z), L.ptr(out), B, big[0], big[1], big[2], direction,
+                                            L.stream_ptr()))
+        return out, 0
+
+    def forward(self, z):
+        return self._run(z, L.NFB_FORWARD)
+
+    def inverse(self, z):
+        return self._run(z, L.NFB_INVERSE)
+
+
+def split_channels(z, mode="channel"):
+    """Split.forward (reshape.py:27-31): contiguous copies of the two channel chunks."""
+    z = require_cuda_f32(z)
+    B, C, H, W = z.shape
+    h = (C + 1) // 2
+    a = torch.empty(B, h, H, W, device=z.device, dtype=z.dtype)
+    b = torch.empty(B, C - h, H, W, device=z.device, dtype=z.dtype)
+    if z.numel():
+        with torch.cuda.device(z.device):
+            L.check(L.lib().nfb_copy_channels(L.ptr(z), L.ptr(a), B, C, 0, h, H * W, L.stream_ptr()))
+            L.check(L.lib().nfb_copy_channels(L.ptr(z), L.ptr(b), B, C, h, C - h, H * W, L.stream_ptr()))
+    return (a, b) if mode == "channel" else (b, a)
+
+
+class ImageMerge(Merge):
+    """Merge for the multiscale driver: `inverse` splits channels (core.py:607-609)."""
+
+    def inverse(self, z):
+        z1, z2 = split_channels(z, self.mode)
+        return [z1, z2], 0
+
+
+class GlowBlock(Flow):
+    """[AffineCouplingBlock(ConvNet2d), Invertible1x1Conv(LU), ActNorm] -- module tree as in the reference
+    (glow.py:48-70) so checkpoints load verbatim."""
+
+    def __init__(self, channels, hidden_channels, scale=True, scale_map="sigmoid", split_mode="channel",
+                 leaky=0.0, init_zeros=True, use_lu=True, net_actnorm=False):
+        super().__init__()
+        if scale_map not in _MAPS:
+            raise NotImplementedError("This scale map is not implemented.")
+        if split_mode not in ("channel", "channel_inv"):
+            raise NotImplementedError("Mode " + split_mode + " is not implemented.")
+        if channels < 2:
+            raise NotImplementedError("GlowBlock with a single channel is not on the CUDA path")
+        num_param = 2 if scale else 1
+        if split_mode == "channel":
+            ch = ((channels + 1) // 2, hidden_channels, hidden_channels, num_param * (channels // 2))
+        else:
+            ch = (channels // 2, hidden_channels, hidden_channels, num_param * ((channels + 1) // 2))
+        param_map = ConvNet2d(ch, (3, 1, 3), leaky, init_zeros, actnorm=net_actnorm)
+        block = Flow()
+        block.flows = nn.ModuleList([Split(split_mode), AffineCoupling(param_map, scale, scale_map),
+                                     Merge(split_mode)])
+        self.flows = nn.ModuleList([block, Invertible1x1Conv(channels, use_lu), ActNorm((channels, 1, 1))])
+        self.channels, self.scale, self.scale_map, self.split_mode = channels, scale, scale_map, split_mode
+
+    def forward(self, z):
+        raise NotImplementedError("GlowBlock.forward (sampling direction on images) is not on the CUDA path yet")
+
+    def inverse(self, z):
+        z = require_cuda_f32(z)
+        if z.dim() != 4 or z.shape[1] != self.channels:
+            raise ValueError("Expected an NCHW tensor with {} channels.".format(self.channels))
+        conv, an = self.flows[1], self.flows[2]
+        if not an._done():
+            an._data_init(z, "inverse")
+        B, C, H, W = z.shape
+        dev = z.device
+        lib = L.lib()
+        w = torch.empty(C, C, device=dev)
+        b = torch.empty(C, device=dev)
+        ldc = torch.empty((), device=dev)
+        out = torch.empty_like(z)
+        ld = torch.empty(B, device=dev)
+        if B == 0:
+            return out, ld
+        with torch.cuda.device(dev):
+            L.check(lib.nfb_glow_fold_actnorm_conv1x1(
+                L.ptr(conv.P), L.ptr(conv.L), L.ptr(conv.U), L.ptr(conv.sign_S), L.ptr(conv.log_S),
+                L.ptr(an.s), L.ptr(an.t), C, H * W, L.ptr(w), L.ptr(b), L.ptr(ldc), L.stream_ptr()))
+            L.check(lib.nfb_conv2d(L.ptr(z), C, 0, L.ptr(w), L.ptr(b), L.ptr(out), B, C, H, W, C, 1, -1.0,
+                                   L.stream_ptr()))
+            h = (C + 1) // 2
+            c0, cin = (0, h) if self.split_mode == "channel" else (h, C - h)
+            param = self.flows[0].flows[1].param_map.apply_native(out, c0, cin)
+            L.check(lib.nfb_affine_coupling_image(
+                L.ptr(out), L.ptr(param), L.ptr(ld), L.ptr(ldc), B, C, H * W, int(bool(self.scale)),
+                _MAPS[self.scale_map], 0 if self.split_mode == "channel" else 1, L.NFB_INVERSE, 0,
+                L.stream_ptr()))
+        return out, ld

@@ -1,3 +1,4 @@
 from .mlp import MLP
 from .resnet import ResidualNet, ResidualBlock
 from .made import MADE, MaskedLinear, MaskedResidualBlock
+from .cnn import ConvNet2d

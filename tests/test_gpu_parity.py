@@ -218,3 +218,39 @@ def test_actnorm_data_dependent_init():
     np.testing.assert_allclose(an.t.detach().cpu().numpy(), t, rtol=1e-5, atol=1e-6)
     np.testing.assert_allclose(z.cpu().numpy(), (x - t) * np.exp(-s), rtol=1e-4, atol=1e-5)
     assert float(an.data_dep_init_done) == 1.0
+
+
+def test_glow_multiscale_log_prob_matches_reference():
+    """SURVEY 8a rows a2/a13-a17 on images: GlowBlock (ConvNet2d coupling + Invertible1x1Conv + ActNorm),
+    Squeeze, channel split, ClassCondDiagGaussian, MultiscaleFlow.log_prob / forward_kld."""
+    from helpers_glow import build_glow_small
+    spec, sd, a = load_golden("glow_small")
+    model = build_glow_small(sd).cuda()
+    x = cuda(a["x"])
+    y = torch.from_numpy(a["y"]).cuda()
+    lp = model.log_prob(x, y).cpu().numpy()
+    np.testing.assert_allclose(lp, a["log_prob_f64"], rtol=RTOL, atol=ATOL)
+    assert float(model.forward_kld(x, y)) == pytest.approx(float(a["kld_f64"]), rel=2e-5)
+    # one block against the oracle, with its log-det
+    z0 = np.random.default_rng(3).normal(size=(5, 24, 2, 2))
+    blk = model.flows[0][0]
+    z, ld = blk.inverse(cuda(z0))
+    zo, ldo = O.glow_block(z0, O._cast(sd, np.float64), "flows.0.0.", {}, "inverse")
+    np.testing.assert_allclose(z.cpu().numpy(), zo, rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(ld.cpu().numpy(), ldo, rtol=1e-4, atol=1e-3)
+    # squeeze round trip + oracle
+    s = nf.flows.Squeeze()
+    zs, _ = s.inverse(cuda(a["x"]))
+    np.testing.assert_array_equal(zs.cpu().numpy(), O.squeeze(a["x"].astype(np.float32), None, "", {}, "inverse")[0])
+    zr, _ = s.forward(zs)
+    np.testing.assert_array_equal(zr.cpu().numpy(), a["x"].astype(np.float32))
+
+
+def test_glow_actnorm_data_dependent_init_on_images():
+    f = np.load("tests/golden/actnorm_init.npz")
+    blk = nf.flows.GlowBlock(6, 8).cuda()
+    z, ld = blk.inverse(cuda(f["x"]))  # first call initialises ActNorm from the batch (normalization.py:33-38)
+    an = blk.flows[2]
+    np.testing.assert_allclose(an.s.detach().cpu().numpy(), f["s"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(an.t.detach().cpu().numpy(), f["t"], rtol=1e-5, atol=1e-6)
+    assert float(an.data_dep_init_done) == 1.0 and torch.isfinite(z).all() and torch.isfinite(ld).all()

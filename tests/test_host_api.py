@@ -98,3 +98,14 @@ def test_shard_rows_cover():
             spans = [shard_rows(n, r, w) for r in range(w)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+
+
+def test_glow_multiscale_state_dict_matches_reference():
+    from helpers_glow import build_glow_small
+    spec, sd, _ = load_golden("glow_small")
+    m = build_glow_small()
+    ours = m.state_dict()
+    assert set(ours) == set(sd)
+    for k, v in sd.items():
+        assert tuple(ours[k].shape) == tuple(v.shape), k
+    build_glow_small(sd)  # strict load of the reference checkpoint
