@@ -11,6 +11,7 @@
 //   SINGLE : any other layer through the generic fp32 kernels (nfb_kernels.cu)
 #include <algorithm>
 #include <cstdarg>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <memory>
@@ -94,7 +95,7 @@ struct FusedPack {
     std::vector<FusedStep> steps_host;
     DevBuf wstream, steps, uncond;
     std::vector<float> bias_h, bias_f;
-    std::vector<int> in_idx, tr_idx, id_idx;
+    std::vector<int> in_idx, tr_idx, id_idx, chunk_order;
     struct Rec { int row0, nrows, kc; size_t off_hi, off_lo; };
     struct Gemm { DevBuf src_row, src_col, row_scale; const float* W; const float* M; int src_cols, n_pad, k_pad; std::vector<Rec> recs; };
     std::vector<int> hperm;  // sorted-by-degree order of the hidden units (identity for unmasked nets)
@@ -103,6 +104,8 @@ struct FusedPack {
     bool pair_ok = false;
     int pair_steps = 0;
     DevBuf pair_wstream, pair_steps_dev, lu_src_row, lu_src_col, bias_lu;
+    FusedLayer host_layer{}, host_pair{};  // packed descriptors (host copies)
+    DevBuf layer_dev, pair_dev;           // ... and their device images (one FusedLayer each)
 };
 
 struct Layer {
@@ -144,6 +147,8 @@ struct nfb_flow {
     const float* base_loc = nullptr;
     const float* base_log_scale = nullptr;
     // workspaces
+    DevBuf stack_layers, progress;  // whole-stack launch: FusedLayer[stack_n] in density order + tile flags
+    int stack_n = 0;
     DevBuf zA, zB, logq, hA, hB, hT, params, E, scratch_sum, loss, err, ar_tmp, pair_tmp, host_x, zfinal, prof;
     long long launches = 0;
 };
@@ -247,7 +252,7 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     const int n_chunks = (T + fpc - 1) / fpc;
     const int kcs_h = H / 64;
     const int crow = fpc * 24;  // rows (MMA N) per final-layer chunk
-    if (n_hidden > 7 || n_chunks * fpc > 72) return NFB_OK;  // bias tables in the kernel parameter bank
+    if (n_hidden > 7 || (n_chunks + 1) * fpc > 82 || n_chunks > 16) return NFB_OK;  // tables inside FusedLayer
 
     // ---- MADE masks: sort hidden units by degree so that every masked matrix is block-triangular, and
     //      find the all-zero [rows x 64-column] blocks to drop (nets/made.py:57-76 degree rules) ----
@@ -349,19 +354,31 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     {
         FusedPack::Gemm& g = F.gemms[n_hidden];
         bool a_waited[4] = {false, false, false, false};
-        for (int c = 0; c < n_chunks; ++c) {
-            const int b = (c + 1) & 1;  // two TMEM chunk buffers (columns 0.. and 256..); chunk 0 uses the second
-            std::vector<int> need;
+        // Which K-chunks does each chunk need (MADE masks)?  The chunk processed FIRST must read every K-chunk:
+        // its records carry all the a_ready[kc] waits, i.e. the MMA warp knows the last hidden epilogue has
+        // finished reading the residual stream (TMEM columns 0..255) before the chunk in processing slot 1
+        // overwrites those columns.  (A short first chunk there is a real race: found on hardware.)
+        std::vector<std::vector<int>> need_of(n_chunks);
+        for (int c = 0; c < n_chunks; ++c)
             for (int kc = 0; kc < kcs_h; ++kc)
-                if (kc == 0 || c == n_chunks - 1 || final_needs(c, kc)) need.push_back(kc);
-            // (the last chunk reads every K-chunk so that each a_ready[kc] of the last hidden epilogue
-            //  is consumed exactly once per tile, keeping the barrier phases in step)
+                if (kc == 0 || c == n_chunks - 1 || final_needs(c, kc)) need_of[c].push_back(kc);
+        // heavy,light,heavy,light: the top chunk (all K-chunks) first, then alternate low/high chunks
+        std::vector<int> order;
+        for (int lo = 0, hi = n_chunks - 1; lo <= hi;) {
+            order.push_back(hi--);
+            if (lo <= hi) order.push_back(lo++);
+        }
+        F.chunk_order = order;
+        for (int ci = 0; ci < n_chunks; ++ci) {
+            const int c = order[ci];
+            const int b = (ci + 1) & 1;  // two TMEM chunk buffers (columns 0.. and 256..); slot 0 uses the second
+            const std::vector<int>& need = need_of[c];
             for (size_t j = 0; j < need.size(); ++j) {
                 const int kc = need[j];
                 int wait = 0;
-                if (j == 0) wait = (c == 0) ? 6 : 2 + b;           // chunk buffer free (+ a_ready[0] for chunk 0)
+                if (j == 0) wait = (ci == 0) ? 6 : 2 + b;          // chunk buffer free (+ a_ready[0] for slot 0)
                 else if (!a_waited[kc]) wait = 1;                     // first reader of this A K-chunk
-                if (j == 0 && c > 0 && !a_waited[kc]) return NFB_OK;  // cannot encode both waits: keep generic path
+                if (j == 0 && ci > 0 && !a_waited[kc]) return NFB_OK; // cannot encode both waits: keep generic path
                 a_waited[kc] = true;
                 add(g, c * crow, crow, kc, chunk_col_host(b), j == 0 ? 1 : 0, wait,
                     j + 1 == need.size() ? 2 + b : 0);
@@ -450,6 +467,22 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         }
         NFB_TRY(F.uncond.upload(tab));
     }
+    FusedLayer& Lh = F.host_layer;
+    memset(&Lh, 0, sizeof(Lh));
+    Lh.D = F.D; Lh.H = F.H; Lh.n_hidden = F.n_hidden; Lh.has_lu = 0; Lh.T = F.T; Lh.F = F.F;
+    Lh.n_chunks = F.n_chunks; Lh.n_id = F.n_id; Lh.n_steps = F.n_steps; Lh.tail = F.tail;
+    Lh.wstream = F.wstream.as<uint8_t>(); Lh.steps = F.steps.as<FusedStep>();
+    Lh.uncond = F.uncond.as<float>();
+    for (int k = 0; k < 64; ++k) {
+        Lh.in_idx[k] = (signed char)(k < (int)F.in_idx.size() ? F.in_idx[k] : -1);
+        Lh.tr_idx[k] = (unsigned char)(k < (int)F.tr_idx.size() ? F.tr_idx[k] : 0);
+        Lh.id_idx[k] = (unsigned char)(k < (int)F.id_idx.size() ? F.id_idx[k] : 0);
+    }
+    for (int k = 0; k < 16; ++k) Lh.chunk_order[k] = (unsigned char)(k < (int)F.chunk_order.size() ? F.chunk_order[k] : 0);
+    memcpy(Lh.bias_h, F.bias_h.data(), std::min(sizeof(Lh.bias_h), F.bias_h.size() * sizeof(float)));
+    memcpy(Lh.bias_f, F.bias_f.data(), std::min(sizeof(Lh.bias_f), F.bias_f.size() * sizeof(float)));
+    NFB_TRY(F.layer_dev.reserve(sizeof(FusedLayer)));
+    NFB_CUDA(cudaMemcpy(F.layer_dev.p, &Lh, sizeof(FusedLayer), cudaMemcpyHostToDevice));
     return NFB_OK;
 }
 
@@ -520,6 +553,16 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     NFB_TRY(download(U.lu.bias, (size_t)U.D, b));
     for (int i = 0; i < U.D; ++i) bl[i] = b[i];
     NFB_TRY(F.bias_lu.upload(bl));
+    FusedLayer& Lp = F.host_pair;
+    Lp = F.host_layer;
+    Lp.has_lu = 1;
+    Lp.n_steps = F.pair_steps;
+    Lp.wstream = F.pair_wstream.as<uint8_t>();
+    Lp.steps = F.pair_steps_dev.as<FusedStep>();
+    Lp.bias_lu = F.bias_lu.as<float>();
+    Lp.lu_logdet = U.lu_logdet.as<float>();
+    NFB_TRY(F.pair_dev.reserve(sizeof(FusedLayer)));
+    NFB_CUDA(cudaMemcpy(F.pair_dev.p, &Lp, sizeof(FusedLayer), cudaMemcpyHostToDevice));
     return NFB_OK;
 }
 
@@ -527,28 +570,32 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
                        long long rows, int accumulate, cudaStream_t st) {
     FusedPack& F = R.fused;
     FusedParams p{};
-    p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows;
-    p.D = F.D; p.H = F.H; p.n_hidden = F.n_hidden; p.has_lu = U ? 1 : 0; p.T = F.T; p.F = F.F;
-    p.n_chunks = F.n_chunks; p.n_id = F.n_id; p.accumulate = accumulate; p.tail = F.tail;
-    p.n_steps = U ? F.pair_steps : F.n_steps;
-    p.wstream = U ? F.pair_wstream.as<uint8_t>() : F.wstream.as<uint8_t>();
-    p.steps = U ? F.pair_steps_dev.as<FusedStep>() : F.steps.as<FusedStep>();
-    p.bias_lu = U ? F.bias_lu.as<float>() : nullptr;
-    memset(p.bias_h, 0, sizeof(p.bias_h));
-    memset(p.bias_f, 0, sizeof(p.bias_f));
-    memcpy(p.bias_h, F.bias_h.data(), std::min(sizeof(p.bias_h), F.bias_h.size() * sizeof(float)));
-    memcpy(p.bias_f, F.bias_f.data(), std::min(sizeof(p.bias_f), F.bias_f.size() * sizeof(float)));
-    for (int k = 0; k < 64; ++k) {
-        p.in_idx[k] = (signed char)(k < (int)F.in_idx.size() ? F.in_idx[k] : -1);
-        p.tr_idx[k] = (unsigned char)(k < (int)F.tr_idx.size() ? F.tr_idx[k] : 0);
-        p.id_idx[k] = (unsigned char)(k < (int)F.id_idx.size() ? F.id_idx[k] : 0);
-    }
-    p.uncond = F.uncond.as<float>();
-    p.lu_logdet = U ? U->lu_logdet.as<float>() : nullptr;
+    p.layers = U ? F.pair_dev.as<FusedLayer>() : F.layer_dev.as<FusedLayer>();
+    p.n_layers = 1;
+    p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = accumulate;
+    p.progress = nullptr;
     p.err = f->err.as<int>();
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
     NFB_TRY(launch_fused_rqs(p, f->sm_count, st));
     f->launches++;
+    return NFB_OK;
+}
+
+// Whole stack in ONE persistent launch: (layer, tile) work units with per-tile progress flags.  logq must be
+// pre-filled (accumulate semantics); zout may alias zin.
+int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, long long rows, cudaStream_t st) {
+    const long long n_tiles = (rows + 127) / 128;
+    NFB_TRY(f->progress.reserve((size_t)n_tiles * sizeof(int)));
+    NFB_CUDA(cudaMemsetAsync(f->progress.p, 0, (size_t)n_tiles * sizeof(int), st));
+    FusedParams p{};
+    p.layers = f->stack_layers.as<FusedLayer>();
+    p.n_layers = f->stack_n;
+    p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = 1;
+    p.progress = f->progress.as<int>();
+    p.err = f->err.as<int>();
+    p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
+    NFB_TRY(launch_fused_rqs(p, f->sm_count, st));
+    f->launches += 2;  // memset + kernel
     return NFB_OK;
 }
 
@@ -931,6 +978,21 @@ int nfb_flow_repack(nfb_flow_t* f, void* stream) {
     }
     for (auto& g : f->groups)
         if (g.kind == G_FUSED_PAIR) NFB_TRY(repack_pair(f, *f->layers[g.first], *f->layers[g.last], st));
+    // whole-stack launch plan (density direction applies the groups last-to-first)
+    f->stack_n = 0;
+    bool all_fused = !f->groups.empty() && getenv("NFB_NO_STACK") == nullptr;
+    for (auto& g : f->groups) all_fused = all_fused && (g.kind == G_FUSED_PAIR || g.kind == G_FUSED);
+    if (all_fused) {
+        std::vector<FusedLayer> arr;
+        for (int k = (int)f->groups.size() - 1; k >= 0; --k) {
+            Group& g = f->groups[k];
+            FusedPack& F = f->layers[g.first]->fused;
+            arr.push_back(g.kind == G_FUSED_PAIR ? F.host_pair : F.host_layer);
+        }
+        NFB_TRY(f->stack_layers.reserve(arr.size() * sizeof(FusedLayer)));
+        NFB_CUDA(cudaMemcpy(f->stack_layers.p, arr.data(), arr.size() * sizeof(FusedLayer), cudaMemcpyHostToDevice));
+        f->stack_n = (int)arr.size();
+    }
     NFB_CUDA(cudaStreamSynchronize(st));
     return NFB_OK;
 }
@@ -1061,6 +1123,8 @@ int nfb_flow_transform(nfb_flow_t* f, int32_t direction, const float* z_in, floa
     float* ld = log_det ? log_det : f->logq.as<float>();
     NFB_TRY(launch_fill(ld, rows, 0.f, st));
     f->launches++;
+    if (direction == NFB_INVERSE && f->stack_n > 0)
+        return launch_fused_stack(f, z_in, z_out, ld, rows, st);
     const int ng = (int)f->groups.size();
     const float* cur = z_in;
     float* bufs[2] = {f->zA.as<float>(), f->zB.as<float>()};

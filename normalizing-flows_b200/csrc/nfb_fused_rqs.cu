@@ -101,7 +101,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* xs = reinterpret_cast<float*>(smem + kOffX);
-    FusedStep* steps = reinterpret_cast<FusedStep*>(smem + kOffSteps);
     const uint32_t bars = sbase + kOffBars;
     float* ldsum = reinterpret_cast<float*>(smem + kOffLd);
     auto bar = [bars](int i) { return bars + 8u * i; };
@@ -110,7 +109,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         if (threadIdx.x == 0 && p.err) atomicExch(p.err, 900);
         return;
     }
-    for (int i = threadIdx.x; i < p.n_steps; i += kFusedThreads) steps[i] = p.steps[i];
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) {
             mbar_init(bar(kBarWFull + i), 1);
@@ -132,6 +130,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
     const long long n_tiles = (p.rows + 127) / 128;
+    const long long n_units = n_tiles * p.n_layers;  // (layer, tile) work units, layer-major
 
     // Warp roles: the SM arbiter favours high warp ids, so the two latency-critical single-lane roles
     // (TMA producer = warp 8, MMA issuer = warp 9) sit above the eight epilogue warps (0-7).
@@ -139,10 +138,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         // ------------------------------ weight producer -----------------------------------
         // whole warp walks the table (warp-uniform control flow); one elected lane issues the copy
         uint32_t slot = 0, par = 0;
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const uint8_t* src = p.wstream;
-            for (int s = 0; s < p.n_steps; ++s) {
-                const uint32_t bytes = (uint32_t)steps[s].bytes16 << 4;
+        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const FusedLayer& L = p.layers[u / n_tiles];
+            const uint8_t* src = L.wstream;
+            const FusedStep* steps = L.steps;  // global (L2-resident); the producer only needs the size
+            const int n_steps = L.n_steps;
+            uint32_t bytes = n_steps ? (uint32_t)__ldg(&steps[0].bytes16) << 4 : 0u;
+            for (int s = 0; s < n_steps; ++s) {
+                const uint32_t nbytes = s + 1 < n_steps ? (uint32_t)__ldg(&steps[s + 1].bytes16) << 4 : 0u;
                 mbar_wait(bar(kBarWEmpty + slot), par ^ 1, p.err, 100 + slot);
                 if (elect_one_sync()) {
                     mbar_expect_tx(bar(kBarWFull + slot), bytes);
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
                 __syncwarp();
                 src += bytes;
+                bytes = nbytes;
                 if (++slot == kSlots) { slot = 0; par ^= 1; }
             }
         }
@@ -161,10 +165,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const uint64_t adesc0 = umma_desc_sw128(sbase + kOffA);
         const uint64_t bdesc0 = umma_desc_sw128(sbase + kOffW);
         constexpr uint32_t kIdesc0 = umma_idesc_bf16(128, 0);
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            FusedStep st = steps[0];
-            for (int s = 0; s < p.n_steps; ++s) {
-                const FusedStep nxt = steps[s + 1 < p.n_steps ? s + 1 : 0];  // prefetch (LDS latency)
+        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const FusedLayer& L = p.layers[u / n_tiles];
+            const uint2* steps = reinterpret_cast<const uint2*>(L.steps);  // 8-byte entries, L2-resident
+            const int n_steps = L.n_steps;
+            union { uint2 raw; FusedStep s; } cur, nx;
+            cur.raw = __ldg(steps);
+            for (int s = 0; s < n_steps; ++s) {
+                nx.raw = __ldg(steps + (s + 1 < n_steps ? s + 1 : 0));  // prefetch one entry ahead
+                const FusedStep st = cur.s;
                 const uint32_t ctl = st.ctl;
                 const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
                 if (wcode == 1 || wcode == 6) {  // first use of A-operand K-chunk kc in this phase
@@ -210,7 +219,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
                 __syncwarp();
                 if (++slot == kSlots) { slot = 0; wpar ^= 1; }
-                st = nxt;
+                cur.raw = nx.raw;
             }
         }
     } else {
@@ -222,36 +231,61 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t aA = sbase + kOffA;
         uint32_t afpar = 0, cfbits = 0;
-        const int D = p.D, H = p.H;
         long long* prof = (p.prof && blockIdx.x == 0 && et == 0) ? p.prof : nullptr;
         int pi = 0;
 #define NFB_STAMP() do { if (prof && pi < 126) prof[pi++] = clock64(); } while (0)
 
-        auto build_a = [&](bool lu_stage) {
-            // A[:, k] for k in [wh*32, wh*32+32): lu_stage -> 3-way split of xs[:, k] (k < D);
-            // otherwise 2-way split of the conditioner input xs[:, in_idx[k]].
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = wh * 32 + g * 8 + j;
-                    int c = lu_stage ? (k < D ? k : -1) : p.in_idx[k];
-                    v[j] = c >= 0 ? xs[xs_index(r, c)] : 0.f;
-                }
-                const uint32_t off = a_chunk_off(r, wh * 4 + g);
-                if (lu_stage) split_store8<3>(v, aA, aA + 4 * kTileA, aA + 1 * kTileA, off);
-                else split_store8<2>(v, aA, aA + 4 * kTileA, 0, off);
-            }
-            fence_proxy_async_smem();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(kBarAReady + 0));
-        };
-
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int layer = (int)(u / n_tiles);
+            const long long tile = u - (long long)layer * n_tiles;
+            const FusedLayer& L = p.layers[layer];
+            const int D = L.D, H = L.H;
+            const float* zsrc = layer == 0 ? p.zin : p.zout;   // layers >= 1 update z in place
             const long long row0 = tile * 128;
-            if (tile != blockIdx.x) prof = nullptr;
+            if (u != blockIdx.x) prof = nullptr;
+            auto build_a = [&](bool lu_stage) {
+                // A[:, k] for k in [wh*32, wh*32+32): lu_stage -> 3-way split of xs[:, k] (k < D);
+                // otherwise 2-way split of the conditioner input xs[:, in_idx[k]].
+    #pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float v[8];
+    #pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = wh * 32 + g * 8 + j;
+                        int c = lu_stage ? (k < D ? k : -1) : L.in_idx[k];
+                        v[j] = c >= 0 ? xs[xs_index(r, c)] : 0.f;
+                    }
+                    const uint32_t off = a_chunk_off(r, wh * 4 + g);
+                    if (lu_stage) split_store8<3>(v, aA, aA + 4 * kTileA, aA + 1 * kTileA, off);
+                    else split_store8<2>(v, aA, aA + 4 * kTileA, 0, off);
+                }
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(kBarAReady + 0));
+            };
+
+            // ---- layer-to-layer dependency: this tile's rows must have left layer-1 (any CTA) ----
+            if (layer > 0) {
+                if (lane == 0) {  // one lane per warp spins (keeps the warp converged for the .aligned ops below)
+                    const int* flag = p.progress + tile;
+                    int seen;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+                        if (seen < layer && clock64() - t0 > 4000000000LL) {
+                            if (p.err) atomicExch(p.err, 500);
+                            asm volatile("trap;");
+                        }
+                    } while (seen < layer);
+                }
+                __syncwarp();
+                {   // every thread performs its own acquire of the (now set) flag before touching the rows
+                    int seen;
+                    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.progress + tile) : "memory");
+                    if (seen < layer) { if (p.err) atomicExch(p.err, 501); asm volatile("trap;"); }
+                }
+            }
             NFB_STAMP();  // [0] tile start
             // ---- load z tile -> xs (coalesced global, swizzled shared) ----
             if (D == 64) {
@@ -260,7 +294,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 for (int k = 0; k < 8; ++k) {
                     const int i4 = et + k * 256, rr = i4 >> 4;
                     const long long gr = row0 + rr;
-                    v[k] = gr < p.rows ? __ldg(reinterpret_cast<const float4*>(p.zin + gr * 64) + (i4 & 15))
+                    v[k] = gr < p.rows ? __ldcg(reinterpret_cast<const float4*>(zsrc + gr * 64) + (i4 & 15))
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
@@ -275,13 +309,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 for (int i = et; i < 128 * D; i += 256) {
                     const int rr = i / D, cc = i - rr * D;
                     const long long gr = row0 + rr;
-                    xs[xs_index(rr, cc)] = gr < p.rows ? __ldg(p.zin + gr * D + cc) : 0.f;
+                    xs[xs_index(rr, cc)] = gr < p.rows ? __ldcg(zsrc + gr * D + cc) : 0.f;
                 }
             }
             epi_bar_sync();
             NFB_STAMP();  // [1] load done
             float ladsum = 0.f;
-            if (p.has_lu) {
+            if (L.has_lu) {
                 build_a(true);
                 NFB_STAMP();  // build_a(lu) done
                 mbar_wait(bar(kBarAccFull), afpar, p.err, 300);
@@ -296,7 +330,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const int c = wh * 32 + j;
-                    if (c < D) xs[xs_index(r, c)] = __uint_as_float(acc[j]) + __ldg(p.bias_lu + c);
+                    if (c < D) xs[xs_index(r, c)] = __uint_as_float(acc[j]) + __ldg(L.bias_lu + c);
                 }
                 epi_bar_sync();
             }
@@ -306,34 +340,34 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             // ---- unconditional spline on the identity features (coupled layer only); runs while
             //      the tensor core is busy with the first GEMMs.  The conditioner input was taken
             //      from the raw values above (Coupling.forward, neural_spline/coupling.py:80-92).
-            if (p.n_id > 0) {
-                const int per = (p.n_id + 1) / 2;
-                for (int i = wh * per; i < min(p.n_id, (wh + 1) * per); ++i) {
-                    const int c = p.id_idx[i];
-                    const float* tb = p.uncond + i * 23;
+            if (L.n_id > 0) {
+                const int per = (L.n_id + 1) / 2;
+                for (int i = wh * per; i < min(L.n_id, (wh + 1) * per); ++i) {
+                    const int c = L.id_idx[i];
+                    const float* tb = L.uncond + i * 23;
                     auto acc = [tb](int k) { return __ldg(tb + k); };
                     float y, l;
-                    rqs_eval<8, false>(xs[xs_index(r, c)], acc, p.tail, 1.0f, y, l);
+                    rqs_eval<8, false>(xs[xs_index(r, c)], acc, L.tail, 1.0f, y, l);
                     xs[xs_index(r, c)] = y;
                     ladsum += l;
                 }
             }
 
             // ---- hidden layers ----
-            for (int ph = 0; ph < p.n_hidden; ++ph) {
+            for (int ph = 0; ph < L.n_hidden; ++ph) {
                 mbar_wait(bar(kBarAccFull), afpar, p.err, 310 + ph);
                 afpar ^= 1;
                 tc_fence_after();
                 NFB_STAMP();  // hidden gemm ph done
                 const uint32_t region = (ph & 1) ? 256u : 0u;
-                const bool relu = ph + 1 < p.n_hidden;
+                const bool relu = ph + 1 < L.n_hidden;
                 // K-chunk order: both column halves convert the same 64 columns, then release that slice of
                 // the next A operand so the next GEMM's kc-step can start while the rest is converted
                 for (int kc = 0; kc < (H >> 6); ++kc) {
                     const int c0 = kc * 64 + wh * 32;
                     uint32_t acc[32];
                     NFB_TMEM_LD32(tlane + region + c0, acc);
-                    const float* bf = p.bias_h + ph * 256 + c0;  // constant bank, warp-uniform index
+                    const float* bf = L.bias_h + ph * 256 + c0;  // constant bank, warp-uniform index
                     tc_wait_ld();
                     float v[32];
 #pragma unroll
@@ -355,12 +389,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 
             // ---- final layer chunks -> spline ----
             // chunk = F features x 24 columns (N = 24 F <= 240); this thread: F/2 of them, one at a time
-            const int fh = p.F >> 1;
-            for (int c = 0; c < p.n_chunks; ++c) {
-                // chunk 0 -> buffer 1 (columns 256..): the last hidden epilogue is still reading the
-                // residual stream (columns 0..255) when the first final-layer MMAs start
-                const int b = (c + 1) & 1;
-                const int t0 = c * p.F + wh * fh;  // first transformed-feature slot of this thread
+            const int fh = L.F >> 1;
+            for (int ci = 0; ci < L.n_chunks; ++ci) {
+                // Processing slot 0 -> buffer 1 (columns 256..): the last hidden epilogue is still reading the
+                // residual stream (columns 0..255) when the first final-layer MMAs start.  The packer puts a
+                // chunk that reads EVERY A K-chunk into slot 0, so the MMA warp has consumed all a_ready[kc]
+                // (= the epilogue has finished reading columns 0..255) before slot 1 overwrites buffer 0.
+                const int b = (ci + 1) & 1;
+                const int c = L.chunk_order[ci];
+                const int t0 = c * L.F + wh * fh;  // first transformed-feature slot of this thread
                 mbar_wait(bar(kBarCFull + b), (cfbits >> b) & 1u, p.err, 400 + b);
                 cfbits ^= 1u << b;
                 tc_fence_after();
@@ -386,10 +423,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
                     }
-                    const bool okA = tA < p.T, okB = hasB && tB < p.T;
-                    const int colA = p.tr_idx[okA ? tA : 0], colB = p.tr_idx[okB ? tB : 0];
-                    const float* bA = p.bias_f + tA * 24;
-                    const float* bB = p.bias_f + (hasB ? tB : tA) * 24;
+                    const bool okA = tA < L.T, okB = hasB && tB < L.T;
+                    const int colA = L.tr_idx[okA ? tA : 0], colB = L.tr_idx[okB ? tB : 0];
+                    const float* bA = L.bias_f + tA * 24;
+                    const float* bB = L.bias_f + (hasB ? tB : tA) * 24;
                     float pvA[24], pvB[24];
 #pragma unroll
                     for (int j = 0; j < 24; ++j) {
@@ -400,8 +437,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     auto accB = [&pvB](int k) { return pvB[k]; };
                     const float xA = xs[xs_index(r, colA)], xB = xs[xs_index(r, colB)];
                     float yA, lA, yB, lB;
-                    rqs_eval<8, false>(xA, accA, p.tail, 1.0f, yA, lA);
-                    rqs_eval<8, false>(xB, accB, p.tail, 1.0f, yB, lB);
+                    rqs_eval<8, false>(xA, accA, L.tail, 1.0f, yA, lA);
+                    rqs_eval<8, false>(xB, accB, L.tail, 1.0f, yB, lB);
                     if (okA) { xs[xs_index(r, colA)] = yA; ladsum += lA; }
                     if (okB) { xs[xs_index(r, colB)] = yB; ladsum += lB; }
                 }
@@ -415,8 +452,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             if (wh == 0) {
                 const long long gr = row0 + r;
                 if (gr < p.rows) {
-                    float tot = ladsum + ldsum[r] + (p.lu_logdet ? __ldg(p.lu_logdet) : 0.f);
-                    p.logq[gr] = p.accumulate ? p.logq[gr] + tot : tot;
+                    float tot = ladsum + ldsum[r] + (L.lu_logdet ? __ldg(L.lu_logdet) : 0.f);
+                    if (layer > 0 || p.accumulate) tot += __ldcg(p.logq + gr);
+                    __stcg(p.logq + gr, tot);
                 }
             }
             if (D == 64) {
@@ -426,16 +464,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     const long long gr = row0 + rr;
                     const float4 v = make_float4(xs[xs_index(rr, c0)], xs[xs_index(rr, c0 + 1)],
                                                  xs[xs_index(rr, c0 + 2)], xs[xs_index(rr, c0 + 3)]);
-                    if (gr < p.rows) *(reinterpret_cast<float4*>(p.zout + gr * 64) + (i4 & 15)) = v;
+                    if (gr < p.rows) __stcg(reinterpret_cast<float4*>(p.zout + gr * 64) + (i4 & 15), v);
                 }
             } else {
                 for (int i = et; i < 128 * D; i += 256) {
                     const int rr = i / D, cc = i - rr * D;
                     const long long gr = row0 + rr;
-                    if (gr < p.rows) p.zout[gr * D + cc] = xs[xs_index(rr, cc)];
+                    if (gr < p.rows) __stcg(p.zout + gr * D + cc, xs[xs_index(rr, cc)]);
                 }
             }
+            // publish this tile: each thread makes ITS OWN global stores visible device-wide, then the barrier,
+            // then one thread releases the flag (a fence by thread 0 alone would not cover stores that other
+            // warps still have in flight to L2)
+            if (p.progress) __threadfence();
             epi_bar_sync();
+            if (p.progress && et == 0) {
+                __threadfence();
+                asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.progress + tile), "r"(layer + 1) : "memory");
+            }
             NFB_STAMP();  // tile stored
             if (prof) prof[127] = pi;
         }
@@ -452,11 +498,11 @@ int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st) {
                                       (int)kFusedSmem));
         attr_done = true;
     }
-    NFB_CHECK(p.n_steps <= (int)kMaxSteps, NFB_ERR_UNSUPPORTED, "fused rqs: %d steps > %d", p.n_steps,
-              kMaxSteps);
-    const long long n_tiles = (p.rows + 127) / 128;
-    if (n_tiles == 0) return NFB_OK;
-    const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
+    NFB_CHECK(p.n_layers >= 1 && (p.n_layers == 1 || p.progress), NFB_ERR_ARG, "fused rqs: bad layer list");
+    const long long n_units = (p.rows + 127) / 128 * p.n_layers;
+    if (n_units == 0) return NFB_OK;
+    // every CTA must be resident (units wait on flags published by other CTAs): grid <= #SMs, 1 CTA/SM
+    const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
     fused_rqs_kernel<<<grid, kFusedThreads, kFusedSmem, st>>>(p);
     NFB_LAUNCH_CHECK();
     return NFB_OK;

@@ -79,28 +79,36 @@ struct __align__(8) FusedStep {
 // wait codes : 0 none, 1 a_ready[kc], 2+i chunk_empty[i], 6 a_ready[kc] + chunk_empty[1]  (kc = a0 & 3)
 // signal codes: 0 none, 1 acc_full, 2+i chunk_full[i]
 
-struct FusedParams {
-    const float* zin;
-    float* zout;
-    float* logq;
-    long long rows;
-    int D, H, n_hidden, has_lu, T, F, n_chunks, n_id, n_steps, accumulate;  // F = features per final-layer chunk
+// One fused [LULinearPermute +] spline block, packed.  Device-resident (uploaded at pack time): the kernel
+// reads it through a pointer so that ONE persistent launch can walk a whole stack of blocks.
+struct FusedLayer {
+    int D, H, n_hidden, has_lu, T, F, n_chunks, n_id, n_steps, pad_;  // F = features per final-layer chunk
     float tail;
     const uint8_t* wstream;
     const FusedStep* steps;
     const float* bias_lu;    // [64]
-    // feature index tables live in the kernel parameter (constant) bank: no L2 round trip per use
+    const float* uncond;     // [n_id][23]
+    const float* lu_logdet;  // device scalar or null
     signed char in_idx[64];    // conditioner input column per k (-1 = zero pad)
     unsigned char tr_idx[64];  // transformed feature columns
     unsigned char id_idx[64];  // identity feature columns (coupled layer)
-    const float* uncond;     // [n_id][23]
-    const float* lu_logdet;  // device scalar or null
-    int* err;
-    long long* prof;         // optional [128] clock64 stamps (debug)
-    // Biases ride in the kernel parameter (constant) bank: every thread of a warp reads the same element,
-    // so LDC broadcasts replace L2 round trips (L1 is ~1 KB with 227 KB of shared memory in use).
+    unsigned char chunk_order[16];  // final-layer chunks in processing order (first one reads every K-chunk)
     float bias_h[7 * 256];   // [n_hidden <= 7][256], residual biases pre-summed along the stream
-    float bias_f[72 * 24];   // [n_chunks*F <= 72][24] final-layer bias in chunk/column order
+    float bias_f[82 * 24];   // [(n_chunks+1)*F <= 82][24] final-layer bias in chunk/column order
+};
+// Launch arguments.  Work units are (layer, 128-row tile) pairs in layer-major order; unit (l, t) may start
+// once progress[t] >= l.  Rows of a tile are private to it, so layers l >= 1 update `zout` in place.
+struct FusedParams {
+    const FusedLayer* layers;  // [n_layers], in application order
+    int n_layers;
+    const float* zin;          // input of layer 0
+    float* zout;               // output of every layer (and input of layers >= 1)
+    float* logq;
+    long long rows;
+    int accumulate;            // layer 0: logq += (1) or = (0); later layers always accumulate
+    int* progress;             // [n_tiles] zero-initialised, or null when n_layers == 1
+    int* err;
+    long long* prof;           // optional [128] clock64 stamps (debug)
 };
 int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st);
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,

@@ -141,3 +141,42 @@ if mode == "spline":
         byt = B * T * (P * 4 + 8) + B * 8
         print(f"spline standalone inverse={inv}: {ms*1e3:.1f} us  {byt/ms/1e6:.1f} GB/s  "
               f"frac of 6580 = {byt/ms/1e6/6580.3:.3f}", flush=True)
+
+if mode == "stackdbg":
+    spec, sd, a = load_golden("nsf_ar_d64_h256_l2")
+    model = build_model(spec, sd).cuda()
+    for B in (48, 1, 47):
+        x = cuda(a["x"][:B])
+        z, ld = model.inverse_and_log_det(x)
+        ez = np.abs(z.cpu().numpy() - a["z_f64"][:B])
+        eld = np.abs(ld.cpu().numpy() - (a["log_prob_f64"][:B] * 0 + sum(a[f"ld_f64__{i}"][:B] for i in range(4))))
+        bad = np.argwhere(ez > 1e-3)
+        print(f"B={B}: z max err {ez.max():.3e} ld max err {eld.max():.3e} bad elems {len(bad)} rows {sorted(set(bad[:,0]))[:10]} cols {sorted(set(bad[:,1]))[:20]}", flush=True)
+    # repeat several times to see nondeterminism
+    x = cuda(a["x"])
+    outs = [model.inverse_and_log_det(x)[0].cpu().numpy() for _ in range(5)]
+    print("run-to-run max diff:", max(np.abs(o - outs[0]).max() for o in outs))
+    # larger batch: compare stack vs oracle on first rows
+    xb = np.tile(a["x"], (40, 1))[:1500]
+    z, ld = model.inverse_and_log_det(cuda(xb))
+    ref = np.tile(a["z_f64"], (40, 1))[:1500]
+    ez = np.abs(z.cpu().numpy() - ref).max(axis=1)
+    badr = np.argwhere(ez > 1e-3)[:, 0]
+    rng_, st = [], None
+    for r_ in badr:
+        if st is None: st = prev = r_
+        elif r_ != prev + 1: rng_.append((st, prev)); st = r_
+        prev = r_
+    if st is not None: rng_.append((st, prev))
+    print("B=1500: bad row ranges:", rng_, "max", ez.max())
+    em = np.abs(z.cpu().numpy() - ref)
+    for (a0, a1) in rng_[:3]:
+        cols = sorted(set(np.argwhere(em[a0:a1 + 1] > 1e-3)[:, 1].tolist()))
+        print(f"   rows {a0}-{a1}: {len(cols)} bad cols: {cols}")
+        print("   ld err there:", np.abs(ld.cpu().numpy()[a0:a0 + 3] - np.tile(sum(a[f'ld_f64__{i}'] for i in range(4)), 40)[:1500][a0:a0 + 3]))
+    for L_ in (1, 3):
+        zz = cuda(xb)
+        for i in range(L_, -1, -1):
+            zz, _ = model.flows[i].inverse(zz)
+        if L_ == 3:
+            print("per-layer path max err", np.abs(zz.cpu().numpy() - ref).max())
