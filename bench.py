@@ -170,6 +170,7 @@ def main():
     import torch.distributed as dist
     import normflows as nf
     from normflows.parallel import forward_kld_dp
+    torch.set_grad_enabled(False)  # the metric is the forward pass (timed under torch.no_grad())
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))

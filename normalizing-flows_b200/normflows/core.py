@@ -71,16 +71,23 @@ class NormalizingFlow(nn.Module):
             log_det = log_det + ld
         return x, log_det
 
+    def _wants_grad(self, x):
+        return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters()))
+
     def log_prob(self, x):
         h = self._stack()
         if h is not None and h.base is not None and x.dim() == 2 and not self._needs_eager_init():
+            if self._wants_grad(x):  # forward on the CUDA kernels, backward via _autograd (interim)
+                from ._autograd import DensityFn
+                return DensityFn.apply(self, x, *self.parameters())
             return h.log_prob(x)
         z, log_q = self.inverse_and_log_det(x)
         return log_q + self.q0.log_prob(z)
 
     def forward_kld(self, x):
         h = self._stack()
-        if h is not None and h.base is not None and x.dim() == 2 and not self._needs_eager_init():
+        if (h is not None and h.base is not None and x.dim() == 2 and not self._needs_eager_init()
+                and not self._wants_grad(x)):
             return h.forward_kld(x)
         return -torch.mean(self.log_prob(x))
 

@@ -34,3 +34,13 @@ def load_golden(name):
 @pytest.fixture(scope="session")
 def golden():
     return load_golden
+
+
+@pytest.fixture(autouse=True)
+def _no_grad_by_default():
+    """The parity tests exercise the density pass; gradient tests opt in with torch.enable_grad()."""
+    import torch
+    prev = torch.is_grad_enabled()
+    torch.set_grad_enabled(False)
+    yield
+    torch.set_grad_enabled(prev)

@@ -240,5 +240,25 @@ def main():
     case_glow()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def case_grads():
+    """Gradients of forward_kld w.r.t. every parameter and the input (fp64), for the autograd check."""
+    for kind in ("ar", "coupled"):
+        m, spec = nsf(kind, 5, 3, 128, 2, seed=20, sigma=0.1, lu_identity=False)
+        m = m.double()
+        x = (torch.randn(64, 5, generator=torch.Generator().manual_seed(21)) * 1.5).double().requires_grad_(True)
+        loss = m.forward_kld(x)
+        loss.backward()
+        out = {"x": x.detach().numpy(), "kld": loss.detach().numpy(), "grad__x": x.grad.numpy()}
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                out["grad__" + k] = p.grad.numpy()
+        np.savez_compressed(os.path.join(HERE, f"grads_nsf_{kind}_d5_h128_l3.npz"), **out)
+        print("wrote grads", kind, len(out))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "grads":
+    case_grads()
