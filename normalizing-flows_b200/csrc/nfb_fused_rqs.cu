@@ -32,7 +32,11 @@
 
 namespace nfb {
 
-constexpr int kFusedThreads = 320;
+constexpr int kNG = 4;                         // epilogue column groups (warps per TMEM lane quadrant)
+constexpr int kEpiWarps = 4 * kNG;             // 16 epilogue warps: 4 per SM sub-partition (latency hiding by TLP)
+constexpr int kEpiThreads = 32 * kEpiWarps;    // 512
+constexpr int kFusedThreads = kEpiThreads + 64;  // + TMA producer warp + MMA issuer warp
+constexpr int kGC = 64 / kNG;                  // columns of a 64-column K-chunk handled per thread (16)
 constexpr uint32_t kTileA = 16384;    // one [128 x 64] bf16 SW128 tile
 constexpr uint32_t kSlotBytes = 32768;  // one record = up to [256 rows x 64 K] bf16
 constexpr int kSlots = 2;
@@ -44,8 +48,8 @@ constexpr uint32_t kMaxSteps = 256;
 constexpr uint32_t kOffBars = kOffSteps + kMaxSteps * 8;  // 231424
 constexpr uint32_t kNumBars = 24;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;  // 231568
-constexpr uint32_t kOffLd = kOffTmemPtr + 16;              // 231584
-constexpr uint32_t kFusedSmem = kOffLd + 128 * 4;          // 232096 <= 232448
+constexpr uint32_t kOffLd = kOffSteps;                     // log-det partials [kNG-1][128] (the old step-table area)
+constexpr uint32_t kFusedSmem = kOffTmemPtr + 16;          // 231584 <= 232448
 static_assert(kFusedSmem <= 232448, "shared memory budget");
 
 // barrier indices
@@ -69,7 +73,7 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
                  : "memory");
 }
 __device__ __forceinline__ void epi_bar_sync() {  // the 256 epilogue threads only
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
 // split 8 consecutive fp32 values into bf16 hi / lo (/ lo2) chunks and store them at the same
@@ -114,13 +118,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             mbar_init(bar(kBarWFull + i), 1);
             mbar_init(bar(kBarWEmpty + i), 1);
             mbar_init(bar(kBarCFull + i), 1);
-            mbar_init(bar(kBarCEmpty + i), 8);
+            mbar_init(bar(kBarCEmpty + i), kEpiWarps);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(bar(kBarAReady + i), 8);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(kBarAReady + i), kEpiWarps);
         mbar_init(bar(kBarAccFull), 1);
         fence_mbar_init();
     }
-    if (warp == 9) {
+    if (warp == kEpiWarps + 1) {
         tmem_alloc(sbase + kOffTmemPtr, 512);
         tmem_relinquish();
     }
@@ -133,8 +137,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     const long long n_units = n_tiles * p.n_layers;  // (layer, tile) work units, layer-major
 
     // Warp roles: the SM arbiter favours high warp ids, so the two latency-critical single-lane roles
-    // (TMA producer = warp 8, MMA issuer = warp 9) sit above the eight epilogue warps (0-7).
-    if (warp == 8) {
+    // (TMA producer, MMA issuer) sit above the epilogue warps (0..kEpiWarps-1).
+    if (warp == kEpiWarps) {
         // ------------------------------ weight producer -----------------------------------
         // whole warp walks the table (warp-uniform control flow); one elected lane issues the copy
         uint32_t slot = 0, par = 0;
@@ -157,7 +161,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 if (++slot == kSlots) { slot = 0; par ^= 1; }
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == kEpiWarps + 1) {
         // ------------------------------ MMA issuer ----------------------------------------
         // Warp-uniform loop; the MMAs of one weight record are issued by one elected lane from
         // descriptors that differ only by an add on the 14-bit address field (16-byte units).
@@ -224,9 +228,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         }
     } else {
         // ------------------------------ epilogue warps ------------------------------------
-        const int et = threadIdx.x;            // 0..255
+        const int et = threadIdx.x;            // 0..kEpiThreads-1
         const int q = warp & 3;                // TMEM lane quadrant this warp may touch
-        const int wh = warp >> 2;              // column half
+        const int wh = warp >> 2;              // column group 0..kNG-1
         const int r = q * 32 + lane;           // tile row owned by this thread
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t aA = sbase + kOffA;
@@ -244,18 +248,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             const long long row0 = tile * 128;
             if (u != blockIdx.x) prof = nullptr;
             auto build_a = [&](bool lu_stage) {
-                // A[:, k] for k in [wh*32, wh*32+32): lu_stage -> 3-way split of xs[:, k] (k < D);
+                // A[:, k] for k in [wh*kGC, (wh+1)*kGC): lu_stage -> 3-way split of xs[:, k] (k < D);
                 // otherwise 2-way split of the conditioner input xs[:, in_idx[k]].
     #pragma unroll
-                for (int g = 0; g < 4; ++g) {
+                for (int g = 0; g < kGC / 8; ++g) {
                     float v[8];
     #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int k = wh * 32 + g * 8 + j;
+                        const int k = wh * kGC + g * 8 + j;
                         int c = lu_stage ? (k < D ? k : -1) : L.in_idx[k];
                         v[j] = c >= 0 ? xs[xs_index(r, c)] : 0.f;
                     }
-                    const uint32_t off = a_chunk_off(r, wh * 4 + g);
+                    const uint32_t off = a_chunk_off(r, wh * (kGC / 8) + g);
                     if (lu_stage) split_store8<3>(v, aA, aA + 4 * kTileA, aA + 1 * kTileA, off);
                     else split_store8<2>(v, aA, aA + 4 * kTileA, 0, off);
                 }
@@ -289,24 +293,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             NFB_STAMP();  // [0] tile start
             // ---- load z tile -> xs (coalesced global, swizzled shared) ----
             if (D == 64) {
-                float4 v[8];
+                float4 v[2048 / kEpiThreads];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i4 = et + k * 256, rr = i4 >> 4;
+                for (int k = 0; k < 2048 / kEpiThreads; ++k) {
+                    const int i4 = et + k * kEpiThreads, rr = i4 >> 4;
                     const long long gr = row0 + rr;
                     v[k] = gr < p.rows ? __ldcg(reinterpret_cast<const float4*>(zsrc + gr * 64) + (i4 & 15))
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i4 = et + k * 256, rr = i4 >> 4, c0 = (i4 & 15) * 4;
+                for (int k = 0; k < 2048 / kEpiThreads; ++k) {
+                    const int i4 = et + k * kEpiThreads, rr = i4 >> 4, c0 = (i4 & 15) * 4;
                     xs[xs_index(rr, c0)] = v[k].x;
                     xs[xs_index(rr, c0 + 1)] = v[k].y;
                     xs[xs_index(rr, c0 + 2)] = v[k].z;
                     xs[xs_index(rr, c0 + 3)] = v[k].w;
                 }
             } else {
-                for (int i = et; i < 128 * D; i += 256) {
+                for (int i = et; i < 128 * D; i += kEpiThreads) {
                     const int rr = i / D, cc = i - rr * D;
                     const long long gr = row0 + rr;
                     xs[xs_index(rr, cc)] = gr < p.rows ? __ldcg(zsrc + gr * D + cc) : 0.f;
@@ -322,14 +326,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 NFB_STAMP();  // LU gemm done
                 afpar ^= 1;
                 tc_fence_after();
-                // x' = acc + b  (64 columns at TMEM col 256; this thread: 32 of them)
-                uint32_t acc[32];
-                NFB_TMEM_LD32(tlane + 256 + wh * 32, acc);
+                // x' = acc + b  (64 columns at TMEM col 256; this thread: kGC of them)
+                uint32_t acc[kGC];
+                NFB_TMEM_LD16(tlane + 256 + wh * kGC, acc);
                 tc_wait_ld();
                 epi_bar_sync();  // every thread has built A from the old xs before it is overwritten
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const int c = wh * 32 + j;
+                for (int j = 0; j < kGC; ++j) {
+                    const int c = wh * kGC + j;
                     if (c < D) xs[xs_index(r, c)] = __uint_as_float(acc[j]) + __ldg(L.bias_lu + c);
                 }
                 epi_bar_sync();
@@ -341,7 +345,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             //      the tensor core is busy with the first GEMMs.  The conditioner input was taken
             //      from the raw values above (Coupling.forward, neural_spline/coupling.py:80-92).
             if (L.n_id > 0) {
-                const int per = (L.n_id + 1) / 2;
+                const int per = (L.n_id + kNG - 1) / kNG;
                 for (int i = wh * per; i < min(L.n_id, (wh + 1) * per); ++i) {
                     const int c = L.id_idx[i];
                     const float* tb = L.uncond + i * 23;
@@ -364,21 +368,27 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 // K-chunk order: both column halves convert the same 64 columns, then release that slice of
                 // the next A operand so the next GEMM's kc-step can start while the rest is converted
                 for (int kc = 0; kc < (H >> 6); ++kc) {
-                    const int c0 = kc * 64 + wh * 32;
-                    uint32_t acc[32];
-                    NFB_TMEM_LD32(tlane + region + c0, acc);
-                    const float* bf = L.bias_h + ph * 256 + c0;  // constant bank, warp-uniform index
-                    tc_wait_ld();
-                    float v[32];
+                    const int c0 = kc * 64 + wh * kGC;
+                    uint32_t acc[kGC];
+                    NFB_TMEM_LD16(tlane + region + c0, acc);
+                    const float4* bf = reinterpret_cast<const float4*>(L.bias_h + ph * 256 + c0);  // warp-uniform
+                    float bv[kGC];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        float t = __uint_as_float(acc[j]) + bf[j];
+                    for (int j = 0; j < kGC / 4; ++j) {
+                        const float4 q = __ldg(bf + j);
+                        bv[4 * j] = q.x; bv[4 * j + 1] = q.y; bv[4 * j + 2] = q.z; bv[4 * j + 3] = q.w;
+                    }
+                    tc_wait_ld();
+                    float v[kGC];
+#pragma unroll
+                    for (int j = 0; j < kGC; ++j) {
+                        float t = __uint_as_float(acc[j]) + bv[j];
                         v[j] = relu ? fmaxf(t, 0.f) : t;
                     }
                     const uint32_t thi = aA + kc * kTileA, tlo = aA + (4 + kc) * kTileA;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        split_store8<2>(v + 8 * j, thi, tlo, 0, a_chunk_off(r, wh * 4 + j));
+                    for (int j = 0; j < kGC / 8; ++j)
+                        split_store8<2>(v + 8 * j, thi, tlo, 0, a_chunk_off(r, wh * (kGC / 8) + j));
                     fence_proxy_async_smem();
                     tc_fence_before();
                     __syncwarp();
@@ -388,8 +398,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             }
 
             // ---- final layer chunks -> spline ----
-            // chunk = F features x 24 columns (N = 24 F <= 240); this thread: F/2 of them, one at a time
-            const int fh = L.F >> 1;
+            // chunk = F features x 24 columns (N = 24 F <= 240).  The F features are dealt round-robin to the kNG
+            // column groups (feature f of the chunk -> group f % kNG); one evaluation at a time per thread,
+            // latency is hidden by the four warps per SM sub-partition.
             for (int ci = 0; ci < L.n_chunks; ++ci) {
                 // Processing slot 0 -> buffer 1 (columns 256..): the last hidden epilogue is still reading the
                 // residual stream (columns 0..255) when the first final-layer MMAs start.  The packer puts a
@@ -397,77 +408,78 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 // (= the epilogue has finished reading columns 0..255) before slot 1 overwrites buffer 0.
                 const int b = (ci + 1) & 1;
                 const int c = L.chunk_order[ci];
-                const int t0 = c * L.F + wh * fh;  // first transformed-feature slot of this thread
                 mbar_wait(bar(kBarCFull + b), (cfbits >> b) & 1u, p.err, 400 + b);
                 cfbits ^= 1u << b;
                 tc_fence_after();
                 NFB_STAMP();  // chunk c available
-                const uint32_t ta = tlane + chunk_col(b) + wh * fh * 24;
-                for (int f = 0; f < fh; f += 2) {
-                    // two independent evaluations in one basic block (ILP): features tA and tB
-                    const bool hasB = f + 1 < fh;          // warp-uniform
-                    const int tA = t0 + f, tB = tA + 1;
-                    uint32_t prA[24], prB[24];
-                    NFB_TMEM_LD16(ta + f * 24, prA);
-                    NFB_TMEM_LD8(ta + f * 24 + 16, prA + 16);
-                    if (hasB) {
-                        NFB_TMEM_LD16(ta + f * 24 + 24, prB);
-                        NFB_TMEM_LD8(ta + f * 24 + 40, prB + 16);
-                    } else {
+                const uint32_t ta = tlane + chunk_col(b);
+                for (int f = wh; f < L.F; f += kNG) {
+                    const int t = c * L.F + f;
+                    uint32_t pr[24];
+                    NFB_TMEM_LD16(ta + f * 24, pr);
+                    NFB_TMEM_LD8(ta + f * 24 + 16, pr + 16);
+                    const float4* bp = reinterpret_cast<const float4*>(L.bias_f + t * 24);  // warp-uniform
+                    float bv[24];
 #pragma unroll
-                        for (int j = 0; j < 24; ++j) prB[j] = 0u;
+                    for (int j = 0; j < 6; ++j) {
+                        const float4 q = __ldg(bp + j);
+                        bv[4 * j] = q.x; bv[4 * j + 1] = q.y; bv[4 * j + 2] = q.z; bv[4 * j + 3] = q.w;
                     }
                     tc_wait_ld();
-                    if (f + 2 >= fh) {  // all of this thread's columns are in registers: free the buffer
+                    if (f + kNG >= L.F) {  // all of this thread's columns are in registers: free the buffer
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
                     }
-                    const bool okA = tA < L.T, okB = hasB && tB < L.T;
-                    const int colA = L.tr_idx[okA ? tA : 0], colB = L.tr_idx[okB ? tB : 0];
-                    const float* bA = L.bias_f + tA * 24;
-                    const float* bB = L.bias_f + (hasB ? tB : tA) * 24;
-                    float pvA[24], pvB[24];
+                    if (t < L.T) {
+                        // the packer folded log2(e) (and the layer's 1/sqrt(H)) into the w/h columns and biases
+                        float lw[8], lh[8], dd[8];
 #pragma unroll
-                    for (int j = 0; j < 24; ++j) {
-                        pvA[j] = __uint_as_float(prA[j]) + bA[j];
-                        pvB[j] = __uint_as_float(prB[j]) + bB[j];
+                        for (int j = 0; j < 8; ++j) {
+                            lw[j] = __uint_as_float(pr[j]) + bv[j];
+                            lh[j] = __uint_as_float(pr[8 + j]) + bv[8 + j];
+                            dd[j] = __uint_as_float(pr[16 + j]) + bv[16 + j];
+                        }
+                        const int col = L.tr_idx[t];
+                        float y, l;
+                        rqs_core<8, false>(xs[xs_index(r, col)], lw, lh, [&dd](int k) { return dd[k]; }, L.tail, y, l);
+                        xs[xs_index(r, col)] = y;
+                        ladsum += l;
                     }
-                    auto accA = [&pvA](int k) { return pvA[k]; };
-                    auto accB = [&pvB](int k) { return pvB[k]; };
-                    const float xA = xs[xs_index(r, colA)], xB = xs[xs_index(r, colB)];
-                    float yA, lA, yB, lB;
-                    rqs_eval<8, false>(xA, accA, L.tail, 1.0f, yA, lA);
-                    rqs_eval<8, false>(xB, accB, L.tail, 1.0f, yB, lB);
-                    if (okA) { xs[xs_index(r, colA)] = yA; ladsum += lA; }
-                    if (okB) { xs[xs_index(r, colB)] = yB; ladsum += lB; }
+                }
+                if (wh >= L.F) {  // (F < kNG: this group had no feature in the chunk) still release the buffer
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
                 }
                 NFB_STAMP();  // chunk c consumed
             }
 
             NFB_STAMP();  // last spline done
             // ---- log-det reduction across the two column halves, then store ----
-            if (wh == 1) ldsum[r] = ladsum;
+            if (wh > 0) ldsum[(wh - 1) * 128 + r] = ladsum;
             epi_bar_sync();
             if (wh == 0) {
                 const long long gr = row0 + r;
                 if (gr < p.rows) {
-                    float tot = ladsum + ldsum[r] + (L.lu_logdet ? __ldg(L.lu_logdet) : 0.f);
+                    float tot = ladsum + (L.lu_logdet ? __ldg(L.lu_logdet) : 0.f);
+#pragma unroll
+                    for (int g = 0; g < kNG - 1; ++g) tot += ldsum[g * 128 + r];
                     if (layer > 0 || p.accumulate) tot += __ldcg(p.logq + gr);
                     __stcg(p.logq + gr, tot);
                 }
             }
             if (D == 64) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int i4 = et + k * 256, rr = i4 >> 4, c0 = (i4 & 15) * 4;
+                for (int k = 0; k < 2048 / kEpiThreads; ++k) {
+                    const int i4 = et + k * kEpiThreads, rr = i4 >> 4, c0 = (i4 & 15) * 4;
                     const long long gr = row0 + rr;
                     const float4 v = make_float4(xs[xs_index(rr, c0)], xs[xs_index(rr, c0 + 1)],
                                                  xs[xs_index(rr, c0 + 2)], xs[xs_index(rr, c0 + 3)]);
                     if (gr < p.rows) __stcg(reinterpret_cast<float4*>(p.zout + gr * 64) + (i4 & 15), v);
                 }
             } else {
-                for (int i = et; i < 128 * D; i += 256) {
+                for (int i = et; i < 128 * D; i += kEpiThreads) {
                     const int rr = i / D, cc = i - rr * D;
                     const long long gr = row0 + rr;
                     if (gr < p.rows) __stcg(p.zout + gr * D + cc, xs[xs_index(rr, cc)]);
@@ -488,7 +500,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) tmem_dealloc(tmem, 512);
+    if (warp == kEpiWarps + 1) tmem_dealloc(tmem, 512);
 }
 
 int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st) {
@@ -517,7 +529,7 @@ __global__ void build_effective_kernel(const float* __restrict__ W, const float*
                                        int src_cols, const int* __restrict__ src_row,
                                        const int* __restrict__ src_col,
                                        const float* __restrict__ row_scale, float* __restrict__ E,
-                                       int n_pad, int k_pad) {
+                                       int n_pad, int k_pad, float gain) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_pad * k_pad) return;
     const int i = idx / k_pad, j = idx - i * k_pad;
@@ -528,6 +540,7 @@ __global__ void build_effective_kernel(const float* __restrict__ W, const float*
         v = W[o];
         if (M) v *= M[o];
         if (row_scale) v *= row_scale[i];
+        v *= gain;
     }
     E[idx] = v;
 }
@@ -576,10 +589,10 @@ int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, u
 
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
                            const int* src_col, const float* row_scale, float* E, int n_pad,
-                           int k_pad, cudaStream_t st) {
+                           int k_pad, float gain, cudaStream_t st) {
     const int n = n_pad * k_pad;
     build_effective_kernel<<<(n + 255) / 256, 256, 0, st>>>(W, M, src_cols, src_row, src_col,
-                                                            row_scale, E, n_pad, k_pad);
+                                                            row_scale, E, n_pad, k_pad, gain);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

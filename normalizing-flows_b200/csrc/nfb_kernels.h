@@ -93,8 +93,8 @@ struct FusedLayer {
     unsigned char tr_idx[64];  // transformed feature columns
     unsigned char id_idx[64];  // identity feature columns (coupled layer)
     unsigned char chunk_order[16];  // final-layer chunks in processing order (first one reads every K-chunk)
-    float bias_h[7 * 256];   // [n_hidden <= 7][256], residual biases pre-summed along the stream
-    float bias_f[82 * 24];   // [(n_chunks+1)*F <= 82][24] final-layer bias in chunk/column order
+    alignas(16) float bias_h[7 * 256];   // [n_hidden <= 7][256], residual biases pre-summed along the stream
+    alignas(16) float bias_f[82 * 24];   // [(n_chunks+1)*F <= 82][24] final-layer bias in chunk/column order
 };
 // Launch arguments.  Work units are (layer, 128-row tile) pairs in layer-major order; unit (l, t) may start
 // once progress[t] >= l.  Rows of a tile are private to it, so layers l >= 1 update `zout` in place.
@@ -113,7 +113,7 @@ struct FusedParams {
 int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st);
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
                            const int* src_col, const float* row_scale, float* E, int n_pad,
-                           int k_pad, cudaStream_t st);
+                           int k_pad, float gain, cudaStream_t st);
 int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, uint8_t* out_hi,
                        uint8_t* out_lo, cudaStream_t st);
 int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit,

@@ -64,86 +64,126 @@ __host__ __device__ __forceinline__ float softplus_f(float u) {
 // The unnormalised boundary derivative, as the reference computes it in fp32 (:36).
 #define NFB_BOUNDARY_UD 0.5397424f /* float32(log(exp(1 - 1e-3) - 1)) = 0.5397424172... */
 
+// Core evaluator.  lw / lh are the width / height logits already multiplied by log2(e) (and by the
+// layer's 1/sqrt(hidden) where it has one); D(i) returns the i-th of the K-1 raw interior derivative
+// parameters.  Everything between the softmax and the rational function is done on the unit interval
+// u = (x + B) / 2B: knot i+1 is  a * prefix_i + 1e-3 (i+1)  with a = (1 - 1e-3 K) / sum -- one FMA per
+// knot on a running sum that the softmax needs anyway (theta, delta and the derivative terms are scale
+// free; only the output is mapped back with one FMA).  The knot positions differ from the reference's
+// cumsum-then-scale order by a few ulp of B, far inside the tolerance; which side an x within that
+// distance of a knot falls on is immaterial because the spline and its derivative are continuous there.
+// K = 8 (the reference default) locates the bin by bisection on the 9 knots: 3 compares + 30 selects
+// carrying {left, right} of both axes and the two derivative logits, instead of a 7-step scan.
+template <int K, bool INVERSE, typename PD>
+__host__ __device__ __forceinline__ void rqs_core(float x, const float (&lw)[K], const float (&lh)[K], PD pd,
+                                                  float tail, float& y, float& lad) {
+    const bool inside = (x >= -tail) && (x <= tail);
+    float mw = lw[0], mh = lh[0];
+#pragma unroll
+    for (int i = 1; i < K; ++i) {
+        mw = fmaxf(mw, lw[i]);
+        mh = fmaxf(mh, lh[i]);
+    }
+    float cw[K], ch[K];
+    float sw = 0.f, sh = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        sw += fast_ex2(lw[i] - mw);
+        sh += fast_ex2(lh[i] - mh);
+        cw[i] = sw;
+        ch[i] = sh;
+    }
+    const float aw = (1.f - kMinBinWidth * K) * fast_rcp(sw);
+    const float ah = (1.f - kMinBinHeight * K) * fast_rcp(sh);
+    float kw[K + 1], kh[K + 1], ud[K + 1];
+    kw[0] = 0.f; kh[0] = 0.f; kw[K] = 1.f; kh[K] = 1.f;
+    ud[0] = NFB_BOUNDARY_UD; ud[K] = NFB_BOUNDARY_UD;
+#pragma unroll
+    for (int i = 0; i < K - 1; ++i) {
+        kw[i + 1] = fmaf(aw, cw[i], kMinBinWidth * (float)(i + 1));
+        kh[i + 1] = fmaf(ah, ch[i], kMinBinHeight * (float)(i + 1));
+        ud[i + 1] = pd(i);
+    }
+    const float two_b = 2.f * tail;
+    const float xu = fmaf(x, fast_rcp(two_b), 0.5f);
+    float l_w, r_w, l_h, r_h, ud0, ud1;
+    if (K == 8) {
+        const float* ks = INVERSE ? kh : kw;
+        const bool c1 = xu >= ks[4];
+        float a_w[5], a_h[5], a_d[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            a_w[j] = c1 ? kw[4 + j] : kw[j];
+            a_h[j] = c1 ? kh[4 + j] : kh[j];
+            a_d[j] = c1 ? ud[4 + j] : ud[j];
+        }
+        const bool c2 = xu >= (INVERSE ? a_h[2] : a_w[2]);
+        float b_w[3], b_h[3], b_d[3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            b_w[j] = c2 ? a_w[2 + j] : a_w[j];
+            b_h[j] = c2 ? a_h[2 + j] : a_h[j];
+            b_d[j] = c2 ? a_d[2 + j] : a_d[j];
+        }
+        const bool c3 = xu >= (INVERSE ? b_h[1] : b_w[1]);
+        l_w = c3 ? b_w[1] : b_w[0]; r_w = c3 ? b_w[2] : b_w[1];
+        l_h = c3 ? b_h[1] : b_h[0]; r_h = c3 ? b_h[2] : b_h[1];
+        ud0 = c3 ? b_d[1] : b_d[0]; ud1 = c3 ? b_d[2] : b_d[1];
+    } else {
+        l_w = kw[0]; r_w = kw[1]; l_h = kh[0]; r_h = kh[1]; ud0 = ud[0]; ud1 = ud[1];
+#pragma unroll
+        for (int i = 1; i < K; ++i) {
+            if (xu >= (INVERSE ? kh[i] : kw[i])) {  // knot i <= x
+                l_w = kw[i]; r_w = kw[i + 1]; l_h = kh[i]; r_h = kh[i + 1]; ud0 = ud[i]; ud1 = ud[i + 1];
+            }
+        }
+    }
+    const float in_w = r_w - l_w, in_h = r_h - l_h;
+    const float d0 = kMinDerivative + softplus_f(ud0);
+    const float d1 = kMinDerivative + softplus_f(ud1);
+    const float rw = fast_rcp(in_w);
+    const float delta = in_h * rw;
+    const float s = d0 + d1 - 2.f * delta;
+    float outu, theta, tomt, den;
+    if (INVERSE) {
+        const float t = xu - l_h;
+        const float a = t * s + in_h * (delta - d0);
+        const float b = in_h * d0 - t * s;
+        const float c = -delta * t;
+        const float disc = fmaxf(b * b - 4.f * a * c, 0.f);
+        theta = (2.f * c) / (-b - sqrtf(disc));
+        outu = theta * in_w + l_w;
+        tomt = theta * (1.f - theta);
+        den = delta + s * tomt;
+    } else {
+        theta = (xu - l_w) * rw;
+        tomt = theta * (1.f - theta);
+        den = delta + s * tomt;
+        const float num = in_h * (delta * theta * theta + d0 * tomt);
+        outu = l_h + num * fast_rcp(den);
+    }
+    const float omt = 1.f - theta;
+    const float dnum = delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * omt * omt);
+    float l = kLn2 * (fast_lg2(dnum) - 2.f * fast_lg2(den));
+    if (INVERSE) l = -l;
+    y = inside ? fmaf(outu, two_b, -tail) : x;
+    lad = inside ? l : 0.f;
+}
+
 // Param accessor: P(i) returns the i-th of the 3K-1 raw parameters [w(K) | h(K) | d(K-1)] of this
 // element.  `wh_scale` multiplies the w and h logits (1/sqrt(hidden) in the coupling layer,
 // neural_spline/coupling.py:334-336; 1 in the autoregressive layer and the unconditional CDF).
 template <int K, bool INVERSE, typename P>
 __host__ __device__ __forceinline__ void rqs_eval(float x, P p, float tail, float wh_scale, float& y,
                                          float& lad) {
-    const bool inside = (x >= -tail) && (x <= tail);
     const float s2 = wh_scale * kLog2e;
-    float ew[K], eh[K];
-    float mw = -3.0e38f, mh = -3.0e38f;
+    float lw[K], lh[K];
 #pragma unroll
     for (int i = 0; i < K; ++i) {
-        ew[i] = p(i) * s2;
-        eh[i] = p(K + i) * s2;
-        mw = fmaxf(mw, ew[i]);
-        mh = fmaxf(mh, eh[i]);
+        lw[i] = p(i) * s2;
+        lh[i] = p(K + i) * s2;
     }
-    float sw = 0.f, sh = 0.f;
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        ew[i] = fast_ex2(ew[i] - mw);
-        eh[i] = fast_ex2(eh[i] - mh);
-        sw += ew[i];
-        sh += eh[i];
-    }
-    const float kw = (1.f - kMinBinWidth * K) * fast_rcp(sw);
-    const float kh = (1.f - kMinBinHeight * K) * fast_rcp(sh);
-    const float two_b = 2.f * tail;
-
-    float cumw = 0.f, cumh = 0.f;
-    float left = -tail, bottom = -tail;
-    float in_cw = -tail, in_w = 1.f, in_ch = -tail, in_h = 1.f;
-    float ud0 = NFB_BOUNDARY_UD, ud1 = NFB_BOUNDARY_UD;
-#pragma unroll
-    for (int i = 0; i < K; ++i) {
-        cumw += kMinBinWidth + kw * ew[i];
-        cumh += kMinBinHeight + kh * eh[i];
-        const float right = (i == K - 1) ? tail : (two_b * cumw - tail);
-        const float top = (i == K - 1) ? tail : (two_b * cumh - tail);
-        const bool ge = INVERSE ? (x >= bottom) : (x >= left);  // knot i <= x ?
-        if (ge) {
-            in_cw = left;
-            in_w = right - left;
-            in_ch = bottom;
-            in_h = top - bottom;
-            ud0 = (i == 0) ? NFB_BOUNDARY_UD : p(2 * K + i - 1);
-            ud1 = (i == K - 1) ? NFB_BOUNDARY_UD : p(2 * K + i);
-        }
-        left = right;
-        bottom = top;
-    }
-    const float d0 = kMinDerivative + softplus_f(ud0);
-    const float d1 = kMinDerivative + softplus_f(ud1);
-    const float rw = fast_rcp(in_w);
-    const float delta = in_h * rw;
-    const float s = d0 + d1 - 2.f * delta;
-    float out, theta, tomt, den;
-    if (INVERSE) {
-        const float t = x - in_ch;
-        const float a = t * s + in_h * (delta - d0);
-        const float b = in_h * d0 - t * s;
-        const float c = -delta * t;
-        const float disc = fmaxf(b * b - 4.f * a * c, 0.f);
-        theta = (2.f * c) / (-b - sqrtf(disc));
-        out = theta * in_w + in_cw;
-        tomt = theta * (1.f - theta);
-        den = delta + s * tomt;
-    } else {
-        theta = (x - in_cw) * rw;
-        tomt = theta * (1.f - theta);
-        den = delta + s * tomt;
-        const float num = in_h * (delta * theta * theta + d0 * tomt);
-        out = in_ch + num * fast_rcp(den);
-    }
-    const float omt = 1.f - theta;
-    const float dnum = delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * omt * omt);
-    float l = kLn2 * (fast_lg2(dnum) - 2.f * fast_lg2(den));
-    if (INVERSE) l = -l;
-    y = inside ? out : x;
-    lad = inside ? l : 0.f;
+    rqs_core<K, INVERSE>(x, lw, lh, [&p](int i) { return p(2 * K + i); }, tail, y, lad);
 }
 
 // Runtime-K version (K <= 32) reading parameters through the accessor twice; used by the

@@ -148,6 +148,9 @@ def test_full_batch_properties(kind):
     idx = np.r_[0:96, 65500:B]
     ref = O.log_prob(spec, sd, x.numpy()[idx].astype(np.float64))
     np.testing.assert_allclose(lpn[idx], ref, rtol=RTOL, atol=ATOL)
+    # the tensor core accumulates with truncation; the packer compensates it (nfb_api.cu kAccStepGain).  Pin
+    # the residual: uncompensated, the median signed error of this stack is +1.2e-3 (ar) / +0.75e-3 (coupled).
+    assert abs(np.median(lpn[idx] - ref)) < 4e-4, np.median(lpn[idx] - ref)
     # the rows where the two GPU paths disagree most: judge each against fp64 truth, relative to what the
     # reference's own fp32 arithmetic (the oracle run in float32) loses on the very same rows
     worst = np.argsort(disc)[-24:]

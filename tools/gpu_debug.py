@@ -4,6 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "normalizing-flows_b200"), os.path.join(ROOT, "tests")]
 import numpy as np
 import torch
+torch.set_grad_enabled(False)  # debug runs compare raw outputs; the autograd hook would tag them
 import normflows as nf
 from normflows.flows.base import NativeFlow
 from conftest import load_golden
@@ -180,3 +181,21 @@ if mode == "stackdbg":
             zz, _ = model.flows[i].inverse(zz)
         if L_ == 3:
             print("per-layer path max err", np.abs(zz.cpu().numpy() - ref).max())
+
+if mode == "bias":
+    # signed error of log_prob against the fp64 oracle on the rough test model: is the fused path biased?
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "tests"))
+    from test_gpu_parity import _random_model, _oracle_of
+    for kind in ("ar", "coupled"):
+        model = _random_model(kind, 64, 4, 256).cuda()
+        spec, sd = _oracle_of(model, kind, 64, 4, 256)
+        x = torch.randn(3000, 64, generator=torch.Generator().manual_seed(1234)) * 1.5
+        ref = O.log_prob(spec, sd, x.numpy().astype(np.float64))
+        for tc in (True, False):
+            NativeFlow.use_tensor_cores = tc
+            lp = model.log_prob(x.cuda()).cpu().numpy().astype(np.float64)
+            e = lp - ref
+            rel = np.abs(e) / np.abs(ref)
+            print(f"bias {kind} tc={tc} comp={os.environ.get('NFB_ACC_COMP_STEP','default')}: mean signed {e.mean():+.3e} median {np.median(e):+.3e} "
+                  f"rms {np.sqrt((e**2).mean()):.3e} | rel mean {rel.mean():.2e} p99 {np.quantile(rel,0.99):.2e} max {rel.max():.2e}", flush=True)
+        NativeFlow.use_tensor_cores = True
