@@ -1219,8 +1219,8 @@ int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, 
 /* debug-only (not part of the ABI header): phase timestamps of CTA 0's first tile */
 __attribute__((visibility("default"))) int nfb_debug_profile(nfb_flow_t* f, int enable, long long* out128) {
     if (!f) return NFB_ERR_ARG;
-    if (enable) { NFB_TRY(f->prof.reserve(128 * 8)); NFB_CUDA(cudaMemset(f->prof.p, 0, 128 * 8)); return NFB_OK; }
-    if (f->prof.p && out128) NFB_CUDA(cudaMemcpy(out128, f->prof.p, 128 * 8, cudaMemcpyDeviceToHost));
+    if (enable) { NFB_TRY(f->prof.reserve(512 * 8)); NFB_CUDA(cudaMemset(f->prof.p, 0, 512 * 8)); return NFB_OK; }
+    if (f->prof.p && out128) NFB_CUDA(cudaMemcpy(out128, f->prof.p, 512 * 8, cudaMemcpyDeviceToHost));
     return NFB_OK;
 }
 

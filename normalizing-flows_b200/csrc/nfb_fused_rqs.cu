@@ -39,10 +39,13 @@ constexpr int kFusedThreads = kEpiThreads + 64;  // + TMA producer warp + MMA is
 constexpr int kGC = 64 / kNG;                  // columns of a 64-column K-chunk handled per thread (16)
 constexpr uint32_t kTileA = 16384;    // one [128 x 64] bf16 SW128 tile
 constexpr uint32_t kSlotBytes = 32768;  // one record = up to [256 rows x 64 K] bf16
-constexpr int kSlots = 2;
+#ifndef NFB_SLOTS
+#define NFB_SLOTS 2
+#endif
+constexpr int kSlots = NFB_SLOTS;  // (3 = timing experiment only: the third slot overlays the x tile)
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffW = 131072;
-constexpr uint32_t kOffX = kOffW + kSlots * kSlotBytes;  // 196608
+constexpr uint32_t kOffX = kOffW + 2 * kSlotBytes;  // 196608
 constexpr uint32_t kOffSteps = kOffX + 32768;            // 229376
 constexpr uint32_t kMaxSteps = 256;
 constexpr uint32_t kOffBars = kOffSteps + kMaxSteps * 8;  // 231424
@@ -192,6 +195,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
                 mbar_wait(bar(kBarWFull + slot), wpar, p.err, 220 + slot);
                 tc_fence_after();
+                if (p.prof && u == 0 && s < 380 && lane == 0) p.prof[128 + s] = clock64();  // debug: issue time
                 if (elect_one_sync()) {
                     const uint32_t d = tmem + (ctl & 511u);
                     const uint32_t idesc = kIdesc0 | ((uint32_t)st.n8 << 17);
@@ -413,7 +417,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 tc_fence_after();
                 NFB_STAMP();  // chunk c available
                 const uint32_t ta = tlane + chunk_col(b);
-                for (int f = wh; f < L.F; f += kNG) {
+                // rotate the deal by the chunk index: with F = 10 the groups get 3,3,2,2 features of a chunk, and
+                // a fixed deal would give groups 0/1 half as much work again as groups 2/3 over the tile
+                const int f0 = (wh + ci) & (kNG - 1);
+                for (int f = f0; f < L.F; f += kNG) {
                     const int t = c * L.F + f;
                     uint32_t pr[24];
                     NFB_TMEM_LD16(ta + f * 24, pr);
@@ -447,7 +454,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         ladsum += l;
                     }
                 }
-                if (wh >= L.F) {  // (F < kNG: this group had no feature in the chunk) still release the buffer
+                if (f0 >= L.F) {  // (F < kNG: this group had no feature in the chunk) still release the buffer
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));

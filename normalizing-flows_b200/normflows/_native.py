@@ -8,7 +8,11 @@ import ctypes as C
 
 import torch
 
+import operator
+
 from . import _lib as L
+
+_VERSION = operator.attrgetter("_version")
 
 
 def require_cuda_f32(t, what="input"):
@@ -32,6 +36,8 @@ class FlowHandle:
         self._sig_ptr = None
         self._sig_ver = None
         self._features = None
+        self._slots = None
+        self._calls = 0
 
     # -- lifetime -------------------------------------------------------------------------
     def close(self):
@@ -45,7 +51,7 @@ class FlowHandle:
         except Exception:
             pass
 
-    def _tensors(self):
+    def _tensors_slow(self):
         ts = []
         for layer in self.layers:
             ts.extend(layer._native_tensors())
@@ -53,17 +59,53 @@ class FlowHandle:
             ts.extend([self.base.loc, self.base.log_scale])
         return ts
 
+    def _build_slots(self):
+        """Walking the module tree through nn.Module.__getattr__ costs ~1.3 ms for a 32-block stack -- more than
+        a fifth of the fused kernel's run time and fully exposed on the synchronous host path.  Remember WHERE
+        each tensor lives instead ((module._parameters | module._buffers, name) pairs): a per-call refresh is
+        then one dict lookup per tensor (~40 us) and still sees `.to()`, `load_state_dict`, optimizer steps and
+        re-registered parameters, because it re-reads the dict entries rather than caching the tensors."""
+        ts = self._tensors_slow()
+        where = {}
+        mods = list(self.layers) + ([self.base] if self.base is not None else [])
+        for root in mods:
+            for m in root.modules():
+                for d in (m._parameters, m._buffers):
+                    for k, v in d.items():
+                        if v is not None:
+                            where.setdefault(id(v), (d, k))
+        slots = [where.get(id(t)) for t in ts]
+        self._slots = None if any(sl is None for sl in slots) else slots  # plain-attribute tensor: slow path
+        self._calls = 0
+        return ts
+
+    def _tensors(self):
+        self._calls += 1
+        if self._slots is None or self._calls & 255 == 0:
+            # every 256th call re-derive the list the slow way: catches a sub-module OBJECT that was swapped
+            # out after the first call (the only change the dict slots cannot see)
+            ts = self._tensors_slow()
+            if self._slots is not None and any(d[k] is not t for (d, k), t in zip(self._slots, ts)):
+                ts = self._build_slots()
+            return ts
+        return [d[k] for d, k in self._slots]
+
     def ensure(self, features, device):
-        ts = self._tensors()
-        for t in ts:
+        if self._h is None and self._slots is None:
+            ts = self._build_slots()
+        else:
+            ts = self._tensors()
+        sig_ptr = (*map(torch.Tensor.data_ptr, ts), features, device.index)
+        sig_ver = tuple(map(_VERSION, ts))
+        if sig_ptr == self._sig_ptr and sig_ver == self._sig_ver and self._h is not None:
+            return self._h
+        for t in ts:  # validated whenever anything changed (new tensors, new device, first call)
             if t.device != device:
                 raise RuntimeError(f"parameter on {t.device} but input on {device}: call model.to(device)")
             if t.dtype.is_floating_point and t.dtype != torch.float32:
                 raise RuntimeError(f"parameter dtype {t.dtype}: the CUDA path computes in float32 only")
             if not t.is_contiguous():
                 raise RuntimeError("non-contiguous parameter")
-        sig_ptr = tuple(t.data_ptr() for t in ts) + (features, device.index)
-        sig_ver = tuple(t._version for t in ts)
         lib = L.lib()
         with torch.cuda.device(device):
             if self._h is None or sig_ptr != self._sig_ptr:

@@ -115,13 +115,15 @@ if mode == "prof":
         lib.nfb_debug_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.nfb_debug_profile(h, 1, None)
         m.forward_kld(x); torch.cuda.synchronize()
-        buf = (C.c_longlong * 128)()
+        buf = (C.c_longlong * 512)()
         lib.nfb_debug_profile(h, 0, buf)
         n = buf[127]
         t = [buf[i] - buf[0] for i in range(n)]
         print(f"prof {kind}: {n} stamps (cycles since tile start; deltas)")
         print("  abs  :", t)
         print("  delta:", [t[i] - t[i - 1] for i in range(1, n)])
+        mm = [buf[128 + i] - buf[0] for i in range(380) if buf[128 + i]]
+        print(f"  mma issue times ({len(mm)} steps):", mm)
 
 if mode == "spline":
     import ctypes as C
