@@ -127,6 +127,11 @@ struct FusedPack {
     DevBuf pair_wstream, pair_steps_dev, lu_src_row, lu_src_col, bias_lu;
     FusedLayer host_layer{}, host_pair{};  // packed descriptors (host copies)
     DevBuf layer_dev, pair_dev;           // ... and their device images (one FusedLayer each)
+    // sampling direction (coupling layers only): [inverse LU map of the PREVIOUS layer in list order + this
+    // block, spline inverted] as one unit of the forward whole-stack launch
+    bool fwd_ok = false;
+    DevBuf fwd_wstream, fwd_steps_dev, fwd_src_row, fwd_src_col, fwd_bias_lu;
+    FusedLayer host_fwd{};
 };
 
 struct Layer {
@@ -145,8 +150,9 @@ struct Layer {
     DevBuf uncond;          // [n_id][3K-1]
     // lu
     nfb_lu_desc_t lu{};
-    DevBuf lu_Wd, lu_Ws, lu_bs, lu_logdet, lu_perm, lu_tmp;
-    std::vector<int> perm_host;
+    DevBuf lu_Wd, lu_Ws, lu_bs, lu_logdet, lu_logdet_neg, lu_perm, lu_tmp;
+    std::vector<int> perm_host, inv_perm_host;
+    std::vector<float> lu_bs_host;
     // affine family
     AffineOp op{};
     std::vector<int> perm_fwd, perm_inv;
@@ -170,6 +176,10 @@ struct nfb_flow {
     // workspaces
     DevBuf stack_layers, progress;  // whole-stack launch: FusedLayer[stack_n] in density order + tile flags
     int stack_n = 0;
+    // sampling-direction plan: units (LU index or -1, spline index) in list order, optional trailing LU
+    std::vector<std::pair<int, int>> fwd_units;
+    int fwd_trailing_lu = -1, fwd_n = 0;
+    DevBuf fwd_layers;
     DevBuf zA, zB, logq, hA, hB, hT, params, E, scratch_sum, loss, err, ar_tmp, pair_tmp, host_x, zfinal, prof;
     long long launches = 0;
 };
@@ -527,6 +537,11 @@ int repack_lu(nfb_flow* f, Layer& L, cudaStream_t st) {
         bs[i] = (float)(-acc);
     }
     NFB_TRY(L.lu_bs.upload(bs));
+    L.lu_bs_host = bs;
+    std::vector<float> ld;
+    NFB_TRY(download(L.lu_logdet.as<float>(), 1, ld));
+    ld[0] = -ld[0];
+    NFB_TRY(L.lu_logdet_neg.upload(ld));
     (void)f;
     return NFB_OK;
 }
@@ -587,8 +602,63 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     return NFB_OK;
 }
 
+// Sampling direction.  Unit = [inverse LU map of layer U (or none) + coupling block R with its splines inverted].
+// x = ((z - b) Winv^T)[:, inv_perm]  (LULinearPermute.forward, flows/mixing.py:551-556: linear.inverse, then
+// permutation.inverse), i.e. one dense map E z + e with E[i, :] = Winv[inv_perm[i], :], e[i] = bs[inv_perm[i]];
+// Winv = (L U)^-1 is formed in fp64 by lu_pack_kernel (the reference solves two triangular systems in fp32).
+int build_fwd_unit(nfb_flow* f, Layer& R, Layer* U) {
+    FusedPack& F = R.fused;
+    F.fwd_ok = false;
+    if (!F.ok || R.kind != L_COUPLED_RQS) return NFB_OK;
+    if (!U) { F.fwd_ok = true; return NFB_OK; }  // first block of the stack: no LU in front of it
+    if (U->D != R.D || U->D > 64 || F.n_steps + 3 > 256) return NFB_OK;
+    std::vector<FusedStep> steps;
+    auto mk = [&](int a0, int a1, int a2, int first, int wait, int signal) {
+        FusedStep s;
+        s.bytes16 = 64 * 8; s.n8 = 8; s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
+        s.ctl = make_ctl(256, first, wait, signal);
+        steps.push_back(s);
+    };
+    mk(0, 4, 1, 1, 1, 0);        // same 6-term schedule as the density pair (build_pair)
+    mk(0, 4, 0xFF, 0, 0, 0);
+    mk(0, 0xFF, 0xFF, 0, 0, 1);
+    steps.insert(steps.end(), F.steps_host.begin(), F.steps_host.end());
+    NFB_TRY(F.fwd_steps_dev.upload(steps));
+    NFB_TRY(F.fwd_wstream.reserve(3 * 8192 + F.rqs_bytes));
+    std::vector<int> sr(64, -1), sc(64, -1);
+    for (int i = 0; i < U->D; ++i) { sr[i] = U->inv_perm_host[i]; sc[i] = i; }
+    NFB_TRY(F.fwd_src_row.upload(sr));
+    NFB_TRY(F.fwd_src_col.upload(sc));
+    F.fwd_ok = true;
+    (void)f;
+    return NFB_OK;
+}
+
+int repack_fwd_unit(nfb_flow* f, Layer& R, Layer* U, cudaStream_t st) {
+    FusedPack& F = R.fused;
+    FusedLayer& Lp = F.host_fwd;
+    Lp = F.host_layer;
+    if (!U) return NFB_OK;  // spline block alone: the density descriptor serves both directions
+    NFB_TRY(f->E.reserve(64 * 64 * 4));
+    NFB_TRY(launch_build_effective(U->lu_Ws.as<float>(), nullptr, U->D, F.fwd_src_row.as<int>(),
+                                   F.fwd_src_col.as<int>(), nullptr, f->E.as<float>(), 64, 64, acc_gain(6 * 4), st));
+    NFB_TRY(launch_swizzle_split(f->E.as<float>(), 64, 64, 64, 3, F.fwd_wstream.as<uint8_t>(), st));
+    NFB_CUDA(cudaMemcpyAsync(F.fwd_wstream.as<uint8_t>() + 3 * 8192, F.wstream.p, F.rqs_bytes,
+                             cudaMemcpyDeviceToDevice, st));
+    std::vector<float> bl(64, 0.f);
+    for (int i = 0; i < U->D; ++i) bl[i] = U->lu_bs_host[U->inv_perm_host[i]];
+    NFB_TRY(F.fwd_bias_lu.upload(bl));
+    Lp.has_lu = 1;
+    Lp.n_steps = F.n_steps + 3;
+    Lp.wstream = F.fwd_wstream.as<uint8_t>();
+    Lp.steps = F.fwd_steps_dev.as<FusedStep>();
+    Lp.bias_lu = F.fwd_bias_lu.as<float>();
+    Lp.lu_logdet = U->lu_logdet_neg.as<float>();
+    return NFB_OK;
+}
+
 int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float* zout, float* logq,
-                       long long rows, int accumulate, cudaStream_t st) {
+                       long long rows, int accumulate, cudaStream_t st, int sample = 0) {
     FusedPack& F = R.fused;
     FusedParams p{};
     p.layers = U ? F.pair_dev.as<FusedLayer>() : F.layer_dev.as<FusedLayer>();
@@ -597,25 +667,26 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
     p.progress = nullptr;
     p.err = f->err.as<int>();
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
-    NFB_TRY(launch_fused_rqs(p, f->sm_count, st));
+    NFB_TRY(launch_fused_rqs(p, f->sm_count, sample, st));
     f->launches++;
     return NFB_OK;
 }
 
 // Whole stack in ONE persistent launch: (layer, tile) work units with per-tile progress flags.  logq must be
 // pre-filled (accumulate semantics); zout may alias zin.
-int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, long long rows, cudaStream_t st) {
+int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, long long rows, cudaStream_t st,
+                       int sample = 0) {
     const long long n_tiles = (rows + 127) / 128;
     NFB_TRY(f->progress.reserve((size_t)n_tiles * sizeof(int)));
     NFB_CUDA(cudaMemsetAsync(f->progress.p, 0, (size_t)n_tiles * sizeof(int), st));
     FusedParams p{};
-    p.layers = f->stack_layers.as<FusedLayer>();
-    p.n_layers = f->stack_n;
+    p.layers = sample ? f->fwd_layers.as<FusedLayer>() : f->stack_layers.as<FusedLayer>();
+    p.n_layers = sample ? f->fwd_n : f->stack_n;
     p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = 1;
     p.progress = f->progress.as<int>();
     p.err = f->err.as<int>();
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
-    NFB_TRY(launch_fused_rqs(p, f->sm_count, st));
+    NFB_TRY(launch_fused_rqs(p, f->sm_count, sample, st));
     f->launches += 2;  // memset + kernel
     return NFB_OK;
 }
@@ -754,12 +825,17 @@ int run_group(nfb_flow* f, Group& g, int direction, const float* zin, float* zou
     case G_SINGLE:
         return apply_layer_generic(f, *f->layers[g.first], direction, zin, zout, logdet, rows, 1, st);
     }
-    // fused groups in the sampling direction: generic kernels, layer by layer
-    if (g.first == g.last)
-        return apply_layer_generic(f, *f->layers[g.first], direction, zin, zout, logdet, rows, 1, st);
+    // fused groups in the sampling direction, layer by layer: a coupling block runs the fused kernel with its
+    // splines inverted; the autoregressive block needs D sequential conditioner passes (generic kernels)
+    auto fwd_block = [&](Layer& R, const float* in, float* out) -> int {
+        if (R.kind == L_COUPLED_RQS && R.fused.ok)
+            return launch_fused_layer(f, R, nullptr, in, out, logdet, rows, 1, st, 1);
+        return apply_layer_generic(f, R, direction, in, out, logdet, rows, 1, st);
+    };
+    if (g.first == g.last) return fwd_block(*f->layers[g.first], zin, zout);
     // pair = [spline block (first), LU (last)] in list order; forward applies first then last
     NFB_TRY(f->pair_tmp.reserve((size_t)rows * f->D * 4));
-    NFB_TRY(apply_layer_generic(f, *f->layers[g.first], direction, zin, f->pair_tmp.as<float>(), logdet, rows, 1, st));
+    NFB_TRY(fwd_block(*f->layers[g.first], zin, f->pair_tmp.as<float>()));
     return apply_layer_generic(f, *f->layers[g.last], direction, f->pair_tmp.as<float>(), zout, logdet, rows, 1, st);
 }
 
@@ -1014,6 +1090,19 @@ int nfb_flow_repack(nfb_flow_t* f, void* stream) {
         NFB_CUDA(cudaMemcpy(f->stack_layers.p, arr.data(), arr.size() * sizeof(FusedLayer), cudaMemcpyHostToDevice));
         f->stack_n = (int)arr.size();
     }
+    // sampling-direction plan (list order); same persistent kernel, SAMPLE instantiation
+    f->fwd_n = 0;
+    if (!f->fwd_units.empty() && getenv("NFB_NO_STACK") == nullptr) {
+        std::vector<FusedLayer> arr;
+        for (auto& u : f->fwd_units) {
+            Layer& R = *f->layers[u.second];
+            NFB_TRY(repack_fwd_unit(f, R, u.first >= 0 ? f->layers[u.first].get() : nullptr, st));
+            arr.push_back(R.fused.host_fwd);
+        }
+        NFB_TRY(f->fwd_layers.reserve(arr.size() * sizeof(FusedLayer)));
+        NFB_CUDA(cudaMemcpy(f->fwd_layers.p, arr.data(), arr.size() * sizeof(FusedLayer), cudaMemcpyHostToDevice));
+        f->fwd_n = (int)arr.size();
+    }
     NFB_CUDA(cudaStreamSynchronize(st));
     return NFB_OK;
 }
@@ -1052,6 +1141,7 @@ int nfb_flow_finalize(nfb_flow_t* f, int32_t use_tensor_cores, void* stream) {
             }
             NFB_TRY(L.lu_perm.upload(L.perm_host));
             NFB_TRY(L.lu_tmp.upload(inv));
+            L.inv_perm_host = inv;
         }
     }
     // execution groups (list order)
@@ -1085,6 +1175,30 @@ int nfb_flow_finalize(nfb_flow_t* f, int32_t use_tensor_cores, void* stream) {
             f->groups.push_back(std::move(g));
             ++i;
         }
+    }
+    // sampling-direction units: every layer must be a fused coupling block or an LU map that directly
+    // precedes one (or closes the list); anything else keeps the group-by-group path
+    f->fwd_units.clear();
+    f->fwd_trailing_lu = -1;
+    {
+        bool ok = f->use_tc && n > 0;
+        int pending = -1;
+        for (int i = 0; i < n && ok; ++i) {
+            Layer& L = *f->layers[i];
+            if (L.kind == L_LU) {
+                ok = pending < 0;
+                pending = i;
+            } else if (L.kind == L_COUPLED_RQS && L.fused.ok) {
+                NFB_TRY(build_fwd_unit(f, L, pending >= 0 ? f->layers[pending].get() : nullptr));
+                ok = L.fused.fwd_ok;
+                f->fwd_units.push_back({pending, i});
+                pending = -1;
+            } else {
+                ok = false;
+            }
+        }
+        if (ok) f->fwd_trailing_lu = pending;
+        else f->fwd_units.clear();
     }
     f->finalized = true;
     return nfb_flow_repack(f, stream);
@@ -1121,9 +1235,12 @@ int nfb_flow_layer_apply(nfb_flow_t* f, int32_t index, int32_t direction, const 
         NFB_TRY(ops.upload(v));
         rc = launch_affine_stack(ops.p, 1, z_in, out, log_det, rows, f->D, 1, direction, st);
         NFB_CUDA(cudaStreamSynchronize(st));  // ops buffer is freed on return
-    } else if ((L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) && L.fused.ok && direction == NFB_INVERSE) {
+    } else if ((L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) && L.fused.ok &&
+               (direction == NFB_INVERSE || L.kind == L_COUPLED_RQS)) {
+        // (the autoregressive block's sampling direction is D sequential conditioner passes: generic kernels)
         if (!log_det) { NFB_TRY(f->logq.reserve((size_t)rows * 4)); }
-        rc = launch_fused_layer(f, L, nullptr, z_in, out, log_det ? log_det : f->logq.as<float>(), rows, 1, st);
+        rc = launch_fused_layer(f, L, nullptr, z_in, out, log_det ? log_det : f->logq.as<float>(), rows, 1, st,
+                                direction == NFB_FORWARD);
     } else {
         rc = apply_layer_generic(f, L, direction, z_in, out, log_det, rows, 1, st);
     }
@@ -1146,6 +1263,12 @@ int nfb_flow_transform(nfb_flow_t* f, int32_t direction, const float* z_in, floa
     f->launches++;
     if (direction == NFB_INVERSE && f->stack_n > 0)
         return launch_fused_stack(f, z_in, z_out, ld, rows, st);
+    if (direction == NFB_FORWARD && f->fwd_n > 0) {
+        if (f->fwd_trailing_lu < 0) return launch_fused_stack(f, z_in, z_out, ld, rows, st, 1);
+        float* tmp = f->zA.as<float>();
+        NFB_TRY(launch_fused_stack(f, z_in, tmp, ld, rows, st, 1));
+        return apply_layer_generic(f, *f->layers[f->fwd_trailing_lu], NFB_FORWARD, tmp, z_out, ld, rows, 1, st);
+    }
     const int ng = (int)f->groups.size();
     const float* cur = z_in;
     float* bufs[2] = {f->zA.as<float>(), f->zB.as<float>()};

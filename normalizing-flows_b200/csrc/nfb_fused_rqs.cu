@@ -103,6 +103,12 @@ __device__ __forceinline__ void split_store8(const float* v, uint32_t t0, uint32
     if (NSPLIT == 3) st_shared_v4(t2 + off, l[0], l[1], l[2], l[3]);
 }
 
+// SAMPLE = false: density direction (Flow.inverse of every layer: x -> z, core.py:70-85).
+// SAMPLE = true : sampling direction of coupling-layer stacks (Flow.forward: z -> x, core.py:40-55): the unit is
+//   still "LU map, then spline block" -- the packer hands it the INVERSE LU map of the previous layer -- but the
+//   unconditional spline runs first and in its inverse branch, the conditioner sees its result, and the
+//   conditional spline is inverted (Coupling.inverse, neural_spline/coupling.py:100-128).
+template <bool SAMPLE>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -342,23 +348,31 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
                 epi_bar_sync();
             }
-            build_a(false);
-            NFB_STAMP();  // net input A built
-
-            // ---- unconditional spline on the identity features (coupled layer only); runs while
-            //      the tensor core is busy with the first GEMMs.  The conditioner input was taken
-            //      from the raw values above (Coupling.forward, neural_spline/coupling.py:80-92).
-            if (L.n_id > 0) {
+            // ---- unconditional spline on the identity features (coupled layer only).
+            // density: the conditioner input is taken from the RAW values first (Coupling.forward,
+            //   neural_spline/coupling.py:80-92) and the spline then runs while the tensor core is busy;
+            // sampling: the inverse spline comes first and the conditioner sees its output (:100-128).
+            auto uncond = [&]() {
                 const int per = (L.n_id + kNG - 1) / kNG;
                 for (int i = wh * per; i < min(L.n_id, (wh + 1) * per); ++i) {
                     const int c = L.id_idx[i];
                     const float* tb = L.uncond + i * 23;
                     auto acc = [tb](int k) { return __ldg(tb + k); };
                     float y, l;
-                    rqs_eval<8, false>(xs[xs_index(r, c)], acc, L.tail, 1.0f, y, l);
+                    rqs_eval<8, SAMPLE>(xs[xs_index(r, c)], acc, L.tail, 1.0f, y, l);
                     xs[xs_index(r, c)] = y;
                     ladsum += l;
                 }
+            };
+            if (SAMPLE && L.n_id > 0) {
+                uncond();
+                epi_bar_sync();  // build_a reads this row's columns written by the other column groups
+            }
+            build_a(false);
+            NFB_STAMP();  // net input A built
+            if (!SAMPLE && L.n_id > 0) {
+                epi_bar_sync();  // every warp has read the raw identity columns of this row into A
+                uncond();
             }
 
             // ---- hidden layers ----
@@ -449,7 +463,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         }
                         const int col = L.tr_idx[t];
                         float y, l;
-                        rqs_core<8, false>(xs[xs_index(r, col)], lw, lh, [&dd](int k) { return dd[k]; }, L.tail, y, l);
+                        rqs_core<8, SAMPLE>(xs[xs_index(r, col)], lw, lh, [&dd](int k) { return dd[k]; }, L.tail, y, l);
                         xs[xs_index(r, col)] = y;
                         ladsum += l;
                     }
@@ -510,10 +524,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     if (warp == kEpiWarps + 1) tmem_dealloc(tmem, 512);
 }
 
-int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st) {
+int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st) {
     static bool attr_done = false;
     if (!attr_done) {
-        NFB_CUDA(cudaFuncSetAttribute(fused_rqs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        NFB_CUDA(cudaFuncSetAttribute(fused_rqs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)kFusedSmem));
+        NFB_CUDA(cudaFuncSetAttribute(fused_rqs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)kFusedSmem));
         attr_done = true;
     }
@@ -522,7 +538,8 @@ int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st) {
     if (n_units == 0) return NFB_OK;
     // every CTA must be resident (units wait on flags published by other CTAs): grid <= #SMs, 1 CTA/SM
     const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
-    fused_rqs_kernel<<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    if (sample) fused_rqs_kernel<true><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    else fused_rqs_kernel<false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

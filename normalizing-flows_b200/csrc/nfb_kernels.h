@@ -110,7 +110,7 @@ struct FusedParams {
     int* err;
     long long* prof;           // optional [128] clock64 stamps (debug)
 };
-int launch_fused_rqs(const FusedParams& p, int sm_count, cudaStream_t st);
+int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st);
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
                            const int* src_col, const float* row_scale, float* E, int n_pad,
                            int k_pad, float gain, cudaStream_t st);

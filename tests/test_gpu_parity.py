@@ -169,6 +169,51 @@ def test_full_batch_properties(kind):
     assert float(model.forward_kld(xc)) == pytest.approx(-float(lp.double().mean()), rel=1e-6)
 
 
+def test_sampling_direction_fused_coupled_stack():
+    """Coupling-layer stacks run the sampling direction (core.py:40-55) through the same persistent kernel:
+    units of [inverse LU map of the previous layer + block with its splines inverted]."""
+    spec, sd, a = load_golden("nsf_coupled_d64_h256_l2")
+    model = build_model(annotate_spec(spec, sd), sd).cuda()
+    n = len(model.flows)
+    # per layer: forward of layer i maps the golden's state i to state i+1 with log-det -ld_i
+    for i in range(n):
+        zout_ref = a["x"] if i == n - 1 else a[f"zl_f64__{i + 1}"]
+        z, ld = model.flows[i].forward(cuda(a[f"zl_f64__{i}"]))
+        np.testing.assert_allclose(z.cpu().numpy(), zout_ref, rtol=1e-4, atol=1e-3, err_msg=f"layer {i}")
+        np.testing.assert_allclose(ld.cpu().numpy(), -a[f"ld_f64__{i}"], rtol=1e-4, atol=5e-3, err_msg=f"layer {i}")
+    xr, ld = model.forward_and_log_det(cuda(a["z_f64"]))
+    assert model._stack().launch_count() <= 8, "coupled stack must sample through the whole-stack launch"
+    np.testing.assert_allclose(xr.cpu().numpy(), a["fwd_x_f64"], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(ld.cpu().numpy(), a["fwd_ld_f64"], rtol=1e-4, atol=2e-2)
+
+    # BASELINE batch size: fused sampling vs the plain-fp32 kernels on every row, vs the fp64 oracle on a
+    # subset, and the round trip x -> z -> x through both fused directions
+    d, layers, hidden = 64, 4, 256
+    model = _random_model("coupled", d, layers, hidden).cuda()
+    spec, sd = _oracle_of(model, "coupled", d, layers, hidden)
+    B = 65536 + 77
+    x = (torch.randn(B, d, generator=torch.Generator().manual_seed(99)) * 1.5).cuda()
+    z, ld_inv = model.inverse_and_log_det(x)
+    x2, ld_fwd = model.forward_and_log_det(z)
+    x2b, _ = model.forward_and_log_det(z)
+    assert torch.equal(x2, x2b), "fused sampling path must be deterministic"
+    ex = (x2 - x).abs().max(dim=1).values.cpu().numpy()
+    assert np.mean(ex < 5e-4) > 0.995 and ex.max() < 5e-2, (np.mean(ex < 5e-4), ex.max())
+    assert np.median(np.abs((ld_inv + ld_fwd).cpu().numpy())) < 2e-3
+    NativeFlow.use_tensor_cores = False
+    x32, ld32 = model.forward_and_log_det(z)
+    NativeFlow.use_tensor_cores = True
+    dx = (x2 - x32).abs().max(dim=1).values.cpu().numpy()
+    assert np.mean(dx < 5e-4) > 0.995 and dx.max() < 5e-2, (np.mean(dx < 5e-4), dx.max())
+    idx = np.r_[0:64, B - 40:B]
+    zo = z.cpu().numpy()[idx].astype(np.float64)
+    xo, ldo = O.forward_and_log_det(spec, sd, zo)
+    e = np.abs(x2.cpu().numpy()[idx] - xo).max(axis=1)
+    assert np.median(e) < 2e-4 and e.max() < 2e-2, np.sort(e)[-4:]
+    el = np.abs(ld_fwd.cpu().numpy()[idx] - ldo)
+    assert np.median(el) < 2e-3 and el.max() < 5e-2, np.sort(el)[-4:]
+
+
 def test_edge_inputs_through_fused_kernel():
     """x exactly at +-B, just outside, far outside and NaN through the fused block."""
     spec, sd, a = load_golden("nsf_ar_d64_h256_l2")

@@ -201,3 +201,15 @@ if mode == "bias":
             print(f"bias {kind} tc={tc} comp={os.environ.get('NFB_ACC_COMP_STEP','default')}: mean signed {e.mean():+.3e} median {np.median(e):+.3e} "
                   f"rms {np.sqrt((e**2).mean()):.3e} | rel mean {rel.mean():.2e} p99 {np.quantile(rel,0.99):.2e} max {rel.max():.2e}", flush=True)
         NativeFlow.use_tensor_cores = True
+
+if mode == "timefwd":
+    # sampling direction (forward_and_log_det) of the coupled 32-layer stack: fused whole-stack launch vs generic kernels
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
+    m = rand_model("coupled", 32)
+    z = torch.randn(B, 64).cuda()
+    for tc in (True, False):
+        NativeFlow.use_tensor_cores = tc
+        ms = timeit(lambda: m.forward_and_log_det(z), n=5 if tc else 2, warm=2 if tc else 1)
+        print(f"timefwd coupled B={B} L=32 use_tc={tc}: {ms:.2f} ms/pass  {B / ms * 1e3:.3e} samples/s "
+              f"launches={m._stack().launch_count()}", flush=True)
+    NativeFlow.use_tensor_cores = True
