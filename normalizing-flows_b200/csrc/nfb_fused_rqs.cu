@@ -14,15 +14,16 @@
 //   6-term 3-way split for the LU linear map that transforms z itself (~2^-24).
 // Plain bf16/tf32 fail the rtol 1e-4 log_prob bar; this is why.
 //
-// Structure (320 threads, 1 CTA/SM, persistent over tiles):
-//   warp 8   weight producer: 1-D bulk TMA (cp.async.bulk -> UBLKCP) of pre-swizzled bf16 records
-//            from the packed weight stream (L2 resident) into a 4 x 16 KB ring.
-//   warp 9   MMA issuer: walks the same step table, one elected lane issues tcgen05.mma
-//            (M=128, N=64/96/128, K=16) and commits to mbarriers; owns the 512-column TMEM alloc.
-//   warps 0-7 epilogue: TMEM -> registers (tcgen05.ld 32x32b), bias/ReLU, bf16 hi/lo split back
-//            into the swizzled A-operand tiles; final layer arrives in 96-column chunks
-//            (4 features x 24) through a 4-deep TMEM ring and is consumed by the spline evaluator
-//            while the tensor core produces the next chunk.
+// Structure (576 threads, 1 CTA/SM, persistent over (layer, tile) work units of the whole stack):
+//   warp 16  weight producer: 1-D bulk TMA (cp.async.bulk -> UBLKCP) of pre-swizzled bf16 records
+//            from the packed weight stream (L2 resident) into a 2 x 32 KB ring.
+//   warp 17  MMA issuer: walks the same step table, one elected lane issues tcgen05.mma
+//            (M=128, N<=256, K=16) and commits to mbarriers; owns the 512-column TMEM alloc.
+//   warps 0-15 epilogue (4 per SM sub-partition = 4 column groups x 4 TMEM lane quadrants):
+//            TMEM -> registers (tcgen05.ld 32x32b), bias/ReLU, bf16 hi/lo split back into the
+//            swizzled A-operand tiles; the final layer arrives in 240-column chunks (10 features
+//            x 24) through a 2-deep TMEM ring and is consumed by the spline evaluator while the
+//            tensor core produces the next chunk.
 // The residual stream h lives in TMEM columns [0,256) and is updated by accumulating the second
 // GEMM of each residual block straight onto it (h += W2 relu(...)); biases are pre-summed on the
 // host side of the packer.  Shared memory: A operand 128 KB (hi|lo x K=256), weight ring 64 KB,
