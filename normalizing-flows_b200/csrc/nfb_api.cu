@@ -35,11 +35,10 @@ static constexpr float kLog2eHost = 1.4426950408889634f;
 // alike.  The packer therefore scales each GEMM's weights by 1 + kAccStepGain * steps; the bias test in
 // tests/test_gpu_parity.py pins the residual.  (Counting, per row of a masked net, only the steps in which
 // the row has a non-zero weight was tried and is no better: mean +1.0e-4 / rms 8.6e-4 against +2e-5 / 6.9e-4.)  NFB_ACC_COMP_STEP overrides the constant (calibration runs).
-static constexpr float kAccStepGain = 2.9e-8f;
 static float acc_gain(int mma_steps) {
     static const float per_step = [] {
         const char* e = getenv("NFB_ACC_COMP_STEP");
-        return e ? (float)atof(e) : kAccStepGain;
+        return e ? (float)atof(e) : nfb::kAccStepGain;
     }();
     return 1.f + per_step * (float)mma_steps;
 }

@@ -7,6 +7,7 @@
 // LeakyReLU).  The coupling epilogue applies shift/scale (interleaved channels, coupling.py:152-160) and
 // reduces log|det| per sample.  Plain fp32 FFMA tiles for now (parity first); the tcgen05 implicit-GEMM
 // version is future work.
+#include <cstdlib>
 #include "nfb_kernels.h"
 
 namespace nfb {
@@ -84,6 +85,16 @@ int launch_conv2d(const float* x, int ctot, int c0, const float* w, const float*
     NFB_CHECK(c0 >= 0 && c0 + cin <= ctot, NFB_ERR_ARG, "conv2d: channel slice out of range");
     const long long M = B * H * W;
     if (M == 0 || cout == 0) return NFB_OK;
+    // conditioner-sized convolutions run on the tensor core (sm_100 only; NFB_CONV_FP32=1 forces this kernel)
+    static const bool tc = [] {
+        int dev = 0, major = 0;
+        if (getenv("NFB_CONV_FP32")) return false;
+        if (cudaGetDevice(&dev) != cudaSuccess) return false;
+        cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+        return major == 10;
+    }();
+    if (tc && conv_tc_supported(cin, cout, ks))
+        return launch_conv2d_tc(x, ctot, c0, w, bias, y, B, cin, H, W, cout, ks, leaky, kAccStepGain, nullptr, st);
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((cout + 63) / 64));
     conv2d_kernel<<<grid, 256, 0, st>>>(x, ctot, c0, w, bias, y, B, cin, H, W, cout, ks, leaky);
     NFB_LAUNCH_CHECK();

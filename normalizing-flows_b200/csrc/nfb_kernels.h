@@ -111,6 +111,14 @@ struct FusedParams {
     long long* prof;           // optional [128] clock64 stamps (debug)
 };
 int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st);
+
+// tcgen05 fp32 accumulation truncates: relative loss per K=16 MMA step, compensated at pack time (nfb_api.cu)
+constexpr float kAccStepGain = 2.9e-8f;
+// implicit-GEMM convolution on the tensor core (csrc/nfb_conv_tc.cu)
+bool conv_tc_supported(int cin, int cout, int ks);
+int launch_conv2d_tc(const float* x, int ctot, int c0, const float* w, const float* bias, float* y, long long B,
+                     int cin, int H, int W, int cout, int ks, float leaky, float gain_per_step, int* err,
+                     cudaStream_t st);
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
                            const int* src_col, const float* row_scale, float* E, int n_pad,
                            int k_pad, float gain, cudaStream_t st);

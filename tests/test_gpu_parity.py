@@ -300,6 +300,36 @@ def test_glow_multiscale_log_prob_matches_reference():
     np.testing.assert_array_equal(zr.cpu().numpy(), a["x"].astype(np.float32))
 
 
+@pytest.mark.parametrize("shape", [
+    # (B, ctot, c0, cin, H, W, cout, ks, leaky)   Glow conditioner shapes (nets/cnn.py:33-61) + awkward ones
+    (5, 12, 0, 6, 16, 16, 256, 3, 0.0),      # first conv, level 1: K = 54 (one padded chunk), N = 256
+    (3, 256, 0, 256, 8, 8, 256, 1, 0.0),     # middle 1x1 conv: K = 256 (4 chunks)
+    (3, 256, 0, 256, 8, 8, 24, 3, -1.0),     # last conv: K = 2304 (36 chunks), N = 24 -> 32, no activation
+    (37, 48, 24, 24, 4, 4, 256, 3, 0.1),     # 4x4 images: a 128-pixel tile spans 8 images; channel slice; ragged M
+    (2, 7, 1, 5, 5, 7, 200, 5, 0.0),         # odd everything, 5x5 kernel, N = 200 -> 208
+])
+def test_conv2d_tensor_core_matches_oracle(shape):
+    """nfb_conv2d routes conditioner-sized convolutions to the tcgen05 implicit-GEMM kernel (csrc/nfb_conv_tc.cu)."""
+    from normflows import _lib as L
+    B, ctot, c0, cin, H, W, cout, ks, leaky = shape
+    rng = np.random.default_rng(sum(shape[:8]))
+    x = rng.normal(size=(B, ctot, H, W)).astype(np.float32)
+    w = (rng.normal(size=(cout, cin, ks, ks)) / np.sqrt(cin * ks * ks)).astype(np.float32)
+    b = rng.normal(size=cout).astype(np.float32)
+    ref = O.conv2d(x[:, c0:c0 + cin].astype(np.float64), w.astype(np.float64), b.astype(np.float64))
+    if leaky >= 0:
+        ref = np.where(ref >= 0, ref, ref * leaky)
+    xd, wd, bd = cuda(x), cuda(w), cuda(b)
+    y = torch.full((B, cout, H, W), float("nan"), device="cuda")
+    L.check(L.lib().nfb_conv2d(L.ptr(xd), ctot, c0, L.ptr(wd), L.ptr(bd), L.ptr(y), B, cin, H, W, cout, ks,
+                               float(leaky), L.stream_ptr()))
+    got = y.cpu().numpy()
+    assert np.isfinite(got).all()
+    # split-bf16 products: ~2^-17 relative per term, K terms of unit scale
+    np.testing.assert_allclose(got, ref, rtol=1e-4, atol=2e-5 * np.sqrt(cin * ks * ks))
+    assert np.abs(np.mean(got - ref)) < 3e-6  # no one-sided accumulate bias left
+
+
 def test_glow_actnorm_data_dependent_init_on_images():
     f = np.load("tests/golden/actnorm_init.npz")
     blk = nf.flows.GlowBlock(6, 8).cuda()
