@@ -36,7 +36,8 @@ constexpr uint32_t kCtTileA = 16384;   // [128 x 64] bf16
 constexpr uint32_t kCtStage = 2 * kCtTileA;  // hi | lo
 constexpr uint32_t kCtBarBytes = 32 * 8;
 constexpr uint32_t kCtSmemMax = 232448;
-enum { CB_AFULL = 0, CB_AEMPTY = 6, CB_WFULL = 12, CB_WEMPTY = 14, CB_ACCFULL = 16, CB_ACCEMPTY = 18 };
+constexpr int kCtMaxSlots = 8;
+enum { CB_AFULL = 0, CB_AEMPTY = 6, CB_WFULL = 12, CB_WEMPTY = 20, CB_ACCFULL = 28, CB_ACCEMPTY = 30 };
 
 __device__ __forceinline__ uint32_t ct_chunk_off(int r, int c8) {
     return (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4);
@@ -48,17 +49,18 @@ __device__ __forceinline__ void ct_st_v4(uint32_t addr, uint32_t a, uint32_t b, 
 
 struct ConvTcParams {
     const float* x; float* y; const float* bias; const uint8_t* wstream;
-    long long M; int ctot, c0, cin, H, W, cout, ks, n_pad, k_chunks, stages; uint32_t slot_bytes; float leaky; int* err;
+    long long M; int ctot, c0, cin, H, W, cout, ks, n_pad, k_chunks, stages, w_slots; uint32_t slot_bytes; float leaky; int* err;
 };
 
-// shared memory: [stages x (A hi | A lo)] [2 x weight slot] [barriers] [tmem ptr]
+// shared memory: [stages x (A hi | A lo)] [w_slots x weight slot] [barriers] [tmem ptr]
 __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int S = p.stages;
     const uint32_t offW = (uint32_t)S * kCtStage;
-    const uint32_t offBars = offW + 2 * p.slot_bytes;
+    const int WS = p.w_slots;
+    const uint32_t offBars = offW + (uint32_t)WS * p.slot_bytes;
     const uint32_t bars = sbase + offBars;
     auto bar = [bars](int i) { return bars + 8u * i; };
     const uint32_t tcols = p.n_pad <= 32 ? 32u : p.n_pad <= 64 ? 64u : p.n_pad <= 128 ? 128u : 256u;
@@ -68,9 +70,11 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcPara
             mbar_init(bar(CB_AFULL + i), kCtBuildWarps);  // one arrive per builder warp
             mbar_init(bar(CB_AEMPTY + i), 1);             // tcgen05.commit
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kCtMaxSlots; ++i) {
             mbar_init(bar(CB_WFULL + i), 1);              // expect_tx
             mbar_init(bar(CB_WEMPTY + i), 1);             // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
             mbar_init(bar(CB_ACCFULL + i), 1);            // tcgen05.commit
             mbar_init(bar(CB_ACCEMPTY + i), kCtBuildWarps);
         }
@@ -90,30 +94,29 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcPara
 
     if (warp == kCtBuildWarps) {
         // ------------------------------ weight producer ------------------------------------
-        uint32_t g = 0;  // running chunk count over all tiles of this CTA
+        uint32_t ws = 0, ws_use = 0;  // ring position over all tiles of this CTA
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x)
-            for (int kc = 0; kc < KC; ++kc, ++g) {
-                const uint32_t s = g & 1u, use = g >> 1;
-                if (use > 0) mbar_wait(bar(CB_WEMPTY + s), (use - 1) & 1u, p.err, 700 + s);
+            for (int kc = 0; kc < KC; ++kc) {
+                if (ws_use > 0) mbar_wait(bar(CB_WEMPTY + ws), (ws_use - 1) & 1u, p.err, 700 + ws);
                 if (elect_one_sync()) {
-                    mbar_expect_tx(bar(CB_WFULL + s), rec_bytes);
-                    bulk_g2s(sbase + offW + s * p.slot_bytes, p.wstream + (size_t)kc * rec_bytes, rec_bytes,
-                             bar(CB_WFULL + s));
+                    mbar_expect_tx(bar(CB_WFULL + ws), rec_bytes);
+                    bulk_g2s(sbase + offW + ws * p.slot_bytes, p.wstream + (size_t)kc * rec_bytes, rec_bytes,
+                             bar(CB_WFULL + ws));
                 }
                 __syncwarp();
+                if (++ws == (uint32_t)WS) { ws = 0; ++ws_use; }
             }
     } else if (warp == kCtBuildWarps + 1) {
         // ------------------------------ MMA issuer ------------------------------------------
         const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)p.n_pad);
-        uint32_t g = 0, st = 0, st_use = 0, it = 0;
+        uint32_t ws = 0, ws_use = 0, st = 0, st_use = 0, it = 0;
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
             const uint32_t ab = it & 1u;  // accumulator buffer
             if (it >= 2) mbar_wait(bar(CB_ACCEMPTY + ab), ((it >> 1) - 1) & 1u, p.err, 750 + ab);
             const uint32_t d = tmem + ab * tcols;
-            for (int kc = 0; kc < KC; ++kc, ++g) {
-                const uint32_t ws = g & 1u;
+            for (int kc = 0; kc < KC; ++kc) {
                 mbar_wait(bar(CB_AFULL + st), st_use & 1u, p.err, 710 + st);
-                mbar_wait(bar(CB_WFULL + ws), (g >> 1) & 1u, p.err, 720 + ws);
+                mbar_wait(bar(CB_WFULL + ws), ws_use & 1u, p.err, 720 + ws);
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint64_t a_hi = umma_desc_sw128(sbase + st * kCtStage);
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcPara
                 }
                 __syncwarp();
                 if (++st == (uint32_t)S) { st = 0; ++st_use; }
+                if (++ws == (uint32_t)WS) { ws = 0; ++ws_use; }
             }
         }
     } else {
@@ -191,10 +195,7 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcPara
                 for (int j = 0; j < 16; ++j)
                     v[j] = (ok && cbase + j < p.cin) ? __ldg(src + (long long)j * HW) : 0.f;
             };
-            float cur[16], nxt[16];
-            gather(0, cur);
-            for (int kc = 0; kc < KC; ++kc) {
-                if (kc + 1 < KC) gather(kc + 1, nxt);  // in flight while this chunk is converted and stored
+            auto emit = [&](const float (&v)[16]) {  // split, store into the next free A stage, publish
                 if (st_use > 0) mbar_wait(bar(CB_AEMPTY + st), (st_use - 1) & 1u, p.err, 730 + st);
                 const uint32_t t_hi = sbase + st * kCtStage, t_lo = t_hi + kCtTileA;
 #pragma unroll
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcPara
                     uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float a = cur[8 * g + 2 * i], b = cur[8 * g + 2 * i + 1];
+                        const float a = v[8 * g + 2 * i], b = v[8 * g + 2 * i + 1];
                         hi[i] = pack_bf16x2(a, b);
                         lo[i] = pack_bf16x2(a - __uint_as_float(hi[i] << 16), b - __uint_as_float(hi[i] & 0xffff0000u));
                     }
@@ -214,8 +215,23 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcPara
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(CB_AFULL + st));
                 if (++st == (uint32_t)S) { st = 0; ++st_use; }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
+            };
+            // three register sets in rotation: the loads of chunks k+1 and k+2 are in flight while chunk k is
+            // converted (the gathers come from HBM/L2 at ~2 k cycles; one chunk of work is ~0.6 k)
+            float a0[16], a1[16], a2[16];
+            gather(0, a0);
+            if (KC > 1) gather(1, a1);
+            for (int kc = 0; kc < KC; kc += 3) {
+                if (kc + 2 < KC) gather(kc + 2, a2);
+                emit(a0);
+                if (kc + 1 < KC) {
+                    if (kc + 3 < KC) gather(kc + 3, a0);
+                    emit(a1);
+                }
+                if (kc + 2 < KC) {
+                    if (kc + 4 < KC) gather(kc + 4, a1);
+                    emit(a2);
+                }
             }
             if (prev_tile >= 0) epilogue(prev_tile, it - 1);  // overlaps this tile's MMAs
             prev_tile = t;
@@ -279,10 +295,14 @@ int launch_conv2d_tc(const float* x, int ctot, int c0, const float* w, const flo
     p.M = M; p.ctot = ctot; p.c0 = c0; p.cin = cin; p.H = H; p.W = W; p.cout = cout; p.ks = ks;
     p.n_pad = n_pad; p.k_chunks = k_chunks; p.leaky = leaky; p.err = err;
     p.slot_bytes = ((uint32_t)n_pad * 256u + 1023u) & ~1023u;
-    const uint32_t fixed = 2 * p.slot_bytes + kCtBarBytes + 16;
+    // weight ring: up to 128 KB / 8 slots (small-N records are latency-, not bandwidth-limited); A stages: the rest
+    int w_slots = (int)(131072u / p.slot_bytes);
+    w_slots = w_slots < 2 ? 2 : (w_slots > kCtMaxSlots ? kCtMaxSlots : w_slots);
+    const uint32_t fixed = (uint32_t)w_slots * p.slot_bytes + kCtBarBytes + 16;
     int stages = (int)((kCtSmemMax - fixed) / kCtStage);
     stages = stages > kCtMaxStages ? kCtMaxStages : stages;  // 3 at N = 256, 6 at N <= 64
     p.stages = stages;
+    p.w_slots = w_slots;
     const uint32_t smem = (uint32_t)stages * kCtStage + fixed;
     const long long n_tiles = (M + 127) / 128;
     const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);

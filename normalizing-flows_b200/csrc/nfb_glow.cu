@@ -79,6 +79,39 @@ conv2d_kernel(const float* __restrict__ x, int ctot, int c0, const float* __rest
     }
 }
 
+// 1x1 convolution with few channels (the folded ActNorm + Invertible1x1Conv of a Glow block, C <= 64): one
+// thread per pixel keeps its cin inputs in registers, the [cout x cin] matrix sits in shared memory and is read
+// as warp-wide broadcasts.  HBM-bound: 4 (cin + cout) bytes per pixel, no tile padding to 64 channels.
+template <int CMAX>
+__global__ void __launch_bounds__(256)
+conv1x1_small_kernel(const float* __restrict__ x, int ctot, int c0, const float* __restrict__ w,
+                     const float* __restrict__ bias, float* __restrict__ y, long long M, int cin, int HW, int cout,
+                     float leaky) {
+    __shared__ float ws[CMAX * CMAX];
+    __shared__ float bs[CMAX];
+    for (int i = threadIdx.x; i < cout * cin; i += 256) ws[i] = w[i];
+    for (int i = threadIdx.x; i < cout; i += 256) bs[i] = bias ? bias[i] : 0.f;
+    __syncthreads();
+    const long long m = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (m >= M) return;
+    const long long bi = m / HW;
+    const int pix = (int)(m - bi * HW);
+    const float* xp = x + (bi * ctot + c0) * (long long)HW + pix;
+    float v[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) v[c] = c < cin ? xp[(long long)c * HW] : 0.f;
+    float* yp = y + bi * (long long)cout * HW + pix;
+    for (int n = 0; n < cout; ++n) {
+        const float* wr = ws + n * cin;
+        float acc = bs[n];
+#pragma unroll
+        for (int c = 0; c < CMAX; ++c)
+            if (c < cin) acc = fmaf(wr[c], v[c], acc);
+        if (leaky >= 0.f) acc = acc >= 0.f ? acc : acc * leaky;
+        yp[(long long)n * HW] = acc;
+    }
+}
+
 int launch_conv2d(const float* x, int ctot, int c0, const float* w, const float* bias, float* y, long long B,
                   int cin, int H, int W, int cout, int ks, float leaky, cudaStream_t st) {
     NFB_CHECK(ks == 1 || ks == 3 || ks == 5, NFB_ERR_UNSUPPORTED, "conv2d: kernel size %d", ks);
@@ -93,6 +126,17 @@ int launch_conv2d(const float* x, int ctot, int c0, const float* w, const float*
         cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
         return major == 10;
     }();
+    if (ks == 1 && cin <= 64 && cout <= 64) {
+        const unsigned g = (unsigned)((M + 255) / 256);
+        if (cin <= 16 && cout <= 16)
+            conv1x1_small_kernel<16><<<g, 256, 0, st>>>(x, ctot, c0, w, bias, y, M, cin, H * W, cout, leaky);
+        else if (cin <= 32 && cout <= 32)
+            conv1x1_small_kernel<32><<<g, 256, 0, st>>>(x, ctot, c0, w, bias, y, M, cin, H * W, cout, leaky);
+        else
+            conv1x1_small_kernel<64><<<g, 256, 0, st>>>(x, ctot, c0, w, bias, y, M, cin, H * W, cout, leaky);
+        NFB_LAUNCH_CHECK();
+        return NFB_OK;
+    }
     if (tc && conv_tc_supported(cin, cout, ks))
         return launch_conv2d_tc(x, ctot, c0, w, bias, y, B, cin, H, W, cout, ks, leaky, kAccStepGain, nullptr, st);
     dim3 grid((unsigned)((M + 63) / 64), (unsigned)((cout + 63) / 64));

@@ -119,17 +119,27 @@ class GlowBlock(Flow):
         B, C, H, W = z.shape
         dev = z.device
         lib = L.lib()
-        w = torch.empty(C, C, device=dev)
-        b = torch.empty(C, device=dev)
-        ldc = torch.empty((), device=dev)
         out = torch.empty_like(z)
         ld = torch.empty(B, device=dev)
         if B == 0:
             return out, ld
+        # the folded 1x1 convolution depends on the parameters only: rebuilt when one of them changes
+        # ((data_ptr, _version) signature, like _native.FlowHandle), not on every call
+        src = (conv.P, conv.L, conv.U, conv.sign_S, conv.log_S, an.s, an.t)
+        sig = tuple((t.data_ptr(), t._version) for t in src) + (H * W, dev)
+        cache = self.__dict__.get("_nfb_fold")
+        if cache is None or cache[0] != sig:
+            w = torch.empty(C, C, device=dev)
+            b = torch.empty(C, device=dev)
+            ldc = torch.empty((), device=dev)
+            with torch.cuda.device(dev):
+                L.check(lib.nfb_glow_fold_actnorm_conv1x1(
+                    L.ptr(conv.P), L.ptr(conv.L), L.ptr(conv.U), L.ptr(conv.sign_S), L.ptr(conv.log_S),
+                    L.ptr(an.s), L.ptr(an.t), C, H * W, L.ptr(w), L.ptr(b), L.ptr(ldc), L.stream_ptr()))
+            self.__dict__["_nfb_fold"] = (sig, w, b, ldc)
+        else:
+            _, w, b, ldc = cache
         with torch.cuda.device(dev):
-            L.check(lib.nfb_glow_fold_actnorm_conv1x1(
-                L.ptr(conv.P), L.ptr(conv.L), L.ptr(conv.U), L.ptr(conv.sign_S), L.ptr(conv.log_S),
-                L.ptr(an.s), L.ptr(an.t), C, H * W, L.ptr(w), L.ptr(b), L.ptr(ldc), L.stream_ptr()))
             L.check(lib.nfb_conv2d(L.ptr(z), C, 0, L.ptr(w), L.ptr(b), L.ptr(out), B, C, H, W, C, 1, -1.0,
                                    L.stream_ptr()))
             h = (C + 1) // 2

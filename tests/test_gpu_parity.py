@@ -307,6 +307,8 @@ def test_glow_multiscale_log_prob_matches_reference():
     (3, 256, 0, 256, 8, 8, 24, 3, -1.0),     # last conv: K = 2304 (36 chunks), N = 24 -> 32, no activation
     (37, 48, 24, 24, 4, 4, 256, 3, 0.1),     # 4x4 images: a 128-pixel tile spans 8 images; channel slice; ragged M
     (2, 7, 1, 5, 5, 7, 200, 5, 0.0),         # odd everything, 5x5 kernel, N = 200 -> 208
+    (9, 12, 0, 12, 16, 16, 12, 1, -1.0),     # folded ActNorm + 1x1 conv: small-channel fp32 kernel
+    (4, 50, 1, 48, 4, 4, 48, 1, -1.0),
 ])
 def test_conv2d_tensor_core_matches_oracle(shape):
     """nfb_conv2d routes conditioner-sized convolutions to the tcgen05 implicit-GEMM kernel (csrc/nfb_conv_tc.cu)."""
