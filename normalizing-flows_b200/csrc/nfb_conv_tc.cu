@@ -182,18 +182,26 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcPara
             const int pix = live ? (int)(m - bi * HW) : 0;
             const int h = pix / p.W, w = pix - h * p.W;
             const float* xb = p.x + (bi * p.ctot + p.c0) * (long long)HW;
-            // this thread's 16 k indices of chunk kc = group G = 4 kc + wh: one tap of channel block cb
-            auto gather = [&](int kc, float (&v)[16]) {
-                const int G = kc * 4 + wh;
-                const int cb = G / kk2, tap = G - cb * kk2;
-                const int kh = tap / ks, kw = tap - kh * ks;
+            // this thread's 16 k indices of chunk kc = group G = 4 kc + wh: one tap of channel block cb.  The
+            // calls come in increasing kc, so (cb, tap) is carried along instead of divided out each time, and
+            // the 16 loads use one 32-bit offset stepped by the plane stride.
+            int g_cb = ks == 1 ? wh : wh / kk2, g_tap = ks == 1 ? 0 : wh % kk2;
+            const int inv_ks = 65536 / ks + 1;  // tap / ks for tap < 25
+            auto gather = [&](float (&v)[16]) {
+                const int kh = (g_tap * inv_ks) >> 16, kw = g_tap - kh * ks;
                 const int hh = h + kh - pad, ww = w + kw - pad;
                 const bool ok = live && hh >= 0 && hh < p.H && ww >= 0 && ww < p.W;
-                const int cbase = cb * 16;
-                const float* src = xb + ((long long)cbase * p.H + hh) * p.W + ww;
+                const int cbase = g_cb * 16;
+                const int nvalid = ok ? p.cin - cbase : 0;  // channels of this block that exist (<= 0: none)
+                const float* src = xb + ((cbase * p.H + hh) * p.W + ww);  // one pointer, stepped by the plane stride
 #pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    v[j] = (ok && cbase + j < p.cin) ? __ldg(src + (long long)j * HW) : 0.f;
+                for (int j = 0; j < 16; ++j) {
+                    v[j] = 0.f;
+                    if (j < nvalid) v[j] = __ldg(src);
+                    src += HW;
+                }
+                if (ks == 1) g_cb += 4;
+                else { g_tap += 4; while (g_tap >= kk2) { g_tap -= kk2; ++g_cb; } }
             };
             auto emit = [&](const float (&v)[16]) {  // split, store into the next free A stage, publish
                 if (st_use > 0) mbar_wait(bar(CB_AEMPTY + st), (st_use - 1) & 1u, p.err, 730 + st);
@@ -219,17 +227,17 @@ __global__ void __launch_bounds__(kCtThreads, 1) conv_tc_kernel(const ConvTcPara
             // three register sets in rotation: the loads of chunks k+1 and k+2 are in flight while chunk k is
             // converted (the gathers come from HBM/L2 at ~2 k cycles; one chunk of work is ~0.6 k)
             float a0[16], a1[16], a2[16];
-            gather(0, a0);
-            if (KC > 1) gather(1, a1);
+            gather(a0);
+            if (KC > 1) gather(a1);
             for (int kc = 0; kc < KC; kc += 3) {
-                if (kc + 2 < KC) gather(kc + 2, a2);
+                if (kc + 2 < KC) gather(a2);
                 emit(a0);
                 if (kc + 1 < KC) {
-                    if (kc + 3 < KC) gather(kc + 3, a0);
+                    if (kc + 3 < KC) gather(a0);
                     emit(a1);
                 }
                 if (kc + 2 < KC) {
-                    if (kc + 4 < KC) gather(kc + 4, a1);
+                    if (kc + 4 < KC) gather(a1);
                     emit(a2);
                 }
             }
