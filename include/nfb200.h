@@ -75,6 +75,12 @@ int nfb_conv2d(const float* x_dev, int32_t x_channels, int32_t c0, const float* 
 int nfb_glow_fold_actnorm_conv1x1(const float* P, const float* L, const float* U, const float* sign_S,
                                   const float* log_S, const float* s, const float* t, int32_t channels,
                                   int32_t hw, float* w_out, float* b_out, float* logdet_out, void* stream);
+/* Sampling direction of the same two layers: Invertible1x1Conv.forward (flows/mixing.py:106-121; W^-1 formed in
+ * double precision like :94-101) followed by ActNorm.forward (flows/affine/coupling.py:38-45), folded into one
+ * 1x1 convolution: w_out = diag(exp(s)) W^-1, b_out = t, *logdet_out = H*W*(sum s - sum log_S).  channels <= 64. */
+int nfb_glow_fold_conv1x1_actnorm_forward(const float* P, const float* L, const float* U, const float* sign_S,
+                                          const float* log_S, const float* s, const float* t, int32_t channels,
+                                          int32_t hw, float* w_out, float* b_out, float* logdet_out, void* stream);
 /* flows/affine/coupling.py:113-171 AffineCoupling on images, in place on the z2 channels of z [B,C,H,W];
  * param = conditioner output [B, (scale?2:1)*n2, H, W] with shift/scale interleaved (:152-153).
  * scale_map 0 exp / 1 sigmoid / 2 sigmoid_inv; split_mode 0 channel / 1 channel_inv (reshape.py:27-31).
@@ -90,6 +96,9 @@ int nfb_squeeze(const float* in_dev, float* out_dev, int64_t batch, int32_t chan
 /* flows/reshape.py:27-31 channel chunk made contiguous: out[b,j,:] = in[b,c0+j,:] */
 int nfb_copy_channels(const float* in_dev, float* out_dev, int64_t batch, int32_t channels, int32_t c0,
                       int32_t n, int32_t hw, void* stream);
+/* flows/reshape.py:68-74 Merge.forward on images: out[b,c0+j,:] = in[b,j,:] (out has `channels` channels) */
+int nfb_paste_channels(const float* in_dev, float* out_dev, int64_t batch, int32_t channels, int32_t c0,
+                       int32_t n, int32_t hw, void* stream);
 /* distributions/base.py:327-344 ClassCondDiagGaussian.log_prob with integer labels y[B] (int64);
  * loc/log_scale: [dim, num_classes] (the reference's (*shape, num_classes) flattened). */
 int nfb_class_cond_diag_gaussian_log_prob(const float* z_dev, const int64_t* y_dev, const float* loc_dev,

@@ -888,6 +888,18 @@ int nfb_glow_fold_actnorm_conv1x1(const float* P, const float* L, const float* U
               "nfb_glow_fold_actnorm_conv1x1: null pointer");
     return launch_glow_fold(P, L, U, sign_S, log_S, s, t, channels, hw, w_out, b_out, logdet_out, S(stream));
 }
+int nfb_glow_fold_conv1x1_actnorm_forward(const float* P, const float* L, const float* U, const float* sign_S,
+                                          const float* log_S, const float* s, const float* t, int32_t channels,
+                                          int32_t hw, float* w_out, float* b_out, float* logdet_out, void* stream) {
+    NFB_CHECK(P && L && U && sign_S && log_S && s && t && w_out && b_out && logdet_out, NFB_ERR_ARG,
+              "nfb_glow_fold_conv1x1_actnorm_forward: null pointer");
+    return launch_glow_fold_fwd(P, L, U, sign_S, log_S, s, t, channels, hw, w_out, b_out, logdet_out, S(stream));
+}
+int nfb_paste_channels(const float* in, float* out, int64_t batch, int32_t channels, int32_t c0, int32_t n,
+                       int32_t hw, void* stream) {
+    NFB_CHECK(in && out, NFB_ERR_ARG, "nfb_paste_channels: null pointer");
+    return launch_paste_channels(in, out, batch, channels, c0, n, hw, S(stream));
+}
 int nfb_affine_coupling_image(float* z, const float* param, float* log_det, const float* logdet_const,
                               int64_t batch, int32_t channels, int32_t hw, int32_t scale, int32_t scale_map,
                               int32_t split_mode, int32_t direction, int32_t accumulate, void* stream) {

@@ -197,6 +197,73 @@ int launch_glow_fold(const float* P, const float* L, const float* U, const float
     return NFB_OK;
 }
 
+// Sampling direction: Invertible1x1Conv.forward (mixing.py:106-121, LU branch :94-101: the reference forms
+// W^-1 = U'^-1 L'^-1 P^T in DOUBLE precision) followed by ActNorm.forward (coupling.py:38-45), folded:
+// w_out[o,c] = exp(s[o]) Winv[o,c];  b_out[o] = t[o];  logdet = HW * (sum s - sum log_S).
+// One block, fp64 triangular inverses by substitution (one column per thread), C <= 64.
+__global__ void glow_fold_fwd_kernel(const float* __restrict__ P, const float* __restrict__ L,
+                                     const float* __restrict__ U, const float* __restrict__ sign_S,
+                                     const float* __restrict__ log_S, const float* __restrict__ s,
+                                     const float* __restrict__ t, int C, int HW, float* __restrict__ w_out,
+                                     float* __restrict__ b_out, float* __restrict__ logdet) {
+    extern __shared__ double shd[];
+    double* Lm = shd;              // C*C unit lower
+    double* Um = shd + C * C;      // C*C upper incl. diagonal
+    double* Li = shd + 2 * C * C;  // L^-1
+    double* Ui = shd + 3 * C * C;  // U^-1
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+        const int r = i / C, c = i % C;
+        Lm[i] = c < r ? (double)L[i] : (c == r ? 1.0 : 0.0);
+        Um[i] = c > r ? (double)U[i] : (c == r ? (double)sign_S[r] * exp((double)log_S[r]) : 0.0);
+        Li[i] = 0.0;
+        Ui[i] = 0.0;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        for (int r = 0; r < C; ++r) {  // column c of L^-1
+            double v = (r == c) ? 1.0 : 0.0;
+            for (int k = c; k < r; ++k) v -= Lm[r * C + k] * Li[k * C + c];
+            Li[r * C + c] = (r < c) ? 0.0 : v;
+        }
+        for (int r = C - 1; r >= 0; --r) {  // column c of U^-1
+            double v = (r == c) ? 1.0 : 0.0;
+            for (int k = r + 1; k <= c; ++k) v -= Um[r * C + k] * Ui[k * C + c];
+            Ui[r * C + c] = (r > c) ? 0.0 : v / Um[r * C + r];
+        }
+    }
+    __syncthreads();
+    // T = U^-1 L^-1 (reuse Lm), then Winv = T P^T: Winv[o,c] = sum_k T[o,k] P[c,k]
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+        const int r = i / C, c = i % C;
+        double acc = 0.0;
+        for (int k = (r > c ? r : c); k < C; ++k) acc += Ui[r * C + k] * Li[k * C + c];
+        Um[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * C; i += blockDim.x) {
+        const int o = i / C, c = i % C;
+        double acc = 0.0;
+        for (int k = 0; k < C; ++k) acc += Um[o * C + k] * (double)P[c * C + k];
+        w_out[i] = (float)(acc * exp((double)s[o]));
+    }
+    for (int o = threadIdx.x; o < C; o += blockDim.x) b_out[o] = t[o];
+    if (threadIdx.x == 0) {
+        double a = 0.0;
+        for (int c = 0; c < C; ++c) a += (double)s[c] - (double)log_S[c];
+        *logdet = (float)(a * HW);
+    }
+}
+int launch_glow_fold_fwd(const float* P, const float* L, const float* U, const float* sign_S, const float* log_S,
+                         const float* s, const float* t, int C, int HW, float* w_out, float* b_out, float* logdet,
+                         cudaStream_t st) {
+    NFB_CHECK(C >= 1 && C <= 64, NFB_ERR_UNSUPPORTED, "Invertible1x1Conv sampling direction: channels %d > 64", C);
+    const size_t smem = (size_t)4 * C * C * sizeof(double);
+    NFB_CUDA(cudaFuncSetAttribute(glow_fold_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    glow_fold_fwd_kernel<<<1, 256, smem, st>>>(P, L, U, sign_S, log_S, s, t, C, HW, w_out, b_out, logdet);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
 // AffineCoupling on images, in place on the z2 channels of z [B,C,H,W]; param [B, (scale?2:1)*n2, H, W].
 // One block per sample; log_det[b] (+)= sum log-scale terms + *logdet_const.
 __global__ void __launch_bounds__(256)
@@ -289,6 +356,25 @@ int launch_copy_channels(const float* in, float* out, long long B, int C, int c0
     const long long total = B * n * HW;
     if (total == 0) return NFB_OK;
     copy_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, C, c0, n, HW);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// out[b, c0 + j, :] = in[b, j, :]   (Merge.forward on images, reshape.py:68-74: the inverse of copy_channels)
+__global__ void paste_channels_kernel(const float* __restrict__ in, float* __restrict__ out, long long B, int C,
+                                      int c0, int n, int HW) {
+    const long long total = B * n * HW;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const long long b = idx / ((long long)n * HW);
+    const long long rem = idx - b * n * HW;
+    out[(b * C + c0) * HW + rem] = in[idx];
+}
+int launch_paste_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st) {
+    NFB_CHECK(c0 >= 0 && n >= 0 && c0 + n <= C, NFB_ERR_ARG, "paste_channels: slice out of range");
+    const long long total = B * n * HW;
+    if (total == 0) return NFB_OK;
+    paste_channels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, C, c0, n, HW);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

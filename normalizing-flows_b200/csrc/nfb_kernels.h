@@ -36,6 +36,10 @@ int launch_coupling_image(float* z, const float* param, float* logdet, const flo
                           int C, int HW, int scale, int smap, int inv_split, int direction, int accumulate,
                           cudaStream_t st);
 int launch_squeeze(const float* in, float* out, long long B, int C, int H, int W, int direction, cudaStream_t st);
+int launch_glow_fold_fwd(const float* P, const float* L, const float* U, const float* sign_S, const float* log_S,
+                         const float* s, const float* t, int C, int HW, float* w_out, float* b_out, float* logdet,
+                         cudaStream_t st);
+int launch_paste_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st);
 int launch_copy_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st);
 int launch_class_cond_gauss(const float* z, const long long* y, const float* loc, const float* log_scale,
                             float* logq, long long B, int dim, int ncls, int accumulate, cudaStream_t st);

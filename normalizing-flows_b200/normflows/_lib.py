@@ -75,9 +75,11 @@ SYMBOLS = {
     "nfb_diag_gaussian_log_prob": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP]),
     "nfb_conv2d": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _F, _VP]),
     "nfb_glow_fold_actnorm_conv1x1": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
+    "nfb_glow_fold_conv1x1_actnorm_forward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "nfb_affine_coupling_image": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "nfb_squeeze": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _I32, _I32, _VP]),
     "nfb_copy_channels": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _I32, _I32, _VP]),
+    "nfb_paste_channels": (C.c_int, [_VP, _VP, _I64, _I32, _I32, _I32, _I32, _VP]),
     "nfb_class_cond_diag_gaussian_log_prob": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _VP]),
     "nfb_flow_create": (C.c_int, [C.POINTER(_VP), _I32]),
     "nfb_flow_destroy": (C.c_int, [_VP]),

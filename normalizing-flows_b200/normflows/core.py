@@ -119,7 +119,7 @@ class NormalizingFlow(nn.Module):
 
 
 class MultiscaleFlow(nn.Module):
-    """Multiscale (Glow) driver (reference: core.py:455-653); density pass only on the CUDA path."""
+    """Multiscale (Glow) driver (reference: core.py:455-653)."""
 
     def __init__(self, q0, flows, merges, transform=None, class_cond=True):
         super().__init__()
@@ -153,6 +153,54 @@ class MultiscaleFlow(nn.Module):
 
     def forward(self, x, y=None):
         return -self.log_prob(x, y)
+
+    def forward_and_log_det(self, z):
+        """core.py:504-525: list of per-level latents -> x; levels first-to-last, each flow's `.forward`."""
+        log_det = 0
+        z_ = None
+        for i in range(len(self.q0)):
+            if i == 0:
+                z_ = z[0]
+            else:
+                z_, ld = self.merges[i - 1]([z_, z[i]])
+                log_det = log_det + ld
+            for flow in self.flows[i]:
+                z_, ld = flow(z_)
+                log_det = log_det + ld
+        return z_, log_det
+
+    def inverse_and_log_det(self, x):
+        """core.py:527-551: x -> list of per-level latents."""
+        log_det = 0
+        z = [None] * len(self.q0)
+        for i in range(len(self.q0) - 1, -1, -1):
+            for flow in reversed(self.flows[i]):
+                x, ld = flow.inverse(x)
+                log_det = log_det + ld
+            if i == 0:
+                z[i] = x
+            else:
+                [x, z[i]], ld = self.merges[i - 1].inverse(x)
+                log_det = log_det + ld
+        return z, log_det
+
+    def sample(self, num_samples=1, y=None, temperature=None):
+        """core.py:553-586: draw every level's latent from its base, push it through the stack."""
+        if temperature is not None:
+            raise NotImplementedError("temperature annealing is off the CUDA path")
+        log_q, z = None, None
+        for i in range(len(self.q0)):
+            z_, log_q_ = self.q0[i](num_samples, y) if self.class_cond else self.q0[i](num_samples)
+            if i == 0:
+                log_q, z = log_q_, z_
+            else:
+                log_q = log_q + log_q_
+                z, ld = self.merges[i - 1]([z, z_])
+                log_q = log_q - ld
+            for flow in self.flows[i]:
+                z, ld = flow(z)
+                log_q = log_q - ld
+        return z, log_q
 
     def save(self, path):
         torch.save(self.state_dict(), path)

@@ -71,6 +71,27 @@ class ClassCondDiagGaussian(BaseDistribution):
         self.log_scale = nn.Parameter(torch.zeros(*shape, num_classes))
         self.temperature = None
 
+    def forward(self, num_samples=1, y=None):
+        """distributions/base.py:302-325: z = loc[..., y] + exp(log_scale[..., y]) * eps and its log-density.
+        The random draws (labels, eps) and the per-class parameter gather are torch device ops (plumbing; the
+        reference's generator stream cannot be reproduced anyway), the density is the CUDA kernel."""
+        dev = self.loc.device
+        if y is not None:
+            num_samples = len(y)
+            if y.dim() != 1:
+                y = torch.argmax(y, dim=1)
+            y = y.to(device=dev, dtype=torch.int64)
+        else:
+            y = torch.randint(self.num_classes, (num_samples,), device=dev)
+        if self.temperature is not None:
+            raise NotImplementedError("temperature annealing is off the CUDA path")
+        with torch.no_grad():
+            eps = torch.randn((num_samples,) + self.shape, dtype=self.loc.dtype, device=dev)
+            loc = self.loc.detach().movedim(-1, 0)[y]
+            log_scale = self.log_scale.detach().movedim(-1, 0)[y]
+            z = (loc + torch.exp(log_scale) * eps).contiguous()
+        return z, self.log_prob(z, y)
+
     def log_prob(self, z, y):
         z = require_cuda_f32(z)
         if y.dim() != 1:

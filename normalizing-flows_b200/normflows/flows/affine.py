@@ -69,11 +69,11 @@ class ActNorm(AffineConstFlow):
         mean = z.mean(dim=self.batch_dims, keepdim=True)
         if direction == "forward":
             s = -torch.log(std + 1e-6)
-            self.s.data.copy_(s)
-            self.t.data.copy_(-mean * torch.exp(s))
+            self.s.copy_(s)  # in place on the Parameter itself: bumps _version, which the packed caches watch
+            self.t.copy_(-mean * torch.exp(s))
         else:
-            self.s.data.copy_(torch.log(std + 1e-6))
-            self.t.data.copy_(mean)
+            self.s.copy_(torch.log(std + 1e-6))
+            self.t.copy_(mean)
         self._mark_done()
 
     def forward(self, z, context=None):

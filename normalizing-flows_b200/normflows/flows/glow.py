@@ -1,9 +1,10 @@
 """Glow building blocks on NCHW tensors (reference: normflows/flows/affine/glow.py:11-84,
 flows/mixing.py:57-133 Invertible1x1Conv, flows/reshape.py:9-128 Split/Merge/Squeeze).
 
-Density direction (`inverse`) runs on the CUDA path: ActNorm.inverse and Invertible1x1Conv.inverse are folded
-into one 1x1 convolution, the ConvNet2d conditioner and the coupling epilogue are kernels in
-csrc/nfb_glow.cu.  The sampling direction of these image layers is not on the CUDA path yet."""
+Both directions run on the CUDA path: ActNorm and Invertible1x1Conv are folded into one 1x1 convolution
+(density: W then exp(-s); sampling: the double-precision inverse of W, then exp(s)), the ConvNet2d conditioner
+runs on the tensor core (csrc/nfb_conv_tc.cu) and the coupling epilogue, Squeeze and channel split/merge are
+kernels in csrc/nfb_glow.cu."""
 import numpy as np
 import torch
 from torch import nn
@@ -73,8 +74,26 @@ def split_channels(z, mode="channel"):
     return (a, b) if mode == "channel" else (b, a)
 
 
+def merge_channels(z1, z2, mode="channel"):
+    """Merge.forward (reshape.py:68-74): concatenate two channel chunks."""
+    z1, z2 = require_cuda_f32(z1), require_cuda_f32(z2)
+    a, b = (z1, z2) if mode == "channel" else (z2, z1)
+    B, ca, H, W = a.shape
+    cb = b.shape[1]
+    out = torch.empty(B, ca + cb, H, W, device=a.device, dtype=a.dtype)
+    if out.numel():
+        with torch.cuda.device(a.device):
+            L.check(L.lib().nfb_paste_channels(L.ptr(a), L.ptr(out), B, ca + cb, 0, ca, H * W, L.stream_ptr()))
+            L.check(L.lib().nfb_paste_channels(L.ptr(b), L.ptr(out), B, ca + cb, ca, cb, H * W, L.stream_ptr()))
+    return out
+
+
 class ImageMerge(Merge):
-    """Merge for the multiscale driver: `inverse` splits channels (core.py:607-609)."""
+    """Merge for the multiscale driver: `inverse` splits channels (core.py:607-609), `forward` joins them."""
+
+    def forward(self, z):
+        z1, z2 = z
+        return merge_channels(z1, z2, self.mode), 0
 
     def inverse(self, z):
         z1, z2 = split_channels(z, self.mode)
@@ -106,8 +125,65 @@ class GlowBlock(Flow):
         self.flows = nn.ModuleList([block, Invertible1x1Conv(channels, use_lu), ActNorm((channels, 1, 1))])
         self.channels, self.scale, self.scale_map, self.split_mode = channels, scale, scale_map, split_mode
 
+    def _folded(self, key, fn, hw, dev):
+        """Folded 1x1 convolution (weights, bias, per-sample log-det constant) of ActNorm + Invertible1x1Conv for
+        one direction; depends on the parameters only, so it is rebuilt when one of them changes
+        ((data_ptr, _version) signature, like _native.FlowHandle), not on every call."""
+        conv, an = self.flows[1], self.flows[2]
+        src = (conv.P, conv.L, conv.U, conv.sign_S, conv.log_S, an.s, an.t)
+        sig = tuple((t.data_ptr(), t._version) for t in src) + (hw, dev)
+        cache = self.__dict__.get(key)
+        if cache is None or cache[0] != sig:
+            C = self.channels
+            w = torch.empty(C, C, device=dev)
+            b = torch.empty(C, device=dev)
+            ldc = torch.empty((), device=dev)
+            with torch.cuda.device(dev):
+                L.check(fn(L.ptr(conv.P), L.ptr(conv.L), L.ptr(conv.U), L.ptr(conv.sign_S), L.ptr(conv.log_S),
+                           L.ptr(an.s), L.ptr(an.t), C, hw, L.ptr(w), L.ptr(b), L.ptr(ldc), L.stream_ptr()))
+            cache = (sig, w, b, ldc)
+            self.__dict__[key] = cache
+        return cache[1], cache[2], cache[3]
+
     def forward(self, z):
-        raise NotImplementedError("GlowBlock.forward (sampling direction on images) is not on the CUDA path yet")
+        """Sampling direction (glow.py:72-77): coupling block, then Invertible1x1Conv.forward, then ActNorm.forward."""
+        z = require_cuda_f32(z)
+        if z.dim() != 4 or z.shape[1] != self.channels:
+            raise ValueError("Expected an NCHW tensor with {} channels.".format(self.channels))
+        an = self.flows[2]
+        B, C, H, W = z.shape
+        dev = z.device
+        lib = L.lib()
+        out = torch.empty_like(z)
+        ld = torch.empty(B, device=dev)
+        if B == 0:
+            return out, ld
+        h = (C + 1) // 2
+        c0, cin = (0, h) if self.split_mode == "channel" else (h, C - h)
+        mid = z.clone()  # the coupling kernel works in place on the transformed half
+        with torch.cuda.device(dev):
+            param = self.flows[0].flows[1].param_map.apply_native(z, c0, cin)
+            if not an._done():
+                # data-dependent init in the sampling direction sees the output of the 1x1 convolution
+                # (normalization.py:19-29); run the first two layers, initialise, then fold
+                w0, b0, _ = self._folded("_nfb_fold_fwd_init", lib.nfb_glow_fold_conv1x1_actnorm_forward, H * W, dev)
+                tmp = mid.clone()
+                L.check(lib.nfb_affine_coupling_image(
+                    L.ptr(tmp), L.ptr(param), None, None, B, C, H * W, int(bool(self.scale)),
+                    _MAPS[self.scale_map], 0 if self.split_mode == "channel" else 1, L.NFB_FORWARD, 0,
+                    L.stream_ptr()))
+                pre = torch.empty_like(z)
+                L.check(lib.nfb_conv2d(L.ptr(tmp), C, 0, L.ptr(w0), L.ptr(b0), L.ptr(pre), B, C, H, W, C, 1, -1.0,
+                                       L.stream_ptr()))
+                an._data_init(pre, "forward")
+            w, b, ldc = self._folded("_nfb_fold_fwd", lib.nfb_glow_fold_conv1x1_actnorm_forward, H * W, dev)
+            L.check(lib.nfb_affine_coupling_image(
+                L.ptr(mid), L.ptr(param), L.ptr(ld), L.ptr(ldc), B, C, H * W, int(bool(self.scale)),
+                _MAPS[self.scale_map], 0 if self.split_mode == "channel" else 1, L.NFB_FORWARD, 0,
+                L.stream_ptr()))
+            L.check(lib.nfb_conv2d(L.ptr(mid), C, 0, L.ptr(w), L.ptr(b), L.ptr(out), B, C, H, W, C, 1, -1.0,
+                                   L.stream_ptr()))
+        return out, ld
 
     def inverse(self, z):
         z = require_cuda_f32(z)
@@ -123,22 +199,7 @@ class GlowBlock(Flow):
         ld = torch.empty(B, device=dev)
         if B == 0:
             return out, ld
-        # the folded 1x1 convolution depends on the parameters only: rebuilt when one of them changes
-        # ((data_ptr, _version) signature, like _native.FlowHandle), not on every call
-        src = (conv.P, conv.L, conv.U, conv.sign_S, conv.log_S, an.s, an.t)
-        sig = tuple((t.data_ptr(), t._version) for t in src) + (H * W, dev)
-        cache = self.__dict__.get("_nfb_fold")
-        if cache is None or cache[0] != sig:
-            w = torch.empty(C, C, device=dev)
-            b = torch.empty(C, device=dev)
-            ldc = torch.empty((), device=dev)
-            with torch.cuda.device(dev):
-                L.check(lib.nfb_glow_fold_actnorm_conv1x1(
-                    L.ptr(conv.P), L.ptr(conv.L), L.ptr(conv.U), L.ptr(conv.sign_S), L.ptr(conv.log_S),
-                    L.ptr(an.s), L.ptr(an.t), C, H * W, L.ptr(w), L.ptr(b), L.ptr(ldc), L.stream_ptr()))
-            self.__dict__["_nfb_fold"] = (sig, w, b, ldc)
-        else:
-            _, w, b, ldc = cache
+        w, b, ldc = self._folded("_nfb_fold", lib.nfb_glow_fold_actnorm_conv1x1, H * W, dev)
         with torch.cuda.device(dev):
             L.check(lib.nfb_conv2d(L.ptr(z), C, 0, L.ptr(w), L.ptr(b), L.ptr(out), B, C, H, W, C, 1, -1.0,
                                    L.stream_ptr()))

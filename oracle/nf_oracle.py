@@ -595,3 +595,34 @@ def multiscale_log_prob(spec, sd, x, y=None):
         else:
             lq = lq + diag_gaussian_log_prob(z_, sd, f"q0.{i}.")
     return lq
+
+
+def multiscale_inverse_and_log_det(spec, sd, x):
+    """core.py:527-551: x -> (list of per-level latents, log_det)."""
+    sd = _cast(sd, x.dtype)
+    n = len(spec["levels"])
+    tot = np.zeros(x.shape[0], dtype=x.dtype)
+    zs = [None] * n
+    for i in range(n - 1, -1, -1):
+        fl = spec["levels"][i]
+        for j in range(len(fl) - 1, -1, -1):
+            x, ld = LAYERS[fl[j]["type"]](x, sd, f"flows.{i}.{j}.", fl[j], "inverse")
+            tot = tot + ld
+        if i == 0:
+            zs[i] = x
+        else:
+            x, zs[i] = _chunk2(x)
+    return zs, tot
+
+
+def multiscale_forward_and_log_det(spec, sd, zs):
+    """core.py:504-525: per-level latents -> x; Merge.forward concatenates channels (flows/reshape.py:68-74)."""
+    sd = _cast(sd, zs[0].dtype)
+    tot = np.zeros(zs[0].shape[0], dtype=zs[0].dtype)
+    z = None
+    for i, fl in enumerate(spec["levels"]):
+        z = zs[0] if i == 0 else np.concatenate([z, zs[i]], axis=1)
+        for j in range(len(fl)):
+            z, ld = LAYERS[fl[j]["type"]](z, sd, f"flows.{i}.{j}.", fl[j], "forward")
+            tot = tot + ld
+    return z, tot

@@ -46,6 +46,14 @@ def dump(name, model, spec, x, y=None, sampling=True, extra=None):
                 lp = m.log_prob(xx, y)
                 out[f"log_prob_{tag}"] = lp.numpy()
                 out[f"kld_{tag}"] = m.forward_kld(xx, y).numpy()
+                # both directions of the multiscale stack (core.py:504-551): latents per level, then back
+                zl, ld = m.inverse_and_log_det(xx)
+                for j, zj in enumerate(zl):
+                    out[f"ms_z{j}_{tag}"] = zj.numpy()
+                out[f"ms_inv_ld_{tag}"] = ld.numpy()
+                fx, fld = m.forward_and_log_det(zl)
+                out[f"ms_fwd_x_{tag}"] = fx.numpy()
+                out[f"ms_fwd_ld_{tag}"] = fld.numpy()
                 continue
             lp = m.log_prob(xx)
             out[f"log_prob_{tag}"] = lp.numpy()
@@ -242,6 +250,8 @@ def main():
 
 if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "glow":
+    case_glow()
 
 
 def case_grads():

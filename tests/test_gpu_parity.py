@@ -300,6 +300,39 @@ def test_glow_multiscale_log_prob_matches_reference():
     np.testing.assert_array_equal(zr.cpu().numpy(), a["x"].astype(np.float32))
 
 
+def test_glow_sampling_direction_matches_reference():
+    """Rows a2/a13/a14 in the sampling direction (core.py:504-525, glow.py:72-77, mixing.py:106-121 with the
+    double-precision inverse of :94-101): per-level latents from the reference -> x, one block, round trip."""
+    from helpers_glow import build_glow_small
+    spec, sd, a = load_golden("glow_small")
+    model = build_glow_small(sd).cuda()
+    n = len(spec["levels"])
+    zs = [cuda(a[f"ms_z{j}_f64"]) for j in range(n)]
+    x, ld = model.forward_and_log_det(zs)
+    np.testing.assert_allclose(x.cpu().numpy(), a["ms_fwd_x_f64"], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(ld.cpu().numpy(), a["ms_fwd_ld_f64"], rtol=1e-4, atol=2e-2)
+    # our own inverse -> forward round trip on the golden images
+    zl, ld_inv = model.inverse_and_log_det(cuda(a["x"]))
+    for j in range(n):
+        np.testing.assert_allclose(zl[j].cpu().numpy(), a[f"ms_z{j}_f64"], rtol=1e-4, atol=5e-4)
+    np.testing.assert_allclose(ld_inv.cpu().numpy(), a["ms_inv_ld_f64"], rtol=1e-4, atol=2e-2)
+    xr, ld_fwd = model.forward_and_log_det(zl)
+    np.testing.assert_allclose(xr.cpu().numpy(), a["x"], rtol=1e-4, atol=5e-4)
+    assert np.abs((ld_inv + ld_fwd).cpu().numpy()).max() < 2e-2
+    # one block against the oracle, with its log-det
+    z0 = np.random.default_rng(4).normal(size=(5, 24, 2, 2))
+    blk = model.flows[0][0]
+    z, ldb = blk.forward(cuda(z0))
+    zo, ldo = O.glow_block(z0, O._cast(sd, np.float64), "flows.0.0.", {}, "forward")
+    np.testing.assert_allclose(z.cpu().numpy(), zo, rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(ldb.cpu().numpy(), ldo, rtol=1e-4, atol=1e-3)
+    # sampling: shapes, finiteness, and log_q consistent with the density of what was drawn
+    y = torch.from_numpy(a["y"]).cuda()
+    xs, lq = model.sample(len(y), y)
+    assert xs.shape == (len(y), 3, 8, 8) and torch.isfinite(xs).all() and torch.isfinite(lq).all()
+    np.testing.assert_allclose(lq.cpu().numpy(), model.log_prob(xs, y).cpu().numpy(), rtol=1e-4, atol=2e-2)
+
+
 @pytest.mark.parametrize("shape", [
     # (B, ctot, c0, cin, H, W, cout, ks, leaky)   Glow conditioner shapes (nets/cnn.py:33-61) + awkward ones
     (5, 12, 0, 6, 16, 16, 256, 3, 0.0),      # first conv, level 1: K = 54 (one padded chunk), N = 256
