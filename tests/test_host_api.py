@@ -109,3 +109,42 @@ def test_glow_multiscale_state_dict_matches_reference():
     for k, v in sd.items():
         assert tuple(ours[k].shape) == tuple(v.shape), k
     build_glow_small(sd)  # strict load of the reference checkpoint
+
+
+def test_flow_handle_tensor_slots_follow_module_state():
+    """FlowHandle remembers WHERE each parameter lives ((dict, key) slots) instead of walking the module tree on
+    every call; the refresh must still see .to()/dtype casts, load_state_dict, re-registered parameters, and --
+    within 256 calls -- a swapped-out sub-module object."""
+    import torch
+    import normflows as nf
+    torch.manual_seed(0)
+    fl = []
+    for i in range(3):
+        fl += [nf.flows.AutoregressiveRationalQuadraticSpline(6, 1, 16), nf.flows.LULinearPermute(6)]
+    fl += [nf.flows.CoupledRationalQuadraticSpline(6, 1, 16)]
+    m = nf.NormalizingFlow(nf.distributions.DiagGaussian(6, trainable=False), fl)
+    h = m._stack()
+    slow = h._build_slots()
+    assert h._slots is not None and len(slow) == len(h._slots) > 40
+    same = lambda a, b: len(a) == len(b) and all(x is y for x, y in zip(a, b))
+    assert same(h._tensors(), slow)
+    # dtype round trip replaces every buffer object and the parameters' storage
+    m.double()
+    m.float()
+    assert same(h._tensors(), h._tensors_slow())
+    # a re-registered parameter is picked up by the dict lookup
+    lin = m.flows[1].linear
+    lin.bias = torch.nn.Parameter(torch.ones_like(lin.bias))
+    assert same(h._tensors(), h._tensors_slow()) and any(t is lin.bias for t in h._tensors())
+    # in-place updates (optimizer step, load_state_dict) keep the objects and bump _version
+    v0 = lin.bias._version
+    with torch.no_grad():
+        lin.bias.add_(1.0)
+    assert lin.bias._version == v0 + 1
+    # a swapped sub-module OBJECT is invisible to the slots until the periodic slow-path check (every 256th call)
+    old_net = m.flows[6].prqct.transform_net
+    m.flows[6].prqct.transform_net = type(old_net)(old_net.initial_layer.in_features, old_net.final_layer.out_features,
+                                                  hidden_features=16, num_blocks=1)
+    for _ in range(256):
+        ts = h._tensors()
+    assert same(ts, h._tensors_slow())
