@@ -295,7 +295,7 @@ def main():
                 "note": "algorithmic = dense fp32-equivalent GEMM flops of the reference (1.327 MFLOP/sample/layer x 32 "
                         "layers, SURVEY 8d).  The kernel runs every product as 3 bf16 tensor-core passes (split "
                         "precision, needed for the rtol 1e-4 bar) so frac <= 1/3 by construction, and skips the "
-                        "all-zero blocks of the MADE masks (~31 % of the dense MMA work); ncu: tensor pipe 42 % active"}
+                        "all-zero blocks of the MADE masks (~31 % of the dense MMA work); ncu: tensor pipe 44 % active"}
 
     if rank != 0:
         if world > 1:
