@@ -254,6 +254,32 @@ if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "glow":
     case_glow()
 
 
+def case_spline_grads():
+    """Gradients of the reference's spline element op w.r.t. every input, by its own autograd in fp64
+    (utils/splines.py:16-97, forward branch): loss = sum(cy * y + cl * logabsdet) with random per-element
+    weights, so the fixture pins d y / d . and d logabsdet / d . separately for each element."""
+    from normflows.utils.splines import unconstrained_rational_quadratic_spline as urqs
+    g = torch.Generator().manual_seed(77)
+    n, K = 600, 8
+    x = (torch.randn(n, generator=g, dtype=torch.float64) * 2.2).requires_grad_(True)  # ~17 % in the tails
+    uw = (torch.randn(n, K, generator=g, dtype=torch.float64) * 1.5).requires_grad_(True)
+    uh = (torch.randn(n, K, generator=g, dtype=torch.float64) * 1.5).requires_grad_(True)
+    ud = (torch.randn(n, K - 1, generator=g, dtype=torch.float64) * 1.5).requires_grad_(True)
+    cy = torch.randn(n, generator=g, dtype=torch.float64)
+    cl = torch.randn(n, generator=g, dtype=torch.float64)
+    y, lad = urqs(x, uw, uh, ud, inverse=False, tail_bound=3.0)
+    (cy * y + cl * lad).sum().backward()
+    np.savez_compressed(os.path.join(HERE, "spline_grads.npz"), x=x.detach().numpy(), uw=uw.detach().numpy(),
+                        uh=uh.detach().numpy(), ud=ud.detach().numpy(), cy=cy.numpy(), cl=cl.numpy(),
+                        y=y.detach().numpy(), lad=lad.detach().numpy(), gx=x.grad.numpy(), guw=uw.grad.numpy(),
+                        guh=uh.grad.numpy(), gud=ud.grad.numpy(), torch_version=torch.__version__)
+    print("wrote spline_grads")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spline_grads":
+    case_spline_grads()
+
+
 def case_grads():
     """Gradients of forward_kld w.r.t. every parameter and the input (fp64), for the autograd check."""
     for kind in ("ar", "coupled"):

@@ -72,3 +72,79 @@ def test_spline_random_vs_oracle(hostlib):
             e_ours, e_ref32 = np.abs(lad - lo), np.abs(l32 - lo)
             assert np.mean(e_ours) < 2e-5
             assert e_ours.max() < max(4 * e_ref32.max(), 1e-3)
+
+
+# ---- analytic backward of the spline element (csrc/nfb_spline_bwd.cuh; SURVEY 8f-1 groundwork) ----
+BWD_SO = os.path.join(ROOT, "tests", "native", "_spline_bwd_host_check.so")
+LOG2E = 1.4426950408889634
+
+
+@pytest.fixture(scope="module")
+def bwdlib():
+    src = os.path.join(ROOT, "tests", "native", "spline_bwd_host_check.cu")
+    hdrs = [os.path.join(ROOT, "normalizing-flows_b200/csrc", h) for h in ("nfb_spline_bwd.cuh", "nfb_spline.cuh")]
+    if not os.path.exists(BWD_SO) or os.path.getmtime(BWD_SO) < max(map(os.path.getmtime, [src] + hdrs)):
+        subprocess.check_call(["nvcc", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-o", BWD_SO, src])
+    return C.CDLL(BWD_SO)
+
+
+def run_bwd(lib, x, uw, uh, ud, gy, gl, tail=3.0, use_float=0):
+    """uw/uh are the reference's natural-log logits; the kernel formulation takes them times log2(e)."""
+    n, K = uw.shape
+    f = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+    x, lw, lh, ud, gy, gl = f(x), f(uw * LOG2E), f(uh * LOG2E), f(ud), f(gy), f(gl)
+    y, lad, gx = np.empty(n), np.empty(n), np.empty(n)
+    glw, glh, gud = np.empty((n, K)), np.empty((n, K)), np.empty((n, K - 1))
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.spline_bwd_check(vp(x), vp(lw), vp(lh), vp(ud), n, C.c_double(tail), vp(gy), vp(gl), int(use_float),
+                         vp(y), vp(lad), vp(gx), vp(glw), vp(glh), vp(gud))
+    return y, lad, gx, glw * LOG2E, glh * LOG2E, gud  # chain rule back to the natural-log logits
+
+
+def test_spline_backward_matches_reference_autograd(bwdlib):
+    f = np.load(os.path.join(ROOT, "tests/golden/spline_grads.npz"))
+    y, lad, gx, guw, guh, gud = run_bwd(bwdlib, f["x"], f["uw"], f["uh"], f["ud"], f["cy"], f["cl"])
+    # (fp64 on both sides; the two formulations order the knot arithmetic differently, and steep bins amplify
+    # the last-bit differences to ~1e-9)
+    np.testing.assert_allclose(y, f["y"], rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(lad, f["lad"], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(gx, f["gx"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(guw, f["guw"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(guh, f["guh"], rtol=1e-6, atol=1e-8)
+    np.testing.assert_allclose(gud, f["gud"], rtol=1e-6, atol=1e-8)
+    assert (np.abs(f["x"]) > 3).sum() > 50 and (np.abs(f["gud"]) > 0).sum() > 500  # tails and interior both hit
+    # float instantiation (what a kernel would run): same numbers to fp32 accuracy
+    y32, lad32, gx32, guw32, guh32, gud32 = run_bwd(bwdlib, f["x"], f["uw"], f["uh"], f["ud"], f["cy"], f["cl"],
+                                                    use_float=1)
+    scale = lambda a: np.abs(a).max()
+    for got, ref in ((gx32, f["gx"]), (guw32, f["guw"]), (guh32, f["guh"]), (gud32, f["gud"])):
+        assert np.mean(np.abs(got - ref) < 2e-4 * scale(ref) + 1e-5) > 0.995
+
+
+def test_spline_backward_matches_finite_differences(bwdlib):
+    rng = np.random.default_rng(5)
+    n, K, eps = 300, 8, 1e-6
+    x = rng.uniform(-2.9, 2.9, size=n)
+    uw, uh, ud = rng.normal(size=(n, K)), rng.normal(size=(n, K)), rng.normal(size=(n, K - 1))
+    one, zero = np.ones(n), np.zeros(n)
+
+    def fwd(x_, uw_, uh_, ud_):
+        y, lad, *_ = run_bwd(bwdlib, x_, uw_, uh_, ud_, zero, zero)
+        return y, lad
+    for which, gy, gl in (("y", one, zero), ("lad", zero, one)):
+        _, _, gx, guw, guh, gud = run_bwd(bwdlib, x, uw, uh, ud, gy, gl)
+        pick = (lambda t: t[0]) if which == "y" else (lambda t: t[1])
+        fd = (pick(fwd(x + eps, uw, uh, ud)) - pick(fwd(x - eps, uw, uh, ud))) / (2 * eps)
+        ok = np.abs(fd - gx) < 1e-5 * (1 + np.abs(gx))  # elements within eps of a knot change bin: skip those
+        assert ok.mean() > 0.98
+        for arr, g in ((uw, guw), (uh, guh), (ud, gud)):
+            for k in range(arr.shape[1]):
+                d = np.zeros_like(arr)
+                d[:, k] = eps
+                args_p = [x, uw, uh, ud]
+                args_m = [x, uw, uh, ud]
+                i = [id(uw), id(uh), id(ud)].index(id(arr)) + 1
+                args_p[i] = arr + d
+                args_m[i] = arr - d
+                fd = (pick(fwd(*args_p)) - pick(fwd(*args_m))) / (2 * eps)
+                assert (np.abs(fd - g[:, k]) < 1e-5 * (1 + np.abs(g[:, k]))).mean() > 0.98, (which, i, k)
