@@ -71,3 +71,74 @@ def forward_kld_dp(model, x_local, group=None, async_op=False):
         ring["pending"][i] = pend
         return pend
     return pend.result()
+
+
+class GradientBuckets:
+    """DDP-style gradient averaging for the training step: parameters are replicated, every
+    rank back-propagates its shard of the batch, then the gradients are summed across ranks and divided by the
+    GLOBAL row count (the loss is a mean over all rows, so ranks with ragged shards weight correctly when each
+    rank's loss was taken over its local rows: g = sum_r n_r g_r / sum_r n_r).
+
+    Gradients are packed into a few flat buffers (default 32 MB each: NVSwitch all-reduce cost is launch latency,
+    not link count, so buckets are sized for few launches) and reduced with one collective per bucket, issued
+    asynchronously in reverse parameter order (the order autograd finishes them); `finish()` waits and scatters
+    the averages back into `.grad`.  Plain torch.distributed: NCCL on GPUs, gloo in the CPU tests."""
+
+    def __init__(self, params, bucket_bytes=32 << 20, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.buckets, cur, size = [], [], 0
+        for p in reversed(self.params):
+            nbytes = p.numel() * p.element_size()
+            if cur and (size + nbytes > bucket_bytes or p.dtype != cur[0].dtype or p.device != cur[0].device):
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += nbytes
+        if cur:
+            self.buckets.append(cur)
+        self._flat = [None] * len(self.buckets)
+        self._work = []
+
+    def start(self, local_rows):
+        """Launch the collectives.  `local_rows`: rows this rank's (mean) loss was computed over."""
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        self._work = []
+        self._rows = None
+        if world == 1:
+            return self
+        first = self.buckets[0][0]
+        self._rows = torch.tensor([float(local_rows)], dtype=torch.float64, device=first.device)
+        for i, bucket in enumerate(self.buckets):
+            n = sum(p.numel() for p in bucket)
+            flat = self._flat[i]
+            if flat is None or flat.numel() != n or flat.device != bucket[0].device or flat.dtype != bucket[0].dtype:
+                flat = torch.empty(n, dtype=bucket[0].dtype, device=bucket[0].device)
+                self._flat[i] = flat
+            off = 0
+            for p in bucket:
+                g = p.grad if p.grad is not None else torch.zeros_like(p)
+                flat[off:off + p.numel()].copy_(g.reshape(-1))
+                off += p.numel()
+            flat.mul_(float(local_rows))  # n_r g_r
+            self._work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        self._work.append(dist.all_reduce(self._rows, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        return self
+
+    def finish(self):
+        if not self._work:
+            return
+        for w in self._work:
+            w.wait()
+        total = float(self._rows.item())
+        for flat, bucket in zip(self._flat, self.buckets):
+            flat.div_(total)
+            off = 0
+            for p in bucket:
+                g = flat[off:off + p.numel()].view_as(p)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+                off += p.numel()
+        self._work = []

@@ -45,3 +45,47 @@ def test_forward_kld_all_reduce_matches_single_process(world):
         assert kld == pytest.approx(float(a["kld_f64"]), rel=1e-6)  # golden kld accumulates in fp32
     spans = sorted((lo, hi) for _, _, lo, hi in res)
     assert spans[0][0] == 0 and spans[-1][1] == a["x"].shape[0]
+
+
+def _grad_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "normalizing-flows_b200"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from normflows.parallel import GradientBuckets, shard_rows
+    torch.manual_seed(0)  # same "model" on every rank
+    params = [torch.nn.Parameter(torch.randn(s)) for s in ((7, 5), (11,), (3, 4, 2), (1,))]
+    frozen = torch.nn.Parameter(torch.randn(4), requires_grad=False)
+    x = torch.randn(13, 5, generator=torch.Generator().manual_seed(1))  # 13 rows: ragged shards
+    lo, hi = shard_rows(13, rank, world)
+
+    def loss_of(rows):  # a mean over rows, like forward_kld
+        h = rows @ params[0].t()
+        return (h.pow(2).sum(1) + (h[:, :3] * params[2].sum((1, 2))).sum(1) + params[1].sum() * rows[:, 0]
+                + params[3] * rows[:, 1]).mean()
+    loss_of(x[lo:hi]).backward()
+    gb = GradientBuckets(params + [frozen], bucket_bytes=200)  # tiny buckets: several collectives
+    assert len(gb.buckets) >= 2
+    gb.start(hi - lo).finish()
+    got = [p.grad.clone() for p in params]
+    for p in params:
+        p.grad = None
+    loss_of(x).backward()  # single-process truth over the full batch
+    err = max(float((g - p.grad).abs().max()) for g, p in zip(got, params))
+    q.put((rank, err, frozen.grad is None))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gradient_buckets_average_like_one_process(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, err, frozen_untouched in res:
+        assert err < 1e-5 and frozen_untouched
