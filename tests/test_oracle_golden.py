@@ -109,3 +109,19 @@ def test_survey_anchor_values():
     x = a["x"]
     lp = O.log_prob(spec, sd, x)
     assert np.all(np.isfinite(lp))
+
+
+@pytest.mark.parametrize("kind", ["ar", "coupled"])
+def test_gradient_oracle_matches_reference_autograd(kind):
+    """oracle/nf_oracle_grad.py (hand-written reverse mode, the checker for native backward kernels) against
+    gradients minted from the reference's own autograd in fp64 (make_golden.py grads): every parameter + input."""
+    from oracle import nf_oracle_grad as G
+    spec, sd, _ = load_golden(f"nsf_{kind}_d5_h128_l3")
+    g = np.load(f"tests/golden/grads_nsf_{kind}_d5_h128_l3.npz")
+    loss, grads, gx = G.forward_kld_grads(spec, sd, g["x"].astype(np.float64))
+    assert loss == pytest.approx(float(g["kld"]), rel=1e-6)  # the reference accumulates log_q in fp32 (core.py:96)
+    np.testing.assert_allclose(gx, g["grad__x"], rtol=1e-9, atol=1e-12)
+    names = [k[6:] for k in g.files if k.startswith("grad__") and k != "grad__x"]
+    assert len(names) >= 48 and set(names) == set(grads)
+    for n in names:
+        np.testing.assert_allclose(grads[n], g["grad__" + n], rtol=1e-9, atol=1e-12, err_msg=n)
