@@ -34,6 +34,13 @@ KIND = os.environ.get("NFB_BENCH_KIND", "ar")  # "ar" (BASELINE config 2) or "co
 # algorithmic work per sample per [spline block + LU]: GEMM flops 2*sum(in*out)
 FLOPS_PER_SAMPLE_LAYER = {"ar": 1_327_104, "coupled": 933_888}
 MIN_BYTES_PER_SAMPLE_LAYER = 520  # z in + z out + log_q r/w
+METRIC = "samples/sec forward_kld, 32-layer RQ-NSF d=64 batch=65536"
+
+
+def workload_name(batch=BATCH):
+    return (f"{'Autoregressive' if KIND == 'ar' else 'Coupled'} RQ-NSF d={D}, {LAYERS} x "
+            f"[spline block(2 blocks, hidden {HIDDEN}, {BINS} bins) + LULinearPermute], "
+            f"batch {batch}/GPU, forward_kld (BASELINE.json configs[1])")
 
 
 def build_model(kind=KIND, layers=LAYERS, seed=0):
@@ -114,7 +121,7 @@ def _cpu_worker(args):
     return dt, float(kld)
 
 
-def cpu_baseline(seconds_target=15.0, kind=KIND):
+def cpu_baseline(seconds_target=15.0, kind=KIND, rows=512, reps=2):
     """The oracle port (numpy restatement of the reference algorithm) on ALL of this host's cores, on a
     bounded sample of the SAME workload: the batch is data-parallel, so `cores // 8` worker processes
     each push `rows` samples through the full 32-layer stack with 8 BLAS threads."""
@@ -122,7 +129,6 @@ def cpu_baseline(seconds_target=15.0, kind=KIND):
     cores = os.cpu_count() or 1
     per = 8 if cores >= 8 else cores
     workers = max(1, cores // per)
-    rows, reps = 512, 2
     ctx = mp.get_context("spawn")
     t0 = time.time()
     with ctx.Pool(workers) as pool:
@@ -143,12 +149,15 @@ def run_reference(args):
     if rank != 0:
         return
     steps = max(1, args.steps)
-    base, dt = cpu_baseline()
-    line = {"impl": "reference", "metric": "samples/sec forward_kld, 32-layer RQ-NSF d=64", "value": base["value"],
+    # one step = one pass of a bounded sample (rows per worker) through the full 32-layer stack on all host cores;
+    # the sample shrinks with the step count so that warm-up + K steps stay within a couple of minutes
+    rows = 512 if steps <= 4 else (256 if steps <= 12 else 96)
+    base, dt = cpu_baseline(rows=rows, reps=steps)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"],
             "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{KIND} RQ-NSF d={D} L={LAYERS} hidden={HIDDEN} (bounded sample: 512 rows per worker per pass)"},
+            "config": {"workload": workload_name(args.batch), "sample": f"{rows} rows per worker process per step"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -303,13 +312,11 @@ def main():
         return
     value = world * B * steps / (elapsed_ms * 1e-3)
     e2e_value = world * B * steps / e2e_s
-    line = {"metric": "samples/sec forward_kld, 32-layer RQ-NSF d=64 batch=65536", "value": value,
+    line = {"metric": METRIC, "value": value,
             "unit": "samples/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": elapsed_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{'Autoregressive' if KIND == 'ar' else 'Coupled'} RQ-NSF d={D}, {LAYERS} x "
-                                   f"[spline block(2 blocks, hidden {HIDDEN}, {BINS} bins) + LULinearPermute], "
-                                   f"batch {B}/GPU, forward_kld (BASELINE.json configs[1])",
+            "config": {"workload": workload_name(B),
                        "global_batch": world * B, "parallelism": f"dp{world}", "dp_collective": dp_mode,
                        "l2_policy": f"{nbuf} rotating input batches ({nbuf * B * D * 4 >> 20} MiB > L2)",
                        "loss": loss_val},
