@@ -326,7 +326,7 @@ def main():
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "gpu_launches": launches_per_step * steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks, "roofline": roof}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # reported baseline: rank 0 at N = 1 only
         line["cpu_baseline"], _ = cpu_baseline()
     print(json.dumps(line), flush=True)
     if world > 1:
