@@ -175,7 +175,7 @@ class CpuReference:
     def __init__(self, rows_total, kind=KIND):
         import multiprocessing as mp
         self.cores = os.cpu_count() or 1
-        self.threads = 8 if self.cores >= 16 else self.cores
+        self.threads = int(os.environ.get("NFB_REF_THREADS", 8 if self.cores >= 16 else self.cores))
         self.workers = max(1, self.cores // self.threads)
         self.rows = max(1, rows_total // self.workers)
         self.rows_total = self.rows * self.workers

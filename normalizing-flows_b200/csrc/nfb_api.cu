@@ -125,6 +125,8 @@ struct FusedPack {
     int pair_steps = 0;
     DevBuf pair_wstream, pair_steps_dev, lu_src_row, lu_src_col, bias_lu;
     FusedLayer host_layer{}, host_pair{};  // packed descriptors (host copies)
+    float b_in0 = 1.f;                     // bound on |conditioner input| * u_row this block was planned for
+    int pa[10] = {}, pw[10] = {};          // per-GEMM power-of-two exponents (A operand / weights), see plan_scales
     DevBuf layer_dev, pair_dev;           // ... and their device images (one FusedLayer each)
     // sampling direction (coupling layers only): [inverse LU map of the PREVIOUS layer in list order + this
     // block, spline inverted] as one unit of the forward whole-stack launch
@@ -150,6 +152,8 @@ struct Layer {
     // lu
     nfb_lu_desc_t lu{};
     DevBuf lu_Wd, lu_Ws, lu_bs, lu_logdet, lu_logdet_neg, lu_perm, lu_tmp;
+    // fp16 operand planning: {inf-norm, max|w|} of W (density map) and W^-1 (sampling map), max |bias| of each
+    float lu_norm_d = 1.f, lu_max_d = 1.f, lu_bmax_d = 0.f, lu_norm_s = 1.f, lu_max_s = 1.f, lu_bmax_s = 0.f;
     std::vector<int> perm_host, inv_perm_host;
     std::vector<float> lu_bs_host;
     // affine family
@@ -179,7 +183,7 @@ struct nfb_flow {
     std::vector<std::pair<int, int>> fwd_units;
     int fwd_trailing_lu = -1, fwd_n = 0;
     DevBuf fwd_layers;
-    DevBuf zA, zB, logq, hA, hB, hT, params, E, scratch_sum, loss, err, ar_tmp, pair_tmp, host_x, zfinal, prof;
+    DevBuf zA, zB, logq, hA, hB, hT, params, E, scratch_sum, loss, err, ar_tmp, pair_tmp, host_x, zfinal, prof, norms;
     long long launches = 0;
 };
 
@@ -446,6 +450,57 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     return NFB_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// fp16 operand planning.  The fused kernel multiplies fp16 hi/lo splits (11-bit mantissas: hi + lo carries
+// 22-23 bits; the bf16 pairs used before carried 16-17 and cost rows of the 32-layer flagship 3e-4 in log_prob).
+// fp16 has a narrow exponent range, so every operand is scaled by a power of two:
+//   A operand of GEMM g  = true activation * u_row * 2^pa[g]      (u_row = 2^-e: per-row unit chosen in the kernel
+//                                                                  from max |x_row|, so that |x| u_row < 1)
+//   weights of GEMM g    = effective weight * 2^pw[g]
+//   true GEMM output     = accumulator * 2^-(pa[g]+pw[g]) / u_row  (applied by the epilogue, exact)
+// pa[g] comes from a GUARANTEED bound on the activation (infinity-norm chain below: no input can overflow fp16),
+// pw[g] from max |w|.  GEMMs 0, 2, 4, ... accumulate onto the residual stream in TMEM and therefore share
+// pa + pw.  For inputs that are post-ReLU (>= 0) the bound uses max(sum w+, sum w-) per row instead of sum |w|.
+// Values far below the bound lose nothing that matters: fp16 subnormals keep the ABSOLUTE error at 2^-25 of the
+// scaled range.  Validated offline against the fp64 oracle by tools/numerics_emul2.py (worst row of the 32-layer
+// flagship: 3.1e-4 with bf16 pairs -> 5e-6, the reference's own fp32 error on that row).
+// ------------------------------------------------------------------------------------------
+int ceil_log2(double v) {
+    if (!(v > 1e-30)) return -100;
+    return (int)std::ceil(std::log2(v));
+}
+int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+float pow2f(int e) { return std::ldexp(1.0f, clampi(e, -120, 120)); }
+
+// nm[g] = {inf-norm, non-negative-input norm, max |w|} of GEMM g (g = n_hidden: final layer); bmax[g] = max |bias|
+void plan_scales(int n_hidden, const std::vector<float>& nm, const std::vector<float>& bmax, double b_in0,
+                 int* pa, int* pw) {
+    const int ng = n_hidden + 1;
+    std::vector<double> bin(ng);
+    auto norm_of = [&](int g) { return (double)((g >= 1 && g < n_hidden) ? nm[3 * g + 1] : nm[3 * g]); };
+    bin[0] = b_in0;
+    double Bh = norm_of(0) * b_in0 + bmax[0];
+    for (int g = 1; g + 1 < n_hidden; g += 2) {  // residual blocks: GEMMs (g, g + 1)
+        bin[g] = Bh;
+        const double Bt = norm_of(g) * Bh + bmax[g];
+        bin[g + 1] = Bt;
+        Bh += norm_of(g + 1) * Bt + bmax[g + 1];
+    }
+    bin[n_hidden] = Bh;
+    for (int g = 0; g < ng; ++g) {
+        pa[g] = clampi(14 - ceil_log2(bin[g]), -60, 14);
+        pw[g] = clampi(13 - ceil_log2(nm[3 * g + 2]), -40, 40);
+    }
+    int P = 1 << 20;
+    for (int g = 0; g < n_hidden; g += 2) P = std::min(P, pa[g] + pw[g]);
+    for (int g = 0; g < n_hidden; g += 2) {
+        int d = pa[g] + pw[g] - P;
+        const int dw = std::min(d, 8);  // the weight scale has ~10 binades of slack before w_lo goes subnormal
+        pw[g] -= dw;
+        pa[g] -= d - dw;
+    }
+}
+
 // (re)pack the weights/biases of a fused block from the live parameters
 int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     FusedPack& F = L.fused;
@@ -454,30 +509,51 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     size_t emax = 0;
     for (auto& g : F.gemms) emax = std::max(emax, (size_t)g.n_pad * g.k_pad);
     NFB_TRY(f->E.reserve(emax * sizeof(float)));
-    for (auto& g : F.gemms) {
+    const int ng = (int)F.gemms.size();
+    NFB_CHECK(ng == F.n_hidden + 1 && ng <= 9, NFB_ERR_STATE, "fused pack: unexpected GEMM count %d", ng);
+    // pass 1: norms of every effective matrix (for the fp16 scale plan)
+    NFB_TRY(f->norms.reserve((size_t)ng * 3 * sizeof(float)));
+    for (int gi = 0; gi < ng; ++gi) {
+        auto& g = F.gemms[gi];
         NFB_TRY(launch_build_effective(g.W, g.M, g.src_cols, g.src_row.as<int>(), g.src_col.as<int>(),
                                        g.row_scale.p ? g.row_scale.as<float>() : nullptr, f->E.as<float>(),
                                        g.n_pad, g.k_pad, acc_gain(3 * g.k_pad / 16), st));
-        for (auto& r : g.recs)
-            NFB_TRY(launch_pack_record(f->E.as<float>(), g.k_pad, r.row0, r.nrows, r.kc,
-                                       F.wstream.as<uint8_t>() + r.off_hi, F.wstream.as<uint8_t>() + r.off_lo, st));
+        NFB_TRY(launch_matrix_norms(f->E.as<float>(), g.n_pad, g.k_pad, f->norms.as<float>() + 3 * gi, st));
     }
     // biases (tiny; synchronous download is fine at pack time)
     NFB_CUDA(cudaStreamSynchronize(st));
+    std::vector<float> nm;
+    NFB_TRY(download(f->norms.as<float>(), (size_t)ng * 3, nm));
     const int H = n.H;
     std::vector<float> bh((size_t)F.n_hidden * 256, 0.f), b0, tmp;
     NFB_TRY(download(n.b0, (size_t)H, b0));
+    std::vector<float> bmax(ng, 0.f);
+    auto amax = [](const std::vector<float>& v) { float m = 0.f; for (float x : v) m = std::max(m, std::fabs(x)); return m; };
+    bmax[0] = amax(b0);
     const std::vector<int>& hp = F.hperm;  // bias index i <-> original hidden unit hp[i]
     std::vector<float> cum = b0;
     for (int j = 0; j < H; ++j) bh[j] = b0[hp[j]];
     for (int b = 0; b < n.nb; ++b) {
         NFB_TRY(download(n.bb[2 * b], (size_t)H, tmp));
+        bmax[1 + 2 * b] = amax(tmp);
         for (int j = 0; j < H; ++j) bh[(size_t)(1 + 2 * b) * 256 + j] = tmp[hp[j]];
         NFB_TRY(download(n.bb[2 * b + 1], (size_t)H, tmp));
+        bmax[2 + 2 * b] = amax(tmp);
         for (int j = 0; j < H; ++j) cum[j] += tmp[j];
         for (int j = 0; j < H; ++j) bh[(size_t)(2 + 2 * b) * 256 + j] = cum[hp[j]];
     }
     F.bias_h = bh;
+    // pass 2: scale plan, then the fp16 records
+    plan_scales(F.n_hidden, nm, bmax, F.b_in0, F.pa, F.pw);
+    for (int gi = 0; gi < ng; ++gi) {
+        auto& g = F.gemms[gi];
+        NFB_TRY(launch_build_effective(g.W, g.M, g.src_cols, g.src_row.as<int>(), g.src_col.as<int>(),
+                                       g.row_scale.p ? g.row_scale.as<float>() : nullptr, f->E.as<float>(),
+                                       g.n_pad, g.k_pad, acc_gain(3 * g.k_pad / 16), st));
+        for (auto& r : g.recs)
+            NFB_TRY(launch_pack_record(f->E.as<float>(), g.k_pad, r.row0, r.nrows, r.kc, pow2f(F.pw[gi]),
+                                       F.wstream.as<uint8_t>() + r.off_hi, F.wstream.as<uint8_t>() + r.off_lo, st));
+    }
     const int crow = F.F * 24;
     std::vector<float> bfin, bf((size_t)(F.n_chunks + 1) * crow, 0.f);  // +1 chunk: the bias prefetch runs one chunk ahead
     NFB_TRY(download(n.bf, (size_t)n.out, bfin));
@@ -509,6 +585,11 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         Lh.id_idx[k] = (unsigned char)(k < (int)F.id_idx.size() ? F.id_idx[k] : 0);
     }
     for (int k = 0; k < 16; ++k) Lh.chunk_order[k] = (unsigned char)(k < (int)F.chunk_order.size() ? F.chunk_order[k] : 0);
+    Lh.a_sc[0] = 1.f; Lh.a_inv[0] = 1.f;
+    for (int gi = 0; gi < ng; ++gi) {
+        Lh.a_sc[1 + gi] = pow2f(F.pa[gi]);
+        Lh.a_inv[1 + gi] = pow2f(-(F.pa[gi] + F.pw[gi]));
+    }
     memcpy(Lh.bias_h, F.bias_h.data(), std::min(sizeof(Lh.bias_h), F.bias_h.size() * sizeof(float)));
     memcpy(Lh.bias_f, F.bias_f.data(), std::min(sizeof(Lh.bias_f), F.bias_f.size() * sizeof(float)));
     NFB_TRY(F.layer_dev.reserve(sizeof(FusedLayer)));
@@ -537,6 +618,17 @@ int repack_lu(nfb_flow* f, Layer& L, cudaStream_t st) {
     }
     NFB_TRY(L.lu_bs.upload(bs));
     L.lu_bs_host = bs;
+    {   // norms for the fp16 scale plan of the fused units this map is part of (row/column permutations leave them unchanged)
+        NFB_TRY(f->norms.reserve(64));
+        std::vector<float> nm;
+        NFB_TRY(launch_matrix_norms(L.lu_Wd.as<float>(), n, n, f->norms.as<float>(), st));
+        NFB_TRY(launch_matrix_norms(L.lu_Ws.as<float>(), n, n, f->norms.as<float>() + 4, st));
+        NFB_CUDA(cudaStreamSynchronize(st));
+        NFB_TRY(download(f->norms.as<float>(), 8, nm));
+        L.lu_norm_d = nm[0]; L.lu_max_d = nm[2]; L.lu_norm_s = nm[4]; L.lu_max_s = nm[6];
+        L.lu_bmax_d = 0.f; L.lu_bmax_s = 0.f;
+        for (int i = 0; i < n; ++i) { L.lu_bmax_d = std::max(L.lu_bmax_d, std::fabs(b[i])); L.lu_bmax_s = std::max(L.lu_bmax_s, std::fabs(bs[i])); }
+    }
     std::vector<float> ld;
     NFB_TRY(download(L.lu_logdet.as<float>(), 1, ld));
     ld[0] = -ld[0];
@@ -549,7 +641,7 @@ int build_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     FusedPack& F = R.fused;
     F.pair_ok = false;
     if (!F.ok || U.D != R.D || U.D > 64) return NFB_OK;
-    if (F.n_steps + 3 > 256) return NFB_OK;
+    if (F.n_steps + 2 > 256) return NFB_OK;
     std::vector<FusedStep> steps;
     auto mk = [&](int a0, int a1, int a2, int first, int wait, int signal) {
         FusedStep s;
@@ -557,13 +649,12 @@ int build_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
         s.ctl = make_ctl(256, first, wait, signal);
         steps.push_back(s);
     };
-    mk(0, 4, 1, 1, 1, 0);        // W_h x {A_h, A_m, A_l}
-    mk(0, 4, 0xFF, 0, 0, 0);     // W_m x {A_h, A_m}
-    mk(0, 0xFF, 0xFF, 0, 0, 1);  // W_l x {A_h}
+    mk(0, 4, 0xFF, 1, 1, 0);     // W_hi x {A_hi, A_lo}
+    mk(0, 4, 0xFF, 0, 0, 1);     // W_lo x {A_hi, A_lo}   (4 terms: the map transforms z itself, ~2^-22)
     steps.insert(steps.end(), F.steps_host.begin(), F.steps_host.end());
     F.pair_steps = (int)steps.size();
     NFB_TRY(F.pair_steps_dev.upload(steps));
-    NFB_TRY(F.pair_wstream.reserve(3 * 8192 + F.rqs_bytes));
+    NFB_TRY(F.pair_wstream.reserve(2 * 8192 + F.rqs_bytes));
     std::vector<int> sr(64), sc(64, -1);
     for (int i = 0; i < 64; ++i) sr[i] = i < U.D ? i : -1;
     for (int j = 0; j < U.D; ++j) sc[U.perm_host[j]] = j;  // E[i, perm[j]] = W[i, j]
@@ -578,10 +669,11 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     FusedPack& F = R.fused;
     if (!F.pair_ok) return NFB_OK;
     NFB_TRY(f->E.reserve(64 * 64 * 4));
+    const int pw_lu = clampi(13 - ceil_log2(U.lu_max_d), -40, 40);
     NFB_TRY(launch_build_effective(U.lu_Wd.as<float>(), nullptr, U.D, F.lu_src_row.as<int>(),
-                                   F.lu_src_col.as<int>(), nullptr, f->E.as<float>(), 64, 64, acc_gain(6 * 4), st));
-    NFB_TRY(launch_swizzle_split(f->E.as<float>(), 64, 64, 64, 3, F.pair_wstream.as<uint8_t>(), st));
-    NFB_CUDA(cudaMemcpyAsync(F.pair_wstream.as<uint8_t>() + 3 * 8192, F.wstream.p, F.rqs_bytes,
+                                   F.lu_src_col.as<int>(), nullptr, f->E.as<float>(), 64, 64, acc_gain(4 * 4), st));
+    NFB_TRY(launch_swizzle_split(f->E.as<float>(), 64, 64, 64, 2, pow2f(pw_lu), F.pair_wstream.as<uint8_t>(), st));
+    NFB_CUDA(cudaMemcpyAsync(F.pair_wstream.as<uint8_t>() + 2 * 8192, F.wstream.p, F.rqs_bytes,
                              cudaMemcpyDeviceToDevice, st));
     std::vector<float> b, bl(64, 0.f);
     NFB_CUDA(cudaStreamSynchronize(st));
@@ -591,6 +683,8 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     FusedLayer& Lp = F.host_pair;
     Lp = F.host_layer;
     Lp.has_lu = 1;
+    Lp.a_sc[0] = pow2f(14);  // |z| u_row < 1
+    Lp.a_inv[0] = pow2f(-(14 + pw_lu));
     Lp.n_steps = F.pair_steps;
     Lp.wstream = F.pair_wstream.as<uint8_t>();
     Lp.steps = F.pair_steps_dev.as<FusedStep>();
@@ -610,7 +704,7 @@ int build_fwd_unit(nfb_flow* f, Layer& R, Layer* U) {
     F.fwd_ok = false;
     if (!F.ok || R.kind != L_COUPLED_RQS) return NFB_OK;
     if (!U) { F.fwd_ok = true; return NFB_OK; }  // first block of the stack: no LU in front of it
-    if (U->D != R.D || U->D > 64 || F.n_steps + 3 > 256) return NFB_OK;
+    if (U->D != R.D || U->D > 64 || F.n_steps + 2 > 256) return NFB_OK;
     std::vector<FusedStep> steps;
     auto mk = [&](int a0, int a1, int a2, int first, int wait, int signal) {
         FusedStep s;
@@ -618,12 +712,11 @@ int build_fwd_unit(nfb_flow* f, Layer& R, Layer* U) {
         s.ctl = make_ctl(256, first, wait, signal);
         steps.push_back(s);
     };
-    mk(0, 4, 1, 1, 1, 0);        // same 6-term schedule as the density pair (build_pair)
-    mk(0, 4, 0xFF, 0, 0, 0);
-    mk(0, 0xFF, 0xFF, 0, 0, 1);
+    mk(0, 4, 0xFF, 1, 1, 0);     // same 4-term schedule as the density pair (build_pair)
+    mk(0, 4, 0xFF, 0, 0, 1);
     steps.insert(steps.end(), F.steps_host.begin(), F.steps_host.end());
     NFB_TRY(F.fwd_steps_dev.upload(steps));
-    NFB_TRY(F.fwd_wstream.reserve(3 * 8192 + F.rqs_bytes));
+    NFB_TRY(F.fwd_wstream.reserve(2 * 8192 + F.rqs_bytes));
     std::vector<int> sr(64, -1), sc(64, -1);
     for (int i = 0; i < U->D; ++i) { sr[i] = U->inv_perm_host[i]; sc[i] = i; }
     NFB_TRY(F.fwd_src_row.upload(sr));
@@ -639,16 +732,19 @@ int repack_fwd_unit(nfb_flow* f, Layer& R, Layer* U, cudaStream_t st) {
     Lp = F.host_layer;
     if (!U) return NFB_OK;  // spline block alone: the density descriptor serves both directions
     NFB_TRY(f->E.reserve(64 * 64 * 4));
+    const int pw_lu = clampi(13 - ceil_log2(U->lu_max_s), -40, 40);
     NFB_TRY(launch_build_effective(U->lu_Ws.as<float>(), nullptr, U->D, F.fwd_src_row.as<int>(),
-                                   F.fwd_src_col.as<int>(), nullptr, f->E.as<float>(), 64, 64, acc_gain(6 * 4), st));
-    NFB_TRY(launch_swizzle_split(f->E.as<float>(), 64, 64, 64, 3, F.fwd_wstream.as<uint8_t>(), st));
-    NFB_CUDA(cudaMemcpyAsync(F.fwd_wstream.as<uint8_t>() + 3 * 8192, F.wstream.p, F.rqs_bytes,
+                                   F.fwd_src_col.as<int>(), nullptr, f->E.as<float>(), 64, 64, acc_gain(4 * 4), st));
+    NFB_TRY(launch_swizzle_split(f->E.as<float>(), 64, 64, 64, 2, pow2f(pw_lu), F.fwd_wstream.as<uint8_t>(), st));
+    NFB_CUDA(cudaMemcpyAsync(F.fwd_wstream.as<uint8_t>() + 2 * 8192, F.wstream.p, F.rqs_bytes,
                              cudaMemcpyDeviceToDevice, st));
     std::vector<float> bl(64, 0.f);
     for (int i = 0; i < U->D; ++i) bl[i] = U->lu_bs_host[U->inv_perm_host[i]];
     NFB_TRY(F.fwd_bias_lu.upload(bl));
     Lp.has_lu = 1;
-    Lp.n_steps = F.n_steps + 3;
+    Lp.a_sc[0] = pow2f(14);
+    Lp.a_inv[0] = pow2f(-(14 + pw_lu));
+    Lp.n_steps = F.n_steps + 2;
     Lp.wstream = F.fwd_wstream.as<uint8_t>();
     Lp.steps = F.fwd_steps_dev.as<FusedStep>();
     Lp.bias_lu = F.fwd_bias_lu.as<float>();
@@ -1062,6 +1158,25 @@ int nfb_flow_set_base_diag_gaussian(nfb_flow_t* f, const float* loc, const float
 int nfb_flow_repack(nfb_flow_t* f, void* stream) {
     NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "nfb_flow_repack: flow not finalized");
     cudaStream_t st = S(stream);
+    // LU maps first: the fused blocks' fp16 scale plans need the norms of the maps in front of them
+    for (auto& Lp : f->layers)
+        if (Lp->kind == L_LU) NFB_TRY(repack_lu(f, *Lp, st));
+    for (auto& Lp : f->layers) {
+        Layer& L = *Lp;
+        if (L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) L.fused.b_in0 = L.kind == L_COUPLED_RQS ? std::max(1.f, L.tail) : 1.f;
+    }
+    for (auto& g : f->groups)
+        if (g.kind == G_FUSED_PAIR) {
+            Layer& R = *f->layers[g.first];
+            Layer& U = *f->layers[g.last];
+            R.fused.b_in0 = std::max(R.fused.b_in0, U.lu_norm_d + U.lu_bmax_d);
+        }
+    for (auto& u : f->fwd_units)
+        if (u.first >= 0) {
+            Layer& R = *f->layers[u.second];
+            Layer& U = *f->layers[u.first];
+            R.fused.b_in0 = std::max(R.fused.b_in0, U.lu_norm_s + U.lu_bmax_s);
+        }
     for (auto& Lp : f->layers) {
         Layer& L = *Lp;
         if (L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) {
@@ -1080,8 +1195,6 @@ int nfb_flow_repack(nfb_flow_t* f, void* stream) {
                 NFB_TRY(L.uncond.upload(tab));
             }
             NFB_TRY(repack_fused(f, L, st));
-        } else if (L.kind == L_LU) {
-            NFB_TRY(repack_lu(f, L, st));
         }
     }
     for (auto& g : f->groups)

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -185,6 +186,11 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return (uint64_t)((smem_addr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) |
            (2ull << 61);
 }
+// fp16 operands (a_format = b_format = 0): the split-precision GEMMs of the fused spline kernel (11-bit mantissas:
+// hi + lo carries 22-23 bits of an fp32 value, against 16-17 for a bf16 pair)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+    return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 // instruction descriptor: c=f32 (bit4), a=bf16 (bit7), b=bf16 (bit10), K-major A and B,
 // N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
@@ -224,6 +230,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     uint32_t r;  // cvt.rn.bf16x2.f32 d, a, b: a -> upper half, b -> lower half
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
     return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo_elem, float hi_elem) {
+    uint32_t r;  // cvt.rn.f16x2.f32 d, a, b: a -> upper half, b -> lower half
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t h) {  // .x = lower half, .y = upper half
+    return __half22float2(*reinterpret_cast<const __half2*>(&h));
 }
 __device__ __forceinline__ float bf16_round(float v) {
     return __bfloat162float(__float2bfloat16_rn(v));

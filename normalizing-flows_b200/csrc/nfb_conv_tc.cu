@@ -278,13 +278,11 @@ bool conv_tc_supported(int cin, int cout, int ks) {
 int launch_conv2d_tc(const float* x, int ctot, int c0, const float* w, const float* bias, float* y, long long B,
                      int cin, int H, int W, int cout, int ks, float leaky, float gain_per_step, int* err,
                      cudaStream_t st) {
-    static int sm_count = 0;
-    if (!sm_count) {
-        NFB_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemMax));
-        int dev = 0;
-        NFB_CUDA(cudaGetDevice(&dev));
-        NFB_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-    }
+    static PerDevice per_dev;  // attribute + SM count of the device this launch goes to (not the first one seen)
+    const int sm_count = per_dev.ensure([] {
+        return cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCtSmemMax);
+    });
+    if (sm_count < 0) return NFB_ERR_CUDA;
     const long long M = B * H * W;
     if (M == 0) return NFB_OK;
     const int T = ks * ks;

@@ -80,29 +80,22 @@ __device__ __forceinline__ void epi_bar_sync() {  // the 256 epilogue threads on
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
 
-// split 8 consecutive fp32 values into bf16 hi / lo (/ lo2) chunks and store them at the same
-// chunk offset of up to three A tiles.
-template <int NSPLIT>
-__device__ __forceinline__ void split_store8(const float* v, uint32_t t0, uint32_t t1, uint32_t t2,
-                                             uint32_t off) {
-    uint32_t h[4], m[4], l[4];
+// split 8 consecutive fp32 values (already in the GEMM's scaled units) into fp16 hi / lo chunks and store them at
+// the same chunk offset of the two A tiles.  hi + lo reproduces the value to ~2^-23 relative (11 + 11 bits + sign).
+__device__ __forceinline__ void split_store8(const float* v, uint32_t t0, uint32_t t1, uint32_t off) {
+    uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const float a = v[2 * i], b = v[2 * i + 1];
-        h[i] = pack_bf16x2(a, b);
-        const float ra = a - __uint_as_float(h[i] << 16);
-        const float rb = b - __uint_as_float(h[i] & 0xffff0000u);
-        m[i] = pack_bf16x2(ra, rb);
-        if (NSPLIT == 3) {
-            const float sa = ra - __uint_as_float(m[i] << 16);
-            const float sb = rb - __uint_as_float(m[i] & 0xffff0000u);
-            l[i] = pack_bf16x2(sa, sb);
-        }
+        h[i] = pack_f16x2(a, b);
+        const float2 hf = unpack_f16x2(h[i]);
+        l[i] = pack_f16x2(a - hf.x, b - hf.y);
     }
     st_shared_v4(t0 + off, h[0], h[1], h[2], h[3]);
-    st_shared_v4(t1 + off, m[0], m[1], m[2], m[3]);
-    if (NSPLIT == 3) st_shared_v4(t2 + off, l[0], l[1], l[2], l[3]);
+    st_shared_v4(t1 + off, l[0], l[1], l[2], l[3]);
 }
+// 2^e as a float, e in [-126, 127]
+__device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t)(127 + e) << 23); }
 
 // SAMPLE = false: density direction (Flow.inverse of every layer: x -> z, core.py:70-85).
 // SAMPLE = true : sampling direction of coupling-layer stacks (Flow.forward: z -> x, core.py:40-55): the unit is
@@ -178,7 +171,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         uint32_t slot = 0, wpar = 0, apar = 0, cebits = 0;
         const uint64_t adesc0 = umma_desc_sw128(sbase + kOffA);
         const uint64_t bdesc0 = umma_desc_sw128(sbase + kOffW);
-        constexpr uint32_t kIdesc0 = umma_idesc_bf16(128, 0);
+        constexpr uint32_t kIdesc0 = umma_idesc_f16(128, 0);
         for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
             const FusedLayer& L = p.layers[u / n_tiles];
             const uint2* steps = reinterpret_cast<const uint2*>(L.steps);  // 8-byte entries, L2-resident
@@ -258,9 +251,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             const float* zsrc = layer == 0 ? p.zin : p.zout;   // layers >= 1 update z in place
             const long long row0 = tile * 128;
             if (u != blockIdx.x) prof = nullptr;
+            float ru = 1.f, ruinv = 1.f;  // this row's power-of-two unit (set after the tile load)
             auto build_a = [&](bool lu_stage) {
-                // A[:, k] for k in [wh*kGC, (wh+1)*kGC): lu_stage -> 3-way split of xs[:, k] (k < D);
-                // otherwise 2-way split of the conditioner input xs[:, in_idx[k]].
+                // A[:, k] for k in [wh*kGC, (wh+1)*kGC): fp16 hi/lo split of xs[:, k] (LU stage, k < D) or of the
+                // conditioner input xs[:, in_idx[k]], in units of u * a_sc
+                const float sc = ru * (lu_stage ? L.a_sc[0] : L.a_sc[1]);
     #pragma unroll
                 for (int g = 0; g < kGC / 8; ++g) {
                     float v[8];
@@ -268,11 +263,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     for (int j = 0; j < 8; ++j) {
                         const int k = wh * kGC + g * 8 + j;
                         int c = lu_stage ? (k < D ? k : -1) : L.in_idx[k];
-                        v[j] = c >= 0 ? xs[xs_index(r, c)] : 0.f;
+                        v[j] = c >= 0 ? xs[xs_index(r, c)] * sc : 0.f;
                     }
-                    const uint32_t off = a_chunk_off(r, wh * (kGC / 8) + g);
-                    if (lu_stage) split_store8<3>(v, aA, aA + 4 * kTileA, aA + 1 * kTileA, off);
-                    else split_store8<2>(v, aA, aA + 4 * kTileA, 0, off);
+                    split_store8(v, aA, aA + 4 * kTileA, a_chunk_off(r, wh * (kGC / 8) + g));
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
@@ -328,6 +321,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
             }
             epi_bar_sync();
+            {   // Row unit u = 2^-e, e = clamp(floor(log2 max|x_row|) + 1, 0, 40): |x| u < 1 for every input of the
+                // row, so every fp16 operand of this unit stays inside the static bounds the packer derived
+                // (nfb_api.cu plan_scales) whatever the magnitude of the data; u = 1 for ordinary rows (|x| < 1 .. 2).
+                float zmax = 0.f;
+#pragma unroll 8
+                for (int c = 0; c < D; ++c) zmax = fmaxf(zmax, fabsf(xs[xs_index(r, c)]));
+                int e = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;
+                e = max(0, min(40, e));
+                ru = pow2i(-e);
+                ruinv = pow2i(e);
+            }
             NFB_STAMP();  // [1] load done
             float ladsum = 0.f;
             if (L.has_lu) {
@@ -345,7 +349,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 #pragma unroll
                 for (int j = 0; j < kGC; ++j) {
                     const int c = wh * kGC + j;
-                    if (c < D) xs[xs_index(r, c)] = __uint_as_float(acc[j]) + __ldg(L.bias_lu + c);
+                    if (c < D) xs[xs_index(r, c)] = fmaf(__uint_as_float(acc[j]), L.a_inv[0] * ruinv, __ldg(L.bias_lu + c));
                 }
                 epi_bar_sync();
             }
@@ -384,6 +388,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 NFB_STAMP();  // hidden gemm ph done
                 const uint32_t region = (ph & 1) ? 256u : 0u;
                 const bool relu = ph + 1 < L.n_hidden;
+                const float inv = L.a_inv[1 + ph] * ruinv;   // accumulator -> true value
+                const float sc = L.a_sc[2 + ph] * ru;       // true value -> the next GEMM's A units
                 // K-chunk order: both column halves convert the same 64 columns, then release that slice of
                 // the next A operand so the next GEMM's kc-step can start while the rest is converted
                 for (int kc = 0; kc < (H >> 6); ++kc) {
@@ -401,13 +407,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     float v[kGC];
 #pragma unroll
                     for (int j = 0; j < kGC; ++j) {
-                        float t = __uint_as_float(acc[j]) + bv[j];
-                        v[j] = relu ? fmaxf(t, 0.f) : t;
+                        float t = fmaf(__uint_as_float(acc[j]), inv, bv[j]);
+                        v[j] = (relu ? fmaxf(t, 0.f) : t) * sc;
                     }
                     const uint32_t thi = aA + kc * kTileA, tlo = aA + (4 + kc) * kTileA;
 #pragma unroll
                     for (int j = 0; j < kGC / 8; ++j)
-                        split_store8<2>(v + 8 * j, thi, tlo, 0, a_chunk_off(r, wh * (kGC / 8) + j));
+                        split_store8(v + 8 * j, thi, tlo, a_chunk_off(r, wh * (kGC / 8) + j));
                     fence_proxy_async_smem();
                     tc_fence_before();
                     __syncwarp();
@@ -420,6 +426,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             // chunk = F features x 24 columns (N = 24 F <= 240).  The F features are dealt round-robin to the kNG
             // column groups (feature f of the chunk -> group f % kNG); one evaluation at a time per thread,
             // latency is hidden by the four warps per SM sub-partition.
+            const float inv_f = L.a_inv[1 + L.n_hidden] * ruinv;
             for (int ci = 0; ci < L.n_chunks; ++ci) {
                 // Processing slot 0 -> buffer 1 (columns 256..): the last hidden epilogue is still reading the
                 // residual stream (columns 0..255) when the first final-layer MMAs start.  The packer puts a
@@ -458,9 +465,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         float lw[8], lh[8], dd[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            lw[j] = __uint_as_float(pr[j]) + bv[j];
-                            lh[j] = __uint_as_float(pr[8 + j]) + bv[8 + j];
-                            dd[j] = __uint_as_float(pr[16 + j]) + bv[16 + j];
+                            lw[j] = fmaf(__uint_as_float(pr[j]), inv_f, bv[j]);
+                            lh[j] = fmaf(__uint_as_float(pr[8 + j]), inv_f, bv[8 + j]);
+                            dd[j] = fmaf(__uint_as_float(pr[16 + j]), inv_f, bv[16 + j]);
                         }
                         const int col = L.tr_idx[t];
                         float y, l;
@@ -526,14 +533,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 }
 
 int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st) {
-    static bool attr_done = false;
-    if (!attr_done) {
-        NFB_CUDA(cudaFuncSetAttribute(fused_rqs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kFusedSmem));
-        NFB_CUDA(cudaFuncSetAttribute(fused_rqs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)kFusedSmem));
-        attr_done = true;
-    }
+    static PerDevice per_dev;  // the opt-in shared-memory size is a per-device function attribute
+    const int dev_sms = per_dev.ensure([] {
+        cudaError_t e = cudaFuncSetAttribute(fused_rqs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)kFusedSmem);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(fused_rqs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)kFusedSmem);
+    });
+    if (dev_sms < 0) return NFB_ERR_CUDA;
+    if (sm_count <= 0 || sm_count > dev_sms) sm_count = dev_sms;  // co-residency bound of the CURRENT device
     NFB_CHECK(p.n_layers >= 1 && (p.n_layers == 1 || p.progress), NFB_ERR_ARG, "fused rqs: bad layer list");
     const long long n_units = (p.rows + 127) / 128 * p.n_layers;
     if (n_units == 0) return NFB_OK;
@@ -571,7 +580,7 @@ __global__ void build_effective_kernel(const float* __restrict__ W, const float*
 }
 // stage 2
 __global__ void swizzle_split_kernel(const float* __restrict__ E, int n_pad, int k_pad,
-                                     int rows_per_rec, int nsplit, uint8_t* __restrict__ out) {
+                                     int rows_per_rec, int nsplit, float scale, uint8_t* __restrict__ out) {
     const int kcs = k_pad / 64;
     const long long total = (long long)n_pad * k_pad;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -579,35 +588,72 @@ __global__ void swizzle_split_kernel(const float* __restrict__ E, int n_pad, int
     const int i = (int)(idx / k_pad), j = (int)(idx - (long long)i * k_pad);
     const int rb = i / rows_per_rec, rr = i - rb * rows_per_rec;
     const int kc = j >> 6, kk = j & 63;
-    const float v = E[idx];
+    const float v = E[idx] * scale;
     const size_t rec_bytes = (size_t)rows_per_rec * 128;
     const size_t in_rec = (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + (((kk >> 3) ^ (rr & 7)) << 4) +
                           (kk & 7) * 2;
     float rem = v;
     for (int s = 0; s < nsplit; ++s) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(rem);
-        rem -= __bfloat162float(h);
+        const __half h = __float2half_rn(rem);
+        rem -= __half2float(h);
         const size_t rec = ((size_t)rb * kcs + kc) * nsplit + s;
-        *reinterpret_cast<__nv_bfloat16*>(out + rec * rec_bytes + in_rec) = h;
+        *reinterpret_cast<__half*>(out + rec * rec_bytes + in_rec) = h;
     }
 }
 
-// one record: rows [row0, row0+nrows) x K-chunk kc of E -> hi and lo swizzled tiles (nrows*128 B each)
-__global__ void pack_record_kernel(const float* __restrict__ E, int k_pad, int row0, int nrows, int kc,
+// one record: rows [row0, row0+nrows) x K-chunk kc of E (times the GEMM's power-of-two weight scale) -> fp16 hi and
+// lo swizzled tiles (nrows*128 B each)
+__global__ void pack_record_kernel(const float* __restrict__ E, int k_pad, int row0, int nrows, int kc, float scale,
                                    uint8_t* __restrict__ out_hi, uint8_t* __restrict__ out_lo) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrows * 64) return;
     const int rr = idx >> 6, kk = idx & 63;
-    const float v = E[(size_t)(row0 + rr) * k_pad + kc * 64 + kk];
+    const float v = E[(size_t)(row0 + rr) * k_pad + kc * 64 + kk] * scale;
     const size_t off = (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + (((kk >> 3) ^ (rr & 7)) << 4) + (kk & 7) * 2;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    *reinterpret_cast<__nv_bfloat16*>(out_hi + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(out_lo + off) = __float2bfloat16_rn(v - __bfloat162float(h));
+    const __half h = __float2half_rn(v);
+    *reinterpret_cast<__half*>(out_hi + off) = h;
+    *reinterpret_cast<__half*>(out_lo + off) = __float2half_rn(v - __half2float(h));
 }
-int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, uint8_t* out_hi,
+int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, float scale, uint8_t* out_hi,
                        uint8_t* out_lo, cudaStream_t st) {
     NFB_CHECK(nrows > 0 && nrows % 8 == 0, NFB_ERR_ARG, "pack_record: bad row count %d", nrows);
-    pack_record_kernel<<<(nrows * 64 + 255) / 256, 256, 0, st>>>(E, k_pad, row0, nrows, kc, out_hi, out_lo);
+    pack_record_kernel<<<(nrows * 64 + 255) / 256, 256, 0, st>>>(E, k_pad, row0, nrows, kc, scale, out_hi, out_lo);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// Norms of an effective matrix E [n x k] (row-major): out[0] = max_i sum_j |E_ij| (infinity norm),
+// out[1] = max_i max(sum_j E_ij^+, sum_j E_ij^-) (the tighter bound for non-negative inputs, i.e. post-ReLU),
+// out[2] = max |E_ij|.  `out` must be zero-initialised; values are >= 0 so integer atomicMax orders them.
+__global__ void matrix_norms_kernel(const float* __restrict__ E, int n, int k, float* __restrict__ out) {
+    const int row = blockIdx.x;
+    float sp = 0.f, sn = 0.f, mx = 0.f;
+    for (int j = threadIdx.x; j < k; j += blockDim.x) {
+        const float v = E[(size_t)row * k + j];
+        sp += fmaxf(v, 0.f);
+        sn += fmaxf(-v, 0.f);
+        mx = fmaxf(mx, fabsf(v));
+    }
+    __shared__ float s[3][4];
+    sp = warp_sum(sp);
+    sn = warp_sum(sn);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { s[0][w] = sp; s[1][w] = sn; s[2][w] = mx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float p = 0.f, q = 0.f, m = 0.f;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { p += s[0][i]; q += s[1][i]; m = fmaxf(m, s[2][i]); }
+        atomicMax(reinterpret_cast<int*>(out), __float_as_int(p + q));
+        atomicMax(reinterpret_cast<int*>(out + 1), __float_as_int(fmaxf(p, q)));
+        atomicMax(reinterpret_cast<int*>(out + 2), __float_as_int(m));
+    }
+    (void)n;
+}
+int launch_matrix_norms(const float* E, int n, int k, float* out3, cudaStream_t st) {
+    NFB_CUDA(cudaMemsetAsync(out3, 0, 3 * sizeof(float), st));
+    matrix_norms_kernel<<<n, 128, 0, st>>>(E, n, k, out3);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }
@@ -621,13 +667,13 @@ int launch_build_effective(const float* W, const float* M, int src_cols, const i
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }
-int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit,
+int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit, float scale,
                          uint8_t* out, cudaStream_t st) {
     NFB_CHECK(n_pad % rows_per_rec == 0 && k_pad % 64 == 0 && rows_per_rec % 8 == 0, NFB_ERR_ARG,
               "swizzle_split: bad shape %d x %d / %d", n_pad, k_pad, rows_per_rec);
     const long long n = (long long)n_pad * k_pad;
     swizzle_split_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(E, n_pad, k_pad, rows_per_rec,
-                                                                      nsplit, out);
+                                                                      nsplit, scale, out);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

@@ -2,7 +2,41 @@
 #pragma once
 #include "nfb_common.cuh"
 
+#include <mutex>
+
 namespace nfb {
+
+// Per-DEVICE one-time setup (function attributes and SM counts are per device/context, not per process):
+// `fn(dev, sm_count)` runs once for each device ordinal a kernel is first launched on; thread-safe.
+struct PerDevice {
+    static constexpr int kMaxDev = 64;
+    std::mutex mu;
+    bool done[kMaxDev] = {};
+    int sm_count[kMaxDev] = {};
+    // returns the device's SM count (> 0) or -1 with the error set
+    template <typename Fn> int ensure(Fn&& fn) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) {
+            nfb_set_error("cudaGetDevice failed or device ordinal out of range");
+            return -1;
+        }
+        std::lock_guard<std::mutex> lock(mu);
+        if (!done[dev]) {
+            int sms = 0;
+            if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+                nfb_set_error("cudaDeviceGetAttribute(MultiProcessorCount) failed");
+                return -1;
+            }
+            if (fn() != cudaSuccess) {
+                nfb_set_error("per-device kernel attribute setup failed: %s", cudaGetErrorString(cudaGetLastError()));
+                return -1;
+            }
+            sm_count[dev] = sms;
+            done[dev] = true;
+        }
+        return sm_count[dev];
+    }
+};
 
 // ---- generic kernels (nfb_kernels.cu) ----
 int launch_rqs_rows(const float* zin, const float* params, float* zout, float* logdet,
@@ -97,6 +131,9 @@ struct FusedLayer {
     unsigned char tr_idx[64];  // transformed feature columns
     unsigned char id_idx[64];  // identity feature columns (coupled layer)
     unsigned char chunk_order[16];  // final-layer chunks in processing order (first one reads every K-chunk)
+    // fp16 operand scaling (all powers of two; nfb_api.cu plan_scales): index 0 = LU stage, 1 + g = GEMM g of the
+    // conditioner (g = n_hidden: final layer).  A operand = true value * u_row * a_sc; true value = acc * a_inv / u_row.
+    float a_sc[10], a_inv[10];
     alignas(16) float bias_h[7 * 256];   // [n_hidden <= 7][256], residual biases pre-summed along the stream
     alignas(16) float bias_f[82 * 24];   // [(n_chunks+1)*F <= 82][24] final-layer bias in chunk/column order
 };
@@ -126,9 +163,10 @@ int launch_conv2d_tc(const float* x, int ctot, int c0, const float* w, const flo
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
                            const int* src_col, const float* row_scale, float* E, int n_pad,
                            int k_pad, float gain, cudaStream_t st);
-int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, uint8_t* out_hi,
+int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, float scale, uint8_t* out_hi,
                        uint8_t* out_lo, cudaStream_t st);
-int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit,
+int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit, float scale,
                          uint8_t* out, cudaStream_t st);
+int launch_matrix_norms(const float* E, int n, int k, float* out3, cudaStream_t st);
 
 }  // namespace nfb

@@ -10,5 +10,6 @@ there is no CPU/eager fallback."""
 from . import distributions, flows, nets
 from .core import NormalizingFlow, MultiscaleFlow
 from . import parallel
+from ._native import invalidate_packed_weights
 
 __version__ = "0.1.0+b200"

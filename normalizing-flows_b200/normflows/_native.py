@@ -14,6 +14,33 @@ from . import _lib as L
 
 _VERSION = operator.attrgetter("_version")
 
+# Packed-weight caches are keyed on (data_ptr, Tensor._version).  `p.data.add_()` / `.data.copy_()` (older
+# optimizers, EMA/SWA swaps, weight clipping) change the values WITHOUT bumping the version the Parameter
+# reports, so the caches also watch a process-wide generation counter that is bumped by
+#   * every torch optimizer step (global post-hook below),
+#   * load_state_dict / train() / eval() on a NormalizingFlow (core.py),
+#   * an explicit `normflows.invalidate_packed_weights()` (or `model.repack()`),
+# which is the documented call after any other out-of-band `.data` mutation.
+_GENERATION = [0]
+
+
+def invalidate_packed_weights():
+    """Force every packed device image (bf16 split weight streams, folded Glow convolutions) to be rebuilt from
+    the current parameter values on its next use."""
+    _GENERATION[0] += 1
+
+
+def generation():
+    return _GENERATION[0]
+
+
+try:  # torch >= 2.0
+    from torch.optim.optimizer import register_optimizer_step_post_hook as _reg_post
+
+    _reg_post(lambda opt, args, kwargs: invalidate_packed_weights())
+except Exception:  # pragma: no cover
+    pass
+
 
 def require_cuda_f32(t, what="input"):
     if not isinstance(t, torch.Tensor):
@@ -38,6 +65,10 @@ class FlowHandle:
         self._features = None
         self._slots = None
         self._calls = 0
+        self._gen = -1
+
+    def invalidate(self):
+        self._gen = -1
 
     # -- lifetime -------------------------------------------------------------------------
     def close(self):
@@ -97,7 +128,8 @@ class FlowHandle:
             ts = self._tensors()
         sig_ptr = (*map(torch.Tensor.data_ptr, ts), features, device.index)
         sig_ver = tuple(map(_VERSION, ts))
-        if sig_ptr == self._sig_ptr and sig_ver == self._sig_ver and self._h is not None:
+        gen = _GENERATION[0]
+        if sig_ptr == self._sig_ptr and sig_ver == self._sig_ver and gen == self._gen and self._h is not None:
             return self._h
         for t in ts:  # validated whenever anything changed (new tensors, new device, first call)
             if t.device != device:
@@ -124,9 +156,10 @@ class FlowHandle:
                     self.close()
                     raise
                 self._sig_ptr, self._sig_ver, self._features = sig_ptr, sig_ver, features
-            elif sig_ver != self._sig_ver:
+            elif sig_ver != self._sig_ver or gen != self._gen:
                 L.check(lib.nfb_flow_repack(self._h, L.stream_ptr()))
                 self._sig_ver = sig_ver
+            self._gen = gen
         return self._h
 
     # -- operations -------------------------------------------------------------------------

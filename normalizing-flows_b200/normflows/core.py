@@ -38,9 +38,38 @@ class NormalizingFlow(nn.Module):
             self.__dict__["_nfb_stack"] = h
         return h
 
+    def repack(self):
+        """Rebuild the packed device image of the weights on the next call.  Needed only after an out-of-band
+        `.data` mutation (EMA swap, clipping): optimizer steps, load_state_dict, train()/eval() and ordinary
+        in-place updates are picked up automatically (see _native.py)."""
+        from ._native import invalidate_packed_weights
+        invalidate_packed_weights()
+
+    def train(self, mode=True):
+        if mode != self.training:
+            self.repack()
+        return super().train(mode)
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.repack()
+        return out
+
     def _needs_eager_init(self):
         from .flows.affine import ActNorm
         return any(isinstance(f, ActNorm) and not f._done() for f in self.flows)
+
+    def _run_pending_inits(self, x, inverse):
+        """Data-dependent initialisation (ActNorm, flows/normalization.py:19-39) happens inside the reference's
+        first pass, transparently to training.  Here: if any layer still waits for it, walk the layers once
+        under no_grad (each ActNorm sees exactly the input the reference would give it), then take the normal
+        path -- fused stack, or DensityFn when gradients are wanted."""
+        if not self._needs_eager_init():
+            return
+        with torch.no_grad():
+            z = x.detach()
+            for flow in (reversed(self.flows) if inverse else self.flows):
+                z, _ = flow.inverse(z) if inverse else flow(z)
 
     # -- reference API ------------------------------------------------------------------------
     def forward(self, z):
@@ -49,7 +78,8 @@ class NormalizingFlow(nn.Module):
 
     def forward_and_log_det(self, z):
         h = self._stack()
-        if h is not None and z.dim() == 2 and not self._needs_eager_init():
+        self._run_pending_inits(z, inverse=False)
+        if h is not None and z.dim() == 2:
             return h.transform(L.NFB_FORWARD, z)
         log_det = torch.zeros(len(z), device=z.device)
         for flow in self.flows:
@@ -63,7 +93,8 @@ class NormalizingFlow(nn.Module):
 
     def inverse_and_log_det(self, x):
         h = self._stack()
-        if h is not None and x.dim() == 2 and not self._needs_eager_init():
+        self._run_pending_inits(x, inverse=True)
+        if h is not None and x.dim() == 2:
             return h.transform(L.NFB_INVERSE, x)
         log_det = torch.zeros(len(x), device=x.device)
         for i in range(len(self.flows) - 1, -1, -1):
@@ -76,7 +107,8 @@ class NormalizingFlow(nn.Module):
 
     def log_prob(self, x):
         h = self._stack()
-        if h is not None and h.base is not None and x.dim() == 2 and not self._needs_eager_init():
+        self._run_pending_inits(x, inverse=True)
+        if h is not None and h.base is not None and x.dim() == 2:
             if self._wants_grad(x):  # forward on the CUDA kernels, backward via _autograd (interim)
                 from ._autograd import DensityFn
                 return DensityFn.apply(self, x, *self.parameters())
@@ -86,8 +118,8 @@ class NormalizingFlow(nn.Module):
 
     def forward_kld(self, x):
         h = self._stack()
-        if (h is not None and h.base is not None and x.dim() == 2 and not self._needs_eager_init()
-                and not self._wants_grad(x)):
+        self._run_pending_inits(x, inverse=True)
+        if h is not None and h.base is not None and x.dim() == 2 and not self._wants_grad(x):
             return h.forward_kld(x)
         return -torch.mean(self.log_prob(x))
 
@@ -95,6 +127,39 @@ class NormalizingFlow(nn.Module):
         z, log_q = self.q0(num_samples)
         x, log_det = self.forward_and_log_det(z)
         return x, log_q - log_det
+
+    def _no_sampling_grad(self, what):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError(
+                f"{what}: gradients through the sampling direction are not on the CUDA path yet "
+                "(evaluate under torch.no_grad(); forward_kld / log_prob are differentiable)")
+
+    def reverse_kld(self, num_samples=1, beta=1.0, score_fn=True):
+        """core.py:104-131.  z ~ q0 pushed through every layer's `.forward` (one persistent launch for coupling
+        stacks), log_q = log q0(z0) - sum log_det; `score_fn=False` re-evaluates log_q by the density pass of the
+        drawn samples (the reference does the same with parameter gradients switched off)."""
+        self._no_sampling_grad("reverse_kld")
+        z, log_q = self.sample(num_samples)
+        if not score_fn:
+            log_q = self.log_prob(z)
+        log_p = self.p.log_prob(z)
+        return torch.mean(log_q) - beta * torch.mean(log_p)
+
+    def reverse_alpha_div(self, num_samples=1, alpha=1, dreg=False):
+        """core.py:133-165 (value; see reverse_kld for the gradient caveat)."""
+        import numpy as np
+        self._no_sampling_grad("reverse_alpha_div")
+        z, log_q = self.sample(num_samples)
+        log_p = self.p.log_prob(z)
+        if dreg:
+            w_const = torch.exp(log_p - log_q).detach()
+            log_q = self.log_prob(z)
+            w = torch.exp(log_p - log_q)
+            w_alpha = w_const ** alpha
+            w_alpha = w_alpha / torch.mean(w_alpha)
+            weights = (1 - alpha) * w_alpha + alpha * w_alpha ** 2
+            return -alpha * torch.mean(weights * torch.log(w))
+        return np.sign(alpha - 1) * torch.logsumexp(alpha * (log_p - log_q), 0)
 
     def save(self, path):
         torch.save(self.state_dict(), path)

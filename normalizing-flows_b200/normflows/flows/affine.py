@@ -64,9 +64,32 @@ class ActNorm(AffineConstFlow):
         self._init_done_host = True
 
     @torch.no_grad()
+    def _batch_stats(self, z):
+        """mean / unbiased std over the batch dims (normalization.py:23-24,35-36).  Under data parallelism
+        (torch.distributed initialised, world > 1) the statistics are those of the GLOBAL batch: one all-reduce
+        of (sum x, sum x^2, n) in float64, so that every replica initialises the same s, t -- the single-process
+        reference has no precedent; per-rank statistics would silently make the replicas different models."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return z.mean(dim=self.batch_dims, keepdim=True), z.std(dim=self.batch_dims, keepdim=True)
+        zd = z.double()
+        n = 1
+        for d in self.batch_dims:
+            n *= z.shape[d]
+        buf = torch.cat([zd.sum(dim=self.batch_dims, keepdim=True).reshape(-1),
+                         (zd * zd).sum(dim=self.batch_dims, keepdim=True).reshape(-1),
+                         torch.tensor([float(n)], dtype=torch.float64, device=z.device)])
+        dist.all_reduce(buf)
+        c = (buf.numel() - 1) // 2
+        n = buf[-1]
+        mean = buf[:c] / n
+        var = (buf[c:2 * c] - n * mean * mean) / (n - 1)
+        shape = [1 if i in self.batch_dims else z.shape[i] for i in range(z.dim())]
+        return mean.reshape(shape).to(z.dtype), var.clamp_min(0).sqrt().reshape(shape).to(z.dtype)
+
+    @torch.no_grad()
     def _data_init(self, z, direction):
-        std = z.std(dim=self.batch_dims, keepdim=True)
-        mean = z.mean(dim=self.batch_dims, keepdim=True)
+        mean, std = self._batch_stats(z)
         if direction == "forward":
             s = -torch.log(std + 1e-6)
             self.s.copy_(s)  # in place on the Parameter itself: bumps _version, which the packed caches watch

@@ -131,7 +131,8 @@ class GlowBlock(Flow):
         ((data_ptr, _version) signature, like _native.FlowHandle), not on every call."""
         conv, an = self.flows[1], self.flows[2]
         src = (conv.P, conv.L, conv.U, conv.sign_S, conv.log_S, an.s, an.t)
-        sig = tuple((t.data_ptr(), t._version) for t in src) + (hw, dev)
+        from .._native import generation
+        sig = tuple((t.data_ptr(), t._version) for t in src) + (hw, dev, generation())
         cache = self.__dict__.get(key)
         if cache is None or cache[0] != sig:
             C = self.channels

@@ -89,3 +89,55 @@ def test_gradient_buckets_average_like_one_process(world):
         assert p.exitcode == 0
     for _, err, frozen_untouched in res:
         assert err < 1e-5 and frozen_untouched
+
+
+def _actnorm_worker(rank, world, port, q):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "normalizing-flows_b200"), os.path.join(ROOT, "tests")]
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import normflows as nf
+    from normflows.parallel import shard_rows
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 6, generator=g) * torch.arange(1, 7) + 2.0           # flat batch, ragged shards
+    img = torch.randn(10, 4, 3, 3, generator=g) * 0.5 - 1.0                  # image batch (batch_dims 0,2,3)
+    out = {}
+    for name, data, shape in (("flat", x, 6), ("img", img, (4, 1, 1))):
+        lo, hi = shard_rows(data.shape[0], rank, world)
+        for direction in ("inverse", "forward"):
+            an = nf.flows.ActNorm(shape)
+            an._data_init(data[lo:hi], direction)   # statistics only (the transform itself needs the GPU)
+            out[f"{name}_{direction}"] = (an.s.detach().clone().numpy(), an.t.detach().clone().numpy())
+    q.put((rank, out))
+    dist.destroy_process_group()
+
+
+def test_actnorm_init_is_global_batch_under_data_parallel():
+    """with replicated parameters every rank must initialise ActNorm's s, t from the GLOBAL
+    batch (all-reduce of sum x, sum x^2, n), identical on all ranks and equal to the single-process statistics
+    (flows/normalization.py:19-39) of the unsharded batch."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000 + 17
+    procs = [ctx.Process(target=_actnorm_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    sys.path[:0] = [os.path.join(ROOT, "normalizing-flows_b200")]
+    import normflows as nf
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(37, 6, generator=g) * torch.arange(1, 7) + 2.0
+    img = torch.randn(10, 4, 3, 3, generator=g) * 0.5 - 1.0
+    for name, data, shape in (("flat", x, 6), ("img", img, (4, 1, 1))):
+        for direction in ("inverse", "forward"):
+            an = nf.flows.ActNorm(shape)
+            an._data_init(data, direction)  # single process, whole batch
+            for r in range(world):
+                s, t = res[r][f"{name}_{direction}"]
+                np.testing.assert_allclose(s, an.s.detach().numpy(), rtol=1e-5, atol=1e-6)
+                np.testing.assert_allclose(t, an.t.detach().numpy(), rtol=1e-5, atol=1e-6)
+            np.testing.assert_array_equal(res[0][f"{name}_{direction}"][0], res[1][f"{name}_{direction}"][0])
+            np.testing.assert_array_equal(res[0][f"{name}_{direction}"][1], res[1][f"{name}_{direction}"][1])
