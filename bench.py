@@ -117,6 +117,20 @@ REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 _W = {}
 
 
+def usable_cpus():
+    """Host cores this process may actually use: min(affinity, cgroup CPU quota).  The GPU boxes of the pool show
+    128 logical CPUs but run the job in a cgroup with a 16-CPU quota (cpu.max = "1600000 100000"); sizing the
+    worker pool by os.cpu_count() oversubscribes the quota 8x and throttles (measured: 3.7 k samples/s either way)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(p))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def reference_available():
     return os.path.isfile(os.path.join(REF_DIR, "normflows", "__init__.py"))
 
@@ -174,8 +188,8 @@ class CpuReference:
 
     def __init__(self, rows_total, kind=KIND):
         import multiprocessing as mp
-        self.cores = os.cpu_count() or 1
-        self.threads = int(os.environ.get("NFB_REF_THREADS", 8 if self.cores >= 16 else self.cores))
+        self.cores = usable_cpus()
+        self.threads = int(os.environ.get("NFB_REF_THREADS", 4 if self.cores >= 8 else self.cores))
         self.workers = max(1, self.cores // self.threads)
         self.rows = max(1, rows_total // self.workers)
         self.rows_total = self.rows * self.workers
@@ -226,7 +240,7 @@ def time_cpu_reference(rows_total, steps, warmup, kind=KIND):
         ref.close()
     total = sum(times)
     value = ref.rows_total * steps / total
-    base = {"value": value, "unit": "samples/s", "cores": ref.workers * ref.threads,
+    base = {"value": value, "unit": "samples/s", "cores": ref.workers * ref.threads, "logical_cpus": os.cpu_count(),
             "kind": "reference" if ref.use_ref else "port",
             "sample": ref.describe(steps, warmup, time.time() - t_start) + f"; kld={kld:.4f}",
             "rows_per_step": ref.rows_total, "same_config": ref.rows_total == BATCH}
@@ -234,19 +248,28 @@ def time_cpu_reference(rows_total, steps, warmup, kind=KIND):
 
 
 def cpu_baseline(kind=KIND):
-    """GPU line's `cpu_baseline` (rank 0, N = 1): 1 warm-up + 3 timed full-batch passes of the reference."""
-    return time_cpu_reference(BATCH if (os.cpu_count() or 1) >= 16 else 4096, steps=3, warmup=1, kind=kind)
+    """GPU line's `cpu_baseline` (rank 0, N = 1): 1 warm-up + 2 timed passes of the reference over a bounded sample
+    (16 384 rows = 4096 per worker at 16 usable cores; ~4 s per pass there)."""
+    return time_cpu_reference(16384 if usable_cpus() >= 8 else 4096, steps=2, warmup=1, kind=kind)
 
 
 def run_reference(args):
     """--impl reference: the unmodified reference's CPU path on all host cores, same metric / workload / batch.
-    One step = one forward_kld pass over the full batch (65 536 rows; 4096 on hosts with < 16 cores, where a full
-    pass takes ~45 s), sharded over worker processes."""
+    One step = one forward_kld pass over the batch sharded over worker processes (65 536 rows for short runs, a
+    16 384-row sample -- 4096 rows per worker -- when K + W > 4; 4096 rows on hosts with < 8 usable cores)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = max(1, args.steps)
-    rows = args.batch if (os.cpu_count() or 1) >= 16 else min(args.batch, 4096)
+    # full batch when the run is short; otherwise a bounded sample (>= 4096 rows per worker process) so that
+    # warm-up + K steps end within a few minutes on the 16-CPU quota of the GPU boxes (~4 k samples/s)
+    cores = usable_cpus()
+    if cores < 8:
+        rows = min(args.batch, 4096)
+    elif cores >= 16 and steps + max(1, args.warmup) <= 4:
+        rows = args.batch
+    else:
+        rows = min(args.batch, 16384)
     base, dt = time_cpu_reference(rows, steps, max(1, args.warmup))
     line = {"impl": "reference", "metric": METRIC, "value": base["value"],
             "unit": "samples/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, args.warmup),

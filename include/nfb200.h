@@ -61,6 +61,22 @@ int nfb_diag_gaussian_log_prob(const float* z_dev, const float* loc_dev, const f
                                float* log_q_dev, int64_t rows, int32_t dim, int32_t accumulate,
                                void* stream);
 
+/* Dense product of the training pass (what `F.linear` and its autograd formulas compute for every Linear of the
+ * conditioners: nets/resnet.py:37-50,92-104, nets/made.py:80-81,199-214): C[M x N] (+)= opA(A) opB(B)^T on the tensor
+ * core (split-bf16, fp32 accumulate).  A, B, C are row-major fp32 device matrices; `a_mn` / `b_mn` = 1 say that the
+ * operand is stored with its M / N dimension contiguous (element (i, k) at base[k*ld + i]) -- forward Y = X W^T is
+ * (0, 0), dgrad gX = gY W is (0, 1) with B = W, wgrad dW = gY^T X is (1, 1) with A = gY, B = X.  Optional fused
+ * epilogue: + bias[N]; * (mask[M x N] > 0); * mulm[M x N]; + resid[M x N]; ReLU; `a_relu` / `b_relu` apply ReLU to an
+ * operand while it is loaded; `accumulate` adds into C (red.global.add).  Products whose output has few tiles are
+ * split along K automatically (C is zeroed first unless `accumulate`). */
+typedef struct nfb_gemm_desc {
+    const float* A; const float* B; float* C;
+    int64_t lda, ldb, ldc, M, N, K;
+    int32_t a_mn, b_mn, a_relu, b_relu, relu_out, accumulate;
+    const float* bias; const float* mask; const float* mulm; int64_t ldmask; const float* resid; int64_t ldres;
+} nfb_gemm_desc_t;
+int nfb_gemm_f32(const nfb_gemm_desc_t* desc, void* stream);
+
 /* ---- image-shaped (NCHW) operators of the Glow block, density direction (device pointers) ---- */
 
 /* nets/cnn.py:33-61 one layer of ConvNet2d: y = act(conv2d(x[:, c0:c0+cin], w[cout,cin,k,k], stride 1, pad k/2) + b);

@@ -128,6 +128,7 @@ struct FusedPack {
     float b_in0 = 1.f;                     // bound on |conditioner input| * u_row this block was planned for
     int pa[10] = {}, pw[10] = {};          // per-GEMM power-of-two exponents (A operand / weights), see plan_scales
     DevBuf layer_dev, pair_dev;           // ... and their device images (one FusedLayer each)
+    DevBuf layer_fwd_dev;                 // block alone in the sampling direction (ar_passes = D for autoregressive)
     // sampling direction (coupling layers only): [inverse LU map of the PREVIOUS layer in list order + this
     // block, spline inverted] as one unit of the forward whole-stack launch
     bool fwd_ok = false;
@@ -185,6 +186,18 @@ struct nfb_flow {
     DevBuf fwd_layers;
     DevBuf zA, zB, logq, hA, hB, hT, params, E, scratch_sum, loss, err, ar_tmp, pair_tmp, host_x, zfinal, prof, norms;
     long long launches = 0;
+    // host-buffer entry points: chunked H2D on a copy stream, gated tile by tile inside the whole-stack kernel
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_reset = nullptr, ev_copied = nullptr;
+    int* h_seq = nullptr;            // pinned: h_seq[c] = rows resident after chunk c
+    DevBuf in_ready;                 // device int: rows of the current host batch that have landed
+    const int* cur_in_ready = nullptr;
+    ~nfb_flow() {
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (ev_reset) cudaEventDestroy(ev_reset);
+        if (ev_copied) cudaEventDestroy(ev_copied);
+        if (h_seq) cudaFreeHost(h_seq);
+    }
 };
 
 namespace {
@@ -594,6 +607,12 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     memcpy(Lh.bias_f, F.bias_f.data(), std::min(sizeof(Lh.bias_f), F.bias_f.size() * sizeof(float)));
     NFB_TRY(F.layer_dev.reserve(sizeof(FusedLayer)));
     NFB_CUDA(cudaMemcpy(F.layer_dev.p, &Lh, sizeof(FusedLayer), cudaMemcpyHostToDevice));
+    {   // sampling-direction image of the block alone: the autoregressive block iterates D conditioner passes
+        FusedLayer Lf = Lh;
+        Lf.ar_passes = L.kind == L_AR_RQS ? L.D : 0;
+        NFB_TRY(F.layer_fwd_dev.reserve(sizeof(FusedLayer)));
+        NFB_CUDA(cudaMemcpy(F.layer_fwd_dev.p, &Lf, sizeof(FusedLayer), cudaMemcpyHostToDevice));
+    }
     return NFB_OK;
 }
 
@@ -702,7 +721,7 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
 int build_fwd_unit(nfb_flow* f, Layer& R, Layer* U) {
     FusedPack& F = R.fused;
     F.fwd_ok = false;
-    if (!F.ok || R.kind != L_COUPLED_RQS) return NFB_OK;
+    if (!F.ok || (R.kind != L_COUPLED_RQS && R.kind != L_AR_RQS)) return NFB_OK;
     if (!U) { F.fwd_ok = true; return NFB_OK; }  // first block of the stack: no LU in front of it
     if (U->D != R.D || U->D > 64 || F.n_steps + 2 > 256) return NFB_OK;
     std::vector<FusedStep> steps;
@@ -730,7 +749,8 @@ int repack_fwd_unit(nfb_flow* f, Layer& R, Layer* U, cudaStream_t st) {
     FusedPack& F = R.fused;
     FusedLayer& Lp = F.host_fwd;
     Lp = F.host_layer;
-    if (!U) return NFB_OK;  // spline block alone: the density descriptor serves both directions
+    Lp.ar_passes = R.kind == L_AR_RQS ? R.D : 0;  // autoregressive block: D conditioner passes inside the unit
+    if (!U) return NFB_OK;  // spline block alone: the density descriptor (+ ar_passes) serves
     NFB_TRY(f->E.reserve(64 * 64 * 4));
     const int pw_lu = clampi(13 - ceil_log2(U->lu_max_s), -40, 40);
     NFB_TRY(launch_build_effective(U->lu_Ws.as<float>(), nullptr, U->D, F.fwd_src_row.as<int>(),
@@ -756,7 +776,7 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
                        long long rows, int accumulate, cudaStream_t st, int sample = 0) {
     FusedPack& F = R.fused;
     FusedParams p{};
-    p.layers = U ? F.pair_dev.as<FusedLayer>() : F.layer_dev.as<FusedLayer>();
+    p.layers = U ? F.pair_dev.as<FusedLayer>() : (sample ? F.layer_fwd_dev.as<FusedLayer>() : F.layer_dev.as<FusedLayer>());
     p.n_layers = 1;
     p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = accumulate;
     p.progress = nullptr;
@@ -779,6 +799,8 @@ int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, 
     p.n_layers = sample ? f->fwd_n : f->stack_n;
     p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = 1;
     p.progress = f->progress.as<int>();
+    p.in_ready = sample ? nullptr : f->cur_in_ready;
+    f->cur_in_ready = nullptr;  // consumed (or not applicable): later launches must not wait on it
     p.err = f->err.as<int>();
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
     NFB_TRY(launch_fused_rqs(p, f->sm_count, sample, st));
@@ -923,7 +945,7 @@ int run_group(nfb_flow* f, Group& g, int direction, const float* zin, float* zou
     // fused groups in the sampling direction, layer by layer: a coupling block runs the fused kernel with its
     // splines inverted; the autoregressive block needs D sequential conditioner passes (generic kernels)
     auto fwd_block = [&](Layer& R, const float* in, float* out) -> int {
-        if (R.kind == L_COUPLED_RQS && R.fused.ok)
+        if ((R.kind == L_COUPLED_RQS || R.kind == L_AR_RQS) && R.fused.ok)
             return launch_fused_layer(f, R, nullptr, in, out, logdet, rows, 1, st, 1);
         return apply_layer_generic(f, R, direction, in, out, logdet, rows, 1, st);
     };
@@ -1021,6 +1043,19 @@ int nfb_class_cond_diag_gaussian_log_prob(const float* z, const int64_t* y, cons
     NFB_CHECK(z && y && loc && log_scale && log_q, NFB_ERR_ARG, "nfb_class_cond_diag_gaussian_log_prob: null pointer");
     return launch_class_cond_gauss(z, reinterpret_cast<const long long*>(y), loc, log_scale, log_q, batch, dim,
                                    num_classes, accumulate, S(stream));
+}
+
+int nfb_gemm_f32(const nfb_gemm_desc_t* d, void* stream) {
+    NFB_CHECK(d && d->A && d->B && d->C, NFB_ERR_ARG, "nfb_gemm_f32: null pointer");
+    NFB_CHECK(d->M >= 0 && d->N >= 0 && d->K > 0 && d->N < (1ll << 30), NFB_ERR_ARG, "nfb_gemm_f32: bad shape");
+    GemmTcArgs a{};
+    a.A = d->A; a.B = d->B; a.C = d->C; a.lda = d->lda; a.ldb = d->ldb; a.ldc = d->ldc; a.M = d->M; a.N = d->N; a.K = d->K;
+    a.a_mn = d->a_mn; a.b_mn = d->b_mn; a.a_relu = d->a_relu; a.b_relu = d->b_relu; a.relu_out = d->relu_out;
+    a.accumulate = d->accumulate; a.bias = d->bias; a.mask = d->mask; a.mulm = d->mulm; a.ldmask = d->ldmask;
+    a.resid = d->resid; a.ldres = d->ldres;
+    static thread_local int* err_dev = nullptr;  // per-thread device word for the kernel's barrier-timeout tag
+    if (!err_dev) { NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&err_dev), 16)); NFB_CUDA(cudaMemset(err_dev, 0, 16)); }
+    return launch_gemm_tc(a, err_dev, S(stream));
 }
 
 int nfb_flow_create(nfb_flow_t** out, int32_t features) {
@@ -1163,6 +1198,8 @@ int nfb_flow_repack(nfb_flow_t* f, void* stream) {
         if (Lp->kind == L_LU) NFB_TRY(repack_lu(f, *Lp, st));
     for (auto& Lp : f->layers) {
         Layer& L = *Lp;
+        // |input| u_row < 1.  Coupled block, sampling direction: the conditioner sees the inverse unconditional
+        // spline's output, bounded by max(|x|, tail); the autoregressive block folds the tail into u_row itself.
         if (L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) L.fused.b_in0 = L.kind == L_COUPLED_RQS ? std::max(1.f, L.tail) : 1.f;
     }
     for (auto& g : f->groups)
@@ -1312,7 +1349,7 @@ int nfb_flow_finalize(nfb_flow_t* f, int32_t use_tensor_cores, void* stream) {
             if (L.kind == L_LU) {
                 ok = pending < 0;
                 pending = i;
-            } else if (L.kind == L_COUPLED_RQS && L.fused.ok) {
+            } else if ((L.kind == L_COUPLED_RQS || L.kind == L_AR_RQS) && L.fused.ok) {
                 NFB_TRY(build_fwd_unit(f, L, pending >= 0 ? f->layers[pending].get() : nullptr));
                 ok = L.fused.fwd_ok;
                 f->fwd_units.push_back({pending, i});
@@ -1359,9 +1396,8 @@ int nfb_flow_layer_apply(nfb_flow_t* f, int32_t index, int32_t direction, const 
         NFB_TRY(ops.upload(v));
         rc = launch_affine_stack(ops.p, 1, z_in, out, log_det, rows, f->D, 1, direction, st);
         NFB_CUDA(cudaStreamSynchronize(st));  // ops buffer is freed on return
-    } else if ((L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) && L.fused.ok &&
-               (direction == NFB_INVERSE || L.kind == L_COUPLED_RQS)) {
-        // (the autoregressive block's sampling direction is D sequential conditioner passes: generic kernels)
+    } else if ((L.kind == L_AR_RQS || L.kind == L_COUPLED_RQS) && L.fused.ok) {
+        // (the autoregressive block's sampling direction runs its D conditioner passes inside the fused unit)
         if (!log_det) { NFB_TRY(f->logq.reserve((size_t)rows * 4)); }
         rc = launch_fused_layer(f, L, nullptr, z_in, out, log_det ? log_det : f->logq.as<float>(), rows, 1, st,
                                 direction == NFB_FORWARD);
@@ -1435,6 +1471,46 @@ int nfb_flow_forward_kld(nfb_flow_t* f, const float* x, int64_t rows, float* los
     return NFB_OK;
 }
 
+namespace {
+constexpr int kH2dChunks = 16;
+// Start the host->device copy of a [rows x D] batch in kH2dChunks pieces on the flow's copy stream; after each
+// piece a 4-byte copy publishes the number of resident rows in f->in_ready.  When the density pass runs as ONE
+// whole-stack launch, that kernel starts immediately on the compute stream and gates its layer-0 tiles on the
+// counter (FusedParams::in_ready), so the transfer overlaps the first layers; any other execution plan simply
+// waits for the last piece (event).  Copy engines do not need SMs, so a resident spinning kernel cannot starve
+// them.  Returns with *gated = 1 if the kernel-side gate is armed.
+int start_h2d(nfb_flow* f, const float* x_host, float* xd, int64_t rows, int* gated) {
+    if (!f->copy_stream) {
+        NFB_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
+        NFB_CUDA(cudaEventCreateWithFlags(&f->ev_reset, cudaEventDisableTiming));
+        NFB_CUDA(cudaEventCreateWithFlags(&f->ev_copied, cudaEventDisableTiming));
+        NFB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&f->h_seq), kH2dChunks * sizeof(int), cudaHostAllocDefault));
+        NFB_TRY(f->in_ready.reserve(16));
+    }
+    const bool gate = f->stack_n > 0 && rows >= 8192 && rows < (1ll << 31) && getenv("NFB_NO_H2D_OVERLAP") == nullptr;
+    NFB_CUDA(cudaMemsetAsync(f->in_ready.p, 0, 4, 0));
+    NFB_CUDA(cudaEventRecord(f->ev_reset, 0));
+    NFB_CUDA(cudaStreamWaitEvent(f->copy_stream, f->ev_reset, 0));  // previous pass has finished with xd / the counter
+    const int64_t per = ((rows + kH2dChunks - 1) / kH2dChunks + 127) / 128 * 128;  // whole tiles per chunk
+    int64_t done = 0;
+    for (int c = 0; c < kH2dChunks && done < rows; ++c) {
+        const int64_t n = std::min(per, rows - done);
+        NFB_CUDA(cudaMemcpyAsync(xd + done * f->D, x_host + done * f->D, (size_t)n * f->D * 4, cudaMemcpyHostToDevice,
+                                 f->copy_stream));
+        done += n;
+        if (gate) {
+            f->h_seq[c] = (int)done;
+            NFB_CUDA(cudaMemcpyAsync(f->in_ready.p, &f->h_seq[c], 4, cudaMemcpyHostToDevice, f->copy_stream));
+        }
+    }
+    NFB_CUDA(cudaEventRecord(f->ev_copied, f->copy_stream));
+    if (gate) f->cur_in_ready = f->in_ready.as<int>();
+    else NFB_CUDA(cudaStreamWaitEvent(0, f->ev_copied, 0));
+    *gated = gate ? 1 : 0;
+    return NFB_OK;
+}
+}  // namespace
+
 int nfb_flow_log_prob_host(nfb_flow_t* f, const float* x_host, float* log_q_host, int64_t rows) {
     NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "flow not finalized");
     NFB_CHECK(x_host && log_q_host, NFB_ERR_ARG, "null pointer");
@@ -1442,8 +1518,11 @@ int nfb_flow_log_prob_host(nfb_flow_t* f, const float* x_host, float* log_q_host
     NFB_TRY(f->host_x.reserve((size_t)rows * f->D * 4 + (size_t)rows * 4));
     float* xd = f->host_x.as<float>();
     float* lq = xd + (size_t)rows * f->D;
-    NFB_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)rows * f->D * 4, cudaMemcpyHostToDevice, 0));
-    NFB_TRY(nfb_flow_log_prob(f, xd, lq, rows, nullptr));
+    int gated = 0;
+    NFB_TRY(start_h2d(f, x_host, xd, rows, &gated));
+    const int rc = nfb_flow_log_prob(f, xd, lq, rows, nullptr);
+    f->cur_in_ready = nullptr;
+    if (rc) return rc;
     NFB_CUDA(cudaMemcpyAsync(log_q_host, lq, (size_t)rows * 4, cudaMemcpyDeviceToHost, 0));
     NFB_CUDA(cudaStreamSynchronize(0));
     return NFB_OK;
@@ -1456,8 +1535,11 @@ int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, 
     NFB_TRY(f->host_x.reserve((size_t)rows * f->D * 4));
     NFB_TRY(f->loss.reserve(16 + (size_t)rows * 4));
     float* xd = f->host_x.as<float>();
-    NFB_CUDA(cudaMemcpyAsync(xd, x_host, (size_t)rows * f->D * 4, cudaMemcpyHostToDevice, 0));
-    NFB_TRY(nfb_flow_forward_kld(f, xd, rows, f->loss.as<float>(), nullptr, nullptr));
+    int gated = 0;
+    NFB_TRY(start_h2d(f, x_host, xd, rows, &gated));
+    const int rc = nfb_flow_forward_kld(f, xd, rows, f->loss.as<float>(), nullptr, nullptr);
+    f->cur_in_ready = nullptr;
+    if (rc) return rc;
     NFB_CUDA(cudaMemcpyAsync(loss_host, f->loss.p, 4, cudaMemcpyDeviceToHost, 0));
     NFB_CUDA(cudaStreamSynchronize(0));
     return NFB_OK;

@@ -147,19 +147,29 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         uint32_t slot = 0, par = 0;
         for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
             const FusedLayer& L = p.layers[u / n_tiles];
-            const uint8_t* src = L.wstream;
             const FusedStep* steps = L.steps;  // global (L2-resident); the producer only needs the size
             const int n_steps = L.n_steps;
-            uint32_t bytes = n_steps ? (uint32_t)__ldg(&steps[0].bytes16) << 4 : 0u;
-            for (int s = 0; s < n_steps; ++s) {
-                const uint32_t nbytes = s + 1 < n_steps ? (uint32_t)__ldg(&steps[s + 1].bytes16) << 4 : 0u;
+            // autoregressive sampling (SAMPLE, ar_passes = D): the LU records are streamed once, the block's D times
+            const int lu_steps = L.has_lu ? 2 : 0;
+            const int reps = (SAMPLE && L.ar_passes > 0) ? L.ar_passes : 1;
+            const int total = n_steps ? lu_steps + reps * (n_steps - lu_steps) : 0;
+            const uint32_t lu_bytes = L.has_lu ? 2u * 8192u : 0u;
+            int s = 0;
+            uint32_t off = 0;
+            uint32_t bytes = total ? (uint32_t)__ldg(&steps[0].bytes16) << 4 : 0u;
+            for (int i = 0; i < total; ++i) {
+                int sn = s + 1;
+                uint32_t offn = off + bytes;
+                if (sn == n_steps) { sn = lu_steps; offn = lu_bytes; }
+                const uint32_t nbytes = i + 1 < total ? (uint32_t)__ldg(&steps[sn].bytes16) << 4 : 0u;
                 mbar_wait(bar(kBarWEmpty + slot), par ^ 1, p.err, 100 + slot);
                 if (elect_one_sync()) {
                     mbar_expect_tx(bar(kBarWFull + slot), bytes);
-                    bulk_g2s(sbase + kOffW + slot * kSlotBytes, src, bytes, bar(kBarWFull + slot));
+                    bulk_g2s(sbase + kOffW + slot * kSlotBytes, L.wstream + off, bytes, bar(kBarWFull + slot));
                 }
                 __syncwarp();
-                src += bytes;
+                s = sn;
+                off = offn;
                 bytes = nbytes;
                 if (++slot == kSlots) { slot = 0; par ^= 1; }
             }
@@ -176,10 +186,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             const FusedLayer& L = p.layers[u / n_tiles];
             const uint2* steps = reinterpret_cast<const uint2*>(L.steps);  // 8-byte entries, L2-resident
             const int n_steps = L.n_steps;
+            const int lu_steps = L.has_lu ? 2 : 0;
+            const int reps = (SAMPLE && L.ar_passes > 0) ? L.ar_passes : 1;
+            const int total = n_steps ? lu_steps + reps * (n_steps - lu_steps) : 0;
             union { uint2 raw; FusedStep s; } cur, nx;
             cur.raw = __ldg(steps);
-            for (int s = 0; s < n_steps; ++s) {
-                nx.raw = __ldg(steps + (s + 1 < n_steps ? s + 1 : 0));  // prefetch one entry ahead
+            int sidx = 0;
+            for (int s = 0; s < total; ++s) {
+                sidx = sidx + 1 == n_steps ? lu_steps : sidx + 1;
+                nx.raw = __ldg(steps + sidx);  // prefetch one entry ahead (wraps to the block's first step)
                 const FusedStep st = cur.s;
                 const uint32_t ctl = st.ctl;
                 const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
@@ -294,6 +309,27 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     if (seen < layer) { if (p.err) atomicExch(p.err, 501); asm volatile("trap;"); }
                 }
             }
+            // ---- host batch still in flight (nfb_api.cu start_h2d): layer-0 tiles wait for their rows ----
+            if (layer == 0 && p.in_ready) {
+                const int need = (int)min(row0 + 128, p.rows);
+                if (lane == 0) {
+                    int seen;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.in_ready) : "memory");
+                        if (seen < need && clock64() - t0 > 20000000000LL) {  // ~10 s: the copy never came
+                            if (p.err) atomicExch(p.err, 510);
+                            asm volatile("trap;");
+                        }
+                    } while (seen < need);
+                }
+                __syncwarp();
+                {   // every thread acquires the (now sufficient) counter itself before reading the rows
+                    int seen;
+                    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(seen) : "l"(p.in_ready) : "memory");
+                    if (seen < need) { if (p.err) atomicExch(p.err, 511); asm volatile("trap;"); }
+                }
+            }
             NFB_STAMP();  // [0] tile start
             // ---- load z tile -> xs (coalesced global, swizzled shared) ----
             if (D == 64) {
@@ -352,6 +388,48 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     if (c < D) xs[xs_index(r, c)] = fmaf(__uint_as_float(acc[j]), L.a_inv[0] * ruinv, __ldg(L.bias_lu + c));
                 }
                 epi_bar_sync();
+            }
+            auto store_tile = [&]() {
+                if (D == 64) {
+#pragma unroll
+                    for (int k = 0; k < 2048 / kEpiThreads; ++k) {
+                        const int i4 = et + k * kEpiThreads, rr = i4 >> 4, c0 = (i4 & 15) * 4;
+                        const long long gr = row0 + rr;
+                        const float4 v = make_float4(xs[xs_index(rr, c0)], xs[xs_index(rr, c0 + 1)],
+                                                     xs[xs_index(rr, c0 + 2)], xs[xs_index(rr, c0 + 3)]);
+                        if (gr < p.rows) __stcg(reinterpret_cast<float4*>(p.zout + gr * 64) + (i4 & 15), v);
+                    }
+                } else {
+                    for (int i = et; i < 128 * D; i += kEpiThreads) {
+                        const int rr = i / D, cc = i - rr * D;
+                        const long long gr = row0 + rr;
+                        if (gr < p.rows) __stcg(p.zout + gr * D + cc, xs[xs_index(rr, cc)]);
+                    }
+                }
+            };
+            // ---- autoregressive block, sampling direction (flows/affine/autoregressive.py:29-38): D conditioner
+            // passes over a running output that starts at zero; every pass inverts the spline on the SAME input S
+            // (this tile after the LU stage) with parameters computed from the current output; after pass j the
+            // first j features are exact.  S is parked in this tile's rows of `zout` (L2) and read back per element,
+            // the running output lives in xs, and nothing else leaves the SM between passes.
+            const bool arsamp = SAMPLE && L.ar_passes > 0;
+            const int reps = arsamp ? L.ar_passes : 1;
+            if (arsamp) {
+                store_tile();
+                float zmax = L.tail;  // |output| <= max(|S|, tail): bound of every pass's conditioner input
+                for (int c = 0; c < D; ++c) zmax = fmaxf(zmax, fabsf(xs[xs_index(r, c)]));
+                int e = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;
+                e = max(0, min(40, e));
+                ru = pow2i(-e);
+                ruinv = pow2i(e);
+                epi_bar_sync();  // every thread has scanned its row; S is in L2 for every thread of the CTA
+                for (int i = et; i < 128 * 64; i += kEpiThreads) xs[i] = 0.f;
+                epi_bar_sync();
+            }
+            for (int rep = 0; rep < reps; ++rep) {
+            if (rep > 0) {
+                ladsum = 0.f;     // the log-det of the last pass is the layer's (autoregressive.py:36-38)
+                epi_bar_sync();   // the previous pass's outputs (all column groups) are in xs
             }
             // ---- unconditional spline on the identity features (coupled layer only).
             // density: the conditioner input is taken from the RAW values first (Coupling.forward,
@@ -471,7 +549,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         }
                         const int col = L.tr_idx[t];
                         float y, l;
-                        rqs_core<8, SAMPLE>(xs[xs_index(r, col)], lw, lh, [&dd](int k) { return dd[k]; }, L.tail, y, l);
+                        float xin = xs[xs_index(r, col)];
+                        if (arsamp) xin = row0 + r < p.rows ? __ldcg(p.zout + (row0 + r) * D + col) : 0.f;
+                        rqs_core<8, SAMPLE>(xin, lw, lh, [&dd](int k) { return dd[k]; }, L.tail, y, l);
                         xs[xs_index(r, col)] = y;
                         ladsum += l;
                     }
@@ -484,6 +564,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 NFB_STAMP();  // chunk c consumed
             }
 
+            }  // passes
             NFB_STAMP();  // last spline done
             // ---- log-det reduction across the two column halves, then store ----
             if (wh > 0) ldsum[(wh - 1) * 128 + r] = ladsum;
@@ -498,22 +579,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     __stcg(p.logq + gr, tot);
                 }
             }
-            if (D == 64) {
-#pragma unroll
-                for (int k = 0; k < 2048 / kEpiThreads; ++k) {
-                    const int i4 = et + k * kEpiThreads, rr = i4 >> 4, c0 = (i4 & 15) * 4;
-                    const long long gr = row0 + rr;
-                    const float4 v = make_float4(xs[xs_index(rr, c0)], xs[xs_index(rr, c0 + 1)],
-                                                 xs[xs_index(rr, c0 + 2)], xs[xs_index(rr, c0 + 3)]);
-                    if (gr < p.rows) __stcg(reinterpret_cast<float4*>(p.zout + gr * 64) + (i4 & 15), v);
-                }
-            } else {
-                for (int i = et; i < 128 * D; i += kEpiThreads) {
-                    const int rr = i / D, cc = i - rr * D;
-                    const long long gr = row0 + rr;
-                    if (gr < p.rows) __stcg(p.zout + gr * D + cc, xs[xs_index(rr, cc)]);
-                }
-            }
+            store_tile();
             // publish this tile: each thread makes ITS OWN global stores visible device-wide, then the barrier,
             // then one thread releases the flag (a fence by thread 0 alone would not cover stores that other
             // warps still have in flight to L2)

@@ -120,7 +120,8 @@ struct __align__(8) FusedStep {
 // One fused [LULinearPermute +] spline block, packed.  Device-resident (uploaded at pack time): the kernel
 // reads it through a pointer so that ONE persistent launch can walk a whole stack of blocks.
 struct FusedLayer {
-    int D, H, n_hidden, has_lu, T, F, n_chunks, n_id, n_steps, pad_;  // F = features per final-layer chunk
+    int D, H, n_hidden, has_lu, T, F, n_chunks, n_id, n_steps;  // F = features per final-layer chunk
+    int ar_passes;  // sampling direction of an autoregressive block: number of conditioner passes (= D), else 0
     float tail;
     const uint8_t* wstream;
     const FusedStep* steps;
@@ -148,10 +149,22 @@ struct FusedParams {
     long long rows;
     int accumulate;            // layer 0: logq += (1) or = (0); later layers always accumulate
     int* progress;             // [n_tiles] zero-initialised, or null when n_layers == 1
+    const int* in_ready;       // optional: number of rows of `zin` that have landed (chunked H2D in flight, written
+                               // by the copy engine); layer-0 tiles wait for their rows.  null = all resident
     int* err;
     long long* prof;           // optional [128] clock64 stamps (debug)
 };
 int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st);
+
+// general fp32 GEMM on the tensor core (csrc/nfb_gemm_tc.cu): training pass of the conditioners
+struct GemmTcArgs {
+    const float* A; const float* B; float* C;
+    long long lda, ldb, ldc, M, N, K;
+    int a_mn = 0, b_mn = 0, a_relu = 0, b_relu = 0, relu_out = 0, accumulate = 0;
+    const float* bias = nullptr; const float* mask = nullptr; const float* mulm = nullptr; long long ldmask = 0;
+    const float* resid = nullptr; long long ldres = 0;
+};
+int launch_gemm_tc(const GemmTcArgs& a, int* err, cudaStream_t st);
 
 // tcgen05 fp32 accumulation truncates: relative loss per K=16 MMA step, compensated at pack time (nfb_api.cu)
 constexpr float kAccStepGain = 2.9e-8f;

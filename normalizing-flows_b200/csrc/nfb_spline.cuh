@@ -49,6 +49,18 @@ __host__ __device__ __forceinline__ float fast_rcp(float x) {
 #endif
 }
 
+// Reciprocal to ~0.5 ulp: MUFU.RCP (1 ulp) plus one Newton step (2 FMAs).  The spline's knot scale, bin width,
+// theta and output all hang on reciprocals; on the ill-conditioned rows of a deep stack the 1-ulp approximations
+// alone moved log_prob by 1e-4 relative (offline error-injection study, DESIGN.md "Numerics"), the refined ones do not.
+__host__ __device__ __forceinline__ float rcp_nr(float x) {
+#ifdef __CUDA_ARCH__
+    const float r = fast_rcp(x);
+    return fmaf(r, fmaf(-x, r, 1.f), r);
+#else
+    return 1.0f / x;
+#endif
+}
+
 // F.softplus(beta=1, threshold=20).  log1p(e) by series for small e: 1+e would round away
 // up to 6e-8 absolute, which matters when the derivative sits at its 1e-3 floor.
 // Branch-free (selects only) so that two independent spline evaluations inlined back to back stay in
@@ -93,8 +105,8 @@ __host__ __device__ __forceinline__ void rqs_core(float x, const float (&lw)[K],
         cw[i] = sw;
         ch[i] = sh;
     }
-    const float aw = (1.f - kMinBinWidth * K) * fast_rcp(sw);
-    const float ah = (1.f - kMinBinHeight * K) * fast_rcp(sh);
+    const float aw = (1.f - kMinBinWidth * K) * rcp_nr(sw);
+    const float ah = (1.f - kMinBinHeight * K) * rcp_nr(sh);
     float kw[K + 1], kh[K + 1], ud[K + 1];
     kw[0] = 0.f; kh[0] = 0.f; kw[K] = 1.f; kh[K] = 1.f;
     ud[0] = NFB_BOUNDARY_UD; ud[K] = NFB_BOUNDARY_UD;
@@ -105,7 +117,7 @@ __host__ __device__ __forceinline__ void rqs_core(float x, const float (&lw)[K],
         ud[i + 1] = pd(i);
     }
     const float two_b = 2.f * tail;
-    const float xu = fmaf(x, fast_rcp(two_b), 0.5f);
+    const float xu = fmaf(x, rcp_nr(two_b), 0.5f);
     float l_w, r_w, l_h, r_h, ud0, ud1;
     if (K == 8) {
         const float* ks = INVERSE ? kh : kw;
@@ -141,7 +153,7 @@ __host__ __device__ __forceinline__ void rqs_core(float x, const float (&lw)[K],
     const float in_w = r_w - l_w, in_h = r_h - l_h;
     const float d0 = kMinDerivative + softplus_f(ud0);
     const float d1 = kMinDerivative + softplus_f(ud1);
-    const float rw = fast_rcp(in_w);
+    const float rw = rcp_nr(in_w);
     const float delta = in_h * rw;
     const float s = d0 + d1 - 2.f * delta;
     float outu, theta, tomt, den;
@@ -160,7 +172,7 @@ __host__ __device__ __forceinline__ void rqs_core(float x, const float (&lw)[K],
         tomt = theta * (1.f - theta);
         den = delta + s * tomt;
         const float num = in_h * (delta * theta * theta + d0 * tomt);
-        outu = l_h + num * fast_rcp(den);
+        outu = l_h + num * rcp_nr(den);
     }
     const float omt = 1.f - theta;
     const float dnum = delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * omt * omt);
@@ -203,8 +215,8 @@ __host__ __device__ __forceinline__ void rqs_eval_dyn(int K, float x, P p, float
         sw += fast_ex2(p(i) * s2 - mw);
         sh += fast_ex2(p(K + i) * s2 - mh);
     }
-    const float kw = (1.f - kMinBinWidth * K) * fast_rcp(sw);
-    const float kh = (1.f - kMinBinHeight * K) * fast_rcp(sh);
+    const float kw = (1.f - kMinBinWidth * K) * rcp_nr(sw);
+    const float kh = (1.f - kMinBinHeight * K) * rcp_nr(sh);
     const float two_b = 2.f * tail;
     float cumw = 0.f, cumh = 0.f, left = -tail, bottom = -tail;
     float in_cw = -tail, in_w = 1.f, in_ch = -tail, in_h = 1.f;
@@ -228,7 +240,7 @@ __host__ __device__ __forceinline__ void rqs_eval_dyn(int K, float x, P p, float
     }
     const float d0 = kMinDerivative + softplus_f(ud0);
     const float d1 = kMinDerivative + softplus_f(ud1);
-    const float rw = fast_rcp(in_w);
+    const float rw = rcp_nr(in_w);
     const float delta = in_h * rw;
     const float s = d0 + d1 - 2.f * delta;
     float out, theta, tomt, den;
@@ -247,7 +259,7 @@ __host__ __device__ __forceinline__ void rqs_eval_dyn(int K, float x, P p, float
         tomt = theta * (1.f - theta);
         den = delta + s * tomt;
         const float num = in_h * (delta * theta * theta + d0 * tomt);
-        out = in_ch + num * fast_rcp(den);
+        out = in_ch + num * rcp_nr(den);
     }
     const float omt = 1.f - theta;
     const float dnum = delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * omt * omt);

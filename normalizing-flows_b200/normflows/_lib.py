@@ -65,6 +65,16 @@ class PermuteDesc(C.Structure):
     _fields_ = [("features", C.c_int32), ("perm", _I32P), ("inv_perm", _I32P)]
 
 
+class GemmDesc(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("ldc", C.c_int64),
+                ("M", C.c_int64), ("N", C.c_int64), ("K", C.c_int64),
+                ("a_mn", C.c_int32), ("b_mn", C.c_int32), ("a_relu", C.c_int32), ("b_relu", C.c_int32),
+                ("relu_out", C.c_int32), ("accumulate", C.c_int32),
+                ("bias", C.c_void_p), ("mask", C.c_void_p), ("mulm", C.c_void_p), ("ldmask", C.c_int64),
+                ("resid", C.c_void_p), ("ldres", C.c_int64)]
+
+
 # every symbol include/nfb200.h declares: (restype, argtypes)
 _VP, _I32, _I64, _F = C.c_void_p, C.c_int32, C.c_int64, C.c_float
 SYMBOLS = {
@@ -73,6 +83,7 @@ SYMBOLS = {
     "nfb_device_info": (C.c_int, [_I32P, _I32P, _I32P]),
     "nfb_rqs_spline": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _F, _F, _I32, _I32, _VP]),
     "nfb_diag_gaussian_log_prob": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP]),
+    "nfb_gemm_f32": (C.c_int, [C.POINTER(GemmDesc), _VP]),
     "nfb_conv2d": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _F, _VP]),
     "nfb_glow_fold_actnorm_conv1x1": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "nfb_glow_fold_conv1x1_actnorm_forward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),

@@ -298,3 +298,30 @@ def case_grads():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "grads":
     case_grads()
+
+
+def case_ar64_sampling():
+    """Sampling direction of the flagship autoregressive shape (d=64, hidden 256): D = 64 sequential conditioner
+    passes per layer (flows/affine/autoregressive.py:29-38).  Same model as nsf_ar_d64_h256_l2 (same constructor
+    seed and perturbation), latents = that fixture's z; stores only the sampling-direction outputs (small file).
+        python tests/golden/make_golden.py ar64fwd"""
+    m, spec = nsf("ar", 64, 2, 256, 2, seed=0, sigma=0.05)
+    x = torch.randn(48, 64, generator=torch.Generator().manual_seed(1234)) * 1.5
+    out = {"torch_version": torch.__version__}
+    for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        mm = m.to(dt)
+        with torch.no_grad():
+            z, _ = mm.inverse_and_log_det(x.to(dt))
+            fx, fld = mm.forward_and_log_det(z)
+            out[f"z_{tag}"], out[f"fwd_x_{tag}"], out[f"fwd_ld_{tag}"] = z.numpy(), fx.numpy(), fld.numpy()
+            # one layer alone (flows.0 = autoregressive block) on the latents
+            y0, ld0 = mm.flows[0].forward(z)
+            out[f"l0_fwd_x_{tag}"], out[f"l0_fwd_ld_{tag}"] = y0.numpy(), ld0.numpy()
+    m.to(torch.float32)
+    np.savez_compressed(os.path.join(HERE, "nsf_ar_d64_h256_l2_fwd.npz"), **out)
+    print("wrote nsf_ar_d64_h256_l2_fwd; round trip err", np.abs(out["fwd_x_f64"] - x.numpy()).max(),
+          "f32 spread", np.abs(out["fwd_x_f32"] - out["fwd_x_f64"]).max())
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ar64fwd":
+    case_ar64_sampling()

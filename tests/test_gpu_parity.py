@@ -489,3 +489,132 @@ def test_trained_weights_parity(kind):
     assert rel.max() < RTOL
     assert abs(np.mean(lp - f["log_prob_f64"])) < 2e-4 * np.mean(np.abs(f["log_prob_f64"])) / 10  # no one-sided bias
     assert float(model.forward_kld(cuda(f["x"]))) == pytest.approx(float(f["kld_f64"]), rel=2e-5)
+
+
+def test_autoregressive_sampling_fused_d64():
+    """Sampling direction of the autoregressive block at the flagship shape (flows/affine/autoregressive.py:29-38:
+    D = 64 sequential conditioner passes) runs INSIDE the fused tcgen05 unit (one launch for the stack), pinned to
+    reference vectors minted by tests/golden/make_golden.py ar64fwd.  The reference's own fp32 run differs from its
+    fp64 run by 2.8e-4 on these latents (64 chained spline inversions per layer); bound ours by the same spread."""
+    spec, sd, _ = load_golden("nsf_ar_d64_h256_l2")
+    f = np.load("tests/golden/nsf_ar_d64_h256_l2_fwd.npz")
+    model = build_model(spec, sd).cuda()
+    z = cuda(f["z_f64"])
+    y0, ld0 = model.flows[0].forward(z)   # one autoregressive layer alone
+    spread0 = max(np.abs(f["l0_fwd_x_f32"] - f["l0_fwd_x_f64"]).max(), 1e-5)
+    e0 = np.abs(y0.cpu().numpy() - f["l0_fwd_x_f64"])
+    assert np.median(e0) < 1e-5 and e0.max() < 4 * spread0, (np.median(e0), e0.max(), spread0)
+    np.testing.assert_allclose(ld0.cpu().numpy(), f["l0_fwd_ld_f64"], rtol=1e-4, atol=20 * spread0)
+    x, ld = model.forward_and_log_det(z)
+    assert model._stack().launch_count() <= 8, "autoregressive stack must sample through the whole-stack launch"
+    spread = np.abs(f["fwd_x_f32"] - f["fwd_x_f64"]).max()
+    ex = np.abs(x.cpu().numpy() - f["fwd_x_f64"])
+    print(f"\\n[ar sampling d64] |x - ref64| median {np.median(ex):.2e} max {ex.max():.2e}; reference fp32 spread {spread:.2e}")
+    assert np.median(ex) < 2e-5 and ex.max() < 4 * spread, (np.median(ex), ex.max(), spread)
+    spread_l = np.abs(f["fwd_ld_f32"] - f["fwd_ld_f64"]).max()
+    el = np.abs(ld.cpu().numpy() - f["fwd_ld_f64"])
+    assert np.median(el) < 2e-3 and el.max() < max(4 * spread_l, 2e-2), (np.median(el), el.max(), spread_l)
+    # deterministic, and consistent with the density pass of what was produced
+    x2, _ = model.forward_and_log_det(z)
+    assert torch.equal(x, x2)
+    zr, ldr = model.inverse_and_log_det(x)
+    assert np.median(np.abs((ld + ldr).cpu().numpy())) < 5e-3
+
+
+def test_reverse_kld_value():
+    """core.py:104-131 on the CUDA path: value against the oracle evaluated on the very samples that were drawn."""
+    spec, sd, _ = load_golden("nsf_coupled_d5_h128_l3")
+    model = build_model(annotate_spec(spec, sd), sd).cuda()
+
+    class Target(torch.nn.Module):
+        def log_prob(self, z):
+            return -0.5 * (z ** 2).sum(1) - 0.5 * z.shape[1] * np.log(2 * np.pi)
+    model.p = Target()
+    torch.manual_seed(11)
+    z0, _ = model.q0(512)
+    torch.manual_seed(11)
+    rk = float(model.reverse_kld(512))
+    x, ldo = O.forward_and_log_det(spec, sd, z0.cpu().numpy().astype(np.float64))
+    lq0 = O.diag_gaussian_log_prob(z0.cpu().numpy().astype(np.float64), O._cast(sd, np.float64), "q0.")
+    ref = np.mean(lq0 - ldo) - np.mean(-0.5 * (x ** 2).sum(1) - 0.5 * x.shape[1] * np.log(2 * np.pi))
+    assert rk == pytest.approx(ref, rel=2e-4, abs=2e-3)
+    torch.manual_seed(11)
+    rk2 = float(model.reverse_kld(512, score_fn=False))
+    assert rk2 == pytest.approx(ref, rel=2e-4, abs=5e-3)
+
+
+def _gemm(A, B, M, N, K, a_mn=0, b_mn=0, **kw):
+    import ctypes as C
+    from normflows import _lib as L
+    d = L.GemmDesc()
+    out = kw.pop("out", None)
+    Cm = out if out is not None else torch.full((M, N), float("nan"), device="cuda")
+    d.A, d.B, d.C = A.data_ptr(), B.data_ptr(), Cm.data_ptr()
+    d.lda, d.ldb, d.ldc = A.stride(0), B.stride(0), Cm.stride(0)
+    d.M, d.N, d.K, d.a_mn, d.b_mn = M, N, K, a_mn, b_mn
+    keep = []
+    for k, v in kw.items():
+        if isinstance(v, torch.Tensor):
+            keep.append(v)
+            setattr(d, k, v.data_ptr())
+            if k in ("mask", "mulm"):
+                d.ldmask = v.stride(0)
+            if k == "resid":
+                d.ldres = v.stride(0)
+        else:
+            setattr(d, k, int(v))
+    L.check(L.lib().nfb_gemm_f32(C.byref(d), L.stream_ptr()))
+    return Cm
+
+
+@pytest.mark.parametrize("shape", [
+    # (M, N, K): forward X W^T -- both operands K-major
+    (300, 256, 256), (1000, 1472, 256), (129, 23, 5), (64, 115, 128), (4096, 64, 64),
+])
+def test_gemm_tc_forward_layout(shape):
+    """csrc/nfb_gemm_tc.cu, K-major x K-major (Y = X W^T + b with the fused epilogues of the training pass)."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N + K)
+    X = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / np.sqrt(K)).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    ref = (X.double() @ W.double().T)
+    got = _gemm(X, W, M, N, K)
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=3e-5)
+    # ReLU on load + bias + ReLU-mask + residual + ReLU out
+    H = torch.randn(M, N, generator=g).cuda()
+    R = torch.randn(M, N, generator=g).cuda()
+    got = _gemm(X, W, M, N, K, a_relu=1, bias=b, mask=H, resid=R, relu_out=1)
+    ref2 = torch.relu((torch.relu(X).double() @ W.double().T + b.double()) * (H > 0) + R.double())
+    np.testing.assert_allclose(got.cpu().numpy(), ref2.cpu().numpy(), rtol=1e-4, atol=3e-5)
+
+
+@pytest.mark.parametrize("shape", [(300, 64, 1472), (1000, 256, 256), (130, 5, 128), (257, 256, 736)])
+def test_gemm_tc_dgrad_layout(shape):
+    """gX = gY W: A = gY K-major, B = W [K x N] row-major = MN-major operand (no transpose in memory)."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    gY = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(K, N, generator=g) / np.sqrt(K)).cuda()
+    got = _gemm(gY, W, M, N, K, b_mn=1)
+    ref = gY.double() @ W.double()
+    np.testing.assert_allclose(got.cpu().numpy(), ref.cpu().numpy(), rtol=1e-4, atol=3e-5)
+
+
+@pytest.mark.parametrize("shape", [(200, 70, 5000), (1472, 256, 9000), (256, 64, 70000), (23, 5, 300)])
+def test_gemm_tc_wgrad_layout(shape):
+    """dW = gY^T X: both operands MN-major (reduction over the batch), split along K with red.global.add."""
+    M, N, K = shape
+    g = torch.Generator().manual_seed(M + N * 5 + K)
+    gY = torch.randn(K, M, generator=g).cuda()
+    X = torch.randn(K, N, generator=g).cuda()
+    mm = (torch.rand(M, N, generator=g) > 0.5).float().cuda()
+    got = _gemm(gY, X, M, N, K, a_mn=1, b_mn=1, b_relu=1, mulm=mm)
+    ref = (gY.double().T @ torch.relu(X).double()) * mm.double()
+    scale = float(ref.abs().max())
+    assert float((got.double() - ref).abs().max()) < 2e-5 * scale + 1e-5
+    # accumulate onto an existing gradient
+    base = torch.randn(M, N, generator=g).cuda()
+    got2 = _gemm(gY, X, M, N, K, a_mn=1, b_mn=1, out=base.clone(), accumulate=1)
+    ref2 = base.double() + gY.double().T @ X.double()
+    assert float((got2.double() - ref2).abs().max()) < 2e-5 * float(ref2.abs().max()) + 1e-5
