@@ -228,6 +228,25 @@ int nfb_flow_log_prob(nfb_flow_t* f, const float* x_dev, float* log_q_dev, int64
 int nfb_flow_forward_kld(nfb_flow_t* f, const float* x_dev, int64_t rows, float* loss_dev,
                          double* sum_dev, void* stream);
 
+/* ---- training pass (`loss.backward()` of examples/neural_spline_flow.ipynb cell 4; core.py:87-102 under autograd) ----
+ * Gradients of sum_r g_logq[r] * log_prob(x_r) w.r.t. every parameter and (optionally) x, for stacks made of
+ * autoregressive / coupled RQ-spline blocks (flows/neural_spline/wrapper.py), LULinearPermute (flows/mixing.py:535-563)
+ * and a DiagGaussian base.  The pass re-runs the density direction keeping each layer group's input, recomputes the
+ * conditioner activations per layer (nets/made.py:199-214, nets/resnet.py:37-50), applies the analytic adjoint of the
+ * spline (utils/splines.py:100-219) and runs dgrad / wgrad of every Linear on the tensor core.
+ * Gradient slots, in list order of the layers:
+ *   spline block : weight, bias of initial_layer; of blocks[i].linear_layers[0], [1] ...; of final_layer; then (coupled
+ *                  only) unconditional_transform.unnormalized_widths, _heights, _derivatives
+ *   LULinearPermute : lower_entries, upper_entries, unconstrained_upper_diag, bias
+ *   base (last two slots) : loc, log_scale
+ * `grad_slots[i]` is a device buffer of nfb_flow_grad_slot_numel(f, i) floats that is OVERWRITTEN, or NULL to skip.
+ * nfb_flow_num_grad_slots returns -1 when the flow holds a layer kind without a native backward. */
+int nfb_flow_num_grad_slots(const nfb_flow_t* f);
+int64_t nfb_flow_grad_slot_numel(const nfb_flow_t* f, int32_t slot);
+int nfb_flow_log_prob_backward(nfb_flow_t* f, const float* x_dev, const float* g_logq_dev, int64_t rows,
+                               float* log_q_dev /* optional out */, float* gx_dev /* optional out */,
+                               float* const* grad_slots, void* stream);
+
 /* ---- host-buffer entry points (what a non-CUDA caller binds; copies are inside) ---- */
 int nfb_flow_log_prob_host(nfb_flow_t* f, const float* x_host, float* log_q_host, int64_t rows);
 int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, float* loss_host);

@@ -191,6 +191,9 @@ struct nfb_flow {
     cudaEvent_t ev_reset = nullptr, ev_copied = nullptr;
     int* h_seq = nullptr;            // pinned: h_seq[c] = rows resident after chunk c
     DevBuf in_ready;                 // device int: rows of the current host batch that have landed
+    // training pass workspaces (nfb_flow_backward)
+    DevBuf tr_store, tr_h, tr_P, tr_gP, tr_ga, tr_gb, tr_xp, tr_gxp, tr_zp, tr_gzp, tr_in, tr_gin, tr_g0, tr_g1, tr_small,
+        tr_glq, tr_t0, tr_t1;
     const int* cur_in_ready = nullptr;
     ~nfb_flow() {
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -1550,6 +1553,326 @@ __attribute__((visibility("default"))) int nfb_debug_profile(nfb_flow_t* f, int 
     if (!f) return NFB_ERR_ARG;
     if (enable) { NFB_TRY(f->prof.reserve(512 * 8)); NFB_CUDA(cudaMemset(f->prof.p, 0, 512 * 8)); return NFB_OK; }
     if (f->prof.p && out128) NFB_CUDA(cudaMemcpy(out128, f->prof.p, 512 * 8, cudaMemcpyDeviceToHost));
+    return NFB_OK;
+}
+
+}  // extern "C"
+
+// ==========================================================================================
+// training pass: gradients of log_prob w.r.t. every parameter and the input
+// ==========================================================================================
+namespace {
+
+int grad_slots_of(const Layer& L) {
+    switch (L.kind) {
+    case L_AR_RQS: return 4 + 4 * L.net.nb;
+    case L_COUPLED_RQS: return 4 + 4 * L.net.nb + 3;
+    case L_LU: return 4;
+    default: return -1;
+    }
+}
+long long grad_slot_numel(const Layer& L, int s) {
+    const NetDesc& n = L.net;
+    if (L.kind == L_LU) {
+        const long long d = L.D;
+        return s == 0 ? d * (d - 1) / 2 : s == 1 ? d * (d - 1) / 2 : d;
+    }
+    const int nlin = 2 + 2 * n.nb;  // linears: initial, blocks..., final
+    if (s < 2 * nlin) {
+        const int lin = s / 2, isb = s & 1;
+        const long long out = lin == 0 ? n.H : (lin == nlin - 1 ? n.out : n.H);
+        const long long in = lin == 0 ? n.in : n.H;
+        return isb ? out : out * in;
+    }
+    const int u = s - 2 * nlin;  // coupled: unconditional widths, heights, derivatives
+    return (long long)L.n_id * (u == 2 ? L.K - 1 : L.K);
+}
+
+struct Gemm {
+    nfb_flow* f; cudaStream_t st;
+    int run(GemmTcArgs a) { f->launches++; return launch_gemm_tc(a, f->err.as<int>(), st); }
+};
+
+// conditioner forward (recompute) into h[0..n_hidden-1] ([rows x H] each) and P ([rows x out])
+int net_recompute(nfb_flow* f, const NetDesc& n, const NetPack& p, const float* in, int ld_in, long long rows, float* hbuf,
+                  float* P, cudaStream_t st) {
+    Gemm g{f, st};
+    const long long HS = rows * n.H;
+    GemmTcArgs a{};
+    a.A = in; a.lda = ld_in; a.B = p.w0; a.ldb = n.in; a.C = hbuf; a.ldc = n.H; a.M = rows; a.N = n.H; a.K = n.in; a.bias = n.b0;
+    NFB_TRY(g.run(a));
+    for (int b = 0; b < n.nb; ++b) {
+        float* hprev = hbuf + (size_t)(2 * b) * HS;
+        float* t = hbuf + (size_t)(2 * b + 1) * HS;
+        float* hnext = hbuf + (size_t)(2 * b + 2) * HS;
+        GemmTcArgs t1{};
+        t1.A = hprev; t1.lda = n.H; t1.a_relu = 1; t1.B = p.wb[2 * b]; t1.ldb = n.H; t1.C = t; t1.ldc = n.H;
+        t1.M = rows; t1.N = n.H; t1.K = n.H; t1.bias = n.bb[2 * b];
+        NFB_TRY(g.run(t1));
+        GemmTcArgs t2{};
+        t2.A = t; t2.lda = n.H; t2.a_relu = 1; t2.B = p.wb[2 * b + 1]; t2.ldb = n.H; t2.C = hnext; t2.ldc = n.H;
+        t2.M = rows; t2.N = n.H; t2.K = n.H; t2.bias = n.bb[2 * b + 1]; t2.resid = hprev; t2.ldres = n.H;
+        NFB_TRY(g.run(t2));
+    }
+    GemmTcArgs fl{};
+    fl.A = hbuf + (size_t)(2 * n.nb) * HS; fl.lda = n.H; fl.B = p.wf; fl.ldb = n.H; fl.C = P; fl.ldc = n.out;
+    fl.M = rows; fl.N = n.out; fl.K = n.H; fl.bias = n.bf;
+    return g.run(fl);
+}
+
+// one Linear's parameter gradients: dW = gY^T act(X) (* mask), db = colsum(gY)
+int linear_wgrad(nfb_flow* f, const float* gY, int n_out, const float* X, int ldx, int n_in, int x_relu, const float* mask,
+                 long long rows, float* dW, float* db, cudaStream_t st) {
+    if (dW) {
+        Gemm g{f, st};
+        GemmTcArgs a{};
+        a.A = gY; a.lda = n_out; a.a_mn = 1; a.B = X; a.ldb = ldx; a.b_mn = 1; a.b_relu = x_relu;
+        a.C = dW; a.ldc = n_in; a.M = n_out; a.N = n_in; a.K = rows; a.mulm = mask; a.ldmask = n_in;
+        NFB_TRY(g.run(a));
+    }
+    if (db) {
+        NFB_CUDA(cudaMemsetAsync(db, 0, (size_t)n_out * 4, st));
+        NFB_TRY(launch_colsum(gY, n_out, rows, n_out, db, st));
+        f->launches += 2;
+    }
+    return NFB_OK;
+}
+
+// backward of one spline layer: xp = the layer's input [rows x D], gy = gradient w.r.t. its output; writes the
+// gradient w.r.t. its input into gxp ([rows x D]) and the parameter gradients into `slots`.
+int rqs_layer_backward(nfb_flow* f, Layer& L, const float* xp, const float* gy, const float* glq, long long rows,
+                       float* gxp, float* const* slots, cudaStream_t st) {
+    const NetDesc& n = L.net;
+    const NetPack& p = L.pack;
+    const int D = L.D, H = n.H, T = L.n_tr, P = 3 * L.K - 1;
+    const bool coupled = L.kind == L_COUPLED_RQS;
+    const int n_hidden = 1 + 2 * n.nb;
+    const long long HS = rows * H;
+    NFB_CHECK(L.K == 8, NFB_ERR_UNSUPPORTED, "native backward: num_bins %d != 8", L.K);
+    NFB_TRY(f->tr_h.reserve((size_t)n_hidden * HS * 4));
+    NFB_TRY(f->tr_P.reserve((size_t)rows * n.out * 4));
+    NFB_TRY(f->tr_gP.reserve((size_t)rows * n.out * 4));
+    NFB_TRY(f->tr_ga.reserve((size_t)HS * 4));
+    NFB_TRY(f->tr_gb.reserve((size_t)HS * 4));
+    float* hb = f->tr_h.as<float>();
+    float* Pm = f->tr_P.as<float>();
+    float* gP = f->tr_gP.as<float>();
+    float* ga = f->tr_ga.as<float>();
+    float* gb = f->tr_gb.as<float>();
+    // conditioner input: all columns (autoregressive) or the gathered identity columns (coupling)
+    const float* in = xp;
+    int ld_in = D;
+    if (coupled) {
+        NFB_TRY(f->tr_in.reserve((size_t)rows * L.n_id * 4));
+        NFB_TRY(f->tr_gin.reserve((size_t)rows * L.n_id * 4));
+        NFB_TRY(launch_gather_cols_ld(xp, D, f->tr_in.as<float>(), L.n_id, L.id_idx.as<int>(), rows, st));
+        in = f->tr_in.as<float>();
+        ld_in = L.n_id;
+    }
+    NFB_TRY(net_recompute(f, n, p, in, ld_in, rows, hb, Pm, st));
+    // spline element backward -> gP, gxp (transformed columns)
+    NFB_TRY(launch_spline_bwd_rows(xp, D, Pm, gy, glq, coupled ? L.tr_idx.as<int>() : nullptr, rows, T, L.K, L.tail,
+                                   L.wh_scale, gP, gxp, st));
+    f->launches++;
+    const int nlin = 2 + 2 * n.nb;
+    if (coupled) {
+        NFB_TRY(f->tr_small.reserve((size_t)(64 * 64 + 64 * 23 + 64) * 4));
+        float* gtab = f->tr_small.as<float>();
+        NFB_CUDA(cudaMemsetAsync(gtab, 0, (size_t)L.n_id * P * 4, st));
+        NFB_TRY(launch_spline_bwd_shared(xp, D, L.uncond.as<float>(), gy, glq, L.id_idx.as<int>(), rows, L.n_id, L.K, L.tail,
+                                         gtab, gxp, st));
+        NFB_TRY(launch_split_table(gtab, L.n_id, slots[2 * nlin], slots[2 * nlin + 1], slots[2 * nlin + 2], st));
+        f->launches += 3;
+    }
+    Gemm g{f, st};
+    // final layer
+    float* hlast = hb + (size_t)(2 * n.nb) * HS;
+    NFB_TRY(linear_wgrad(f, gP, n.out, hlast, H, H, 0, n.mf, rows, slots[2 * (nlin - 1)], slots[2 * (nlin - 1) + 1], st));
+    {
+        GemmTcArgs a{};
+        a.A = gP; a.lda = n.out; a.B = p.wf; a.ldb = H; a.b_mn = 1; a.C = ga; a.ldc = H; a.M = rows; a.N = H; a.K = n.out;
+        NFB_TRY(g.run(a));  // g_h(last)
+    }
+    for (int b = n.nb - 1; b >= 0; --b) {
+        float* hprev = hb + (size_t)(2 * b) * HS;
+        float* t = hb + (size_t)(2 * b + 1) * HS;
+        const int l1 = 1 + 2 * b, l2 = 2 + 2 * b;  // linear indices of the block's two layers
+        // h_next = h_prev + W2 relu(t) + b2
+        NFB_TRY(linear_wgrad(f, ga, H, t, H, H, 1, n.mb[2 * b + 1], rows, slots[2 * l2], slots[2 * l2 + 1], st));
+        GemmTcArgs a{};
+        a.A = ga; a.lda = H; a.B = p.wb[2 * b + 1]; a.ldb = H; a.b_mn = 1; a.C = gb; a.ldc = H; a.M = rows; a.N = H; a.K = H;
+        a.mask = t; a.ldmask = H;
+        NFB_TRY(g.run(a));  // g_t = (g_h W2) * (t > 0)
+        // t = W1 relu(h_prev) + b1
+        NFB_TRY(linear_wgrad(f, gb, H, hprev, H, H, 1, n.mb[2 * b], rows, slots[2 * l1], slots[2 * l1 + 1], st));
+        GemmTcArgs c{};
+        c.A = gb; c.lda = H; c.B = p.wb[2 * b]; c.ldb = H; c.b_mn = 1; c.C = ga; c.ldc = H; c.M = rows; c.N = H; c.K = H;
+        c.mask = hprev; c.ldmask = H; c.resid = ga; c.ldres = H;
+        NFB_TRY(g.run(c));  // g_h_prev = g_h + (g_t W1) * (h_prev > 0)     (in place)
+    }
+    // initial layer
+    NFB_TRY(linear_wgrad(f, ga, H, in, ld_in, n.in, 0, n.m0, rows, slots[0], slots[1], st));
+    if (!coupled) {
+        GemmTcArgs a{};
+        a.A = ga; a.lda = H; a.B = p.w0; a.ldb = n.in; a.b_mn = 1; a.C = gxp; a.ldc = D; a.M = rows; a.N = D; a.K = H;
+        a.resid = gxp; a.ldres = D;
+        NFB_TRY(g.run(a));  // + conditioner path (in place)
+    } else {
+        GemmTcArgs a{};
+        a.A = ga; a.lda = H; a.B = p.w0; a.ldb = n.in; a.b_mn = 1; a.C = f->tr_gin.as<float>(); a.ldc = L.n_id;
+        a.M = rows; a.N = L.n_id; a.K = H;
+        NFB_TRY(g.run(a));
+        NFB_TRY(launch_scatter_cols(f->tr_gin.as<float>(), gxp, L.id_idx.as<int>(), rows, L.n_id, D, 1, st));
+        f->launches++;
+    }
+    return NFB_OK;
+}
+
+// backward of LULinearPermute (density direction x' = W z[:, perm] + b): gxp = gradient w.r.t. x'; writes gradient
+// w.r.t. z into gz.  glq_sum: device scalar sum of the upstream gradients on log_q (for logabsdet).
+int lu_layer_backward(nfb_flow* f, Layer& L, const float* zin, const float* gxp, const float* glq_sum, long long rows,
+                      float* gz, float* const* slots, cudaStream_t st) {
+    const int D = L.D;
+    NFB_TRY(f->tr_zp.reserve((size_t)rows * D * 4));
+    NFB_TRY(f->tr_gzp.reserve((size_t)rows * D * 4));
+    NFB_TRY(f->tr_small.reserve((size_t)(64 * 64 + 64 * 23 + 64) * 4));
+    float* zp = f->tr_zp.as<float>();
+    float* gzp = f->tr_gzp.as<float>();
+    float* dW = f->tr_small.as<float>() + 64 * 23 + 64;
+    Gemm g{f, st};
+    NFB_TRY(launch_gather_cols(zin, zp, L.lu_perm.as<int>(), rows, D, 1, st));
+    f->launches++;
+    if (slots[0] || slots[1] || slots[2]) {
+        GemmTcArgs a{};
+        a.A = gxp; a.lda = D; a.a_mn = 1; a.B = zp; a.ldb = D; a.b_mn = 1; a.C = dW; a.ldc = D; a.M = D; a.N = D; a.K = rows;
+        NFB_TRY(g.run(a));
+        NFB_TRY(launch_lu_param_bwd(dW, L.lu.lower_entries, L.lu.upper_entries, L.lu.unconstrained_upper_diag, L.lu.eps, D,
+                                    glq_sum, slots[0], slots[1], slots[2], st));
+        f->launches++;
+    }
+    if (slots[3]) {
+        NFB_CUDA(cudaMemsetAsync(slots[3], 0, (size_t)D * 4, st));
+        NFB_TRY(launch_colsum(gxp, D, rows, D, slots[3], st));
+        f->launches += 2;
+    }
+    GemmTcArgs a{};
+    a.A = gxp; a.lda = D; a.B = L.lu_Wd.as<float>(); a.ldb = D; a.b_mn = 1; a.C = gzp; a.ldc = D; a.M = rows; a.N = D; a.K = D;
+    NFB_TRY(g.run(a));
+    NFB_TRY(launch_scatter_cols(gzp, gz, L.lu_perm.as<int>(), rows, D, D, 0, st));
+    f->launches++;
+    return NFB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nfb_flow_num_grad_slots(const nfb_flow_t* f) {
+    if (!f) return -1;
+    int n = 0;
+    for (auto& L : f->layers) {
+        const int k = grad_slots_of(*L);
+        if (k < 0) return -1;  // a layer kind without a native backward
+        n += k;
+    }
+    return n + (f->base_loc ? 2 : 0);
+}
+
+int64_t nfb_flow_grad_slot_numel(const nfb_flow_t* f, int32_t slot) {
+    if (!f || slot < 0) return -1;
+    for (auto& L : f->layers) {
+        const int k = grad_slots_of(*L);
+        if (k < 0) return -1;
+        if (slot < k) return grad_slot_numel(*L, slot);
+        slot -= k;
+    }
+    return (f->base_loc && slot < 2) ? f->D : -1;
+}
+
+int nfb_flow_log_prob_backward(nfb_flow_t* f, const float* x, const float* g_logq, int64_t rows, float* log_q_out,
+                               float* gx_out, float* const* grad_slots, void* stream) {
+    NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "flow not finalized");
+    NFB_CHECK(f->base_loc && f->base_log_scale, NFB_ERR_STATE, "no base distribution set");
+    NFB_CHECK(x && g_logq && grad_slots, NFB_ERR_ARG, "null pointer");
+    const int n_slots = nfb_flow_num_grad_slots(f);
+    NFB_CHECK(n_slots >= 0, NFB_ERR_UNSUPPORTED, "native backward covers spline blocks + LULinearPermute + DiagGaussian");
+    if (rows == 0) return NFB_OK;
+    cudaStream_t st = S(stream);
+    const int D = f->D;
+    const int ng = (int)f->groups.size();
+    const size_t ZS = (size_t)rows * D;
+    f->launches = 0;
+    NFB_TRY(ensure_ws(f, rows));
+    NFB_TRY(f->tr_store.reserve((size_t)(ng + 1) * ZS * 4));
+    NFB_TRY(f->tr_glq.reserve((size_t)rows * 4 + 64));
+    NFB_TRY(f->tr_g0.reserve(ZS * 4));
+    NFB_TRY(f->tr_g1.reserve(ZS * 4));
+    NFB_TRY(f->tr_xp.reserve(ZS * 4));
+    NFB_TRY(f->tr_gxp.reserve(ZS * 4));
+    float* store = f->tr_store.as<float>();
+    float* lq = f->tr_glq.as<float>();  // scratch log_q when the caller does not want it
+    float* glq_sum = lq + rows;          // (64-byte tail of the buffer)
+    float* logq = log_q_out ? log_q_out : lq;
+    // ---- forward, keeping every group's input (density order: groups last-to-first) ----
+    NFB_CUDA(cudaMemcpyAsync(store, x, ZS * 4, cudaMemcpyDeviceToDevice, st));
+    NFB_TRY(launch_fill(logq, rows, 0.f, st));
+    for (int k = 0; k < ng; ++k)
+        NFB_TRY(run_group(f, f->groups[ng - 1 - k], NFB_INVERSE, store + (size_t)k * ZS, store + (size_t)(k + 1) * ZS, logq,
+                          rows, st));
+    const float* zfin = store + (size_t)ng * ZS;
+    NFB_TRY(launch_diag_gauss(zfin, f->base_loc, f->base_log_scale, logq, rows, D, 1, st));
+    // ---- backward ----
+    // slot offsets per layer
+    std::vector<int> off(f->layers.size() + 1, 0);
+    for (size_t i = 0; i < f->layers.size(); ++i) off[i + 1] = off[i] + grad_slots_of(*f->layers[i]);
+    float* const* base_slots = grad_slots + off[f->layers.size()];
+    NFB_CUDA(cudaMemsetAsync(glq_sum, 0, 4, st));
+    NFB_TRY(launch_colsum(g_logq, 1, rows, 1, glq_sum, st));
+    float* g = f->tr_g0.as<float>();
+    float* g2 = f->tr_g1.as<float>();
+    {
+        float *t0 = nullptr, *t1 = nullptr;
+        if (base_slots[0] || base_slots[1]) {
+            NFB_TRY(f->tr_t0.reserve(ZS * 4));
+            NFB_TRY(f->tr_t1.reserve(ZS * 4));
+            t0 = f->tr_t0.as<float>(); t1 = f->tr_t1.as<float>();
+        }
+        NFB_TRY(launch_diag_gauss_bwd(zfin, f->base_loc, f->base_log_scale, g_logq, rows, D, g, t0, t1, st));
+        for (int j = 0; j < 2; ++j)
+            if (base_slots[j]) {
+                NFB_CUDA(cudaMemsetAsync(base_slots[j], 0, (size_t)D * 4, st));
+                NFB_TRY(launch_colsum(j == 0 ? t0 : t1, D, rows, D, base_slots[j], st));
+            }
+    }
+    for (int k = ng - 1; k >= 0; --k) {
+        Group& grp = f->groups[ng - 1 - k];
+        const float* zin = store + (size_t)k * ZS;
+        NFB_CHECK(grp.kind != G_AFFINE, NFB_ERR_UNSUPPORTED, "native backward: affine-family group");
+        Layer& A = *f->layers[grp.first];
+        Layer* Bl = grp.last != grp.first ? f->layers[grp.last].get() : nullptr;  // pair: first = spline block, last = LU
+        Layer* R = (A.kind == L_AR_RQS || A.kind == L_COUPLED_RQS) ? &A : nullptr;
+        Layer* U = A.kind == L_LU ? &A : Bl;
+        NFB_CHECK(R || U, NFB_ERR_UNSUPPORTED, "native backward: unsupported layer in group");
+        const float* xp = zin;
+        if (R && U) {  // recompute the LU output (the spline block's input)
+            NFB_TRY(launch_linear(zin, D, U->lu_perm.as<int>(), U->lu_Wd.as<float>(), U->lu.bias, nullptr, 0,
+                                  f->tr_xp.as<float>(), D, rows, D, D, 0, 0, 0.f, st));
+            xp = f->tr_xp.as<float>();
+        }
+        const float* gcur = g;
+        if (R) {
+            NFB_TRY(rqs_layer_backward(f, *R, xp, g, g_logq, rows, f->tr_gxp.as<float>(), grad_slots + off[grp.first], st));
+            gcur = f->tr_gxp.as<float>();
+        }
+        if (U) {
+            const int ui = (U == &A) ? grp.first : grp.last;
+            NFB_TRY(lu_layer_backward(f, *U, zin, gcur, glq_sum, rows, g2, grad_slots + off[ui], st));
+            std::swap(g, g2);
+        } else {
+            NFB_CUDA(cudaMemcpyAsync(g, gcur, ZS * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    if (gx_out) NFB_CUDA(cudaMemcpyAsync(gx_out, g, ZS * 4, cudaMemcpyDeviceToDevice, st));
     return NFB_OK;
 }
 

@@ -141,8 +141,70 @@ def log_prob(model, x):
     return lq
 
 
+def _net_slots(net):
+    ps = [net.initial_layer.weight, net.initial_layer.bias]
+    for blk in net.blocks:
+        for lin in blk.linear_layers:
+            ps += [lin.weight, lin.bias]
+    return ps + [net.final_layer.weight, net.final_layer.bias]
+
+
+def grad_slot_tensors(model):
+    """Parameters in the order of the C ABI's gradient slots (include/nfb200.h nfb_flow_log_prob_backward), or None
+    if a layer has no native backward."""
+    from .flows import neural_spline as ns, mixing
+    out = []
+    for layer in model.flows:
+        if isinstance(layer, ns.AutoregressiveRationalQuadraticSpline):
+            out += _net_slots(layer.mprqat.autoregressive_net)
+        elif isinstance(layer, ns.CoupledRationalQuadraticSpline):
+            u = layer.prqct.unconditional_transform
+            out += _net_slots(layer.prqct.transform_net)
+            out += [u.unnormalized_widths, u.unnormalized_heights, u.unnormalized_derivatives]
+        elif isinstance(layer, mixing.LULinearPermute):
+            lin = layer.linear
+            out += [lin.lower_entries, lin.upper_entries, lin.unconstrained_upper_diag, lin.bias]
+        else:
+            return None
+    return out + [model.q0.loc, model.q0.log_scale]
+
+
+def native_backward(model, x, grad_out, need_x):
+    """Gradients from libnfb200.so (csrc/nfb_api.cu nfb_flow_log_prob_backward: tensor-core dgrad/wgrad + analytic
+    spline adjoint).  Returns (gx | None, {id(param): grad}) or None when the stack is not covered."""
+    import ctypes as C
+    from . import _lib as L
+    slots = grad_slot_tensors(model)
+    h = model._stack()
+    if slots is None or h is None or h.base is None or x.dim() != 2:
+        return None
+    handle = h.ensure(x.shape[1], x.device)
+    lib = L.lib()
+    n = lib.nfb_flow_num_grad_slots(handle)
+    if n < 0:
+        return None
+    if n != len(slots):
+        raise RuntimeError(f"gradient slot mismatch: library {n}, python {len(slots)}")
+    bufs = []
+    for i, p in enumerate(slots):
+        want = isinstance(p, torch.nn.Parameter) and p.requires_grad
+        if want and lib.nfb_flow_grad_slot_numel(handle, i) != p.numel():
+            raise RuntimeError(f"gradient slot {i}: size mismatch")
+        bufs.append(torch.empty_like(p) if want else None)
+    arr = (C.c_void_p * n)(*[b.data_ptr() if b is not None else None for b in bufs])
+    g = grad_out.detach().to(torch.float32).contiguous()
+    xx = x.detach().contiguous()
+    gx = torch.empty_like(xx) if need_x else None
+    with torch.cuda.device(x.device):
+        L.check(lib.nfb_flow_log_prob_backward(handle, L.ptr(xx), L.ptr(g), xx.shape[0], None, L.ptr(gx), arr,
+                                               L.stream_ptr()))
+    return gx, {id(p): b for p, b in zip(slots, bufs) if b is not None}
+
+
 class DensityFn(torch.autograd.Function):
-    """log_prob(x) with the CUDA kernels in forward and a re-materialised torch graph in backward."""
+    """log_prob(x) on the CUDA path.  backward: native kernels (dgrad / wgrad on the tensor core, analytic spline
+    adjoint) for spline-block + LULinearPermute stacks; other stacks re-materialise a torch graph (interim)."""
+    use_native_backward = True
 
     @staticmethod
     def forward(ctx, model, x, *params):
@@ -156,6 +218,11 @@ class DensityFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         model = ctx.model
         need_x = ctx.needs_input_grad[1]
+        if DensityFn.use_native_backward:
+            res = native_backward(model, x, grad_out, need_x)
+            if res is not None:
+                gx, gmap = res
+                return (None, gx, *[gmap.get(id(p)) if p.requires_grad else None for p in model.parameters()])
         with torch.enable_grad():
             xx = x.detach().requires_grad_(need_x)
             lq = log_prob(model, xx)

@@ -111,6 +111,9 @@ SYMBOLS = {
     "nfb_flow_transform": (C.c_int, [_VP, _I32, _VP, _VP, _VP, _I64, _VP]),
     "nfb_flow_log_prob": (C.c_int, [_VP, _VP, _VP, _I64, _VP]),
     "nfb_flow_forward_kld": (C.c_int, [_VP, _VP, _I64, _VP, _VP, _VP]),
+    "nfb_flow_num_grad_slots": (C.c_int, [_VP]),
+    "nfb_flow_grad_slot_numel": (_I64, [_VP, _I32]),
+    "nfb_flow_log_prob_backward": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP, C.POINTER(_VP), _VP]),
     "nfb_flow_log_prob_host": (C.c_int, [_VP, _VP, _VP, _I64]),
     "nfb_flow_forward_kld_host": (C.c_int, [_VP, _VP, _I64, _VP]),
 }

@@ -325,3 +325,35 @@ def case_ar64_sampling():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ar64fwd":
     case_ar64_sampling()
+
+
+def case_grads_d64():
+    """Gradients of forward_kld at the flagship block shape (d=64, hidden 256, 2 blocks; same models and inputs as
+    nsf_{ar,coupled}_d64_h256_l2), fp64 autograd of the reference.  Small tensors are stored whole; weight matrices as
+    two seeded random projections (grad @ v, u @ grad), which pin every entry without storing 5 MB per model.
+        python tests/golden/make_golden.py grads64"""
+    for kind in ("ar", "coupled"):
+        m, spec = nsf(kind, 64, 2, 256, 2, seed=0, sigma=0.05)
+        m = m.double()
+        x = (torch.randn(48, 64, generator=torch.Generator().manual_seed(1234)) * 1.5).double().requires_grad_(True)
+        loss = m.forward_kld(x)
+        loss.backward()
+        out = {"x": x.detach().numpy(), "kld": loss.detach().numpy(), "grad__x": x.grad.numpy()}
+        g = torch.Generator().manual_seed(77)
+        for k, p in m.named_parameters():
+            if p.grad is None:
+                continue
+            if p.grad.numel() <= 4096 or p.grad.dim() != 2:
+                out["grad__" + k] = p.grad.numpy()
+            else:
+                v = torch.randn(p.shape[1], generator=g, dtype=torch.float64)
+                u = torch.randn(p.shape[0], generator=g, dtype=torch.float64)
+                out["gradv__" + k], out["gradu__" + k] = (p.grad @ v).numpy(), (u @ p.grad).numpy()
+                out["projv__" + k], out["proju__" + k] = v.numpy(), u.numpy()
+                out["gnorm__" + k] = np.asarray(p.grad.norm().item())
+        np.savez_compressed(os.path.join(HERE, f"grads_nsf_{kind}_d64_h256_l2.npz"), **out)
+        print("wrote grads64", kind, len(out), float(loss))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "grads64":
+    case_grads_d64()
