@@ -321,6 +321,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH, help="rows per GPU (weak scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-eager", action="store_true")
+    ap.add_argument("--no-train-step", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -459,6 +460,50 @@ def main():
                         "precision, needed for the rtol 1e-4 bar) so frac <= 1/3 by construction, and skips the "
                         "all-zero blocks of the MADE masks (~31 % of the dense MMA work); ncu: tensor pipe 44 % active"}
 
+    # ---- training step (extra key; every rank takes part): forward_kld + native backward (tensor-core dgrad /
+    # wgrad, analytic spline adjoint) + DDP-style bucketed gradient all-reduce (NCCL when world > 1) + Adam step.
+    # The optimizer step invalidates the packed weights, so each timed step includes the device-side repack. ----
+    train = None
+    if not args.no_train_step:
+        from normflows.parallel import GradientBuckets
+        try:
+            torch.set_grad_enabled(True)
+            params = list(model.parameters())
+            opt = torch.optim.Adam(params, lr=1e-6)
+            buckets = GradientBuckets(params)
+
+            def tstep(i):
+                opt.zero_grad(set_to_none=True)
+                l = model.forward_kld(xs[i % nbuf])
+                l.backward()
+                buckets.start(B).finish()
+                opt.step()
+                return l
+            for i in range(2):
+                tl = tstep(i)
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n_t = 5
+            t0e.record()
+            for i in range(n_t):
+                tl = tstep(i)
+            t1e.record()
+            torch.cuda.synchronize()
+            t_ms = t0e.elapsed_time(t1e) / n_t
+            if world > 1:
+                tt = torch.tensor([t_ms], device=dev)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                t_ms = float(tt)
+            train = {"ms_per_step": t_ms, "value": world * B / (t_ms * 1e-3), "unit": "samples/s", "loss": float(tl.detach()),
+                     "what": "forward_kld + loss.backward() (libnfb200 nfb_flow_log_prob_backward) + bucketed gradient "
+                             "all-reduce + Adam step + repack of the packed weights, batch %d/GPU, 2 warm-up + %d timed" % (B, n_t)}
+        except Exception as e:  # an extra key must never take the headline down
+            train = {"unavailable": repr(e)[:300]}
+        finally:
+            torch.set_grad_enabled(False)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -478,7 +523,7 @@ def main():
                     "api": "nfb_flow_forward_kld_host (pinned host batch)"},
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "gpu_launches": launches_per_step * steps, "gpu_launches_per_step": launches_per_step,
-            "clocks": clocks, "roofline": roof}
+            "clocks": clocks, "roofline": roof, "train_step": train}
     if world == 1 and reference_available() and not args.no_reference_eager:
         # the denominator of north_star's >= 10x target: the unmodified reference, PyTorch eager, same B200
         try:
