@@ -102,7 +102,16 @@ __device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t
 //   still "LU map, then spline block" -- the packer hands it the INVERSE LU map of the previous layer -- but the
 //   unconditional spline runs first and in its inverse branch, the conditioner sees its result, and the
 //   conditional spline is inverted (Coupling.inverse, neural_spline/coupling.py:100-128).
-template <bool SAMPLE>
+// PAIR = true: launched as clusters of 2 CTAs.  A unit is (layer, PAIR of adjacent tiles): CTA r of the cluster owns tile
+//   2 tp + r (its own A tiles, x tile, TMEM accumulators and epilogue), streams bytes [r/2, (r+1)/2) of every weight
+//   record (rows [r N/2, (r+1) N/2) of the [N x 64] tile) into a 4 x 16 KB ring, and the LEADER's (rank 0) MMA warp issues
+//   tcgen05.mma.cta_group::2 (M = 256: rows 0..127 from CTA 0, 128..255 from CTA 1; each SM's tensor core reads both B
+//   halves) once both CTAs' operands are in.  Per SM this halves the weight bytes pulled from L2 and the B bytes the MMA
+//   reads from shared memory -- the two limits of the single-CTA schedule (profiles/r01c_fused_stack_ncu_summary.md).
+//   Synchronisation across the pair: epilogue warps of BOTH CTAs arrive (cluster scope) on the leader's a_ready /
+//   chunk_empty barriers; the peer's otherwise idle MMA warp relays "my half of the record has landed" to the leader's
+//   w_full barrier; tcgen05.commit multicasts slot-free / accumulator-ready to the barriers of both CTAs.
+template <bool SAMPLE, bool PAIR>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -116,28 +125,45 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         if (threadIdx.x == 0 && p.err) atomicExch(p.err, 900);
         return;
     }
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    constexpr uint32_t kEpiArrivals = PAIR ? 2 * kEpiWarps : kEpiWarps;  // a_ready / chunk_empty count both CTAs' warps
     if (threadIdx.x == 0) {
         for (int i = 0; i < 4; ++i) {
-            mbar_init(bar(kBarWFull + i), 1);
+            mbar_init(bar(kBarWFull + i), (PAIR && rank == 0) ? 2 : 1);  // leader: own expect_tx + the peer's relay
             mbar_init(bar(kBarWEmpty + i), 1);
             mbar_init(bar(kBarCFull + i), 1);
-            mbar_init(bar(kBarCEmpty + i), kEpiWarps);
+            mbar_init(bar(kBarCEmpty + i), kEpiArrivals);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(bar(kBarAReady + i), kEpiWarps);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(kBarAReady + i), kEpiArrivals);
         mbar_init(bar(kBarAccFull), 1);
         fence_mbar_init();
     }
+    if (PAIR) {
+        __syncthreads();
+        cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
+    }
     if (warp == kEpiWarps + 1) {
-        tmem_alloc(sbase + kOffTmemPtr, 512);
-        tmem_relinquish();
+        if (PAIR) { tmem_alloc2(sbase + kOffTmemPtr, 512); tmem_relinquish2(); }
+        else { tmem_alloc(sbase + kOffTmemPtr, 512); tmem_relinquish(); }
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
+    if (PAIR) cluster_sync_all();
 
     const long long n_tiles = (p.rows + 127) / 128;
-    const long long n_units = n_tiles * p.n_layers;  // (layer, tile) work units, layer-major
+    // work units, layer-major: (layer, tile) -- or (layer, pair of tiles) for CTA pairs; `tstride` tiles per unit
+    constexpr int tstride = PAIR ? 2 : 1;
+    const long long n_tu = (n_tiles + tstride - 1) / tstride;   // tile units per layer
+    const long long n_units = n_tu * p.n_layers;
+    const long long u_first = PAIR ? (long long)cluster_id_x() : (long long)blockIdx.x;
+    const long long u_step = PAIR ? (long long)cluster_nctaid_x() : (long long)gridDim.x;
+    // cluster-scope arrive on the LEADER's barrier (rank 0 maps onto itself)
+    auto arrive_leader = [&](uint32_t local_bar) {
+        if (PAIR) mbar_arrive_cluster(mapa_rank(local_bar, 0));
+        else mbar_arrive(local_bar);
+    };
 
     // Warp roles: the SM arbiter favours high warp ids, so the two latency-critical single-lane roles
     // (TMA producer, MMA issuer) sit above the epilogue warps (0..kEpiWarps-1).
@@ -145,8 +171,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         // ------------------------------ weight producer -----------------------------------
         // whole warp walks the table (warp-uniform control flow); one elected lane issues the copy
         uint32_t slot = 0, par = 0;
-        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const FusedLayer& L = p.layers[u / n_tiles];
+        constexpr uint32_t kRingSlots = PAIR ? 4 : kSlots;
+        constexpr uint32_t kRingBytes = PAIR ? kSlotBytes / 2 : kSlotBytes;
+        for (long long u = u_first; u < n_units; u += u_step) {
+            const FusedLayer& L = p.layers[u / n_tu];
             const FusedStep* steps = L.steps;  // global (L2-resident); the producer only needs the size
             const int n_steps = L.n_steps;
             // autoregressive sampling (SAMPLE, ar_passes = D): the LU records are streamed once, the block's D times
@@ -164,14 +192,16 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 const uint32_t nbytes = i + 1 < total ? (uint32_t)__ldg(&steps[sn].bytes16) << 4 : 0u;
                 mbar_wait(bar(kBarWEmpty + slot), par ^ 1, p.err, 100 + slot);
                 if (elect_one_sync()) {
-                    mbar_expect_tx(bar(kBarWFull + slot), bytes);
-                    bulk_g2s(sbase + kOffW + slot * kSlotBytes, L.wstream + off, bytes, bar(kBarWFull + slot));
+                    const uint32_t nb = PAIR ? bytes >> 1 : bytes;   // this CTA's half: rows [rank N/2, (rank+1) N/2)
+                    mbar_expect_tx(bar(kBarWFull + slot), nb);
+                    bulk_g2s(sbase + kOffW + slot * kRingBytes, L.wstream + off + (PAIR ? rank * nb : 0u), nb,
+                             bar(kBarWFull + slot));
                 }
                 __syncwarp();
                 s = sn;
                 off = offn;
                 bytes = nbytes;
-                if (++slot == kSlots) { slot = 0; par ^= 1; }
+                if (++slot == kRingSlots) { slot = 0; par ^= 1; }
             }
         }
     } else if (warp == kEpiWarps + 1) {
@@ -181,9 +211,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         uint32_t slot = 0, wpar = 0, apar = 0, cebits = 0;
         const uint64_t adesc0 = umma_desc_sw128(sbase + kOffA);
         const uint64_t bdesc0 = umma_desc_sw128(sbase + kOffW);
-        constexpr uint32_t kIdesc0 = umma_idesc_f16(128, 0);
-        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const FusedLayer& L = p.layers[u / n_tiles];
+        constexpr uint32_t kIdesc0 = umma_idesc_f16(PAIR ? 256 : 128, 0);
+        constexpr uint32_t kRingSlots = PAIR ? 4 : kSlots;
+        constexpr uint32_t kRingBytes = PAIR ? kSlotBytes / 2 : kSlotBytes;
+        for (long long u = u_first; u < n_units; u += u_step) {
+            const FusedLayer& L = p.layers[u / n_tu];
             const uint2* steps = reinterpret_cast<const uint2*>(L.steps);  // 8-byte entries, L2-resident
             const int n_steps = L.n_steps;
             const int lu_steps = L.has_lu ? 2 : 0;
@@ -195,6 +227,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             for (int s = 0; s < total; ++s) {
                 sidx = sidx + 1 == n_steps ? lu_steps : sidx + 1;
                 nx.raw = __ldg(steps + sidx);  // prefetch one entry ahead (wraps to the block's first step)
+                if (PAIR && rank != 0) {
+                    // peer CTA: relay "my half of this record has landed" to the leader's w_full barrier
+                    mbar_wait(bar(kBarWFull + slot), wpar, p.err, 230 + slot);
+                    if (elect_one_sync()) mbar_arrive_cluster(mapa_rank(bar(kBarWFull + slot), 0));
+                    __syncwarp();
+                    if (++slot == kRingSlots) { slot = 0; wpar ^= 1; }
+                    cur.raw = nx.raw;
+                    continue;
+                }
                 const FusedStep st = cur.s;
                 const uint32_t ctl = st.ctl;
                 const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
@@ -214,7 +255,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 if (elect_one_sync()) {
                     const uint32_t d = tmem + (ctl & 511u);
                     const uint32_t idesc = kIdesc0 | ((uint32_t)st.n8 << 17);
-                    const uint64_t bd = bdesc0 + (uint64_t)(slot * (kSlotBytes >> 4));
+                    const uint64_t bd = bdesc0 + (uint64_t)(slot * (kRingBytes >> 4));
                     uint32_t accum = ((ctl >> 9) & 1u) ^ 1u;
                     // A code: 0..7 = shared-memory tile; 0x80|t = tensor memory (final layer), t = split*4+kc
                     auto issue4 = [&](uint32_t code) {
@@ -226,22 +267,35 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                             umma_bf16_ts(d, at + 24, bd + 6, idesc, 1u);
                         } else {
                             const uint64_t ad = adesc0 + (uint64_t)(code * (kTileA >> 4));
-                            umma_bf16(d, ad, bd, idesc, accum);
-                            umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-                            umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-                            umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                            if (PAIR) {
+                                umma2_f16(d, ad, bd, idesc, accum);
+                                umma2_f16(d, ad + 2, bd + 2, idesc, 1u);
+                                umma2_f16(d, ad + 4, bd + 4, idesc, 1u);
+                                umma2_f16(d, ad + 6, bd + 6, idesc, 1u);
+                            } else {
+                                umma_bf16(d, ad, bd, idesc, accum);
+                                umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                                umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                                umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                            }
                         }
                         accum = 1u;
                     };
                     issue4(st.a0);
                     if (st.a1 != 0xFF) issue4(st.a1);
                     if (st.a2 != 0xFF) issue4(st.a2);
-                    umma_commit(bar(kBarWEmpty + slot));
-                    if (scode == 1) umma_commit(bar(kBarAccFull));
-                    else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
+                    if (PAIR) {
+                        umma2_commit_mc(bar(kBarWEmpty + slot));
+                        if (scode == 1) umma2_commit_mc(bar(kBarAccFull));
+                        else if (scode >= 2) umma2_commit_mc(bar(kBarCFull + (scode - 2)));
+                    } else {
+                        umma_commit(bar(kBarWEmpty + slot));
+                        if (scode == 1) umma_commit(bar(kBarAccFull));
+                        else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
+                    }
                 }
                 __syncwarp();
-                if (++slot == kSlots) { slot = 0; wpar ^= 1; }
+                if (++slot == kRingSlots) { slot = 0; wpar ^= 1; }
                 cur.raw = nx.raw;
             }
         }
@@ -258,14 +312,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         int pi = 0;
 #define NFB_STAMP() do { if (prof && pi < 126) prof[pi++] = clock64(); } while (0)
 
-        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const int layer = (int)(u / n_tiles);
-            const long long tile = u - (long long)layer * n_tiles;
+        for (long long u = u_first; u < n_units; u += u_step) {
+            const int layer = (int)(u / n_tu);
+            const long long tile = (u - (long long)layer * n_tu) * tstride + rank;  // (may be one past the end: phantom)
+            const bool tile_live = tile < n_tiles;
             const FusedLayer& L = p.layers[layer];
             const int D = L.D, H = L.H;
             const float* zsrc = layer == 0 ? p.zin : p.zout;   // layers >= 1 update z in place
             const long long row0 = tile * 128;
-            if (u != blockIdx.x) prof = nullptr;
+            if (u != u_first) prof = nullptr;
             float ru = 1.f, ruinv = 1.f;  // this row's power-of-two unit (set after the tile load)
             auto build_a = [&](bool lu_stage) {
                 // A[:, k] for k in [wh*kGC, (wh+1)*kGC): fp16 hi/lo split of xs[:, k] (LU stage, k < D) or of the
@@ -285,11 +340,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 fence_proxy_async_smem();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar(kBarAReady + 0));
+                if (lane == 0) arrive_leader(bar(kBarAReady + 0));
             };
 
             // ---- layer-to-layer dependency: this tile's rows must have left layer-1 (any CTA) ----
-            if (layer > 0) {
+            if (layer > 0 && tile_live) {
                 if (lane == 0) {  // one lane per warp spins (keeps the warp converged for the .aligned ops below)
                     const int* flag = p.progress + tile;
                     int seen;
@@ -310,7 +365,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
             }
             // ---- host batch still in flight (nfb_api.cu start_h2d): layer-0 tiles wait for their rows ----
-            if (layer == 0 && p.in_ready) {
+            if (layer == 0 && p.in_ready && tile_live) {
                 const int need = (int)min(row0 + 128, p.rows);
                 if (lane == 0) {
                     int seen;
@@ -495,7 +550,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     fence_proxy_async_smem();
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(kBarAReady + kc));
+                    if (lane == 0) arrive_leader(bar(kBarAReady + kc));
                 }
                 NFB_STAMP();  // hidden epilogue ph done
             }
@@ -536,7 +591,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     if (f + kNG >= L.F) {  // all of this thread's columns are in registers: free the buffer
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
+                        if (lane == 0) arrive_leader(bar(kBarCEmpty + b));
                     }
                     if (t < L.T) {
                         // the packer folded log2(e) (and the layer's 1/sqrt(H)) into the w/h columns and biases
@@ -559,7 +614,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 if (f0 >= L.F) {  // (F < kNG: this group had no feature in the chunk) still release the buffer
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
+                    if (lane == 0) arrive_leader(bar(kBarCEmpty + b));
                 }
                 NFB_STAMP();  // chunk c consumed
             }
@@ -585,7 +640,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             // warps still have in flight to L2)
             if (p.progress) __threadfence();
             epi_bar_sync();
-            if (p.progress && et == 0) {
+            if (p.progress && et == 0 && tile_live) {
                 __threadfence();
                 asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.progress + tile), "r"(layer + 1) : "memory");
             }
@@ -595,27 +650,58 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == kEpiWarps + 1) tmem_dealloc(tmem, 512);
+    if (PAIR) cluster_sync_all();  // the peer may still signal our barriers / the leader's MMAs read our B half
+    if (warp == kEpiWarps + 1) {
+        if (PAIR) tmem_dealloc2(tmem, 512);
+        else tmem_dealloc(tmem, 512);
+    }
 }
 
 int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st) {
     static PerDevice per_dev;  // the opt-in shared-memory size is a per-device function attribute
     const int dev_sms = per_dev.ensure([] {
-        cudaError_t e = cudaFuncSetAttribute(fused_rqs_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)kFusedSmem);
-        if (e != cudaSuccess) return e;
-        return cudaFuncSetAttribute(fused_rqs_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)kFusedSmem);
+        cudaError_t e = cudaSuccess;
+        const void* fns[4] = {(const void*)fused_rqs_kernel<false, false>, (const void*)fused_rqs_kernel<true, false>,
+                              (const void*)fused_rqs_kernel<false, true>, (const void*)fused_rqs_kernel<true, true>};
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+            e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
+        return e;
     });
     if (dev_sms < 0) return NFB_ERR_CUDA;
     if (sm_count <= 0 || sm_count > dev_sms) sm_count = dev_sms;  // co-residency bound of the CURRENT device
     NFB_CHECK(p.n_layers >= 1 && (p.n_layers == 1 || p.progress), NFB_ERR_ARG, "fused rqs: bad layer list");
-    const long long n_units = (p.rows + 127) / 128 * p.n_layers;
-    if (n_units == 0) return NFB_OK;
+    const long long n_tiles = (p.rows + 127) / 128;
+    if (n_tiles == 0) return NFB_OK;
+    // CTA pairs (cta_group::2) whenever there are at least two tiles; NFB_NO_PAIR=1 keeps the single-CTA schedule (A/B)
+    static const bool no_pair = getenv("NFB_NO_PAIR") != nullptr;
+    if (n_tiles >= 2 && !no_pair) {
+        const long long n_units = (n_tiles + 1) / 2 * p.n_layers;
+        cudaLaunchConfig_t cfg{};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = kFusedSmem; cfg.stream = st;
+        cfg.gridDim = dim3(2 * (unsigned)(sm_count / 2));
+        // every cluster must be resident (units wait on flags published by other clusters)
+        int max_clusters = 0;
+        const void* fn = sample ? (const void*)fused_rqs_kernel<true, true> : (const void*)fused_rqs_kernel<false, true>;
+        NFB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
+        NFB_CHECK(max_clusters >= 1, NFB_ERR_STATE, "fused rqs: no CTA pair fits on this device");
+        long long n_cl = sm_count / 2;
+        if (n_cl > max_clusters) n_cl = max_clusters;
+        if (n_cl > n_units) n_cl = n_units;
+        cfg.gridDim = dim3(2 * (unsigned)n_cl);
+        if (sample) NFB_CUDA(cudaLaunchKernelEx(&cfg, fused_rqs_kernel<true, true>, p));
+        else NFB_CUDA(cudaLaunchKernelEx(&cfg, fused_rqs_kernel<false, true>, p));
+        NFB_LAUNCH_CHECK();
+        return NFB_OK;
+    }
+    const long long n_units = n_tiles * p.n_layers;
     // every CTA must be resident (units wait on flags published by other CTAs): grid <= #SMs, 1 CTA/SM
     const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
-    if (sample) fused_rqs_kernel<true><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
-    else fused_rqs_kernel<false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    if (sample) fused_rqs_kernel<true, false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    else fused_rqs_kernel<false, false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

@@ -571,6 +571,7 @@ def _gemm(A, B, M, N, K, a_mn=0, b_mn=0, **kw):
 @pytest.mark.parametrize("shape", [
     # (M, N, K): forward X W^T -- both operands K-major
     (300, 256, 256), (1000, 1472, 256), (129, 23, 5), (64, 115, 128), (4096, 64, 64),
+    (40000, 512, 192),   # 313 x 2 output tiles on 148 CTAs: several units per CTA (accumulator double-buffering)
 ])
 def test_gemm_tc_forward_layout(shape):
     """csrc/nfb_gemm_tc.cu, K-major x K-major (Y = X W^T + b with the fused epilogues of the training pass)."""
@@ -694,15 +695,21 @@ def test_native_backward_full_batch_and_training_step():
     DensityFn.use_native_backward = True
     assert float(loss.detach()) == pytest.approx(float(loss_ref), rel=2e-5)
     assert len(grads[True]) == len(grads[False]) > 40
-    worst = {True: 0.0, False: 0.0}
+    # ReLU kinks: a pre-activation within round-off of zero switches a whole row's contribution on or off, so single
+    # entries of a weight gradient can differ by ~1/sqrt(rows) from the fp64 value in ANY fp32-class implementation.
+    # Judge each tensor by its relative Frobenius error (tight) and bound single entries loosely.
+    worst = {True: [0.0, 0.0], False: [0.0, 0.0]}
     for k in grads[True]:
         ref = gref[k]
         scale = float(np.abs(ref).max()) + 1e-8
         for native in (True, False):
-            e = float(np.abs(grads[native][k].double().cpu().numpy() - ref).max()) / scale
-            worst[native] = max(worst[native], e)
-            assert e <= 2e-3, (k, native, e, scale)
-    print(f"\n[grad vs fp64 oracle, 1061 rows] worst relative-to-scale error: native {worst[True]:.2e}, interim torch {worst[False]:.2e}")
+            d = grads[native][k].double().cpu().numpy() - ref
+            fro = float(np.linalg.norm(d) / (np.linalg.norm(ref) + 1e-12))
+            e = float(np.abs(d).max()) / scale
+            worst[native] = [max(worst[native][0], fro), max(worst[native][1], e)]
+            assert fro <= 2e-3 and e <= 3e-2, (k, native, fro, e, scale)
+    print(f"\n[grad vs fp64 oracle, 1061 rows] worst (rel. Frobenius, max entry / scale): native {worst[True][0]:.2e}, "
+          f"{worst[True][1]:.2e}; interim torch {worst[False][0]:.2e}, {worst[False][1]:.2e}")
     opt = torch.optim.Adam(model.parameters(), lr=2e-4)
     l0 = float(model.forward_kld(x).detach())
     for _ in range(5):

@@ -19,11 +19,6 @@
 void nfb_set_error(const char*, ...) {}
 using namespace nfb;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
 __device__ __forceinline__ void cluster_sync() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -34,16 +29,6 @@ __device__ __forceinline__ uint32_t mapa(uint32_t smem_addr, uint32_t rank) {
 }
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tmem_alloc2(uint32_t dst_smem, uint32_t ncols) {
-    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_relinquish2() {
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
-    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 __device__ __forceinline__ void umma2_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                            uint32_t accumulate) {
@@ -70,9 +55,9 @@ struct Out {
     long long cycles2, cycles1;
 };
 
-// A[m][k] = ((m * 3 + k) % 7) - 3 ;  B[n][k] = ((n * 5 + 2 k) % 5) - 2   (exact in bf16, sums exact in fp32)
+// A[m][k] = ((m * 3 + k) % 7) - 3 ;  B[n][k] = ((n * 3 + 2 k) % 5) - 2   (exact in bf16, sums exact in fp32)
 __host__ __device__ inline float a_val(int m, int k) { return (float)(((m * 3 + k) % 7) - 3); }
-__host__ __device__ inline float b_val(int n, int k) { return (float)(((n * 5 + 2 * k) % 5) - 2); }
+__host__ __device__ inline float b_val(int n, int k) { return (float)(((n * 3 + 2 * k) % 5) - 2); }
 
 template <int N, bool SWAP_HALVES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) pair_kernel(Out* out, int iters) {
