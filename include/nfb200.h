@@ -61,6 +61,18 @@ int nfb_diag_gaussian_log_prob(const float* z_dev, const float* loc_dev, const f
                                float* log_q_dev, int64_t rows, int32_t dim, int32_t accumulate,
                                void* stream);
 
+/* flows/affine/autoregressive.py:96-128 MaskedAffineAutoregressive, element-wise part: params [rows, features, 2] =
+ * (unconstrained_scale, shift) from the MADE conditioner; scale = sigmoid(u + 2) + 1e-3.  inverse = 0: y = scale x + shift,
+ * log_det (+)= sum log scale; inverse = 1: y = (x - shift) / scale, log_det (+)= -sum log scale. */
+int nfb_maf_affine(const float* x_dev, const float* params_dev, float* y_dev, float* log_det_dev, int64_t rows,
+                   int32_t features, int32_t inverse, int32_t accumulate, void* stream);
+
+/* transforms.py:8-47 Logit pre-transform of image data (RealNVP): direction NFB_INVERSE = Logit.inverse (density pass:
+ * y = logit(alpha + (1 - 2 alpha) x)), NFB_FORWARD = Logit.forward (sampling); log_det[b] (+)= the per-sample log-det
+ * over the `inner` elements of sample b.  in/out: [batch, inner] contiguous; may alias. */
+int nfb_logit_transform(const float* in_dev, float* out_dev, float* log_det_dev, int64_t batch, int64_t inner,
+                        float alpha, int32_t direction, int32_t accumulate, void* stream);
+
 /* Dense product of the training pass (what `F.linear` and its autograd formulas compute for every Linear of the
  * conditioners: nets/resnet.py:37-50,92-104, nets/made.py:80-81,199-214): C[M x N] (+)= opA(A) opB(B)^T on the tensor
  * core (split-bf16, fp32 accumulate).  A, B, C are row-major fp32 device matrices; `a_mn` / `b_mn` = 1 say that the

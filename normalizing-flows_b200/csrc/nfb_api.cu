@@ -1048,6 +1048,21 @@ int nfb_class_cond_diag_gaussian_log_prob(const float* z, const int64_t* y, cons
                                    num_classes, accumulate, S(stream));
 }
 
+int nfb_maf_affine(const float* x, const float* params, float* y, float* log_det, int64_t rows, int32_t features,
+                   int32_t inverse, int32_t accumulate, void* stream) {
+    NFB_CHECK(x && params && y, NFB_ERR_ARG, "nfb_maf_affine: null pointer");
+    NFB_CHECK(features >= 1, NFB_ERR_ARG, "nfb_maf_affine: bad feature count");
+    return launch_maf_affine(x, params, y, log_det, rows, features, inverse, accumulate, S(stream));
+}
+
+int nfb_logit_transform(const float* in, float* out, float* log_det, int64_t batch, int64_t inner, float alpha,
+                        int32_t direction, int32_t accumulate, void* stream) {
+    NFB_CHECK(in && out, NFB_ERR_ARG, "nfb_logit_transform: null pointer");
+    NFB_CHECK(direction == NFB_INVERSE || direction == NFB_FORWARD, NFB_ERR_ARG, "bad direction");
+    NFB_CHECK(alpha >= 0.f && alpha < 0.5f, NFB_ERR_ARG, "Logit: alpha must be in [0, 0.5)");
+    return launch_logit(in, out, log_det, batch, inner, alpha, direction, accumulate, S(stream));
+}
+
 int nfb_gemm_f32(const nfb_gemm_desc_t* d, void* stream) {
     NFB_CHECK(d && d->A && d->B && d->C, NFB_ERR_ARG, "nfb_gemm_f32: null pointer");
     NFB_CHECK(d->M >= 0 && d->N >= 0 && d->K > 0 && d->N < (1ll << 30), NFB_ERR_ARG, "nfb_gemm_f32: bad shape");
@@ -1551,8 +1566,8 @@ int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, 
 /* debug-only (not part of the ABI header): phase timestamps of CTA 0's first tile */
 __attribute__((visibility("default"))) int nfb_debug_profile(nfb_flow_t* f, int enable, long long* out128) {
     if (!f) return NFB_ERR_ARG;
-    if (enable) { NFB_TRY(f->prof.reserve(512 * 8)); NFB_CUDA(cudaMemset(f->prof.p, 0, 512 * 8)); return NFB_OK; }
-    if (f->prof.p && out128) NFB_CUDA(cudaMemcpy(out128, f->prof.p, 512 * 8, cudaMemcpyDeviceToHost));
+    if (enable) { NFB_TRY(f->prof.reserve(1280 * 8)); NFB_CUDA(cudaMemset(f->prof.p, 0, 1280 * 8)); return NFB_OK; }
+    if (f->prof.p && out128) NFB_CUDA(cudaMemcpy(out128, f->prof.p, 1280 * 8, cudaMemcpyDeviceToHost));
     return NFB_OK;
 }
 

@@ -238,6 +238,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
                 const FusedStep st = cur.s;
                 const uint32_t ctl = st.ctl;
+                if (p.prof && u == 0 && s < 380 && lane == 0) p.prof[512 + s] = clock64();  // debug: step reached
                 const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
                 if (wcode == 1 || wcode == 6) {  // first use of A-operand K-chunk kc in this phase
                     const uint32_t kc = st.a0 & 3u;
@@ -249,6 +250,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     mbar_wait(bar(kBarCEmpty + i), ((cebits >> i) & 1u) ^ 1u, p.err, 210 + i);
                     cebits ^= 1u << i;
                 }
+                if (p.prof && u == 0 && s < 380 && lane == 0) p.prof[896 + s] = clock64();  // debug: operands (A / chunk) ready
                 mbar_wait(bar(kBarWFull + slot), wpar, p.err, 220 + slot);
                 tc_fence_after();
                 if (p.prof && u == 0 && s < 380 && lane == 0) p.prof[128 + s] = clock64();  // debug: issue time

@@ -411,4 +411,58 @@ int launch_class_cond_gauss(const float* z, const long long* y, const float* loc
     return NFB_OK;
 }
 
+// -----------------------------------------------------------------------------------------
+// Input pre-transforms of MultiscaleFlow (normflows/transforms.py): Logit (:8-47) and Shift (:50-75).
+// One block per sample: element-wise map + block reduction of the per-sample log-det.  HBM-bound (8 B/element).
+//   direction NFB_INVERSE (density pass, Logit.inverse): y = log(u) - log(1-u), u = alpha + beta x,
+//       log_det = log(beta) n - sum(log u + log(1-u))
+//   direction NFB_FORWARD (sampling, Logit.forward):     y = (sigmoid(x) - alpha) / beta,
+//       log_det = -log(beta) n + sum(logsigmoid(x) + logsigmoid(-x))
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) logit_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                    float* __restrict__ logdet, long long inner, float alpha,
+                                                    int direction, int accumulate) {
+    const long long b = blockIdx.x;
+    const float beta = 1.f - 2.f * alpha;
+    const float* src = in + b * inner;
+    float* dst = out + b * inner;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < inner; i += 256) {
+        const float x = src[i];
+        if (direction == 0) {
+            const float u = alpha + beta * x;
+            const float lu = logf(u), l1 = logf(1.f - u);
+            dst[i] = lu - l1;
+            acc -= lu + l1;
+        } else {
+            // logsigmoid(x) = -softplus(-x); stable for both signs
+            const float ax = fabsf(x);
+            const float sp = log1pf(expf(-ax));           // softplus(-|x|)
+            const float ls_pos = -sp - fmaxf(-x, 0.f);    // logsigmoid(x)
+            const float ls_neg = -sp - fmaxf(x, 0.f);     // logsigmoid(-x)
+            dst[i] = (1.f / (1.f + expf(-x)) - alpha) / beta;
+            acc += ls_pos + ls_neg;
+        }
+    }
+    __shared__ float red[8];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0 && logdet) {
+        float s = 0.f;
+        for (int j = 0; j < 8; ++j) s += red[j];
+        const float c = logf(beta) * (float)inner;
+        const float v = direction == 0 ? c + s : -c + s;
+        logdet[b] = accumulate ? logdet[b] + v : v;
+    }
+}
+int launch_logit(const float* in, float* out, float* logdet, long long B, long long inner, float alpha, int direction,
+                 int accumulate, cudaStream_t st) {
+    if (B == 0 || inner == 0) return NFB_OK;
+    logit_kernel<<<(unsigned)B, 256, 0, st>>>(in, out, logdet, inner, alpha, direction, accumulate);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
 }  // namespace nfb
+

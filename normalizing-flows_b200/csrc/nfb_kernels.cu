@@ -445,4 +445,37 @@ int launch_sum(const float* v, long long n, double scale, double* scratch /*>=10
     return NFB_OK;
 }
 
+// -----------------------------------------------------------------------------------------
+// Masked affine autoregressive flow, element-wise part (flows/affine/autoregressive.py:96-128):
+//   params [rows, D, 2] = (unconstrained_scale, shift) per feature; scale = sigmoid(u + 2) + 1e-3
+//   forward: y = scale x + shift, log_det += sum log scale;   inverse: y = (x - shift) / scale, log_det -= sum log scale
+// One warp per row (lanes stride the features), shuffle reduction of the log-det.  HBM-bound: 16 B per element.
+// -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) maf_affine_kernel(const float* __restrict__ x, const float* __restrict__ params,
+                                                         float* __restrict__ y, float* __restrict__ logdet,
+                                                         long long rows, int d, int inverse, int accumulate) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float acc = 0.f;
+    for (int j = lane; j < d; j += 32) {
+        const float2 p = reinterpret_cast<const float2*>(params + row * 2 * d)[j];
+        const float scale = 1.f / (1.f + expf(-(p.x + 2.f))) + 1e-3f;
+        const float ls = logf(scale);
+        const float v = x[row * d + j];
+        y[row * d + j] = inverse ? (v - p.y) / scale : fmaf(scale, v, p.y);
+        acc += inverse ? -ls : ls;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0 && logdet) logdet[row] = accumulate ? logdet[row] + acc : acc;
+}
+int launch_maf_affine(const float* x, const float* params, float* y, float* logdet, long long rows, int d, int inverse,
+                      int accumulate, cudaStream_t st) {
+    if (rows == 0 || d == 0) return NFB_OK;
+    maf_affine_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, params, y, logdet, rows, d, inverse, accumulate);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
 }  // namespace nfb
+

@@ -48,6 +48,8 @@ int launch_rqs_shared(const float* zin, const float* table, float* zout, float* 
 int launch_linear(const float* X, int ldx, const int* xidx, const float* W, const float* bias,
                   const float* R, int ldr, float* Y, int ldy, long long M, int N, int K, int act_in,
                   int act_out, float slope, cudaStream_t st);
+int launch_maf_affine(const float* x, const float* params, float* y, float* logdet, long long rows, int d, int inverse,
+                      int accumulate, cudaStream_t st);
 int launch_mask_mul(const float* w, const float* m, float* out, long long n, cudaStream_t st);
 int launch_lu_pack(const float* lower_e, const float* upper_e, const float* udiag, float eps, int n,
                    float* W, float* Winv, float* logabsdet, cudaStream_t st);
@@ -75,6 +77,8 @@ int launch_glow_fold_fwd(const float* P, const float* L, const float* U, const f
                          cudaStream_t st);
 int launch_paste_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st);
 int launch_copy_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st);
+int launch_logit(const float* in, float* out, float* logdet, long long B, long long inner, float alpha, int direction,
+                 int accumulate, cudaStream_t st);
 int launch_class_cond_gauss(const float* z, const long long* y, const float* loc, const float* log_scale,
                             float* logq, long long B, int dim, int ncls, int accumulate, cudaStream_t st);
 

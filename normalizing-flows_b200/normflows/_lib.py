@@ -83,6 +83,8 @@ SYMBOLS = {
     "nfb_device_info": (C.c_int, [_I32P, _I32P, _I32P]),
     "nfb_rqs_spline": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _F, _F, _I32, _I32, _VP]),
     "nfb_diag_gaussian_log_prob": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP]),
+    "nfb_maf_affine": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _VP]),
+    "nfb_logit_transform": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _F, _I32, _I32, _VP]),
     "nfb_gemm_f32": (C.c_int, [C.POINTER(GemmDesc), _VP]),
     "nfb_conv2d": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _F, _VP]),
     "nfb_glow_fold_actnorm_conv1x1": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),

@@ -247,6 +247,44 @@ class FlowHandle:
         return [i for i in range(len(self.layers)) if L.lib().nfb_flow_layer_is_fused(self._h, i)]
 
 
+def linear(x, weight, bias=None, a_relu=False, relu_out=False, resid=None):
+    """act(x) @ weight.T + bias (+ resid) on the tensor core (csrc/nfb_gemm_tc.cu through nfb_gemm_f32).
+    x: [M, K] CUDA float32 (row stride free), weight: [N, K]; returns a new [M, N] tensor."""
+    x = require_cuda_f32(x)
+    if x.dim() != 2:
+        raise ValueError("linear expects a 2-D input")
+    weight = weight.contiguous()
+    M, K = x.shape
+    N = weight.shape[0]
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    if M == 0:
+        return out
+    d = L.GemmDesc()
+    d.A, d.B, d.C = x.data_ptr(), weight.data_ptr(), out.data_ptr()
+    d.lda, d.ldb, d.ldc, d.M, d.N, d.K = x.stride(0), K, N, M, N, K
+    d.a_relu, d.relu_out = int(a_relu), int(relu_out)
+    if bias is not None:
+        d.bias = bias.contiguous().data_ptr()
+    if resid is not None:
+        resid = resid.contiguous()
+        d.resid, d.ldres = resid.data_ptr(), resid.stride(0)
+    with torch.cuda.device(x.device):
+        L.check(L.lib().nfb_gemm_f32(C.byref(d), L.stream_ptr()))
+    return out
+
+
+def resnet_forward(net, x, masked):
+    """ResidualNet.forward (nets/resnet.py:92-104) / MADE.forward (nets/made.py:296-304) for a stand-alone call of
+    the module: pre-activation residual blocks, every Linear one tensor-core GEMM with fused bias / ReLU / residual."""
+    eff = (lambda l: l.weight * l.mask) if masked else (lambda l: l.weight)
+    h = linear(x, eff(net.initial_layer), net.initial_layer.bias)
+    for blk in net.blocks:
+        l0, l1 = blk.linear_layers
+        t = linear(h, eff(l0), l0.bias, a_relu=True)
+        h = linear(t, eff(l1), l1.bias, a_relu=True, resid=h)
+    return linear(h, eff(net.final_layer), net.final_layer.bias)
+
+
 def resnet_desc(net, masked):
     """Fill an nfb_resnet_desc_t from a ResidualNet / MADE shim; returns (desc, keepalive)."""
     nb = len(net.blocks)

@@ -188,8 +188,6 @@ class MultiscaleFlow(nn.Module):
 
     def __init__(self, q0, flows, merges, transform=None, class_cond=True):
         super().__init__()
-        if transform is not None:
-            raise NotImplementedError("input transforms are out of scope of the CUDA path")
         self.q0 = nn.ModuleList(q0)
         self.num_levels = len(self.q0)
         self.flows = nn.ModuleList([nn.ModuleList(f) for f in flows])
@@ -202,6 +200,9 @@ class MultiscaleFlow(nn.Module):
         from .flows.glow import split_channels
         log_q = 0
         z = x
+        if self.transform is not None:  # core.py:600-602
+            z, log_det = self.transform.inverse(z)
+            log_q = log_q + log_det
         for i in range(len(self.q0) - 1, -1, -1):
             for j in range(len(self.flows[i]) - 1, -1, -1):
                 z, log_det = self.flows[i][j].inverse(z)
@@ -232,11 +233,17 @@ class MultiscaleFlow(nn.Module):
             for flow in self.flows[i]:
                 z_, ld = flow(z_)
                 log_det = log_det + ld
+        if self.transform is not None:  # core.py:522-524
+            z_, ld = self.transform(z_)
+            log_det = log_det + ld
         return z_, log_det
 
     def inverse_and_log_det(self, x):
         """core.py:527-551: x -> list of per-level latents."""
         log_det = 0
+        if self.transform is not None:  # core.py:536-538
+            x, ld = self.transform.inverse(x)
+            log_det = log_det + ld
         z = [None] * len(self.q0)
         for i in range(len(self.q0) - 1, -1, -1):
             for flow in reversed(self.flows[i]):
@@ -252,7 +259,7 @@ class MultiscaleFlow(nn.Module):
     def sample(self, num_samples=1, y=None, temperature=None):
         """core.py:553-586: draw every level's latent from its base, push it through the stack."""
         if temperature is not None:
-            raise NotImplementedError("temperature annealing is off the CUDA path")
+            self.set_temperature(temperature)
         log_q, z = None, None
         for i in range(len(self.q0)):
             z_, log_q_ = self.q0[i](num_samples, y) if self.class_cond else self.q0[i](num_samples)
@@ -265,7 +272,23 @@ class MultiscaleFlow(nn.Module):
             for flow in self.flows[i]:
                 z, ld = flow(z)
                 log_q = log_q - ld
+        if self.transform is not None:  # core.py:577-579
+            z, ld = self.transform(z)
+            log_q = log_q - ld
+        if temperature is not None:
+            self.reset_temperature()
         return z, log_q
+
+    def set_temperature(self, temperature):
+        """core.py:634-647."""
+        for q0 in self.q0:
+            if hasattr(q0, "temperature"):
+                q0.temperature = temperature
+            else:
+                raise NotImplementedError("One base function does not support temperature annealed sampling")
+
+    def reset_temperature(self):
+        self.set_temperature(None)
 
     def save(self, path):
         torch.save(self.state_dict(), path)

@@ -71,6 +71,9 @@ class ClassCondDiagGaussian(BaseDistribution):
         self.log_scale = nn.Parameter(torch.zeros(*shape, num_classes))
         self.temperature = None
 
+    def _log_scale(self):
+        return self.log_scale if self.temperature is None else self.log_scale + np.log(self.temperature)
+
     def forward(self, num_samples=1, y=None):
         """distributions/base.py:302-325: z = loc[..., y] + exp(log_scale[..., y]) * eps and its log-density.
         The random draws (labels, eps) and the per-class parameter gather are torch device ops (plumbing; the
@@ -83,12 +86,10 @@ class ClassCondDiagGaussian(BaseDistribution):
             y = y.to(device=dev, dtype=torch.int64)
         else:
             y = torch.randint(self.num_classes, (num_samples,), device=dev)
-        if self.temperature is not None:
-            raise NotImplementedError("temperature annealing is off the CUDA path")
         with torch.no_grad():
             eps = torch.randn((num_samples,) + self.shape, dtype=self.loc.dtype, device=dev)
             loc = self.loc.detach().movedim(-1, 0)[y]
-            log_scale = self.log_scale.detach().movedim(-1, 0)[y]
+            log_scale = self._log_scale().detach().movedim(-1, 0)[y]
             z = (loc + torch.exp(log_scale) * eps).contiguous()
         return z, self.log_prob(z, y)
 
@@ -97,12 +98,11 @@ class ClassCondDiagGaussian(BaseDistribution):
         if y.dim() != 1:
             y = torch.argmax(y, dim=1)  # one-hot rows (base.py:336-337 accepts both)
         y = y.to(device=z.device, dtype=torch.int64).contiguous()
-        if self.temperature is not None:
-            raise NotImplementedError("temperature annealing is off the density path")
+        ls = self._log_scale().contiguous()  # temperature annealing: log_scale + log T (base.py:318-319,339-340)
         out = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
         if z.shape[0]:
             with torch.cuda.device(z.device):
                 L.check(L.lib().nfb_class_cond_diag_gaussian_log_prob(
-                    L.ptr(z), L.ptr(y), L.ptr(self.loc), L.ptr(self.log_scale), L.ptr(out), z.shape[0], self.d,
+                    L.ptr(z), L.ptr(y), L.ptr(self.loc), L.ptr(ls), L.ptr(out), z.shape[0], self.d,
                     self.num_classes, 0, L.stream_ptr()))
         return out

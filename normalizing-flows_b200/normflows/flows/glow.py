@@ -19,22 +19,75 @@ _MAPS = {"exp": 0, "sigmoid": 1, "sigmoid_inv": 2}
 
 
 class Invertible1x1Conv(Flow):
-    """Parameter container; same parameters/buffers as the reference (mixing.py:63-86)."""
+    """Same parameters/buffers as the reference (mixing.py:63-86), both parameterisations: LU (P, L, U, sign_S, log_S)
+    or the plain matrix W (`use_lu=False`, :85-86).  The 1x1 convolution itself runs in csrc/nfb_glow.cu; the small
+    C x C parameter preparation (assembling W, the double-precision inverse of :94-101 / :110-114, slogdet of
+    :117,129) is folded once per parameter version."""
 
     def __init__(self, num_channels, use_lu=False):
         super().__init__()
-        if not use_lu:
-            raise NotImplementedError("Invertible1x1Conv(use_lu=False) is not on the CUDA path")
         self.num_channels, self.use_lu = num_channels, use_lu
         Q, _ = torch.linalg.qr(torch.randn(num_channels, num_channels))
-        P, Lm, U = torch.linalg.lu(Q)
-        self.register_buffer("P", P)
-        self.L = nn.Parameter(Lm)
-        S = U.diag()
-        self.register_buffer("sign_S", torch.sign(S))
-        self.log_S = nn.Parameter(torch.log(torch.abs(S)))
-        self.U = nn.Parameter(torch.triu(U, diagonal=1))
-        self.register_buffer("eye", torch.diag(torch.ones(num_channels)))
+        if use_lu:
+            P, Lm, U = torch.linalg.lu(Q)
+            self.register_buffer("P", P)
+            self.L = nn.Parameter(Lm)
+            S = U.diag()
+            self.register_buffer("sign_S", torch.sign(S))
+            self.log_S = nn.Parameter(torch.log(torch.abs(S)))
+            self.U = nn.Parameter(torch.triu(U, diagonal=1))
+            self.register_buffer("eye", torch.diag(torch.ones(num_channels)))
+        else:
+            self.W = nn.Parameter(Q)
+
+    def _sources(self):
+        return (self.P, self.L, self.U, self.sign_S, self.log_S) if self.use_lu else (self.W,)
+
+    def folded(self, direction, s, t, hw, dev):
+        """(w [C, C], b [C], logdet constant) of this layer fused with an ActNorm(s, t) on the channel axis:
+        density (NFB_INVERSE): ActNorm.inverse then conv with W;  sampling: conv with W^-1 then ActNorm.forward."""
+        C = self.num_channels
+        if self.use_lu:
+            fn = (L.lib().nfb_glow_fold_actnorm_conv1x1 if direction == L.NFB_INVERSE
+                  else L.lib().nfb_glow_fold_conv1x1_actnorm_forward)
+            w, b, ldc = torch.empty(C, C, device=dev), torch.empty(C, device=dev), torch.empty((), device=dev)
+            with torch.cuda.device(dev):
+                L.check(fn(L.ptr(self.P), L.ptr(self.L), L.ptr(self.U), L.ptr(self.sign_S), L.ptr(self.log_S),
+                           L.ptr(s), L.ptr(t), C, hw, L.ptr(w), L.ptr(b), L.ptr(ldc), L.stream_ptr()))
+            return w, b, ldc
+        with torch.no_grad():  # plain-matrix parameterisation: C x C parameter preparation in torch (like the reference)
+            W = self.W.detach()
+            sv, tv = s.detach().reshape(-1), t.detach().reshape(-1)
+            logabsdet = torch.linalg.slogdet(W.double())[1]
+            if direction == L.NFB_INVERSE:
+                w = (W * torch.exp(-sv)[None, :]).contiguous()
+                b = -(w @ tv)
+                ldc = (hw * (logabsdet - sv.double().sum())).float()
+            else:
+                w = (torch.exp(sv)[:, None] * torch.inverse(W.double()).float()).contiguous()
+                b = tv.clone()
+                ldc = (hw * (sv.double().sum() - logabsdet)).float()
+        return w, b.contiguous(), ldc
+
+    def _conv1x1(self, z, direction):
+        z = require_cuda_f32(z)
+        if z.dim() != 4 or z.shape[1] != self.num_channels:
+            raise ValueError("Expected an NCHW tensor with {} channels.".format(self.num_channels))
+        B, C, H, W = z.shape
+        zero = torch.zeros(C, device=z.device)
+        w, b, ldc = self.folded(direction, zero, zero, H * W, z.device)
+        out = torch.empty_like(z)
+        if B:
+            with torch.cuda.device(z.device):
+                L.check(L.lib().nfb_conv2d(L.ptr(z), C, 0, L.ptr(w), L.ptr(b), L.ptr(out), B, C, H, W, C, 1, -1.0,
+                                           L.stream_ptr()))
+        return out, ldc  # 0-dim log-det like the reference (broadcasts in log_q += log_det)
+
+    def forward(self, z):
+        return self._conv1x1(z, L.NFB_FORWARD)
+
+    def inverse(self, z):
+        return self._conv1x1(z, L.NFB_INVERSE)
 
 
 class Squeeze(Flow):
@@ -130,18 +183,13 @@ class GlowBlock(Flow):
         one direction; depends on the parameters only, so it is rebuilt when one of them changes
         ((data_ptr, _version) signature, like _native.FlowHandle), not on every call."""
         conv, an = self.flows[1], self.flows[2]
-        src = (conv.P, conv.L, conv.U, conv.sign_S, conv.log_S, an.s, an.t)
+        src = conv._sources() + (an.s, an.t)
         from .._native import generation
         sig = tuple((t.data_ptr(), t._version) for t in src) + (hw, dev, generation())
         cache = self.__dict__.get(key)
         if cache is None or cache[0] != sig:
-            C = self.channels
-            w = torch.empty(C, C, device=dev)
-            b = torch.empty(C, device=dev)
-            ldc = torch.empty((), device=dev)
-            with torch.cuda.device(dev):
-                L.check(fn(L.ptr(conv.P), L.ptr(conv.L), L.ptr(conv.U), L.ptr(conv.sign_S), L.ptr(conv.log_S),
-                           L.ptr(an.s), L.ptr(an.t), C, hw, L.ptr(w), L.ptr(b), L.ptr(ldc), L.stream_ptr()))
+            direction = L.NFB_INVERSE if fn is L.lib().nfb_glow_fold_actnorm_conv1x1 else L.NFB_FORWARD
+            w, b, ldc = conv.folded(direction, an.s, an.t, hw, dev)
             cache = (sig, w, b, ldc)
             self.__dict__[key] = cache
         return cache[1], cache[2], cache[3]

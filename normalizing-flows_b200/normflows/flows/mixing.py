@@ -7,7 +7,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
-from .base import NativeFlow
+from .base import Flow, NativeFlow
 
 
 class _PermutationBuf(nn.Module):
@@ -90,3 +90,50 @@ class Permute(NativeFlow):
         fa, ia = (C.c_int32 * len(f))(*f), (C.c_int32 * len(i))(*i)
         d.perm, d.inv_perm = fa, ia
         L.check(L.lib().nfb_flow_add_permute(handle, C.byref(d)))
+
+
+class InvertibleAffine(Flow):
+    """Invertible affine map without shift, the 2-D ([batch, channels]) version of the invertible 1x1 convolution
+    (reference: flows/mixing.py:136-207; both parameterisations).  z' = z W runs as one tensor-core GEMM
+    (csrc/nfb_gemm_tc.cu); assembling W / its double-precision inverse / slogdet is C x C parameter preparation."""
+
+    def __init__(self, num_channels, use_lu=True):
+        super().__init__()
+        self.num_channels, self.use_lu = num_channels, use_lu
+        Q, _ = torch.linalg.qr(torch.randn(num_channels, num_channels))
+        if use_lu:
+            P, Lm, U = torch.linalg.lu(Q)
+            self.register_buffer("P", P)
+            self.L = nn.Parameter(Lm)
+            S = U.diag()
+            self.register_buffer("sign_S", torch.sign(S))
+            self.log_S = nn.Parameter(torch.log(torch.abs(S)))
+            self.U = nn.Parameter(torch.triu(U, diagonal=1))
+            self.register_buffer("eye", torch.diag(torch.ones(num_channels)))
+        else:
+            self.W = nn.Parameter(Q)
+
+    @torch.no_grad()
+    def _matrix(self, inverse):
+        """(W or W^-1, log|det W|) as the reference forms them (:160-177, :179-205)."""
+        if self.use_lu:
+            Lm = torch.tril(self.L, diagonal=-1) + self.eye
+            Um = torch.triu(self.U, diagonal=1) + torch.diag(self.sign_S * torch.exp(self.log_S))
+            if inverse:
+                W = (torch.inverse(Um.double()) @ torch.inverse(Lm.double())).float() @ self.P.t()
+            else:
+                W = self.P @ Lm @ Um
+            return W, torch.sum(self.log_S)
+        W = torch.inverse(self.W.double()).float() if inverse else self.W.detach()
+        return W, torch.linalg.slogdet(self.W.double())[1].float()
+
+    def _run(self, z, inverse_matrix):
+        from .._native import linear
+        W, logdet = self._matrix(inverse_matrix)
+        return linear(z, W.t().contiguous()), (-logdet if inverse_matrix else logdet)
+
+    def forward(self, z, context=None):
+        return self._run(z, True)
+
+    def inverse(self, z, context=None):
+        return self._run(z, False)

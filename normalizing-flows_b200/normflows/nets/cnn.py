@@ -9,14 +9,17 @@ from .. import _lib as L
 class ConvNet2d(nn.Module):
     def __init__(self, channels, kernel_size, leaky=0.0, init_zeros=True, actnorm=False, weight_std=None):
         super().__init__()
-        if actnorm:
-            raise NotImplementedError("ConvNet2d(actnorm=True) is not on the CUDA path")
+        from ..utils.nn import ActNorm
         mods = []
         for i in range(len(kernel_size) - 1):
-            conv = nn.Conv2d(channels[i], channels[i + 1], kernel_size[i], padding=kernel_size[i] // 2)
+            conv = nn.Conv2d(channels[i], channels[i + 1], kernel_size[i], padding=kernel_size[i] // 2,
+                             bias=(not actnorm))
             if weight_std is not None:
                 conv.weight.data.normal_(mean=0.0, std=weight_std)
-            mods += [conv, nn.LeakyReLU(leaky)]
+            mods.append(conv)
+            if actnorm:  # nets/cnn.py:45-46: activation normalisation after every conv but the last
+                mods.append(ActNorm((channels[i + 1],) + (1, 1)))
+            mods.append(nn.LeakyReLU(leaky))
         i = len(kernel_size)
         mods.append(nn.Conv2d(channels[i - 1], channels[i], kernel_size[i - 1], padding=kernel_size[i - 1] // 2))
         if init_zeros:
@@ -32,16 +35,33 @@ class ConvNet2d(nn.Module):
         """y = net(x[:, c0:c0+cin]) for a contiguous CUDA NCHW tensor x; returns [B, out, H, W]."""
         import torch
         B, ctot, H, W = x.shape
-        convs = self.conv_layers()
+        from ..utils.nn import ActNorm
+        mods = list(self.net)
         cur, cur_tot, cur_c0 = x, ctot, c0
         with torch.cuda.device(x.device):
-            for j, conv in enumerate(convs):
-                last = j + 1 == len(convs)
+            for j, conv in enumerate(mods):
+                if not isinstance(conv, nn.Conv2d):
+                    continue
+                last = conv is mods[-1]
+                an = mods[j + 1].actNorm if j + 1 < len(mods) and isinstance(mods[j + 1], ActNorm) else None
+                w, b = conv.weight, conv.bias
                 y = torch.empty(B, conv.out_channels, H, W, device=x.device, dtype=torch.float32)
-                L.check(L.lib().nfb_conv2d(L.ptr(cur), cur_tot, cur_c0, L.ptr(conv.weight), L.ptr(conv.bias),
-                                           L.ptr(y), B, conv.in_channels, H, W, conv.out_channels,
-                                           conv.kernel_size[0], -1.0 if last else float(self.leaky),
-                                           L.stream_ptr()))
+
+                def run(wt, bt, act):
+                    L.check(L.lib().nfb_conv2d(L.ptr(cur), cur_tot, cur_c0, L.ptr(wt), L.ptr(bt), L.ptr(y), B,
+                                               conv.in_channels, H, W, conv.out_channels, conv.kernel_size[0], act,
+                                               L.stream_ptr()))
+                if an is not None:
+                    # ActNorm after the conv = per-channel affine: folded into the conv's weights and bias.  First
+                    # call: raw conv output -> data-dependent init (flows/normalization.py:19-29), then the fold.
+                    if not an._done():
+                        run(w, None, -1.0)
+                        an._data_init(y, "forward")
+                    with torch.no_grad():
+                        e = torch.exp(an.s.detach().reshape(-1))
+                        w = (conv.weight.detach() * e[:, None, None, None]).contiguous()
+                        b = an.t.detach().reshape(-1).contiguous()
+                run(w, b, -1.0 if last else float(self.leaky))
                 cur, cur_tot, cur_c0 = y, conv.out_channels, 0
         return cur
 

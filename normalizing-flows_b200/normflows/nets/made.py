@@ -73,3 +73,10 @@ class MADE(nn.Module):
         self.blocks = nn.ModuleList(blocks)
         self.final_layer = MaskedLinear(prev, features * output_multiplier, features, random_mask, True,
                                         out_degrees_=in_deg)
+
+    def forward(self, inputs, context=None):
+        """nets/made.py:296-304, stand-alone call: masked weights, pre-activation residual blocks."""
+        if context is not None:
+            raise NotImplementedError("context features are not on the CUDA path yet")
+        from .._native import resnet_forward
+        return resnet_forward(self, inputs, masked=True)

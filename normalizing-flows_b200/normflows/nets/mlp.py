@@ -1,8 +1,7 @@
 """MLP parameter container (reference: normflows/nets/mlp.py:5-58).
 
-Same constructor and `state_dict` keys (`net.<i>.weight|bias`).  The arithmetic runs inside the
-affine-stack kernel (csrc/nfb_affine.cu); calling the module directly evaluates it through the same
-library as a one-layer affine problem is not needed -- it is only ever used as s/t/param_map."""
+Same constructor and `state_dict` keys (`net.<i>.weight|bias`).  Inside a flow the arithmetic runs in the
+affine-stack kernel (csrc/nfb_affine.cu); calling the module directly runs one tensor-core GEMM per layer."""
 from torch import nn
 
 
@@ -29,5 +28,15 @@ class MLP(nn.Module):
         return [m for m in self.net if isinstance(m, nn.Linear)]
 
     def forward(self, x):
-        raise RuntimeError("MLP is a parameter container on the CUDA path; it is evaluated inside the "
-                           "fused affine kernels (MaskedAffineFlow / AffineCouplingBlock)")
+        """Stand-alone evaluation (nets/mlp.py:57-58): one tensor-core GEMM per Linear (csrc/nfb_gemm_tc.cu).  Inside
+        MaskedAffineFlow / AffineCouplingBlock the net is evaluated by the fused affine kernel instead."""
+        import torch
+        from .._native import linear
+        lins = self.linear_layers()
+        h = x
+        for i, lin in enumerate(lins):
+            last = i + 1 == len(lins)
+            h = linear(h, lin.weight, lin.bias, relu_out=(not last and self.leaky == 0.0))
+            if not last and self.leaky != 0.0:
+                h = torch.where(h > 0, h, h * self.leaky)
+        return h

@@ -44,3 +44,10 @@ class ResidualNet(nn.Module):
         self.initial_layer = nn.Linear(in_features, hidden_features)
         self.blocks = nn.ModuleList([ResidualBlock(hidden_features, None, activation) for _ in range(num_blocks)])
         self.final_layer = nn.Linear(hidden_features, out_features)
+
+    def forward(self, inputs, context=None):
+        """nets/resnet.py:92-104, stand-alone call (inside a flow the net is part of the fused kernel)."""
+        if context is not None:
+            raise NotImplementedError("context features are not on the CUDA path yet")
+        from .._native import resnet_forward
+        return resnet_forward(self, inputs, masked=False)

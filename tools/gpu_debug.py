@@ -106,7 +106,7 @@ if mode == "prof":
     import ctypes as C
     from normflows import _lib as L
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 65536
-    for kind in ("ar", "coupled"):
+    for kind in ("ar",):
         m = rand_model(kind, 2)
         x = (torch.randn(B, 64) * 1.5).cuda()
         m.forward_kld(x); torch.cuda.synchronize()
@@ -115,7 +115,7 @@ if mode == "prof":
         lib.nfb_debug_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.nfb_debug_profile(h, 1, None)
         m.forward_kld(x); torch.cuda.synchronize()
-        buf = (C.c_longlong * 512)()
+        buf = (C.c_longlong * 1280)()
         lib.nfb_debug_profile(h, 0, buf)
         n = buf[127]
         t = [buf[i] - buf[0] for i in range(n)]
@@ -124,6 +124,11 @@ if mode == "prof":
         print("  delta:", [t[i] - t[i - 1] for i in range(1, n)])
         mm = [buf[128 + i] - buf[0] for i in range(380) if buf[128 + i]]
         print(f"  mma issue times ({len(mm)} steps):", mm)
+        reach = [buf[512 + i] - buf[0] for i in range(len(mm))]
+        opnd = [buf[896 + i] - buf[0] for i in range(len(mm))]
+        print("  step reached      :", reach)
+        print("  waited for A/chunk:", [opnd[i] - reach[i] for i in range(len(mm))])
+        print("  waited for weights:", [mm[i] - opnd[i] for i in range(len(mm))])
 
 if mode == "spline":
     import ctypes as C
