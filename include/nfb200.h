@@ -61,6 +61,18 @@ int nfb_diag_gaussian_log_prob(const float* z_dev, const float* loc_dev, const f
                                float* log_q_dev, int64_t rows, int32_t dim, int32_t accumulate,
                                void* stream);
 
+/* ---- invertible residual block (flows/residual.py:12-251, nets/lipschitz.py:14-67,642-648), element-wise pieces;
+ * the Linear layers of g, of its Jacobian-vector and vector-Jacobian products run through nfb_gemm_f32 ---- */
+/* Swish of the Lipschitz MLP: a = x sigmoid(b x) / 1.1 with b = softplus(beta); da (optional) = d a / d x */
+int nfb_swish(const float* x_dev, float beta_softplus, int64_t n, float* a_dev, float* da_dev, void* stream);
+/* dst[t*n + i] = src[t*n + i] * m[i], t < nt (tangents / cotangents through an activation; in place allowed) */
+int nfb_mul_rows(const float* src_dev, const float* m_dev, int64_t n, int32_t nt, float* dst_dev, void* stream);
+/* residual.py:148-161 (2-D, eval / brute_force): jt [2, batch, 2] = Jacobian columns -> out[r] = log|det(I + J_r)| */
+int nfb_logabsdet_i_plus_j_2x2(const float* jt_dev, int64_t batch, float* out_dev, void* stream);
+/* out[r] (+)= c * sum_j a[r, j] b[r, j]  (one Hutchinson trace term v^T J^k eps per sample, residual.py:355-366) */
+int nfb_rowdot(const float* a_dev, const float* b_dev, int64_t rows, int32_t d, float c, int32_t accumulate,
+               float* out_dev, void* stream);
+
 /* flows/affine/autoregressive.py:96-128 MaskedAffineAutoregressive, element-wise part: params [rows, features, 2] =
  * (unconstrained_scale, shift) from the MADE conditioner; scale = sigmoid(u + 2) + 1e-3.  inverse = 0: y = scale x + shift,
  * log_det (+)= sum log scale; inverse = 1: y = (x - shift) / scale, log_det (+)= -sum log scale. */

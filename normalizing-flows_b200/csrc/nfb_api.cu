@@ -784,6 +784,7 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
     p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = accumulate;
     p.progress = nullptr;
     p.err = f->err.as<int>();
+    p.poll_all = getenv("NFB_POLL_ALL") != nullptr;
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
     NFB_TRY(launch_fused_rqs(p, f->sm_count, sample, st));
     f->launches++;
@@ -805,6 +806,7 @@ int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, 
     p.in_ready = sample ? nullptr : f->cur_in_ready;
     f->cur_in_ready = nullptr;  // consumed (or not applicable): later launches must not wait on it
     p.err = f->err.as<int>();
+    p.poll_all = getenv("NFB_POLL_ALL") != nullptr;
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
     NFB_TRY(launch_fused_rqs(p, f->sm_count, sample, st));
     f->launches += 2;  // memset + kernel
@@ -1046,6 +1048,24 @@ int nfb_class_cond_diag_gaussian_log_prob(const float* z, const int64_t* y, cons
     NFB_CHECK(z && y && loc && log_scale && log_q, NFB_ERR_ARG, "nfb_class_cond_diag_gaussian_log_prob: null pointer");
     return launch_class_cond_gauss(z, reinterpret_cast<const long long*>(y), loc, log_scale, log_q, batch, dim,
                                    num_classes, accumulate, S(stream));
+}
+
+int nfb_swish(const float* x, float beta_softplus, int64_t n, float* a, float* da, void* stream) {
+    NFB_CHECK(x && a, NFB_ERR_ARG, "nfb_swish: null pointer");
+    return launch_swish(x, beta_softplus, n, a, da, S(stream));
+}
+int nfb_mul_rows(const float* src, const float* m, int64_t n, int32_t nt, float* dst, void* stream) {
+    NFB_CHECK(src && m && dst, NFB_ERR_ARG, "nfb_mul_rows: null pointer");
+    return launch_mul_rows(src, m, n, nt, dst, S(stream));
+}
+int nfb_logabsdet_i_plus_j_2x2(const float* jt, int64_t batch, float* out, void* stream) {
+    NFB_CHECK(jt && out, NFB_ERR_ARG, "nfb_logabsdet_i_plus_j_2x2: null pointer");
+    return launch_logdet2(jt, batch, out, S(stream));
+}
+int nfb_rowdot(const float* a, const float* b, int64_t rows, int32_t d, float c, int32_t accumulate, float* out,
+               void* stream) {
+    NFB_CHECK(a && b && out, NFB_ERR_ARG, "nfb_rowdot: null pointer");
+    return launch_rowdot(a, b, rows, d, c, accumulate, out, S(stream));
 }
 
 int nfb_maf_affine(const float* x, const float* params, float* y, float* log_det, int64_t rows, int32_t features,
@@ -1566,8 +1586,8 @@ int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, 
 /* debug-only (not part of the ABI header): phase timestamps of CTA 0's first tile */
 __attribute__((visibility("default"))) int nfb_debug_profile(nfb_flow_t* f, int enable, long long* out128) {
     if (!f) return NFB_ERR_ARG;
-    if (enable) { NFB_TRY(f->prof.reserve(1280 * 8)); NFB_CUDA(cudaMemset(f->prof.p, 0, 1280 * 8)); return NFB_OK; }
-    if (f->prof.p && out128) NFB_CUDA(cudaMemcpy(out128, f->prof.p, 1280 * 8, cudaMemcpyDeviceToHost));
+    if (enable) { NFB_TRY(f->prof.reserve(2048 * 8)); NFB_CUDA(cudaMemset(f->prof.p, 0, 2048 * 8)); return NFB_OK; }
+    if (f->prof.p && out128) NFB_CUDA(cudaMemcpy(out128, f->prof.p, 2048 * 8, cudaMemcpyDeviceToHost));
     return NFB_OK;
 }
 

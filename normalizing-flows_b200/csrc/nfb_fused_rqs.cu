@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     issue4(st.a0);
                     if (st.a1 != 0xFF) issue4(st.a1);
                     if (st.a2 != 0xFF) issue4(st.a2);
+                    if (p.prof && u == 0 && s < 380) p.prof[1280 + s] = clock64();  // debug: MMAs of this record issued
                     if (PAIR) {
                         umma2_commit_mc(bar(kBarWEmpty + slot));
                         if (scode == 1) umma2_commit_mc(bar(kBarAccFull));
@@ -295,6 +296,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         if (scode == 1) umma_commit(bar(kBarAccFull));
                         else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
                     }
+                    if (p.prof && u == 0 && s < 380) p.prof[1664 + s] = clock64();  // debug: commits issued
                 }
                 __syncwarp();
                 if (++slot == kRingSlots) { slot = 0; wpar ^= 1; }
@@ -310,6 +312,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t aA = sbase + kOffA;
         uint32_t afpar = 0, cfbits = 0;
+        // epilogue-side waits: one polling lane per warp (p.poll_all = debug A/B: every thread polls, the old behaviour)
+        auto ewait = [&](uint32_t b, uint32_t parity, int tag) {
+            if (p.poll_all) mbar_wait(b, parity, p.err, tag);
+            else mbar_wait_warp(b, parity, p.err, tag);
+        };
         long long* prof = (p.prof && blockIdx.x == 0 && et == 0) ? p.prof : nullptr;
         int pi = 0;
 #define NFB_STAMP() do { if (prof && pi < 126) prof[pi++] = clock64(); } while (0)
@@ -430,7 +437,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             if (L.has_lu) {
                 build_a(true);
                 NFB_STAMP();  // build_a(lu) done
-                mbar_wait(bar(kBarAccFull), afpar, p.err, 300);
+                ewait(bar(kBarAccFull), afpar, 300);
                 NFB_STAMP();  // LU gemm done
                 afpar ^= 1;
                 tc_fence_after();
@@ -517,7 +524,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 
             // ---- hidden layers ----
             for (int ph = 0; ph < L.n_hidden; ++ph) {
-                mbar_wait(bar(kBarAccFull), afpar, p.err, 310 + ph);
+                ewait(bar(kBarAccFull), afpar, 310 + ph);
                 afpar ^= 1;
                 tc_fence_after();
                 NFB_STAMP();  // hidden gemm ph done
@@ -569,7 +576,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 // (= the epilogue has finished reading columns 0..255) before slot 1 overwrites buffer 0.
                 const int b = (ci + 1) & 1;
                 const int c = L.chunk_order[ci];
-                mbar_wait(bar(kBarCFull + b), (cfbits >> b) & 1u, p.err, 400 + b);
+                ewait(bar(kBarCFull + b), (cfbits >> b) & 1u, 400 + b);
                 cfbits ^= 1u << b;
                 tc_fence_after();
                 NFB_STAMP();  // chunk c available

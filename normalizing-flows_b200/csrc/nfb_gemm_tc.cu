@@ -157,47 +157,47 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
         const bool b_al = (p.ldb % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.B) & 15) == 0);
         uint32_t st = 0, st_use = 0, it = 0;
 
-        // one operand tile: R "rows" of the GEMM's M/N dimension x 64 k, from a row-major fp32 matrix.
+        // One operand tile = R "rows" of the GEMM's M/N dimension x 64 k, from a row-major fp32 matrix, handled in
+        // groups of 8 contiguous source elements (one 16-byte bf16 chunk of the swizzled tile):
         //   K-major : element (i, k) at src[(i0+i)*ld + k0+k]; group g = (row = g>>3, 16-byte chunk c8 = g&7)
         //   MN-major: element (i, k) at src[(k0+k)*ld + i0+i]; group g = (k row = g / (R/8), chunk cm = g % (R/8))
-        auto build = [&](const float* src, long long ld, int mn, bool al, int relu, long long i0, long long i_end,
-                         long long k0, long long k_end, int R, uint32_t t_hi, uint32_t t_lo) {
-            const int groups = R * 8;
-            for (int g = bt; g < groups; g += kGtBuildThreads) {
-                long long row, col;   // global row / first column of the 8 contiguous source elements
-                long long row_end, col_end;
-                uint32_t off;
-                if (!mn) {
-                    const int i = g >> 3, c8 = g & 7;
-                    row = i0 + i; col = k0 + c8 * 8; row_end = i_end; col_end = k_end;
-                    off = (uint32_t)((i >> 3) * 1024 + (i & 7) * 128 + ((c8 ^ (i & 7)) << 4));
-                } else {
-                    const int per = R >> 3;
-                    const int kr = g / per, cm = g - kr * per;
-                    row = k0 + kr; col = i0 + cm * 8; row_end = k_end; col_end = i_end;
-                    off = (uint32_t)((cm >> 3) * 8192 + (kr >> 3) * 1024 + (kr & 7) * 128 + (((cm & 7) ^ (kr & 7)) << 4));
-                }
-                float v[8];
-                if (row < row_end && col + 8 <= col_end && al) {
-                    const float4* s4 = reinterpret_cast<const float4*>(src + row * ld + col);
-                    const float4 x0 = __ldg(s4), x1 = __ldg(s4 + 1);
-                    v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        v[j] = (row < row_end && col + j < col_end) ? __ldg(src + row * ld + col + j) : 0.f;
-                }
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float a = v[2 * i], b = v[2 * i + 1];
-                    if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-                    hi[i] = pack_bf16x2(a, b);
-                    lo[i] = pack_bf16x2(a - __uint_as_float(hi[i] << 16), b - __uint_as_float(hi[i] & 0xffff0000u));
-                }
-                gt_st_v4(t_hi + off, hi[0], hi[1], hi[2], hi[3]);
-                gt_st_v4(t_lo + off, lo[0], lo[1], lo[2], lo[3]);
+        // A thread owns up to 2 groups of A and 4 of B per K chunk.  ALL their global loads are issued first (12
+        // independent LDG.128 in flight per thread, and before the wait for the stage to be free), then converted and
+        // stored: one memory round trip per chunk instead of one per group.
+        auto load_group = [&](const float* src, long long ld, int mn, bool al, long long i0, long long i_end, long long k0,
+                              long long k_end, int R, int g, float (&v)[8], uint32_t& off) {
+            long long row, col, row_end, col_end;
+            if (!mn) {
+                const int i = g >> 3, c8 = g & 7;
+                row = i0 + i; col = k0 + c8 * 8; row_end = i_end; col_end = k_end;
+                off = (uint32_t)((i >> 3) * 1024 + (i & 7) * 128 + ((c8 ^ (i & 7)) << 4));
+            } else {
+                const int per = R >> 3;
+                const int kr = g / per, cm = g - kr * per;
+                row = k0 + kr; col = i0 + cm * 8; row_end = k_end; col_end = i_end;
+                off = (uint32_t)((cm >> 3) * 8192 + (kr >> 3) * 1024 + (kr & 7) * 128 + (((cm & 7) ^ (kr & 7)) << 4));
             }
+            if (row < row_end && col + 8 <= col_end && al) {
+                const float4* s4 = reinterpret_cast<const float4*>(src + row * ld + col);
+                const float4 x0 = __ldg(s4), x1 = __ldg(s4 + 1);
+                v[0] = x0.x; v[1] = x0.y; v[2] = x0.z; v[3] = x0.w; v[4] = x1.x; v[5] = x1.y; v[6] = x1.z; v[7] = x1.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    v[j] = (row < row_end && col + j < col_end) ? __ldg(src + row * ld + col + j) : 0.f;
+            }
+        };
+        auto store_group = [&](const float (&v)[8], int relu, uint32_t t_hi, uint32_t t_lo, uint32_t off) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                float a = v[2 * i], b = v[2 * i + 1];
+                if (relu) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+                hi[i] = pack_bf16x2(a, b);
+                lo[i] = pack_bf16x2(a - __uint_as_float(hi[i] << 16), b - __uint_as_float(hi[i] & 0xffff0000u));
+            }
+            gt_st_v4(t_hi + off, hi[0], hi[1], hi[2], hi[3]);
+            gt_st_v4(t_lo + off, lo[0], lo[1], lo[2], lo[3]);
         };
 
         auto epilogue = [&](long long u, uint32_t i) {
@@ -260,13 +260,27 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
             const long long k0 = (long long)ks * p.k_per_split;
             const long long k1 = k0 + p.k_per_split < p.K ? k0 + p.k_per_split : p.K;
             const int KC = (int)((k1 - k0 + 63) / 64);
+            const int nb_groups = NT * 8;  // B groups per chunk (A: 1024)
             for (int kc = 0; kc < KC; ++kc) {
-                if (st_use > 0) mbar_wait(bar(GB_EMPTY + st), (st_use - 1) & 1u, p.err, 830 + st);
                 const uint32_t sa = sbase + st * stage_bytes;
                 const long long kk = k0 + (long long)kc * 64;
-                build(p.A, p.lda, p.a_mn, a_al, p.a_relu, mt * 128, p.M, kk, k1, 128, sa, sa + kGtTileA);
-                build(p.B, p.ldb, p.b_mn, b_al, p.b_relu, (long long)nt * NT, p.N, kk, k1, NT, sa + 2 * kGtTileA,
-                      sa + 2 * kGtTileA + b_tile);
+                float va[2][8], vb[4][8];
+                uint32_t oa[2], ob[4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    load_group(p.A, p.lda, p.a_mn, a_al, mt * 128, p.M, kk, k1, 128, bt + i * kGtBuildThreads, va[i], oa[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (bt + i * kGtBuildThreads < nb_groups)
+                        load_group(p.B, p.ldb, p.b_mn, b_al, (long long)nt * NT, p.N, kk, k1, NT, bt + i * kGtBuildThreads,
+                                   vb[i], ob[i]);
+                if (st_use > 0) mbar_wait(bar(GB_EMPTY + st), (st_use - 1) & 1u, p.err, 830 + st);  // (loads in flight)
+#pragma unroll
+                for (int i = 0; i < 2; ++i) store_group(va[i], p.a_relu, sa, sa + kGtTileA, oa[i]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (bt + i * kGtBuildThreads < nb_groups)
+                        store_group(vb[i], p.b_relu, sa + 2 * kGtTileA, sa + 2 * kGtTileA + b_tile, ob[i]);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar(GB_FULL + st));

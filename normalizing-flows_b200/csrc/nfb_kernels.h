@@ -156,6 +156,7 @@ struct FusedParams {
     const int* in_ready;       // optional: number of rows of `zin` that have landed (chunked H2D in flight, written
                                // by the copy engine); layer-0 tiles wait for their rows.  null = all resident
     int* err;
+    int poll_all;              // debug A/B: every epilogue thread polls its mbarrier (1) instead of one lane per warp (0)
     long long* prof;           // optional [128] clock64 stamps (debug)
 };
 int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st);
@@ -188,6 +189,13 @@ int launch_gather_cols_ld(const float* in, int ld_in, float* out, int n_out, con
                           cudaStream_t st);
 int launch_axpy(const float* x, float a, float* y, long long n, int accumulate, cudaStream_t st);
 int launch_split_table(const float* tab, int n, float* gw, float* gh, float* gd, cudaStream_t st);
+
+// ---- invertible residual block, element-wise pieces (nfb_residual.cu) ----
+int launch_swish(const float* x, float b, long long n, float* a, float* da, cudaStream_t st);
+int launch_mul_rows(const float* S, const float* m, long long n, int nt, float* T, cudaStream_t st);
+int launch_logdet2(const float* jt, long long B, float* out, cudaStream_t st);
+int launch_rowdot(const float* a, const float* b, long long rows, int d, float c, int accumulate, float* out,
+                  cudaStream_t st);
 
 // tcgen05 fp32 accumulation truncates: relative loss per K=16 MMA step, compensated at pack time (nfb_api.cu)
 constexpr float kAccStepGain = 2.9e-8f;

@@ -273,6 +273,55 @@ def linear(x, weight, bias=None, a_relu=False, relu_out=False, resid=None):
     return out
 
 
+def linear_t(x, weight):
+    """x @ weight for weight [K, N] row-major (the dgrad / vector-Jacobian layout: no transpose in memory)."""
+    x = require_cuda_f32(x)
+    weight = weight.contiguous()
+    M, K = x.shape
+    N = weight.shape[1]
+    out = torch.empty(M, N, dtype=torch.float32, device=x.device)
+    if M == 0:
+        return out
+    d = L.GemmDesc()
+    d.A, d.B, d.C = x.data_ptr(), weight.data_ptr(), out.data_ptr()
+    d.lda, d.ldb, d.ldc, d.M, d.N, d.K, d.b_mn = x.stride(0), N, N, M, N, K, 1
+    with torch.cuda.device(x.device):
+        L.check(L.lib().nfb_gemm_f32(C.byref(d), L.stream_ptr()))
+    return out
+
+
+def swish(x, b, want_derivative=False):
+    """(x sigmoid(b x) / 1.1, derivative or None) -- nets/lipschitz.py:642-648 with b = softplus(beta)."""
+    x = require_cuda_f32(x)
+    a = torch.empty_like(x)
+    da = torch.empty_like(x) if want_derivative else None
+    if x.numel():
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nfb_swish(L.ptr(x), float(b), x.numel(), L.ptr(a), L.ptr(da), L.stream_ptr()))
+    return a, da
+
+
+def mul_rows(src, m, nt):
+    """src: [nt, ...] stacked tensors, m: [...]; returns src * m broadcast over the leading dim."""
+    out = torch.empty_like(src)
+    if src.numel():
+        with torch.cuda.device(src.device):
+            L.check(L.lib().nfb_mul_rows(L.ptr(src), L.ptr(m), m.numel(), int(nt), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def rowdot(a, b, c=1.0, out=None):
+    """out[r] (+)= c * sum_j a[r, j] b[r, j]"""
+    acc = out is not None
+    if out is None:
+        out = torch.empty(a.shape[0], dtype=torch.float32, device=a.device)
+    if a.shape[0]:
+        with torch.cuda.device(a.device):
+            L.check(L.lib().nfb_rowdot(L.ptr(a), L.ptr(b), a.shape[0], a.shape[1], float(c), int(acc), L.ptr(out),
+                                       L.stream_ptr()))
+    return out
+
+
 def resnet_forward(net, x, masked):
     """ResidualNet.forward (nets/resnet.py:92-104) / MADE.forward (nets/made.py:296-304) for a stand-alone call of
     the module: pre-activation residual blocks, every Linear one tensor-core GEMM with fused bias / ReLU / residual."""

@@ -5,3 +5,4 @@ from .autoregressive import Autoregressive, MaskedAffineAutoregressive
 from .affine import (AffineConstFlow, ActNorm, MaskedAffineFlow, AffineCouplingBlock, AffineCoupling,
                      Split, Merge)
 from .glow import GlowBlock, Invertible1x1Conv, Squeeze, ImageMerge
+from .residual import Residual, iResBlock

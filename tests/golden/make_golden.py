@@ -464,3 +464,68 @@ def case_neighbours():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "neighbours":
     case_neighbours()
+
+
+def case_residual():
+    """BASELINE config 5 family: Residual (iResBlock) with a LipschitzMLP (flows/residual.py, nets/lipschitz.py).
+    Exact 2-D eval path (deterministic), and the stochastic power-series estimators with the random truncation n and
+    the Hutchinson probe INJECTED (np.random.geometric / torch.randn_like patched while minting) so that the values
+    are reproducible: eval-mode basic estimator (4-D) and training-mode Neumann surrogate (2-D and 4-D).
+        python tests/golden/make_golden.py residual"""
+    from normflows.flows import residual as R
+    torch.manual_seed(41)
+    g = torch.Generator().manual_seed(42)
+    out = {"torch_version": torch.__version__}
+    for d in (2, 4):
+        flows = []
+        for _ in range(3):
+            net = nf.nets.LipschitzMLP([d, 32, 32, d], init_zeros=False, lipschitz_const=0.9)
+            flows += [nf.flows.Residual(net, reduce_memory=True)]
+        model = nf.NormalizingFlow(nf.distributions.DiagGaussian(d, trainable=False), flows)
+        perturb(model, 0.4, 43 + d)
+        with torch.no_grad():
+            nf.utils.update_lipschitz(model, 50)
+        x = torch.randn(64, d, generator=g) * 1.2
+        out[f"x{d}"] = x.numpy()
+        for k, v in model.state_dict().items():
+            out[f"sd{d}__" + k] = v.detach().numpy()
+        md = model.double()
+        n_inj = [np.array([3]), np.array([1]), np.array([2])]          # one draw per block, in call order
+        eps = torch.randn(3, 64, d, generator=g, dtype=torch.float64)
+        out[f"n_inj{d}"], out[f"eps{d}"] = np.stack(n_inj), eps.numpy()
+
+        def run(train):
+            calls = {"i": 0, "j": 0}
+            orig_geo, orig_rl = np.random.geometric, torch.randn_like
+
+            def geo(p, n):
+                i = calls["i"]; calls["i"] += 1
+                return n_inj[i % 3]
+
+            def rl(t, **kw):
+                j = calls["j"]; calls["j"] += 1
+                return eps[j % 3].to(t)
+            np.random.geometric, torch.randn_like = geo, rl
+            try:
+                md.train(train)
+                # density pass applies flows last-to-first: block 2 is called first -> inject in that order
+                z, ld = md.inverse_and_log_det(x.double())
+                return z.detach().numpy(), ld.detach().numpy()
+            finally:
+                np.random.geometric, torch.randn_like = orig_geo, orig_rl
+                md.eval()
+        z, ld = run(False)
+        out[f"eval_z{d}"], out[f"eval_ld{d}"] = z, ld
+        z, ld = run(True)
+        out[f"train_z{d}"], out[f"train_ld{d}"] = z, ld
+        if d == 2:
+            with torch.no_grad():
+                out["eval_logprob2"] = md.log_prob(x.double()).numpy()
+                xs, lds = md.forward_and_log_det(torch.from_numpy(out["eval_z2"]))
+            out["fwd_x2"], out["fwd_ld2"] = xs.detach().numpy(), lds.detach().numpy()
+    np.savez_compressed(os.path.join(HERE, "residual.npz"), **out)
+    print("wrote residual", out["eval_ld2"][:3], out["train_ld2"][:3], np.abs(out["fwd_x2"] - out["x2"]).max())
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "residual":
+    case_residual()

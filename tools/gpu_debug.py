@@ -115,7 +115,7 @@ if mode == "prof":
         lib.nfb_debug_profile.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         lib.nfb_debug_profile(h, 1, None)
         m.forward_kld(x); torch.cuda.synchronize()
-        buf = (C.c_longlong * 1280)()
+        buf = (C.c_longlong * 2048)()
         lib.nfb_debug_profile(h, 0, buf)
         n = buf[127]
         t = [buf[i] - buf[0] for i in range(n)]
@@ -129,6 +129,11 @@ if mode == "prof":
         print("  step reached      :", reach)
         print("  waited for A/chunk:", [opnd[i] - reach[i] for i in range(len(mm))])
         print("  waited for weights:", [mm[i] - opnd[i] for i in range(len(mm))])
+        issued = [buf[1280 + i] - buf[0] for i in range(len(mm))]
+        comm = [buf[1664 + i] - buf[0] for i in range(len(mm))]
+        print("  MMA issue took    :", [issued[i] - mm[i] for i in range(len(mm))])
+        print("  commits took      :", [comm[i] - issued[i] for i in range(len(mm))])
+        print("  to next step      :", [reach[i + 1] - comm[i] for i in range(len(mm) - 1)])
 
 if mode == "spline":
     import ctypes as C
