@@ -200,51 +200,75 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
             gt_st_v4(t_lo + off, lo[0], lo[1], lo[2], lo[3]);
         };
 
+        // Epilogue through shared memory.  tcgen05.ld hands every thread one ROW of the accumulator (lane = row), so a
+        // direct global access would touch 32 different cache lines per warp instruction (measured: ~33 k cycles per
+        // 128 x 256 tile).  Instead each 64-column slab is parked in a [128][65] fp32 staging tile, and after a barrier
+        // thread t processes (row t / 16 + 32 j, columns 4 (t % 16) ..): bias / mask / residual loads and the store (or
+        // red.add) are then 256 contiguous bytes per 16 lanes.
+        float* stg = reinterpret_cast<float*>(smem + offBars + kGtBarBytes + 16);
+        auto epi_sync = [] { asm volatile("bar.sync 1, %0;" ::"n"(kGtBuildThreads) : "memory"); };
         auto epilogue = [&](long long u, uint32_t i) {
             const uint32_t ab = i & 1u;
-            mbar_wait(bar(GB_ACCFULL + ab), (i >> 1) & 1u, p.err, 840 + ab);
+            mbar_wait_warp(bar(GB_ACCFULL + ab), (i >> 1) & 1u, p.err, 840 + ab);
             tc_fence_after();
             const long long tile = u / p.k_splits;
             const long long mt = tile / n_tiles;
             const int nt = (int)(tile - mt * n_tiles);
-            const long long m = mt * 128 + r;
-            const bool live = m < p.M;
-            for (int c0 = wh * 16; c0 < NT; c0 += 64) {
-                uint32_t acc[16];
-                NFB_TMEM_LD16(tlane + ab * 256u + c0, acc);
-                tc_wait_ld();
-                const int n0 = nt * NT + c0;
-                if (live && n0 < p.N) {
-                    float v[16];
+            const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && !p.atomic_out;
+            for (int cb = 0; cb < NT; cb += 64) {
+                const int c0 = cb + wh * 16;
+                if (c0 < NT) {
+                    uint32_t acc[16];
+                    NFB_TMEM_LD16(tlane + ab * 256u + c0, acc);
+                    tc_wait_ld();
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const int n = n0 + j;
-                        float t = __uint_as_float(acc[j]);
-                        if (n < p.N) {
-                            if (p.bias) t += __ldg(p.bias + n);
-                            if (p.mask) t = __ldg(p.mask + m * p.ldmask + n) > 0.f ? t : 0.f;
-                            if (p.mulm) t *= __ldg(p.mulm + m * p.ldmask + n);
-                            if (p.resid) t += __ldg(p.resid + m * p.ldres + n);
-                            if (p.relu_out) t = fmaxf(t, 0.f);
-                        }
-                        v[j] = t;
+                    for (int j = 0; j < 16; ++j) stg[r * 65 + wh * 16 + j] = __uint_as_float(acc[j]);
+                }
+                epi_sync();
+                const int cq = (bt & 15) * 4;            // first of this thread's 4 columns inside the slab
+                const int n0 = nt * NT + cb + cq;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int rr = (bt >> 4) + 32 * j;
+                    const long long m = mt * 128 + rr;
+                    if (m >= p.M || cb + cq >= NT || n0 >= p.N) continue;
+                    float v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = stg[rr * 65 + cq + q];
+                    const bool full = n0 + 4 <= p.N;
+                    if (p.bias) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (n0 + q < p.N) v[q] += __ldg(p.bias + n0 + q);
+                    }
+                    if (p.mask) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (n0 + q < p.N) v[q] = __ldg(p.mask + m * p.ldmask + n0 + q) > 0.f ? v[q] : 0.f;
+                    }
+                    if (p.mulm) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (n0 + q < p.N) v[q] *= __ldg(p.mulm + m * p.ldmask + n0 + q);
+                    }
+                    if (p.resid) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) if (n0 + q < p.N) v[q] += __ldg(p.resid + m * p.ldres + n0 + q);
+                    }
+                    if (p.relu_out) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v[q] = fmaxf(v[q], 0.f);
                     }
                     float* dst = p.C + m * p.ldc + n0;
                     if (p.atomic_out) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + j < p.N) atomicAdd(dst + j, v[j]);
-                    } else if (n0 + 16 <= p.N && (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) &&
-                               (n0 % 4 == 0)) {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        for (int q = 0; q < 4; ++q) if (n0 + q < p.N) atomicAdd(dst + q, v[q]);
+                    } else if (full && vec_ok) {
+                        *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            if (n0 + j < p.N) dst[j] = v[j];
+                        for (int q = 0; q < 4; ++q) if (n0 + q < p.N) dst[q] = v[q];
                     }
                 }
+                epi_sync();  // the staging tile is reused by the next slab
             }
             tc_fence_before();
             __syncwarp();
@@ -338,11 +362,12 @@ int launch_gemm_tc(const GemmTcArgs& a, int* err, cudaStream_t st) {
     if (ks > 1 && !a.accumulate)  // the partial products are added with red.global.add: start from zero
         NFB_CUDA(cudaMemset2DAsync(a.C, (size_t)a.ldc * 4, 0, (size_t)a.N * 4, (size_t)a.M, st));
     const uint32_t stage_bytes = 2 * kGtTileA + 2 * (uint32_t)nt * 128u;
-    int stages = (int)((kGtSmemMax - kGtBarBytes - 16) / stage_bytes);
+    constexpr uint32_t kStgBytes = 128 * 65 * 4;  // epilogue staging tile
+    int stages = (int)((kGtSmemMax - kGtBarBytes - 16 - kStgBytes) / stage_bytes);
     stages = stages > kGtMaxStages ? kGtMaxStages : stages;
     NFB_CHECK(stages >= 2, NFB_ERR_STATE, "gemm_tc: stage does not fit");
     p.stages = stages;
-    const uint32_t smem = (uint32_t)stages * stage_bytes + kGtBarBytes + 16;
+    const uint32_t smem = (uint32_t)stages * stage_bytes + kGtBarBytes + 16 + kStgBytes;
     const long long n_units = tiles * ks;
     const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
     gemm_tc_kernel<<<grid, kGtThreads, smem, st>>>(p);
