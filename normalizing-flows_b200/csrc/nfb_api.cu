@@ -784,7 +784,7 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
     p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = accumulate;
     p.progress = nullptr;
     p.err = f->err.as<int>();
-    p.poll_all = getenv("NFB_POLL_ALL") != nullptr;
+    p.poll_all = getenv("NFB_POLL_LANE0") == nullptr;
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
     NFB_TRY(launch_fused_rqs(p, f->sm_count, sample, st));
     f->launches++;
@@ -806,7 +806,7 @@ int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, 
     p.in_ready = sample ? nullptr : f->cur_in_ready;
     f->cur_in_ready = nullptr;  // consumed (or not applicable): later launches must not wait on it
     p.err = f->err.as<int>();
-    p.poll_all = getenv("NFB_POLL_ALL") != nullptr;
+    p.poll_all = getenv("NFB_POLL_LANE0") == nullptr;
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;
     NFB_TRY(launch_fused_rqs(p, f->sm_count, sample, st));
     f->launches += 2;  // memset + kernel

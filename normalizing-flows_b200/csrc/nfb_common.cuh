@@ -102,15 +102,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
 }
 
-// Warp-level wait for the epilogue warps: ONE lane polls (with a short sleep between polls), the others park at the
-// warp barrier.  512 threads spinning on one shared-memory word compete with the tensor core's operand fetches for
-// the shared-memory pipe; a single poller per warp does not.  bar.warp.sync orders lane 0's acquire before the other
-// lanes' subsequent accesses.
+// Warp-level wait: ONE lane polls, the others park at the warp barrier (bar.warp.sync orders lane 0's acquire before
+// the other lanes' subsequent accesses).  Used where a whole warp waits for one event.
 __device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int* err, int tag) {
     if ((threadIdx.x & 31) == 0 && !mbar_try_wait(bar, parity)) {
         long long t0 = clock64();
         while (!mbar_try_wait(bar, parity)) {
-            __nanosleep(32);
             if (clock64() - t0 > 4000000000LL) {
                 if (err) atomicExch(err, tag);
                 __threadfence_system();

@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t aA = sbase + kOffA;
         uint32_t afpar = 0, cfbits = 0;
-        // epilogue-side waits: one polling lane per warp (p.poll_all = debug A/B: every thread polls, the old behaviour)
+        // epilogue-side waits: every thread polls (default; measured 3-4 % faster than one polling lane per warp)
         auto ewait = [&](uint32_t b, uint32_t parity, int tag) {
             if (p.poll_all) mbar_wait(b, parity, p.err, tag);
             else mbar_wait_warp(b, parity, p.err, tag);
@@ -681,9 +681,12 @@ int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_
     NFB_CHECK(p.n_layers >= 1 && (p.n_layers == 1 || p.progress), NFB_ERR_ARG, "fused rqs: bad layer list");
     const long long n_tiles = (p.rows + 127) / 128;
     if (n_tiles == 0) return NFB_OK;
-    // CTA pairs (cta_group::2) whenever there are at least two tiles; NFB_NO_PAIR=1 keeps the single-CTA schedule (A/B)
-    static const bool no_pair = getenv("NFB_NO_PAIR") != nullptr;
-    if (n_tiles >= 2 && !no_pair) {
+    // CTA pairs (cta_group::2): validated (all parity tests pass) but measured 2-3 % SLOWER than the single-CTA
+    // schedule on the flagship (profiles/r02_pair_vs_single.md: each SM's shared memory still serves its B half to
+    // both tensor cores, so the operand-fetch bandwidth that bounds the GEMM phases does not drop); kept behind
+    // NFB_PAIR=1 for measurement.
+    static const bool use_pair = getenv("NFB_PAIR") != nullptr;
+    if (n_tiles >= 2 && use_pair) {
         const long long n_units = (n_tiles + 1) / 2 * p.n_layers;
         cudaLaunchConfig_t cfg{};
         cudaLaunchAttribute attr[1];

@@ -156,7 +156,7 @@ struct FusedParams {
     const int* in_ready;       // optional: number of rows of `zin` that have landed (chunked H2D in flight, written
                                // by the copy engine); layer-0 tiles wait for their rows.  null = all resident
     int* err;
-    int poll_all;              // debug A/B: every epilogue thread polls its mbarrier (1) instead of one lane per warp (0)
+    int poll_all;              // every epilogue thread polls its mbarrier (1, default) or one lane per warp (0: NFB_POLL_LANE0)
     long long* prof;           // optional [128] clock64 stamps (debug)
 };
 int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st);
