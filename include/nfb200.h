@@ -69,6 +69,9 @@ int nfb_swish(const float* x_dev, float beta_softplus, int64_t n, float* a_dev, 
 int nfb_mul_rows(const float* src_dev, const float* m_dev, int64_t n, int32_t nt, float* dst_dev, void* stream);
 /* residual.py:148-161 (2-D, eval / brute_force): jt [2, batch, 2] = Jacobian columns -> out[r] = log|det(I + J_r)| */
 int nfb_logabsdet_i_plus_j_2x2(const float* jt_dev, int64_t batch, float* out_dev, void* stream);
+/* nets/resnet.py:48-50, nets/made.py:212-214: out = h + t * sigmoid(c), the GLU gate of a context-conditioned residual
+ * block (t = block output, c = context_layer(context), h = block input); element-wise over n values */
+int nfb_glu_residual(const float* h_dev, const float* t_dev, const float* c_dev, int64_t n, float* out_dev, void* stream);
 /* out[r] (+)= c * sum_j a[r, j] b[r, j]  (one Hutchinson trace term v^T J^k eps per sample, residual.py:355-366) */
 int nfb_rowdot(const float* a_dev, const float* b_dev, int64_t rows, int32_t d, float c, int32_t accumulate,
                float* out_dev, void* stream);

@@ -1062,6 +1062,10 @@ int nfb_logabsdet_i_plus_j_2x2(const float* jt, int64_t batch, float* out, void*
     NFB_CHECK(jt && out, NFB_ERR_ARG, "nfb_logabsdet_i_plus_j_2x2: null pointer");
     return launch_logdet2(jt, batch, out, S(stream));
 }
+int nfb_glu_residual(const float* h, const float* t, const float* c, int64_t n, float* out, void* stream) {
+    NFB_CHECK(h && t && c && out, NFB_ERR_ARG, "nfb_glu_residual: null pointer");
+    return launch_glu_residual(h, t, c, n, out, S(stream));
+}
 int nfb_rowdot(const float* a, const float* b, int64_t rows, int32_t d, float c, int32_t accumulate, float* out,
                void* stream) {
     NFB_CHECK(a && b && out, NFB_ERR_ARG, "nfb_rowdot: null pointer");

@@ -194,6 +194,7 @@ int launch_split_table(const float* tab, int n, float* gw, float* gh, float* gd,
 int launch_swish(const float* x, float b, long long n, float* a, float* da, cudaStream_t st);
 int launch_mul_rows(const float* S, const float* m, long long n, int nt, float* T, cudaStream_t st);
 int launch_logdet2(const float* jt, long long B, float* out, cudaStream_t st);
+int launch_glu_residual(const float* h, const float* t, const float* c, long long n, float* out, cudaStream_t st);
 int launch_rowdot(const float* a, const float* b, long long rows, int d, float c, int accumulate, float* out,
                   cudaStream_t st);
 

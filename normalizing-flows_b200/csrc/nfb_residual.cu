@@ -58,6 +58,20 @@ int launch_logdet2(const float* jt, long long B, float* out, cudaStream_t st) {
     return NFB_OK;
 }
 
+// out = h + t * sigmoid(c): the GLU gate of a context-conditioned residual block (nets/resnet.py:48-50,
+// nets/made.py:212-214: F.glu(cat(temps, context_layer(context))) + inputs)
+__global__ void glu_residual_kernel(const float* __restrict__ h, const float* __restrict__ t, const float* __restrict__ c,
+                                    long long n, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = fmaf(t[i], 1.f / (1.f + __expf(-c[i])), h[i]);
+}
+int launch_glu_residual(const float* h, const float* t, const float* c, long long n, float* out, cudaStream_t st) {
+    if (n == 0) return NFB_OK;
+    glu_residual_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h, t, c, n, out);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
 // out[r] = (accumulate ? out[r] : 0) + c * sum_j a[r, j] * b[r, j]   (one warp per row)
 __global__ void __launch_bounds__(256) rowdot_kernel(const float* __restrict__ a, const float* __restrict__ b, long long rows,
                                                      int d, float c, int accumulate, float* __restrict__ out) {

@@ -86,6 +86,7 @@ SYMBOLS = {
     "nfb_swish": (C.c_int, [_VP, _F, _I64, _VP, _VP, _VP]),
     "nfb_mul_rows": (C.c_int, [_VP, _VP, _I64, _I32, _VP, _VP]),
     "nfb_logabsdet_i_plus_j_2x2": (C.c_int, [_VP, _I64, _VP, _VP]),
+    "nfb_glu_residual": (C.c_int, [_VP, _VP, _VP, _I64, _VP, _VP]),
     "nfb_rowdot": (C.c_int, [_VP, _VP, _I64, _I32, _F, _I32, _VP, _VP]),
     "nfb_maf_affine": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _VP]),
     "nfb_logit_transform": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _F, _I32, _I32, _VP]),

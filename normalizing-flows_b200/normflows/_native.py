@@ -322,16 +322,52 @@ def rowdot(a, b, c=1.0, out=None):
     return out
 
 
-def resnet_forward(net, x, masked):
-    """ResidualNet.forward (nets/resnet.py:92-104) / MADE.forward (nets/made.py:296-304) for a stand-alone call of
-    the module: pre-activation residual blocks, every Linear one tensor-core GEMM with fused bias / ReLU / residual."""
+def glu_residual(h, t, c):
+    out = torch.empty_like(h)
+    if h.numel():
+        with torch.cuda.device(h.device):
+            L.check(L.lib().nfb_glu_residual(L.ptr(h), L.ptr(t), L.ptr(c), h.numel(), L.ptr(out), L.stream_ptr()))
+    return out
+
+
+def resnet_forward(net, x, masked, context=None):
+    """ResidualNet.forward (nets/resnet.py:92-104) / MADE.forward (nets/made.py:296-304) outside the fused kernel
+    (stand-alone call of the module, or a context-conditioned layer): pre-activation residual blocks, every Linear one
+    tensor-core GEMM with fused bias / ReLU / residual; with a context the blocks end in the GLU gate
+    h + t * sigmoid(context_layer(context)) (csrc/nfb_residual.cu)."""
     eff = (lambda l: l.weight * l.mask) if masked else (lambda l: l.weight)
-    h = linear(x, eff(net.initial_layer), net.initial_layer.bias)
+    if context is not None:
+        context = require_cuda_f32(context, "context")
+    if context is None:
+        h = linear(x, eff(net.initial_layer), net.initial_layer.bias)
+    elif masked:   # MADE: initial_layer(inputs) + context_layer(context)   (made.py:297-300)
+        h = linear(x, eff(net.initial_layer), net.initial_layer.bias)
+        h = linear(context, net.context_layer.weight, net.context_layer.bias, resid=h)
+    else:          # ResidualNet: initial_layer(cat(inputs, context))        (resnet.py:98-99)
+        h = linear(torch.cat((require_cuda_f32(x), context), dim=1), net.initial_layer.weight, net.initial_layer.bias)
     for blk in net.blocks:
         l0, l1 = blk.linear_layers
         t = linear(h, eff(l0), l0.bias, a_relu=True)
-        h = linear(t, eff(l1), l1.bias, a_relu=True, resid=h)
+        if context is None:
+            h = linear(t, eff(l1), l1.bias, a_relu=True, resid=h)
+        else:
+            t = linear(t, eff(l1), l1.bias, a_relu=True)
+            h = glu_residual(h, t, linear(context, blk.context_layer.weight, blk.context_layer.bias))
     return linear(h, eff(net.final_layer), net.final_layer.bias)
+
+
+def rqs_spline(x, params, num_bins, tail_bound, wh_scale, inverse):
+    """utils/splines.py:16-97 on contiguous [rows, feats] inputs with per-element parameters (csrc/nfb_kernels.cu)."""
+    x = require_cuda_f32(x)
+    params = params.contiguous()
+    y = torch.empty_like(x)
+    ld = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    if x.shape[0]:
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nfb_rqs_spline(L.ptr(x), L.ptr(params), L.ptr(y), L.ptr(ld), x.shape[0], x.shape[1],
+                                           num_bins, C.c_float(tail_bound), C.c_float(wh_scale), int(inverse), 0,
+                                           L.stream_ptr()))
+    return y, ld
 
 
 def resnet_desc(net, masked):

@@ -1,2 +1,2 @@
-from .base import BaseDistribution, DiagGaussian, ClassCondDiagGaussian
+from .base import BaseDistribution, DiagGaussian, ClassCondDiagGaussian, ConditionalDiagGaussian
 from .target import TwoMoons

@@ -106,3 +106,42 @@ class ClassCondDiagGaussian(BaseDistribution):
                     L.ptr(z), L.ptr(y), L.ptr(self.loc), L.ptr(ls), L.ptr(out), z.shape[0], self.d,
                     self.num_classes, 0, L.stream_ptr()))
         return out
+
+
+class ConditionalDiagGaussian(BaseDistribution):
+    """Diagonal Gaussian whose mean / log-scale come from a context encoder (distributions/base.py:106-155): the
+    encoder output's first half is the mean, the second half the log standard deviation.  The per-sample density is a
+    row-wise kernel launch on the standardised residual."""
+
+    def __init__(self, shape, context_encoder):
+        super().__init__()
+        if isinstance(shape, int):
+            shape = (shape,)
+        shape = tuple(shape)
+        self.shape, self.n_dim, self.d = shape, len(shape), int(np.prod(shape))
+        self.context_encoder = context_encoder
+
+    def _params(self, context):
+        enc = self.context_encoder(context)
+        split = enc.shape[-1] // 2
+        return enc[..., :split], enc[..., split:]
+
+    def forward(self, num_samples=1, context=None):
+        mean, log_scale = self._params(context)
+        eps = torch.randn((num_samples,) + self.shape, dtype=mean.dtype, device=mean.device)
+        z = mean + torch.exp(log_scale) * eps
+        log_p = -0.5 * self.d * np.log(2 * np.pi) - torch.sum(log_scale + 0.5 * eps ** 2, list(range(1, self.n_dim + 1)))
+        return z, log_p
+
+    def log_prob(self, z, context=None):
+        z = require_cuda_f32(z)
+        mean, log_scale = self._params(context)
+        # standardise per sample, then the unit-Gaussian density kernel; the log-scale term is a row sum
+        u = ((z - mean) * torch.exp(-log_scale)).contiguous().reshape(z.shape[0], -1)
+        zeros = torch.zeros(self.d, device=z.device)
+        out = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        if z.shape[0]:
+            with torch.cuda.device(z.device):
+                L.check(L.lib().nfb_diag_gaussian_log_prob(L.ptr(u), L.ptr(zeros), L.ptr(zeros), L.ptr(out), z.shape[0],
+                                                           self.d, 0, L.stream_ptr()))
+        return out - torch.sum(log_scale.reshape(z.shape[0], -1), dim=1)

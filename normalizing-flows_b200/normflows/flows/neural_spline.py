@@ -31,9 +31,9 @@ class _ARTransform(nn.Module):
     """Holds `autoregressive_net` under the reference's attribute name (`mprqat`)."""
 
     def __init__(self, features, hidden_features, num_bins, num_blocks, permute_mask, activation,
-                 dropout_probability, init_identity):
+                 dropout_probability, init_identity, context_features=None):
         super().__init__()
-        self.autoregressive_net = MADE(features, hidden_features, None, num_blocks,
+        self.autoregressive_net = MADE(features, hidden_features, context_features, num_blocks,
                                        output_multiplier=3 * num_bins - 1, use_residual_blocks=True,
                                        random_mask=False, permute_mask=permute_mask, activation=activation,
                                        dropout_probability=dropout_probability, use_batch_norm=False)
@@ -47,14 +47,38 @@ class AutoregressiveRationalQuadraticSpline(NativeFlow):
                  num_bins=8, tail_bound=3, activation=nn.ReLU, dropout_probability=0.0,
                  permute_mask=False, init_identity=True):
         super().__init__()
-        if num_context_channels is not None:
-            raise NotImplementedError("context channels are not on the CUDA path yet")
         if torch.is_tensor(tail_bound):
             raise NotImplementedError("per-feature tail bounds are not on the CUDA path")
         _check_bins(num_bins)
         self.features, self.num_bins, self.tail_bound = num_input_channels, num_bins, float(tail_bound)
+        self.num_context_channels = num_context_channels
         self.mprqat = _ARTransform(num_input_channels, num_hidden_channels, num_bins, num_blocks,
-                                   permute_mask, activation(), dropout_probability, init_identity)
+                                   permute_mask, activation(), dropout_probability, init_identity,
+                                   context_features=num_context_channels)
+
+    # Context-conditioned layer (ConditionalNormalizingFlow, core.py:216-366): the conditioner takes the context through
+    # the MADE's context layers + GLU gates, so it runs as stand-alone tensor-core GEMMs (nets.MADE.forward) and the
+    # spline as the stand-alone HBM-bound kernel (csrc/nfb_kernels.cu rqs_rows_kernel) instead of the fused block.
+    def _conditional(self, z, context, sampling):
+        from .._native import require_cuda_f32, rqs_spline
+        z = require_cuda_f32(z)
+        net = self.mprqat.autoregressive_net
+        if not sampling:  # wrapper.inverse -> Autoregressive.forward: one pass (affine/autoregressive.py:24-27)
+            return rqs_spline(z, net(z, context), self.num_bins, self.tail_bound, 1.0, False)
+        out, ld = torch.zeros_like(z), None  # D passes (:29-38)
+        for _ in range(self.features):
+            out, ld = rqs_spline(z, net(out, context), self.num_bins, self.tail_bound, 1.0, True)
+        return out, ld
+
+    def forward(self, z, context=None):
+        if self.num_context_channels is not None or context is not None:
+            return self._conditional(z, context, True)
+        return super().forward(z)
+
+    def inverse(self, z, context=None):
+        if self.num_context_channels is not None or context is not None:
+            return self._conditional(z, context, False)
+        return super().inverse(z)
 
     def _native_tensors(self):
         net = self.mprqat.autoregressive_net
@@ -82,7 +106,7 @@ class _CoupledTransform(nn.Module):
     """`prqct`: feature index buffers, the conditioner and the unconditional transform."""
 
     def __init__(self, features, hidden_features, num_blocks, num_bins, reverse_mask, activation,
-                 dropout_probability, init_identity):
+                 dropout_probability, init_identity, context_features=None):
         super().__init__()
         idx = torch.arange(features)
         start = 0 if reverse_mask else 1  # utils/masks.py:14-16 with even=reverse_mask
@@ -94,7 +118,7 @@ class _CoupledTransform(nn.Module):
         n_id, n_tr = int((~mask).sum()), int(mask.sum())
         if n_id == 0 or n_tr == 0:
             raise ValueError("Mask can't be empty.")
-        self.transform_net = ResidualNet(n_id, n_tr * (3 * num_bins - 1), hidden_features, None, num_blocks,
+        self.transform_net = ResidualNet(n_id, n_tr * (3 * num_bins - 1), hidden_features, context_features, num_blocks,
                                          activation, dropout_probability, False)
         if init_identity:
             nn.init.constant_(self.transform_net.final_layer.weight, 0.0)
@@ -108,16 +132,52 @@ class CoupledRationalQuadraticSpline(NativeFlow):
                  num_bins=8, tails="linear", tail_bound=3.0, activation=nn.ReLU, dropout_probability=0.0,
                  reverse_mask=False, init_identity=True):
         super().__init__()
-        if num_context_channels is not None:
-            raise NotImplementedError("context channels are not on the CUDA path yet")
         if tails != "linear":
             raise NotImplementedError("only tails='linear' is on the CUDA path")
         if torch.is_tensor(tail_bound):
             raise NotImplementedError("per-feature tail bounds are not on the CUDA path")
         _check_bins(num_bins)
         self.features, self.num_bins, self.tail_bound = num_input_channels, num_bins, float(tail_bound)
+        self.num_context_channels = num_context_channels
         self.prqct = _CoupledTransform(num_input_channels, num_hidden_channels, num_blocks, num_bins,
-                                       reverse_mask, activation(), dropout_probability, init_identity)
+                                       reverse_mask, activation(), dropout_probability, init_identity,
+                                       context_features=num_context_channels)
+
+    def _conditional(self, z, context, sampling):
+        """Context-conditioned coupling layer outside the fused block (see AutoregressiveRationalQuadraticSpline):
+        Coupling.forward / .inverse of neural_spline/coupling.py:71-128 with the unconditional CDF of :221-253."""
+        from .._native import require_cuda_f32, rqs_spline
+        z = require_cuda_f32(z)
+        p, k = self.prqct, self.num_bins
+        idf, trf = p.identity_features, p.transform_features
+        u = p.unconditional_transform
+        b = z.shape[0]
+        up = torch.cat([u.unnormalized_widths, u.unnormalized_heights, u.unnormalized_derivatives], dim=1)
+        up = up.reshape(1, -1).expand(b, -1).contiguous()  # _share_across_batch (:217-219)
+        ident, trans = z[:, idf].contiguous(), z[:, trf].contiguous()
+        wh = 1.0 / float(np.sqrt(p.transform_net.hidden_features))
+        if not sampling:
+            params = p.transform_net(ident, context)
+            yt, ld = rqs_spline(trans, params, k, self.tail_bound, wh, False)
+            yi, ldi = rqs_spline(ident, up, k, self.tail_bound, 1.0, False)
+        else:
+            yi, ldi = rqs_spline(ident, up, k, self.tail_bound, 1.0, True)
+            params = p.transform_net(yi, context)
+            yt, ld = rqs_spline(trans, params, k, self.tail_bound, wh, True)
+        out = torch.empty_like(z)
+        out[:, idf] = yi
+        out[:, trf] = yt
+        return out, ld + ldi
+
+    def forward(self, z, context=None):
+        if self.num_context_channels is not None or context is not None:
+            return self._conditional(z, context, True)
+        return super().forward(z)
+
+    def inverse(self, z, context=None):
+        if self.num_context_channels is not None or context is not None:
+            return self._conditional(z, context, False)
+        return super().inverse(z)
 
     def _native_tensors(self):
         p = self.prqct

@@ -38,6 +38,8 @@ class MaskedResidualBlock(nn.Module):
         super().__init__()
         _check_plain(activation, dropout_probability, use_batch_norm, context_features)
         features = len(in_degrees)
+        if context_features is not None:  # made.py:159-160
+            self.context_layer = nn.Linear(context_features, features)
         l0 = MaskedLinear(in_degrees, features, autoregressive_features, False, False)
         l1 = MaskedLinear(l0.degrees, features, autoregressive_features, False, False)
         self.linear_layers = nn.ModuleList([l0, l1])
@@ -66,9 +68,11 @@ class MADE(nn.Module):
         if permute_mask:
             in_deg = in_deg[torch.randperm(features)]
         self.initial_layer = MaskedLinear(in_deg, hidden_features, features, random_mask, False)
+        if context_features is not None:  # made.py:261-262
+            self.context_layer = nn.Linear(context_features, hidden_features)
         blocks, prev = [], self.initial_layer.degrees
         for _ in range(num_blocks):
-            blocks.append(MaskedResidualBlock(prev, features, None, random_mask, activation))
+            blocks.append(MaskedResidualBlock(prev, features, context_features, random_mask, activation))
             prev = blocks[-1].degrees
         self.blocks = nn.ModuleList(blocks)
         self.final_layer = MaskedLinear(prev, features * output_multiplier, features, random_mask, True,
@@ -76,7 +80,5 @@ class MADE(nn.Module):
 
     def forward(self, inputs, context=None):
         """nets/made.py:296-304, stand-alone call: masked weights, pre-activation residual blocks."""
-        if context is not None:
-            raise NotImplementedError("context features are not on the CUDA path yet")
         from .._native import resnet_forward
-        return resnet_forward(self, inputs, masked=True)
+        return resnet_forward(self, inputs, masked=True, context=context)

@@ -17,8 +17,6 @@ def _check_plain(activation, dropout_probability, use_batch_norm, context_featur
         raise NotImplementedError("dropout in the conditioner is not on the CUDA path")
     if use_batch_norm:
         raise NotImplementedError("batch-norm in the conditioner is not on the CUDA path")
-    if context_features is not None:
-        raise NotImplementedError("context features are not on the CUDA path yet")
 
 
 class ResidualBlock(nn.Module):
@@ -26,6 +24,8 @@ class ResidualBlock(nn.Module):
                  use_batch_norm=False, zero_initialization=True):
         super().__init__()
         _check_plain(activation, dropout_probability, use_batch_norm, context_features)
+        if context_features is not None:  # registered before linear_layers, like the reference (resnet.py:27-31)
+            self.context_layer = nn.Linear(context_features, features)
         self.linear_layers = nn.ModuleList([nn.Linear(features, features) for _ in range(2)])
         if zero_initialization:
             init.uniform_(self.linear_layers[-1].weight, -1e-3, 1e-3)
@@ -41,13 +41,11 @@ class ResidualNet(nn.Module):
             raise NotImplementedError("preprocessing is not on the CUDA path")
         self.hidden_features = hidden_features
         self.context_features = context_features
-        self.initial_layer = nn.Linear(in_features, hidden_features)
-        self.blocks = nn.ModuleList([ResidualBlock(hidden_features, None, activation) for _ in range(num_blocks)])
+        self.initial_layer = nn.Linear(in_features + (context_features or 0), hidden_features)
+        self.blocks = nn.ModuleList([ResidualBlock(hidden_features, context_features, activation) for _ in range(num_blocks)])
         self.final_layer = nn.Linear(hidden_features, out_features)
 
     def forward(self, inputs, context=None):
         """nets/resnet.py:92-104, stand-alone call (inside a flow the net is part of the fused kernel)."""
-        if context is not None:
-            raise NotImplementedError("context features are not on the CUDA path yet")
         from .._native import resnet_forward
-        return resnet_forward(self, inputs, masked=False)
+        return resnet_forward(self, inputs, masked=False, context=context)

@@ -529,3 +529,38 @@ def case_residual():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "residual":
     case_residual()
+
+
+def case_conditional():
+    """ConditionalNormalizingFlow (core.py:216-366) with context-conditioned spline layers (GLU context branch of
+    nets/resnet.py:48-50 and nets/made.py:212-214, context layers :261-262,:297-300) and ConditionalDiagGaussian.
+        python tests/golden/make_golden.py conditional"""
+    torch.manual_seed(51)
+    d, c = 6, 3
+    flows = []
+    for i in range(2):
+        flows += [nf.flows.CoupledRationalQuadraticSpline(d, 2, 32, num_context_channels=c, reverse_mask=bool(i % 2))]
+        flows += [nf.flows.LULinearPermute(d)]
+        flows += [nf.flows.AutoregressiveRationalQuadraticSpline(d, 2, 32, num_context_channels=c)]
+    enc = nf.nets.MLP([c, 16, 2 * d])
+    model = nf.ConditionalNormalizingFlow(nf.distributions.base.ConditionalDiagGaussian(d, enc), flows)
+    perturb(model, 0.1, 52)
+    g = torch.Generator().manual_seed(53)
+    x = torch.randn(48, d, generator=g) * 1.3
+    ctx = torch.randn(48, c, generator=g)
+    out = {"torch_version": torch.__version__, "x": x.numpy(), "context": ctx.numpy()}
+    for k, v in model.state_dict().items():
+        out["sd__" + k] = v.detach().numpy()
+    md = model.double()
+    with torch.no_grad():
+        out["log_prob"] = md.log_prob(x.double(), ctx.double()).numpy()
+        out["kld"] = md.forward_kld(x.double(), ctx.double()).numpy()
+        z, ld = md.inverse_and_log_det(x.double(), ctx.double())
+        xr, ldf = md.forward_and_log_det(z, ctx.double())
+    out["z"], out["inv_ld"], out["fwd_x"], out["fwd_ld"] = z.numpy(), ld.numpy(), xr.numpy(), ldf.numpy()
+    np.savez_compressed(os.path.join(HERE, "conditional.npz"), **out)
+    print("wrote conditional", out["log_prob"][:3], np.abs(out["fwd_x"] - out["x"]).max())
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "conditional":
+    case_conditional()

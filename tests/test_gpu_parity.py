@@ -874,3 +874,33 @@ def test_residual_flow_matches_reference(d):
             acc += est.view(256, 16).mean(0)
         mean_est = (acc / reps).cpu().numpy()
         assert np.abs(mean_est - exact.view(-1).cpu().numpy()).max() < 0.05, (mean_est, exact.view(-1).cpu().numpy())
+
+
+def test_conditional_normalizing_flow_with_context():
+    """ConditionalNormalizingFlow with context-conditioned coupled / autoregressive spline layers (GLU
+    context branch) and a ConditionalDiagGaussian base, against the reference (make_golden.py conditional)."""
+    f = np.load("tests/golden/conditional.npz")
+    torch.manual_seed(51)
+    d, c = 6, 3
+    flows = []
+    for i in range(2):
+        flows += [nf.flows.CoupledRationalQuadraticSpline(d, 2, 32, num_context_channels=c, reverse_mask=bool(i % 2))]
+        flows += [nf.flows.LULinearPermute(d)]
+        flows += [nf.flows.AutoregressiveRationalQuadraticSpline(d, 2, 32, num_context_channels=c)]
+    enc = nf.nets.MLP([c, 16, 2 * d])
+    model = nf.ConditionalNormalizingFlow(nf.distributions.ConditionalDiagGaussian(d, enc), flows)
+    model.load_state_dict({k[4:]: torch.from_numpy(np.asarray(f[k])) for k in f.files if k.startswith("sd__")}, strict=True)
+    model = model.cuda()
+    x, ctx = cuda(f["x"]), cuda(f["context"])
+    lp = model.log_prob(x, ctx).cpu().numpy()
+    np.testing.assert_allclose(lp, f["log_prob"], rtol=RTOL, atol=ATOL)
+    assert float(model.forward_kld(x, ctx)) == pytest.approx(float(f["kld"]), rel=2e-5)
+    z, ld = model.inverse_and_log_det(x, ctx)
+    np.testing.assert_allclose(z.cpu().numpy(), f["z"], rtol=1e-4, atol=2e-4)
+    np.testing.assert_allclose(ld.cpu().numpy(), f["inv_ld"], rtol=1e-4, atol=2e-3)
+    xr, ldf = model.forward_and_log_det(cuda(f["z"]), ctx)
+    np.testing.assert_allclose(xr.cpu().numpy(), f["fwd_x"], rtol=1e-4, atol=1e-3)
+    np.testing.assert_allclose(ldf.cpu().numpy(), f["fwd_ld"], rtol=1e-4, atol=1e-2)
+    torch.manual_seed(1)
+    xs, lq = model.sample(48, ctx)
+    np.testing.assert_allclose(lq.cpu().numpy(), model.log_prob(xs, ctx).cpu().numpy(), rtol=1e-4, atol=2e-2)
