@@ -193,7 +193,7 @@ struct nfb_flow {
     DevBuf in_ready;                 // device int: rows of the current host batch that have landed
     // training pass workspaces (nfb_flow_backward)
     DevBuf tr_store, tr_h, tr_P, tr_gP, tr_ga, tr_gb, tr_xp, tr_gxp, tr_zp, tr_gzp, tr_in, tr_gin, tr_g0, tr_g1, tr_small,
-        tr_glq, tr_t0, tr_t1;
+        tr_glq, tr_t0, tr_t1, tr_wpack;
     const int* cur_in_ready = nullptr;
     ~nfb_flow() {
         if (copy_stream) cudaStreamDestroy(copy_stream);
@@ -794,14 +794,14 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
 // Whole stack in ONE persistent launch: (layer, tile) work units with per-tile progress flags.  logq must be
 // pre-filled (accumulate semantics); zout may alias zin.
 int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, long long rows, cudaStream_t st,
-                       int sample = 0) {
+                       int sample = 0, long long z_stride = 0) {
     const long long n_tiles = (rows + 127) / 128;
     NFB_TRY(f->progress.reserve((size_t)n_tiles * sizeof(int)));
     NFB_CUDA(cudaMemsetAsync(f->progress.p, 0, (size_t)n_tiles * sizeof(int), st));
     FusedParams p{};
     p.layers = sample ? f->fwd_layers.as<FusedLayer>() : f->stack_layers.as<FusedLayer>();
     p.n_layers = sample ? f->fwd_n : f->stack_n;
-    p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = 1;
+    p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = 1; p.z_stride = z_stride;
     p.progress = f->progress.as<int>();
     p.in_ready = sample ? nullptr : f->cur_in_ready;
     f->cur_in_ready = nullptr;  // consumed (or not applicable): later launches must not wait on it
@@ -1630,6 +1630,16 @@ long long grad_slot_numel(const Layer& L, int s) {
 struct Gemm {
     nfb_flow* f; cudaStream_t st;
     int run(GemmTcArgs a) { f->launches++; return launch_gemm_tc(a, f->err.as<int>(), st); }
+    // B is a WEIGHT matrix (reused by every 128-row tile of the batch): split it to bf16 hi | lo records once
+    // (launch_gemm_pack_b) and let the GEMM stream them by TMA instead of converting them per tile.
+    int run_w(GemmTcArgs a) {
+        const size_t bytes = gemm_tc_packed_b_bytes(a.N, a.K, a.b_mn);
+        NFB_TRY(f->tr_wpack.reserve(bytes));
+        NFB_TRY(launch_gemm_pack_b(a.B, a.ldb, a.b_mn, a.N, a.K, f->tr_wpack.as<uint8_t>(), st));
+        a.b_packed = f->tr_wpack.as<uint8_t>();
+        f->launches += 2;
+        return launch_gemm_tc(a, f->err.as<int>(), st);
+    }
 };
 
 // conditioner forward (recompute) into h[0..n_hidden-1] ([rows x H] each) and P ([rows x out])
@@ -1639,7 +1649,7 @@ int net_recompute(nfb_flow* f, const NetDesc& n, const NetPack& p, const float* 
     const long long HS = rows * n.H;
     GemmTcArgs a{};
     a.A = in; a.lda = ld_in; a.B = p.w0; a.ldb = n.in; a.C = hbuf; a.ldc = n.H; a.M = rows; a.N = n.H; a.K = n.in; a.bias = n.b0;
-    NFB_TRY(g.run(a));
+    NFB_TRY(g.run_w(a));
     for (int b = 0; b < n.nb; ++b) {
         float* hprev = hbuf + (size_t)(2 * b) * HS;
         float* t = hbuf + (size_t)(2 * b + 1) * HS;
@@ -1647,16 +1657,16 @@ int net_recompute(nfb_flow* f, const NetDesc& n, const NetPack& p, const float* 
         GemmTcArgs t1{};
         t1.A = hprev; t1.lda = n.H; t1.a_relu = 1; t1.B = p.wb[2 * b]; t1.ldb = n.H; t1.C = t; t1.ldc = n.H;
         t1.M = rows; t1.N = n.H; t1.K = n.H; t1.bias = n.bb[2 * b];
-        NFB_TRY(g.run(t1));
+        NFB_TRY(g.run_w(t1));
         GemmTcArgs t2{};
         t2.A = t; t2.lda = n.H; t2.a_relu = 1; t2.B = p.wb[2 * b + 1]; t2.ldb = n.H; t2.C = hnext; t2.ldc = n.H;
         t2.M = rows; t2.N = n.H; t2.K = n.H; t2.bias = n.bb[2 * b + 1]; t2.resid = hprev; t2.ldres = n.H;
-        NFB_TRY(g.run(t2));
+        NFB_TRY(g.run_w(t2));
     }
     GemmTcArgs fl{};
     fl.A = hbuf + (size_t)(2 * n.nb) * HS; fl.lda = n.H; fl.B = p.wf; fl.ldb = n.H; fl.C = P; fl.ldc = n.out;
     fl.M = rows; fl.N = n.out; fl.K = n.H; fl.bias = n.bf;
-    return g.run(fl);
+    return g.run_w(fl);
 }
 
 // one Linear's parameter gradients: dW = gY^T act(X) (* mask), db = colsum(gY)
@@ -1730,7 +1740,7 @@ int rqs_layer_backward(nfb_flow* f, Layer& L, const float* xp, const float* gy, 
     {
         GemmTcArgs a{};
         a.A = gP; a.lda = n.out; a.B = p.wf; a.ldb = H; a.b_mn = 1; a.C = ga; a.ldc = H; a.M = rows; a.N = H; a.K = n.out;
-        NFB_TRY(g.run(a));  // g_h(last)
+        NFB_TRY(g.run_w(a));  // g_h(last)
     }
     for (int b = n.nb - 1; b >= 0; --b) {
         float* hprev = hb + (size_t)(2 * b) * HS;
@@ -1741,13 +1751,13 @@ int rqs_layer_backward(nfb_flow* f, Layer& L, const float* xp, const float* gy, 
         GemmTcArgs a{};
         a.A = ga; a.lda = H; a.B = p.wb[2 * b + 1]; a.ldb = H; a.b_mn = 1; a.C = gb; a.ldc = H; a.M = rows; a.N = H; a.K = H;
         a.mask = t; a.ldmask = H;
-        NFB_TRY(g.run(a));  // g_t = (g_h W2) * (t > 0)
+        NFB_TRY(g.run_w(a));  // g_t = (g_h W2) * (t > 0)
         // t = W1 relu(h_prev) + b1
         NFB_TRY(linear_wgrad(f, gb, H, hprev, H, H, 1, n.mb[2 * b], rows, slots[2 * l1], slots[2 * l1 + 1], st));
         GemmTcArgs c{};
         c.A = gb; c.lda = H; c.B = p.wb[2 * b]; c.ldb = H; c.b_mn = 1; c.C = ga; c.ldc = H; c.M = rows; c.N = H; c.K = H;
         c.mask = hprev; c.ldmask = H; c.resid = ga; c.ldres = H;
-        NFB_TRY(g.run(c));  // g_h_prev = g_h + (g_t W1) * (h_prev > 0)     (in place)
+        NFB_TRY(g.run_w(c));  // g_h_prev = g_h + (g_t W1) * (h_prev > 0)     (in place)
     }
     // initial layer
     NFB_TRY(linear_wgrad(f, ga, H, in, ld_in, n.in, 0, n.m0, rows, slots[0], slots[1], st));
@@ -1755,7 +1765,7 @@ int rqs_layer_backward(nfb_flow* f, Layer& L, const float* xp, const float* gy, 
         GemmTcArgs a{};
         a.A = ga; a.lda = H; a.B = p.w0; a.ldb = n.in; a.b_mn = 1; a.C = gxp; a.ldc = D; a.M = rows; a.N = D; a.K = H;
         a.resid = gxp; a.ldres = D;
-        NFB_TRY(g.run(a));  // + conditioner path (in place)
+        NFB_TRY(g.run_w(a));  // + conditioner path (in place)
     } else {
         GemmTcArgs a{};
         a.A = ga; a.lda = H; a.B = p.w0; a.ldb = n.in; a.b_mn = 1; a.C = f->tr_gin.as<float>(); a.ldc = L.n_id;
@@ -1855,9 +1865,14 @@ int nfb_flow_log_prob_backward(nfb_flow_t* f, const float* x, const float* g_log
     // ---- forward, keeping every group's input (density order: groups last-to-first) ----
     NFB_CUDA(cudaMemcpyAsync(store, x, ZS * 4, cudaMemcpyDeviceToDevice, st));
     NFB_TRY(launch_fill(logq, rows, 0.f, st));
-    for (int k = 0; k < ng; ++k)
-        NFB_TRY(run_group(f, f->groups[ng - 1 - k], NFB_INVERSE, store + (size_t)k * ZS, store + (size_t)(k + 1) * ZS, logq,
-                          rows, st));
+    if (f->stack_n == ng && ng > 0) {
+        // all groups fused: ONE persistent launch, layer l writing its output to store[l + 1]
+        NFB_TRY(launch_fused_stack(f, store, store + ZS, logq, rows, st, 0, (long long)ZS));
+    } else {
+        for (int k = 0; k < ng; ++k)
+            NFB_TRY(run_group(f, f->groups[ng - 1 - k], NFB_INVERSE, store + (size_t)k * ZS, store + (size_t)(k + 1) * ZS,
+                              logq, rows, st));
+    }
     const float* zfin = store + (size_t)ng * ZS;
     NFB_TRY(launch_diag_gauss(zfin, f->base_loc, f->base_log_scale, logq, rows, D, 1, st));
     // ---- backward ----

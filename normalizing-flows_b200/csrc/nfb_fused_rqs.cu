@@ -327,7 +327,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             const bool tile_live = tile < n_tiles;
             const FusedLayer& L = p.layers[layer];
             const int D = L.D, H = L.H;
-            const float* zsrc = layer == 0 ? p.zin : p.zout;   // layers >= 1 update z in place
+            // layers >= 1 update z in place (z_stride = 0) or, for the training pass, every layer writes its own
+            // buffer zout + layer * z_stride so that the backward finds each layer's input
+            float* zdst = p.zout + (long long)layer * p.z_stride;
+            const float* zsrc = layer == 0 ? p.zin : p.zout + (long long)(layer - 1) * p.z_stride;
             const long long row0 = tile * 128;
             if (u != u_first) prof = nullptr;
             float ru = 1.f, ruinv = 1.f;  // this row's power-of-two unit (set after the tile load)
@@ -461,13 +464,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         const long long gr = row0 + rr;
                         const float4 v = make_float4(xs[xs_index(rr, c0)], xs[xs_index(rr, c0 + 1)],
                                                      xs[xs_index(rr, c0 + 2)], xs[xs_index(rr, c0 + 3)]);
-                        if (gr < p.rows) __stcg(reinterpret_cast<float4*>(p.zout + gr * 64) + (i4 & 15), v);
+                        if (gr < p.rows) __stcg(reinterpret_cast<float4*>(zdst + gr * 64) + (i4 & 15), v);
                     }
                 } else {
                     for (int i = et; i < 128 * D; i += kEpiThreads) {
                         const int rr = i / D, cc = i - rr * D;
                         const long long gr = row0 + rr;
-                        if (gr < p.rows) __stcg(p.zout + gr * D + cc, xs[xs_index(rr, cc)]);
+                        if (gr < p.rows) __stcg(zdst + gr * D + cc, xs[xs_index(rr, cc)]);
                     }
                 }
             };
@@ -614,7 +617,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         const int col = L.tr_idx[t];
                         float y, l;
                         float xin = xs[xs_index(r, col)];
-                        if (arsamp) xin = row0 + r < p.rows ? __ldcg(p.zout + (row0 + r) * D + col) : 0.f;
+                        if (arsamp) xin = row0 + r < p.rows ? __ldcg(zdst + (row0 + r) * D + col) : 0.f;
                         rqs_core<8, SAMPLE>(xin, lw, lh, [&dd](int k) { return dd[k]; }, L.tail, y, l);
                         xs[xs_index(r, col)] = y;
                         ladsum += l;

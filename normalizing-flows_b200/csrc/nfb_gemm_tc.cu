@@ -66,6 +66,8 @@ struct GemmTcParams {
     int k_splits;            // >= 1
     long long k_per_split;   // multiple of 64
     int stages, terms;       // pipeline depth; 3 = split-bf16, 1 = plain bf16
+    const uint8_t* b_packed; // optional: B pre-split to bf16 hi | lo tiles in the stage layout, one record per
+                             // (n tile, K chunk): streamed by bulk TMA instead of being converted by the builders
     int* err;
 };
 
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGtMaxStages; ++i) {
-            mbar_init(bar(GB_FULL + i), kGtBuildWarps);
+            mbar_init(bar(GB_FULL + i), kGtBuildWarps + (p.b_packed ? 1 : 0));  // (+ the TMA producer's expect_tx)
             mbar_init(bar(GB_EMPTY + i), 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -105,7 +107,26 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
     const int n_tiles = (p.N + NT - 1) / NT;
     const long long n_units = m_tiles * n_tiles * p.k_splits;
 
-    if (warp == kGtBuildWarps + 1) {
+    if (warp == kGtBuildWarps && p.b_packed) {
+        // ------------------------------ B producer (pre-packed operand) ----------------------
+        const int kc_total = (int)((p.K + 63) / 64);
+        const uint32_t rec = 2 * b_tile;
+        uint32_t st = 0, st_use = 0;
+        for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const long long tile = u / p.k_splits;
+            const int nt = (int)(tile % n_tiles);
+            for (int kc = 0; kc < kc_total; ++kc) {  // (k_splits == 1 with a packed operand)
+                if (st_use > 0) mbar_wait(bar(GB_EMPTY + st), (st_use - 1) & 1u, p.err, 860 + st);
+                if (elect_one_sync()) {
+                    mbar_expect_tx(bar(GB_FULL + st), rec);
+                    bulk_g2s(sbase + st * stage_bytes + 2 * kGtTileA, p.b_packed + ((size_t)nt * kc_total + kc) * rec, rec,
+                             bar(GB_FULL + st));
+                }
+                __syncwarp();
+                if (++st == (uint32_t)S) { st = 0; ++st_use; }
+            }
+        }
+    } else if (warp == kGtBuildWarps + 1) {
         // ------------------------------ MMA issuer ------------------------------------------
         const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)NT) | ((uint32_t)p.a_mn << 15) | ((uint32_t)p.b_mn << 16);
         // K-major: 8-row groups 1024 B apart, a K=16 step is 32 B further along the row.
@@ -295,7 +316,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
                     load_group(p.A, p.lda, p.a_mn, a_al, mt * 128, p.M, kk, k1, 128, bt + i * kGtBuildThreads, va[i], oa[i]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (bt + i * kGtBuildThreads < nb_groups)
+                    if (!p.b_packed && bt + i * kGtBuildThreads < nb_groups)
                         load_group(p.B, p.ldb, p.b_mn, b_al, (long long)nt * NT, p.N, kk, k1, NT, bt + i * kGtBuildThreads,
                                    vb[i], ob[i]);
                 if (st_use > 0) mbar_wait(bar(GB_EMPTY + st), (st_use - 1) & 1u, p.err, 830 + st);  // (loads in flight)
@@ -303,7 +324,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
                 for (int i = 0; i < 2; ++i) store_group(va[i], p.a_relu, sa, sa + kGtTileA, oa[i]);
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (bt + i * kGtBuildThreads < nb_groups)
+                    if (!p.b_packed && bt + i * kGtBuildThreads < nb_groups)
                         store_group(vb[i], p.b_relu, sa + 2 * kGtTileA, sa + 2 * kGtTileA + b_tile, ob[i]);
                 fence_proxy_async_smem();
                 __syncwarp();
@@ -318,6 +339,67 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
     tc_fence_before();
     __syncthreads();
     if (warp == kGtBuildWarps + 1) tmem_dealloc(tmem, 512);
+}
+
+// Pre-pack a B operand (weights: reused by every 128-row tile of the batch) into bf16 hi | lo records in the exact stage
+// layout of gemm_tc_kernel, one record per (n tile, K chunk).  Same group addressing as the builders.
+__global__ void gemm_pack_b_kernel(const float* __restrict__ B, long long ldb, int b_mn, int N, long long K, int NT,
+                                   uint8_t* __restrict__ out) {
+    const int kc_total = (int)((K + 63) / 64);
+    const int groups = NT * 8;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int n_tiles = (N + NT - 1) / NT;
+    if (gid >= (long long)n_tiles * kc_total * groups) return;
+    const int g = (int)(gid % groups);
+    const long long t = gid / groups;
+    const int kc = (int)(t % kc_total), nt = (int)(t / kc_total);
+    const long long i0 = (long long)nt * NT, k0 = (long long)kc * 64;
+    long long row, col, row_end, col_end;
+    uint32_t off;
+    if (!b_mn) {
+        const int i = g >> 3, c8 = g & 7;
+        row = i0 + i; col = k0 + c8 * 8; row_end = N; col_end = K;
+        off = (uint32_t)((i >> 3) * 1024 + (i & 7) * 128 + ((c8 ^ (i & 7)) << 4));
+    } else {
+        const int per = NT >> 3;
+        const int kr = g / per, cm = g - kr * per;
+        row = k0 + kr; col = i0 + cm * 8; row_end = K; col_end = N;
+        off = (uint32_t)((cm >> 3) * 8192 + (kr >> 3) * 1024 + (kr & 7) * 128 + (((cm & 7) ^ (kr & 7)) << 4));
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float v[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const long long c = col + 2 * i + j;
+            v[j] = (row < row_end && c < col_end) ? B[row * ldb + c] : 0.f;
+        }
+        hi[i] = pack_bf16x2(v[0], v[1]);
+        lo[i] = pack_bf16x2(v[0] - __uint_as_float(hi[i] << 16), v[1] - __uint_as_float(hi[i] & 0xffff0000u));
+    }
+    const uint32_t b_tile = (uint32_t)NT * 128u;
+    uint8_t* rec = out + ((size_t)nt * kc_total + kc) * (2 * b_tile);
+    *reinterpret_cast<uint4*>(rec + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(rec + b_tile + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+int gemm_tc_n_tile(long long N, int b_mn) {
+    int nt = N >= 256 ? 256 : (int)((N + 15) / 16 * 16);
+    if (b_mn) nt = (nt + 63) / 64 * 64;
+    return nt;
+}
+size_t gemm_tc_packed_b_bytes(long long N, long long K, int b_mn) {
+    const int nt = gemm_tc_n_tile(N, b_mn);
+    return (size_t)((N + nt - 1) / nt) * (size_t)((K + 63) / 64) * (size_t)nt * 256;
+}
+int launch_gemm_pack_b(const float* B, long long ldb, int b_mn, long long N, long long K, uint8_t* out, cudaStream_t st) {
+    const int nt = gemm_tc_n_tile(N, b_mn);
+    const long long total = (N + nt - 1) / nt * ((K + 63) / 64) * (long long)nt * 8;
+    if (total == 0) return NFB_OK;
+    gemm_pack_b_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, ldb, b_mn, (int)N, K, nt, out);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
 }
 
 // -------------------------------------------------------------------------------------------------------------
@@ -340,8 +422,7 @@ int launch_gemm_tc(const GemmTcArgs& a, int* err, cudaStream_t st) {
     p.relu_out = a.relu_out; p.terms = terms; p.err = err;
     // n tile: as wide as possible (one B tile is reused by the whole 128-row A tile), multiple of 16.  MN-major B needs
     // whole 64-wide blocks.
-    int nt = a.N >= 256 ? 256 : (a.N + 15) / 16 * 16;
-    if (a.b_mn) nt = (nt + 63) / 64 * 64;
+    const int nt = gemm_tc_n_tile(a.N, a.b_mn);
     p.n_tile = nt;
     const long long m_tiles = (a.M + 127) / 128;
     const int n_tiles = (a.N + nt - 1) / nt;
@@ -357,6 +438,7 @@ int launch_gemm_tc(const GemmTcArgs& a, int* err, cudaStream_t st) {
     long long kps = ((a.K + ks - 1) / ks + 63) / 64 * 64;
     ks = (int)((a.K + kps - 1) / kps);
     p.k_splits = ks; p.k_per_split = kps;
+    p.b_packed = (ks == 1 && !a.b_relu) ? a.b_packed : nullptr;  // (a split or ReLU-on-load product converts B itself)
     p.atomic_out = (ks > 1 || a.accumulate) ? 1 : 0;
     if (ks > 1) NFB_CHECK(!a.bias && !a.mask && !a.resid && !a.relu_out, NFB_ERR_ARG, "gemm_tc: split-K with a non-linear epilogue");
     if (ks > 1 && !a.accumulate)  // the partial products are added with red.global.add: start from zero

@@ -149,6 +149,7 @@ struct FusedParams {
     int n_layers;
     const float* zin;          // input of layer 0
     float* zout;               // output of every layer (and input of layers >= 1)
+    long long z_stride;        // 0: layers update zout in place; > 0: layer l writes zout + l * z_stride (training pass)
     float* logq;
     long long rows;
     int accumulate;            // layer 0: logq += (1) or = (0); later layers always accumulate
@@ -168,8 +169,11 @@ struct GemmTcArgs {
     int a_mn = 0, b_mn = 0, a_relu = 0, b_relu = 0, relu_out = 0, accumulate = 0;
     const float* bias = nullptr; const float* mask = nullptr; const float* mulm = nullptr; long long ldmask = 0;
     const float* resid = nullptr; long long ldres = 0;
+    const uint8_t* b_packed = nullptr;  // optional: B pre-packed by launch_gemm_pack_b (same B, ldb, b_mn, N, K)
 };
 int launch_gemm_tc(const GemmTcArgs& a, int* err, cudaStream_t st);
+size_t gemm_tc_packed_b_bytes(long long N, long long K, int b_mn);
+int launch_gemm_pack_b(const float* B, long long ldb, int b_mn, long long N, long long K, uint8_t* out, cudaStream_t st);
 
 // ---- training pass: element-wise / reduction kernels (nfb_backward.cu) ----
 int launch_spline_bwd_rows(const float* xin, int ldx, const float* params, const float* g_out, const float* g_lq,
