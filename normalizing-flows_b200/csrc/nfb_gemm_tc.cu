@@ -71,6 +71,7 @@ struct GemmTcParams {
     int* err;
 };
 
+template <bool PACKED>
 __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -85,7 +86,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGtMaxStages; ++i) {
-            mbar_init(bar(GB_FULL + i), kGtBuildWarps + (p.b_packed ? 1 : 0));  // (+ the TMA producer's expect_tx)
+            mbar_init(bar(GB_FULL + i), kGtBuildWarps + (PACKED ? 1 : 0));  // (+ the TMA producer's expect_tx)
             mbar_init(bar(GB_EMPTY + i), 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
     const int n_tiles = (p.N + NT - 1) / NT;
     const long long n_units = m_tiles * n_tiles * p.k_splits;
 
-    if (warp == kGtBuildWarps && p.b_packed) {
+    if (PACKED && warp == kGtBuildWarps) {
         // ------------------------------ B producer (pre-packed operand) ----------------------
         const int kc_total = (int)((p.K + 63) / 64);
         const uint32_t rec = 2 * b_tile;
@@ -296,43 +297,84 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
             if (lane == 0) mbar_arrive(bar(GB_ACCEMPTY + ab));
         };
 
-        long long prev = -1;
-        for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
+        // The builders walk this CTA's K chunks as ONE stream across unit boundaries.  With a pre-packed B operand a
+        // thread only owns two A groups per chunk (16 registers), so the loads of chunk j+1 are issued BEFORE chunk j is
+        // converted and stored: the HBM latency of the activation stream (~2 k cycles) is then hidden behind one
+        // chunk's worth of work instead of being exposed once per chunk.
+        struct Pos { long long u, mt, k0, k1; int nt, kc, KC; };
+        auto unit_pos = [&](long long u, int kc) {
+            Pos q;
+            q.u = u; q.kc = kc;
             const int ks = (int)(u % p.k_splits);
             const long long tile = u / p.k_splits;
-            const long long mt = tile / n_tiles;
-            const int nt = (int)(tile - mt * n_tiles);
-            const long long k0 = (long long)ks * p.k_per_split;
-            const long long k1 = k0 + p.k_per_split < p.K ? k0 + p.k_per_split : p.K;
-            const int KC = (int)((k1 - k0 + 63) / 64);
-            const int nb_groups = NT * 8;  // B groups per chunk (A: 1024)
-            for (int kc = 0; kc < KC; ++kc) {
-                const uint32_t sa = sbase + st * stage_bytes;
-                const long long kk = k0 + (long long)kc * 64;
-                float va[2][8], vb[4][8];
-                uint32_t oa[2], ob[4];
+            q.mt = tile / n_tiles;
+            q.nt = (int)(tile - q.mt * n_tiles);
+            q.k0 = (long long)ks * p.k_per_split;
+            q.k1 = q.k0 + p.k_per_split < p.K ? q.k0 + p.k_per_split : p.K;
+            q.KC = (int)((q.k1 - q.k0 + 63) / 64);
+            return q;
+        };
+        const int nb_groups = NT * 8;  // B groups per chunk (A: 1024)
+        constexpr bool packed = PACKED;
+        float va[2][8], vb[4][8], na[2][8];
+        uint32_t oa[2], ob[4], noa[2];
+        auto load_a = [&](const Pos& q, float (&v)[2][8], uint32_t (&o)[2]) {
 #pragma unroll
-                for (int i = 0; i < 2; ++i)
-                    load_group(p.A, p.lda, p.a_mn, a_al, mt * 128, p.M, kk, k1, 128, bt + i * kGtBuildThreads, va[i], oa[i]);
+            for (int i = 0; i < 2; ++i)
+                load_group(p.A, p.lda, p.a_mn, a_al, q.mt * 128, p.M, q.k0 + (long long)q.kc * 64, q.k1, 128,
+                           bt + i * kGtBuildThreads, v[i], o[i]);
+        };
+        long long prev = -1;
+        Pos cur{};
+        if ((long long)blockIdx.x < n_units) {
+            cur = unit_pos(blockIdx.x, 0);
+            load_a(cur, va, oa);
+        }
+        for (bool more = (long long)blockIdx.x < n_units; more;) {
+            Pos nxt = cur;
+            if (++nxt.kc == cur.KC) nxt = unit_pos(cur.u + gridDim.x, 0);
+            const bool has_next = nxt.u < n_units;
+            if (packed && has_next) load_a(nxt, na, noa);  // prefetch: in flight during this chunk's convert / store
+            if (!packed) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
-                    if (!p.b_packed && bt + i * kGtBuildThreads < nb_groups)
-                        load_group(p.B, p.ldb, p.b_mn, b_al, (long long)nt * NT, p.N, kk, k1, NT, bt + i * kGtBuildThreads,
-                                   vb[i], ob[i]);
-                if (st_use > 0) mbar_wait(bar(GB_EMPTY + st), (st_use - 1) & 1u, p.err, 830 + st);  // (loads in flight)
-#pragma unroll
-                for (int i = 0; i < 2; ++i) store_group(va[i], p.a_relu, sa, sa + kGtTileA, oa[i]);
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (!p.b_packed && bt + i * kGtBuildThreads < nb_groups)
-                        store_group(vb[i], p.b_relu, sa + 2 * kGtTileA, sa + 2 * kGtTileA + b_tile, ob[i]);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar(GB_FULL + st));
-                if (++st == (uint32_t)S) { st = 0; ++st_use; }
+                    if (bt + i * kGtBuildThreads < nb_groups)
+                        load_group(p.B, p.ldb, p.b_mn, b_al, (long long)cur.nt * NT, p.N, cur.k0 + (long long)cur.kc * 64,
+                                   cur.k1, NT, bt + i * kGtBuildThreads, vb[i], ob[i]);
             }
-            if (prev >= 0) epilogue(prev, it - 1);  // overlaps this unit's MMAs
-            prev = u;
+            const uint32_t sa = sbase + st * stage_bytes;
+            if (st_use > 0) mbar_wait(bar(GB_EMPTY + st), (st_use - 1) & 1u, p.err, 830 + st);  // (loads in flight)
+#pragma unroll
+            for (int i = 0; i < 2; ++i) store_group(va[i], p.a_relu, sa, sa + kGtTileA, oa[i]);
+            if (!packed) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (bt + i * kGtBuildThreads < nb_groups)
+                        store_group(vb[i], p.b_relu, sa + 2 * kGtTileA, sa + 2 * kGtTileA + b_tile, ob[i]);
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(GB_FULL + st));
+            if (++st == (uint32_t)S) { st = 0; ++st_use; }
+            if (cur.kc == cur.KC - 1) {  // unit complete: the previous unit's epilogue overlaps this unit's MMAs
+                if (prev >= 0) epilogue(prev, it - 1);
+                prev = cur.u;
+                ++it;
+            }
+            if (has_next) {
+                if (packed) {
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        oa[i] = noa[i];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) va[i][j] = na[i][j];
+                    }
+                } else {
+                    load_a(nxt, va, oa);
+                }
+            }
+            cur = nxt;
+            more = has_next;
         }
         if (prev >= 0) epilogue(prev, it - 1);
     }
@@ -408,7 +450,9 @@ int launch_gemm_pack_b(const float* B, long long ldb, int b_mn, long long N, lon
 int launch_gemm_tc(const GemmTcArgs& a, int* err, cudaStream_t st) {
     static PerDevice per_dev;
     const int sm_count = per_dev.ensure([] {
-        return cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGtSmemMax);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGtSmemMax);
+        if (e != cudaSuccess) return e;
+        return cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGtSmemMax);
     });
     if (sm_count < 0) return NFB_ERR_CUDA;
     NFB_CHECK(a.A && a.B && a.C, NFB_ERR_ARG, "gemm_tc: null operand");
@@ -452,7 +496,8 @@ int launch_gemm_tc(const GemmTcArgs& a, int* err, cudaStream_t st) {
     const uint32_t smem = (uint32_t)stages * stage_bytes + kGtBarBytes + 16 + kStgBytes;
     const long long n_units = tiles * ks;
     const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
-    gemm_tc_kernel<<<grid, kGtThreads, smem, st>>>(p);
+    if (p.b_packed) gemm_tc_kernel<true><<<grid, kGtThreads, smem, st>>>(p);
+    else gemm_tc_kernel<false><<<grid, kGtThreads, smem, st>>>(p);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }
