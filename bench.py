@@ -322,6 +322,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-reference-eager", action="store_true")
     ap.add_argument("--no-train-step", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip BASELINE configs C1 / C2' / C3 / C5 (extra keys)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -524,6 +525,15 @@ def main():
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "gpu_launches": launches_per_step * steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks, "roofline": roof, "train_step": train}
+    if world == 1 and not args.no_extra_configs:
+        # the other BASELINE configurations (parity-test cases, not bench lines), as `extra` keys: C1 Real NVP,
+        # C2' coupled variant, C3 Glow, C5 residual flow -- tools/bench_configs.py, in a subprocess (fresh model state)
+        try:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_configs.py")], capture_output=True,
+                                 text=True, timeout=900)
+            line["extra"] = [json.loads(ln) for ln in out.stdout.splitlines() if ln.startswith("{")]
+        except Exception as e:
+            line["extra"] = {"unavailable": repr(e)[:200]}
     if world == 1 and reference_available() and not args.no_reference_eager:
         # the denominator of north_star's >= 10x target: the unmodified reference, PyTorch eager, same B200
         try:

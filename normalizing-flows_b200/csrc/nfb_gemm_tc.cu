@@ -106,7 +106,10 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
 
     const long long m_tiles = (p.M + 127) / 128;
     const int n_tiles = (p.N + NT - 1) / NT;
-    const long long n_units = m_tiles * n_tiles * p.k_splits;
+    const long long n_out_tiles = m_tiles * n_tiles;
+    // units are K-split-major: the CTAs that run at the same time work on the SAME k range of different output tiles,
+    // so an operand slab that several tiles share (the activations of a weight gradient) is re-read from L2, not HBM
+    const long long n_units = n_out_tiles * p.k_splits;
 
     if (PACKED && warp == kGtBuildWarps) {
         // ------------------------------ B producer (pre-packed operand) ----------------------
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
         const uint32_t rec = 2 * b_tile;
         uint32_t st = 0, st_use = 0;
         for (long long u = blockIdx.x; u < n_units; u += gridDim.x) {
-            const long long tile = u / p.k_splits;
+            const long long tile = u % n_out_tiles;
             const int nt = (int)(tile % n_tiles);
             for (int kc = 0; kc < kc_total; ++kc) {  // (k_splits == 1 with a packed operand)
                 if (st_use > 0) mbar_wait(bar(GB_EMPTY + st), (st_use - 1) & 1u, p.err, 860 + st);
@@ -136,7 +139,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
         const uint32_t a_step = p.a_mn ? 128u : 2u, b_step = p.b_mn ? 128u : 2u;  // descriptor address units (16 B)
         uint32_t st = 0, st_use = 0, it = 0;
         for (long long u = blockIdx.x; u < n_units; u += gridDim.x, ++it) {
-            const int ks = (int)(u % p.k_splits);
+            const int ks = (int)(u / n_out_tiles);
             const long long k0 = (long long)ks * p.k_per_split;
             const long long k1 = k0 + p.k_per_split < p.K ? k0 + p.k_per_split : p.K;
             const int KC = (int)((k1 - k0 + 63) / 64);
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
             const uint32_t ab = i & 1u;
             mbar_wait_warp(bar(GB_ACCFULL + ab), (i >> 1) & 1u, p.err, 840 + ab);
             tc_fence_after();
-            const long long tile = u / p.k_splits;
+            const long long tile = u % n_out_tiles;
             const long long mt = tile / n_tiles;
             const int nt = (int)(tile - mt * n_tiles);
             const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15) == 0) && !p.atomic_out;
@@ -305,8 +308,8 @@ __global__ void __launch_bounds__(kGtThreads, 1) gemm_tc_kernel(const GemmTcPara
         auto unit_pos = [&](long long u, int kc) {
             Pos q;
             q.u = u; q.kc = kc;
-            const int ks = (int)(u % p.k_splits);
-            const long long tile = u / p.k_splits;
+            const int ks = (int)(u / n_out_tiles);
+            const long long tile = u % n_out_tiles;
             q.mt = tile / n_tiles;
             q.nt = (int)(tile - q.mt * n_tiles);
             q.k0 = (long long)ks * p.k_per_split;
@@ -474,7 +477,7 @@ int launch_gemm_tc(const GemmTcArgs& a, int* err, cudaStream_t st) {
     int ks = 1;
     const long long tiles = m_tiles * n_tiles;
     if (tiles < sm_count && a.K >= 2048) {
-        ks = (int)((2LL * sm_count + tiles - 1) / tiles);
+        ks = (int)((2LL * sm_count) / tiles);  // <= 2 units per CTA: no third, mostly empty wave
         const long long max_ks = (a.K + 511) / 512;  // at least 8 chunks per split
         if (ks > max_ks) ks = (int)max_ks;
         if (ks < 1) ks = 1;

@@ -82,8 +82,30 @@ def coupled_nsf():
             "ms": ms, "samples_per_s": 65536 / ms * 1e3, "launches": m._stack().launch_count()}
 
 
+def residual_flow():
+    """BASELINE config 5: 16 x Residual(LipschitzMLP([2, 128, 128, 128, 2])) (examples/residual.ipynb), batch 131 072,
+    forward_kld in TRAINING mode = the stochastic (Russian-roulette + Hutchinson) log-det estimator of
+    flows/residual.py:163-217, and in eval mode = the exact 2 x 2 Jacobian path (:148-161)."""
+    import numpy as np
+    torch.manual_seed(0)
+    np.random.seed(0)
+    flows = [nf.flows.Residual(nf.nets.LipschitzMLP([2, 128, 128, 128, 2], init_zeros=True, lipschitz_const=0.9),
+                               reduce_memory=True) for _ in range(16)]
+    m = nf.NormalizingFlow(nf.distributions.DiagGaussian(2, trainable=False), flows).cuda()
+    x = nf.distributions.TwoMoons().sample(131072).cuda()
+    m.train()
+    ms_train = timed(lambda: m.forward_kld(x), warmup=2, iters=8)
+    m.eval()
+    ms_eval = timed(lambda: m.forward_kld(x), warmup=2, iters=8)
+    return {"config": "C5 Residual flow 2-D, 16 x iResBlock(LipschitzMLP[2,128,128,128,2]), batch 131072, forward_kld",
+            "ms_stochastic_estimator": ms_train, "samples_per_s_stochastic": 131072 / ms_train * 1e3,
+            "ms_exact_2x2": ms_eval, "samples_per_s_exact": 131072 / ms_eval * 1e3}
+
+
+CONFIGS = (("c1", real_nvp), ("c2", coupled_nsf), ("c3", glow), ("c5", residual_flow))
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["c1", "c2", "c3"]
-    for name, fn in (("c1", real_nvp), ("c2", coupled_nsf), ("c3", glow)):
+    which = sys.argv[1:] or ["c1", "c2", "c3", "c5"]
+    for name, fn in CONFIGS:
         if name in which:
             print(json.dumps(fn()), flush=True)
