@@ -521,7 +521,9 @@ def main():
                        "loss": loss_val},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * D * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": e2e_s / steps * 1e3, "loss": e2e_loss,
-                    "api": "nfb_flow_forward_kld_host (pinned host batch)"},
+                    "api": "nfb_flow_forward_kld_host (pinned host batch; chunked H2D overlapped with the kernel)"
+                           + ("" if world == 1 else "; at N > 1 every rank calls it on its own shard and no collective is "
+                              "included (throughput of N independent host calls, not forward_kld_dp end to end)")},
             "host_enqueue_ms_per_step": host_enqueue_ms,
             "gpu_launches": launches_per_step * steps, "gpu_launches_per_step": launches_per_step,
             "clocks": clocks, "roofline": roof, "train_step": train}

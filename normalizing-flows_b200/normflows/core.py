@@ -235,6 +235,43 @@ class ConditionalNormalizingFlow(NormalizingFlow):
         return torch.mean(log_q) - beta * torch.mean(log_p)
 
 
+class ClassCondFlow(nn.Module):
+    """Class-conditional flow: the class goes to the base distribution only (reference: core.py:368-452).  The layer
+    stack itself runs through the same fused launch as NormalizingFlow (one persistent kernel for spline stacks)."""
+
+    def __init__(self, q0, flows):
+        super().__init__()
+        self.q0 = q0
+        self.flows = nn.ModuleList(flows)
+        self._inner = None
+
+    def _flow(self):
+        # an inner NormalizingFlow that shares the layer modules (no base: only its transform paths are used)
+        inner = self.__dict__.get("_nfb_inner")
+        if inner is None or list(inner.flows) != list(self.flows):
+            inner = NormalizingFlow(None, list(self.flows))
+            self.__dict__["_nfb_inner"] = inner
+        return inner
+
+    def log_prob(self, x, y):
+        z, log_q = self._flow().inverse_and_log_det(x)
+        return log_q + self.q0.log_prob(z, y)
+
+    def forward_kld(self, x, y):
+        return -torch.mean(self.log_prob(x, y))
+
+    def sample(self, num_samples=1, y=None):
+        z, log_q = self.q0(num_samples, y)
+        x, log_det = self._flow().forward_and_log_det(z)
+        return x, log_q - log_det
+
+    def save(self, path):
+        torch.save(self.state_dict(), path)
+
+    def load(self, path):
+        self.load_state_dict(torch.load(path))
+
+
 class MultiscaleFlow(nn.Module):
     """Multiscale (Glow) driver (reference: core.py:455-653)."""
 

@@ -904,3 +904,25 @@ def test_conditional_normalizing_flow_with_context():
     torch.manual_seed(1)
     xs, lq = model.sample(48, ctx)
     np.testing.assert_allclose(lq.cpu().numpy(), model.log_prob(xs, ctx).cpu().numpy(), rtol=1e-4, atol=2e-2)
+
+
+def test_class_cond_flow():
+    """ClassCondFlow (core.py:368-452): class label to the base only; the layer stack runs as one fused launch."""
+    spec, sd, a = load_golden("nsf_coupled_d5_h128_l3")
+    inner = build_model(annotate_spec(spec, sd), sd)
+    torch.manual_seed(5)
+    q0 = nf.distributions.ClassCondDiagGaussian(5, 3)
+    with torch.no_grad():
+        q0.loc.normal_(0, 0.5)
+        q0.log_scale.normal_(0, 0.2)
+    model = nf.ClassCondFlow(q0, list(inner.flows)).cuda()
+    x = cuda(a["x"])
+    y = torch.randint(3, (x.shape[0],), generator=torch.Generator().manual_seed(6)).cuda()
+    lp = model.log_prob(x, y).cpu().numpy()
+    z, ld = O.inverse_and_log_det(spec, sd, a["x"].astype(np.float64))
+    qsd = {"q0.loc": q0.loc.detach().cpu().numpy().astype(np.float64), "q0.log_scale": q0.log_scale.detach().cpu().numpy().astype(np.float64)}
+    ref = ld + O.class_cond_diag_gaussian_log_prob(z, y.cpu().numpy(), qsd, "q0.")
+    np.testing.assert_allclose(lp, ref, rtol=RTOL, atol=ATOL)
+    assert float(model.forward_kld(x, y)) == pytest.approx(-float(ref.mean()), rel=2e-5)
+    xs, lq = model.sample(64, y[:64])
+    np.testing.assert_allclose(lq.cpu().numpy(), model.log_prob(xs, y[:64]).cpu().numpy(), rtol=1e-4, atol=2e-2)
