@@ -112,6 +112,20 @@ int nfb_gemm_f32(const nfb_gemm_desc_t* desc, void* stream);
 int nfb_conv2d(const float* x_dev, int32_t x_channels, int32_t c0, const float* w_dev, const float* b_dev,
                float* y_dev, int64_t batch, int32_t cin, int32_t height, int32_t width, int32_t cout,
                int32_t ksize, float leaky, void* stream);
+/* nets/cnn.py:33-61 ConvNet2d with kernel sizes (3, 1, 3) -- the parameter map of a GlowBlock's coupling
+ * (flows/affine/glow.py:48-62) -- as ONE kernel: conv3x3 + LeakyReLU, conv1x1 + LeakyReLU and the nine stacked 1x1
+ * products of the last 3x3 convolution, the two hidden tensors never leaving the SM.  x: channel slice [c0, c0+cin) of
+ * an NCHW tensor with `x_channels` channels; w1 [hidden, cin, 3, 3], w2 [hidden, hidden(,1,1)], w3_taps [9*cout, hidden]
+ * (row (kh*3+kw)*cout + n = W3[n, :, kh, kw]); y_taps: [B, 9*cout, H, W], to be summed by nfb_tap_shift_add (+ bias). */
+int nfb_glow_conditioner(const float* x_dev, int32_t x_channels, int32_t c0, int32_t cin, const float* w1_dev,
+                         const float* b1_dev, const float* w2_dev, const float* b2_dev, const float* w3_taps_dev,
+                         float* y_taps_dev, int64_t batch, int32_t height, int32_t width, int32_t hidden, int32_t cout,
+                         float leaky, void* stream);
+/* Second half of a k x k convolution computed as k*k stacked 1x1 products (the last, 256 -> few-channel layer of
+ * ConvNet2d, nets/cnn.py:50-57): y_taps [B, k*k*cout, H, W] holds, for tap t = kh*k + kw, channel t*cout + n =
+ * sum_c W[n, c, kh, kw] x[b, c]; out[b, n, y, x] = bias[n] + sum_t y_taps[b, t*cout + n, y + kh - k/2, x + kw - k/2]. */
+int nfb_tap_shift_add(const float* y_taps_dev, const float* bias_dev, float* out_dev, int64_t batch, int32_t cout,
+                      int32_t height, int32_t width, int32_t ksize, void* stream);
 /* flows/normalization.py:31-39 ActNorm.inverse followed by flows/mixing.py:123-133 Invertible1x1Conv.inverse
  * (LU parameterisation :88-104) folded into one 1x1 convolution: w_out[C,C], b_out[C] for nfb_conv2d, and
  * *logdet_out = H*W*(sum log_S - sum s), the per-sample log|det| of both layers. */

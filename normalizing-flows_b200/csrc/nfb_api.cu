@@ -1004,6 +1004,24 @@ int nfb_conv2d(const float* x, int32_t x_channels, int32_t c0, const float* w, c
     NFB_CHECK(x && w && y, NFB_ERR_ARG, "nfb_conv2d: null pointer");
     return launch_conv2d(x, x_channels, c0, w, b, y, batch, cin, height, width, cout, ksize, leaky, S(stream));
 }
+int nfb_glow_conditioner(const float* x, int32_t x_channels, int32_t c0, int32_t cin, const float* w1, const float* b1,
+                         const float* w2, const float* b2, const float* w3_taps, float* y_taps, int64_t batch,
+                         int32_t height, int32_t width, int32_t hidden, int32_t cout, float leaky, void* stream) {
+    NFB_CHECK(x && w1 && b1 && w2 && b2 && w3_taps && y_taps, NFB_ERR_ARG, "nfb_glow_conditioner: null pointer");
+    NFB_CHECK(glow_cond_supported(cin, hidden, cout, 3, 1, 3), NFB_ERR_UNSUPPORTED,
+              "nfb_glow_conditioner: needs hidden %% 64 == 0 (<= 256), 9 cin <= 256, 9 cout <= 256");
+    static thread_local int* err_dev = nullptr;
+    if (!err_dev) { NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&err_dev), 16)); NFB_CUDA(cudaMemset(err_dev, 0, 16)); }
+    static const float gain = [] { const char* e = getenv("NFB_ACC_COMP_STEP"); return e ? (float)atof(e) : nfb::kAccStepGain; }();
+    return launch_glow_conditioner(x, x_channels, c0, cin, w1, b1, w2, b2, w3_taps, y_taps, batch, height, width, hidden,
+                                   cout, leaky, gain, err_dev, S(stream));
+}
+int nfb_tap_shift_add(const float* y_taps, const float* bias, float* out, int64_t batch, int32_t cout, int32_t height,
+                      int32_t width, int32_t ksize, void* stream) {
+    NFB_CHECK(y_taps && out, NFB_ERR_ARG, "nfb_tap_shift_add: null pointer");
+    NFB_CHECK(ksize >= 1 && (ksize & 1), NFB_ERR_ARG, "nfb_tap_shift_add: odd kernel sizes only");
+    return launch_tap_shift_add(y_taps, bias, out, batch, cout, height, width, ksize, S(stream));
+}
 int nfb_glow_fold_actnorm_conv1x1(const float* P, const float* L, const float* U, const float* sign_S,
                                   const float* log_S, const float* s, const float* t, int32_t channels,
                                   int32_t hw, float* w_out, float* b_out, float* logdet_out, void* stream) {

@@ -464,5 +464,45 @@ int launch_logit(const float* in, float* out, float* logdet, long long B, long l
     return NFB_OK;
 }
 
+// -----------------------------------------------------------------------------------------
+// Last convolution of the Glow conditioner (nets/cnn.py:50-57: k x k, 256 -> few channels) as k*k 1x1 products + a
+// shifted sum.  An im2col GEMM spends its time gathering K = 256 k^2 values per pixel for a handful of outputs
+// (measured: 456 us, tensor pipe 5 % active); instead ONE 1x1 convolution with the taps stacked along the output
+// channels, Y[b, tap*cout + n] = sum_c W[n, c, tap] h[b, c] (K = 256, N = k^2 cout: the tensor-core kernel at a
+// 1x1 conv's cost), followed by this HBM-bound pass:
+//   out[b, n, y, x] = bias[n] + sum_{kh, kw} Y[b, (kh k + kw) cout + n, y + kh - p, x + kw - p]    (zero outside)
+// -----------------------------------------------------------------------------------------
+__global__ void tap_shift_add_kernel(const float* __restrict__ Y, const float* __restrict__ bias, float* __restrict__ out,
+                                     long long B, int cout, int H, int W, int ks) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long HW = (long long)H * W;
+    if (i >= B * cout * HW) return;
+    const int x = (int)(i % W);
+    const int y = (int)((i / W) % H);
+    const int n = (int)((i / HW) % cout);
+    const long long b = i / (HW * cout);
+    const int p = ks >> 1;
+    float acc = bias ? bias[n] : 0.f;
+    const float* yb = Y + b * (long long)(ks * ks * cout) * HW;
+    for (int kh = 0; kh < ks; ++kh) {
+        const int yy = y + kh - p;
+        if (yy < 0 || yy >= H) continue;
+        for (int kw = 0; kw < ks; ++kw) {
+            const int xx = x + kw - p;
+            if (xx < 0 || xx >= W) continue;
+            acc += yb[((long long)((kh * ks + kw) * cout + n)) * HW + (long long)yy * W + xx];
+        }
+    }
+    out[i] = acc;
+}
+int launch_tap_shift_add(const float* Y, const float* bias, float* out, long long B, int cout, int H, int W, int ks,
+                         cudaStream_t st) {
+    const long long n = B * cout * H * W;
+    if (n == 0) return NFB_OK;
+    tap_shift_add_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(Y, bias, out, B, cout, H, W, ks);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
 }  // namespace nfb
 

@@ -92,6 +92,9 @@ SYMBOLS = {
     "nfb_logit_transform": (C.c_int, [_VP, _VP, _VP, _I64, _I64, _F, _I32, _I32, _VP]),
     "nfb_gemm_f32": (C.c_int, [C.POINTER(GemmDesc), _VP]),
     "nfb_conv2d": (C.c_int, [_VP, _I32, _I32, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _F, _VP]),
+    "nfb_glow_conditioner": (C.c_int, [_VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32,
+                                       _F, _VP]),
+    "nfb_tap_shift_add": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _VP]),
     "nfb_glow_fold_actnorm_conv1x1": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "nfb_glow_fold_conv1x1_actnorm_forward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "nfb_affine_coupling_image": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),

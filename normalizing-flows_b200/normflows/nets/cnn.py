@@ -37,6 +37,22 @@ class ConvNet2d(nn.Module):
         B, ctot, H, W = x.shape
         from ..utils.nn import ActNorm
         mods = list(self.net)
+        convs = self.conv_layers()
+        if (len(convs) == 3 and len(mods) == 5 and [cv.kernel_size[0] for cv in convs] == [3, 1, 3]
+                and convs[0].out_channels == convs[1].out_channels == convs[1].in_channels
+                and convs[0].out_channels % 64 == 0 and convs[0].out_channels <= 256
+                and 9 * cin <= 256 and 9 * convs[2].out_channels <= 256 and self.leaky >= 0.0):
+            # the Glow conditioner shape: ONE fused tensor-core kernel (csrc/nfb_glow_fused.cu) + the shifted tap sum
+            c1, c2, c3 = convs
+            cout, hid = c3.out_channels, c1.out_channels
+            yt = torch.empty(B, 9 * cout, H, W, device=x.device, dtype=torch.float32)
+            out = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
+            with torch.cuda.device(x.device):
+                L.check(L.lib().nfb_glow_conditioner(L.ptr(x), ctot, c0, cin, L.ptr(c1.weight), L.ptr(c1.bias),
+                                                     L.ptr(c2.weight), L.ptr(c2.bias), L.ptr(self._tap_weights(c3)),
+                                                     L.ptr(yt), B, H, W, hid, cout, float(self.leaky), L.stream_ptr()))
+                L.check(L.lib().nfb_tap_shift_add(L.ptr(yt), L.ptr(c3.bias), L.ptr(out), B, cout, H, W, 3, L.stream_ptr()))
+            return out
         cur, cur_tot, cur_c0 = x, ctot, c0
         with torch.cuda.device(x.device):
             for j, conv in enumerate(mods):
@@ -61,9 +77,36 @@ class ConvNet2d(nn.Module):
                         e = torch.exp(an.s.detach().reshape(-1))
                         w = (conv.weight.detach() * e[:, None, None, None]).contiguous()
                         b = an.t.detach().reshape(-1).contiguous()
-                run(w, b, -1.0 if last else float(self.leaky))
+                k = conv.kernel_size[0]
+                if (last and an is None and k > 1 and conv.in_channels >= 128 and k * k * conv.out_channels <= 256
+                        and conv.out_channels <= 64):
+                    # k x k conv with few outputs: k*k stacked 1x1 products on the tensor core + a shifted sum
+                    # (csrc/nfb_glow.cu tap_shift_add_kernel) instead of an im2col GEMM with K = k*k*cin
+                    wt = self._tap_weights(conv)
+                    yt = torch.empty(B, k * k * conv.out_channels, H, W, device=x.device, dtype=torch.float32)
+                    L.check(L.lib().nfb_conv2d(L.ptr(cur), cur_tot, cur_c0, L.ptr(wt), None, L.ptr(yt), B,
+                                               conv.in_channels, H, W, k * k * conv.out_channels, 1, -1.0, L.stream_ptr()))
+                    L.check(L.lib().nfb_tap_shift_add(L.ptr(yt), L.ptr(b), L.ptr(y), B, conv.out_channels, H, W, k,
+                                                      L.stream_ptr()))
+                else:
+                    run(w, b, -1.0 if last else float(self.leaky))
                 cur, cur_tot, cur_c0 = y, conv.out_channels, 0
         return cur
+
+    def _tap_weights(self, conv):
+        """[cout, cin, k, k] -> [k*k*cout, cin, 1, 1] with row (kh*k + kw)*cout + n = W[n, :, kh, kw]; cached per
+        parameter version (and packed-weight generation)."""
+        import torch
+        from .._native import generation
+        sig = (conv.weight.data_ptr(), conv.weight._version, generation())
+        cache = self.__dict__.get("_nfb_tapw")
+        if cache is None or cache[0] != sig:
+            with torch.no_grad():
+                w = conv.weight.detach()
+                wt = w.permute(2, 3, 0, 1).reshape(-1, w.shape[1], 1, 1).contiguous()
+            cache = (sig, wt)
+            self.__dict__["_nfb_tapw"] = cache
+        return cache[1]
 
     def forward(self, x):
         from .._native import require_cuda_f32
