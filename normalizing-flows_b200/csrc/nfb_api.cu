@@ -124,6 +124,11 @@ struct FusedPack {
     bool pair_ok = false;
     int pair_steps = 0;
     DevBuf pair_wstream, pair_steps_dev, lu_src_row, lu_src_col, bias_lu;
+    // LU fold (density pair): first conditioner matrix times the LU map, packed as GEMM 0 of the pair (repack_fused)
+    bool fold_ok = false;                  // decided per repack (scale plan permitting)
+    DevBuf pair_steps_fold_dev, in_idx_dev, fold_lu, fold_G, fold_delta, fold_recs;
+    std::vector<float> fold_delta_host;    // W0 b_lu in sorted hidden order
+    int pw_fold = 0;
     FusedLayer host_layer{}, host_pair{};  // packed descriptors (host copies)
     float b_in0 = 1.f;                     // bound on |conditioner input| * u_row this block was planned for
     int pa[10] = {}, pw[10] = {};          // per-GEMM power-of-two exponents (A operand / weights), see plan_scales
@@ -489,13 +494,20 @@ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 float pow2f(int e) { return std::ldexp(1.0f, clampi(e, -120, 120)); }
 
 // nm[g] = {inf-norm, non-negative-input norm, max |w|} of GEMM g (g = n_hidden: final layer); bmax[g] = max |bias|
+// fold (optional): {inf-norm, -, max |w|} of the folded first matrix G = W0 E_lu (its input is z itself: |z| u_row < 1,
+// A scale pinned to 2^14 because the LU stage reads the same operand) and max |b0 + W0 b_lu|.  The folded GEMM also
+// accumulates onto the residual stream, so it joins the pa + pw = P constraint; *pw_fold < -100 on return = "do not fold"
+// (its weights would have to be scaled down by more than 12 binades to meet P: the lo halves of the LARGEST weights would
+// then fall below fp16's normal range and the pair would carry fewer than 22 bits; smaller weights only ever lose absolute
+// precision of 2^-25 of the scaled range, like every other operand of this kernel).
 void plan_scales(int n_hidden, const std::vector<float>& nm, const std::vector<float>& bmax, double b_in0,
-                 int* pa, int* pw) {
+                 int* pa, int* pw, const float* fold_nm = nullptr, float fold_bmax = 0.f, int* pw_fold = nullptr) {
     const int ng = n_hidden + 1;
     std::vector<double> bin(ng);
     auto norm_of = [&](int g) { return (double)((g >= 1 && g < n_hidden) ? nm[3 * g + 1] : nm[3 * g]); };
     bin[0] = b_in0;
     double Bh = norm_of(0) * b_in0 + bmax[0];
+    if (fold_nm) Bh = std::max(Bh, (double)fold_nm[0] + fold_bmax);
     for (int g = 1; g + 1 < n_hidden; g += 2) {  // residual blocks: GEMMs (g, g + 1)
         bin[g] = Bh;
         const double Bt = norm_of(g) * Bh + bmax[g];
@@ -509,18 +521,30 @@ void plan_scales(int n_hidden, const std::vector<float>& nm, const std::vector<f
     }
     int P = 1 << 20;
     for (int g = 0; g < n_hidden; g += 2) P = std::min(P, pa[g] + pw[g]);
+    int pwf = 0;
+    if (fold_nm) {
+        pwf = clampi(13 - ceil_log2(fold_nm[2]), -40, 40);
+        P = std::min(P, 14 + pwf);
+    }
     for (int g = 0; g < n_hidden; g += 2) {
         int d = pa[g] + pw[g] - P;
         const int dw = std::min(d, 8);  // the weight scale has ~10 binades of slack before w_lo goes subnormal
         pw[g] -= dw;
         pa[g] -= d - dw;
     }
+    if (fold_nm && pw_fold) *pw_fold = (14 + pwf - P <= 12) ? P - 14 : -1000;
 }
 
 // (re)pack the weights/biases of a fused block from the live parameters
-int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
+// Ufold: the LU layer in front of this block in the density direction (fused pair), or null.  When given (and the
+// scale plan allows it) the first conditioner GEMM of the PAIR is packed as G = W0 E_lu[in_idx, :] so that it reads z
+// itself: hidden GEMM 0 no longer waits for the LU stage and its epilogue (fused_rqs_kernel, `folded`).
+int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr) {
     FusedPack& F = L.fused;
     if (!F.ok) return NFB_OK;
+    F.fold_ok = false;
+    static const bool no_fold = getenv("NFB_NO_FOLD") != nullptr;
+    if (no_fold || !F.pair_ok) Ufold = nullptr;
     const NetDesc& n = L.net;
     size_t emax = 0;
     for (auto& g : F.gemms) emax = std::max(emax, (size_t)g.n_pad * g.k_pad);
@@ -528,7 +552,7 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     const int ng = (int)F.gemms.size();
     NFB_CHECK(ng == F.n_hidden + 1 && ng <= 9, NFB_ERR_STATE, "fused pack: unexpected GEMM count %d", ng);
     // pass 1: norms of every effective matrix (for the fp16 scale plan)
-    NFB_TRY(f->norms.reserve((size_t)ng * 3 * sizeof(float)));
+    NFB_TRY(f->norms.reserve((size_t)(ng + 1) * 3 * sizeof(float)));
     for (int gi = 0; gi < ng; ++gi) {
         auto& g = F.gemms[gi];
         NFB_TRY(launch_build_effective(g.W, g.M, g.src_cols, g.src_row.as<int>(), g.src_col.as<int>(),
@@ -559,8 +583,36 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         for (int j = 0; j < H; ++j) bh[(size_t)(2 + 2 * b) * 256 + j] = cum[hp[j]];
     }
     F.bias_h = bh;
+    // LU fold: G = gain * E0 E_lu[in_idx, :], delta = E0 b_lu[in_idx] (fp64 accumulation), norms of G
+    std::vector<float> fold_nm;
+    float fold_bmax = 0.f;
+    if (Ufold) {
+        auto& g0 = F.gemms[0];
+        NFB_TRY(F.fold_lu.reserve(64 * 64 * 4));
+        NFB_TRY(F.fold_G.reserve((size_t)H * 64 * 4));
+        NFB_TRY(F.fold_delta.reserve((size_t)H * 4));
+        NFB_TRY(launch_build_effective(g0.W, g0.M, g0.src_cols, g0.src_row.as<int>(), g0.src_col.as<int>(), nullptr,
+                                       f->E.as<float>(), H, 64, 1.f, st));
+        NFB_TRY(launch_build_effective(Ufold->lu_Wd.as<float>(), nullptr, Ufold->D, F.lu_src_row.as<int>(),
+                                       F.lu_src_col.as<int>(), nullptr, F.fold_lu.as<float>(), 64, 64, 1.f, st));
+        NFB_TRY(launch_fold_lu(f->E.as<float>(), F.fold_lu.as<float>(), Ufold->lu.bias, F.in_idx_dev.as<int>(), H,
+                               Ufold->D, acc_gain(3 * 64 / 16), F.fold_G.as<float>(), F.fold_delta.as<float>(), st));
+        NFB_TRY(launch_matrix_norms(F.fold_G.as<float>(), H, 64, f->norms.as<float>() + 3 * ng, st));
+        NFB_CUDA(cudaStreamSynchronize(st));
+        NFB_TRY(download(f->norms.as<float>() + 3 * ng, 3, fold_nm));
+        NFB_TRY(download(F.fold_delta.as<float>(), (size_t)H, F.fold_delta_host));
+        for (int j = 0; j < H; ++j) fold_bmax = std::max(fold_bmax, std::fabs(bh[j] + F.fold_delta_host[j]));
+    }
     // pass 2: scale plan, then the fp16 records
-    plan_scales(F.n_hidden, nm, bmax, F.b_in0, F.pa, F.pw);
+    plan_scales(F.n_hidden, nm, bmax, F.b_in0, F.pa, F.pw, Ufold ? fold_nm.data() : nullptr, fold_bmax, &F.pw_fold);
+    if (getenv("NFB_DEBUG_PACK"))
+        fprintf(stderr, "[nfb pack] fold: U=%p pair_ok=%d pw_fold=%d pa0=%d pw0=%d\n", (void*)Ufold, (int)F.pair_ok, F.pw_fold, F.pa[0], F.pw[0]);
+    if (Ufold && F.pw_fold > -100) {
+        NFB_TRY(F.fold_recs.reserve((size_t)H * 256));
+        NFB_TRY(launch_pack_record(F.fold_G.as<float>(), 64, 0, H, 0, pow2f(F.pw_fold), F.fold_recs.as<uint8_t>(),
+                                   F.fold_recs.as<uint8_t>() + (size_t)H * 128, st));
+        F.fold_ok = true;
+    }
     for (int gi = 0; gi < ng; ++gi) {
         auto& g = F.gemms[gi];
         NFB_TRY(launch_build_effective(g.W, g.M, g.src_cols, g.src_row.as<int>(), g.src_col.as<int>(),
@@ -672,10 +724,16 @@ int build_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
         steps.push_back(s);
     };
     mk(0, 4, 0xFF, 1, 1, 0);     // W_hi x {A_hi, A_lo}
-    mk(0, 4, 0xFF, 0, 0, 1);     // W_lo x {A_hi, A_lo}   (4 terms: the map transforms z itself, ~2^-22)
+    mk(0, 4, 0xFF, 0, 0, 7);     // W_lo x {A_hi, A_lo}   (4 terms: the map transforms z itself, ~2^-22); signals lu_full
     steps.insert(steps.end(), F.steps_host.begin(), F.steps_host.end());
     F.pair_steps = (int)steps.size();
     NFB_TRY(F.pair_steps_dev.upload(steps));
+    {   // folded variant: GEMM 0 of the block reads the LU stage's A operand (already waited for by the LU records)
+        std::vector<FusedStep> sf = steps;
+        sf[2].ctl = (uint16_t)(sf[2].ctl & ~(7u << 10));
+        NFB_TRY(F.pair_steps_fold_dev.upload(sf));
+        NFB_TRY(F.in_idx_dev.upload(F.in_idx));
+    }
     NFB_TRY(F.pair_wstream.reserve(2 * 8192 + F.rqs_bytes));
     std::vector<int> sr(64), sc(64, -1);
     for (int i = 0; i < 64; ++i) sr[i] = i < U.D ? i : -1;
@@ -710,6 +768,16 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     Lp.n_steps = F.pair_steps;
     Lp.wstream = F.pair_wstream.as<uint8_t>();
     Lp.steps = F.pair_steps_dev.as<FusedStep>();
+    if (F.fold_ok) {
+        // the block's first two records (GEMM 0, K-chunk 0, all H rows) are replaced by the folded matrix
+        NFB_CUDA(cudaMemcpyAsync(F.pair_wstream.as<uint8_t>() + 2 * 8192, F.fold_recs.p, (size_t)F.H * 256,
+                                 cudaMemcpyDeviceToDevice, st));
+        NFB_CUDA(cudaStreamSynchronize(st));
+        Lp.fold_lu = 1;
+        Lp.steps = F.pair_steps_fold_dev.as<FusedStep>();
+        for (int ph = 0; ph < F.n_hidden; ph += 2)   // b0 (+ W0 b_lu) is part of every pre-summed residual bias
+            for (int j = 0; j < F.H; ++j) Lp.bias_h[ph * 256 + j] += F.fold_delta_host[j];
+    }
     Lp.bias_lu = F.bias_lu.as<float>();
     Lp.lu_logdet = U.lu_logdet.as<float>();
     NFB_TRY(F.pair_dev.reserve(sizeof(FusedLayer)));
@@ -735,7 +803,7 @@ int build_fwd_unit(nfb_flow* f, Layer& R, Layer* U) {
         steps.push_back(s);
     };
     mk(0, 4, 0xFF, 1, 1, 0);     // same 4-term schedule as the density pair (build_pair)
-    mk(0, 4, 0xFF, 0, 0, 1);
+    mk(0, 4, 0xFF, 0, 0, 7);
     steps.insert(steps.end(), F.steps_host.begin(), F.steps_host.end());
     NFB_TRY(F.fwd_steps_dev.upload(steps));
     NFB_TRY(F.fwd_wstream.reserve(2 * 8192 + F.rqs_bytes));
@@ -1291,7 +1359,10 @@ int nfb_flow_repack(nfb_flow_t* f, void* stream) {
                 }
                 NFB_TRY(L.uncond.upload(tab));
             }
-            NFB_TRY(repack_fused(f, L, st));
+            Layer* Ufold = nullptr;
+            for (auto& g : f->groups)
+                if (g.kind == G_FUSED_PAIR && f->layers[g.first].get() == &L) Ufold = f->layers[g.last].get();
+            NFB_TRY(repack_fused(f, L, st, Ufold));
         }
     }
     for (auto& g : f->groups)

@@ -9,25 +9,30 @@
 // z is read once and written once per block; the [B, T*(3K-1)] parameter tensor the reference
 // materialises never exists.
 //
-// Tensor-core numerics: every GEMM runs as split-bf16 on tcgen05 (fp32 accumulate in TMEM):
-//   a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo     (conditioner layers; ~2^-17 relative per product)
-//   6-term 3-way split for the LU linear map that transforms z itself (~2^-24).
+// Tensor-core numerics: every GEMM runs as a split-fp16 product on tcgen05 (fp32 accumulate in TMEM), operands
+// scaled by powers of two (nfb_api.cu plan_scales):
+//   a*w ~= a_hi*w_hi + a_lo*w_hi + a_hi*w_lo     (conditioner layers; ~2^-22 relative per product)
+//   all four terms for the LU linear map that transforms z itself.
 // Plain bf16/tf32 fail the rtol 1e-4 log_prob bar; this is why.
 //
 // Structure (576 threads, 1 CTA/SM, persistent over (layer, tile) work units of the whole stack):
-//   warp 16  weight producer: 1-D bulk TMA (cp.async.bulk -> UBLKCP) of pre-swizzled bf16 records
+//   warp 16  weight producer: 1-D bulk TMA (cp.async.bulk -> UBLKCP) of pre-swizzled fp16 records
 //            from the packed weight stream (L2 resident) into a 2 x 32 KB ring.
 //   warp 17  MMA issuer: walks the same step table, one elected lane issues tcgen05.mma
 //            (M=128, N<=256, K=16) and commits to mbarriers; owns the 512-column TMEM alloc.
 //   warps 0-15 epilogue (4 per SM sub-partition = 4 column groups x 4 TMEM lane quadrants):
-//            TMEM -> registers (tcgen05.ld 32x32b), bias/ReLU, bf16 hi/lo split back into the
-//            swizzled A-operand tiles; the final layer arrives in 240-column chunks (10 features
+//            TMEM -> registers (tcgen05.ld 32x32b, software-pipelined one K-chunk ahead), bias/ReLU, fp16 hi/lo split
+//            back into the swizzled A-operand tiles; the final layer arrives in 240-column chunks (10 features
 //            x 24) through a 2-deep TMEM ring and is consumed by the spline evaluator while the
 //            tensor core produces the next chunk.
 // The residual stream h lives in TMEM columns [0,256) and is updated by accumulating the second
 // GEMM of each residual block straight onto it (h += W2 relu(...)); biases are pre-summed on the
 // host side of the packer.  Shared memory: A operand 128 KB (hi|lo x K=256), weight ring 64 KB,
 // x/y tile 32 KB (XOR-swizzled, conflict-free column access).
+// Round 2b measured three alternatives to this ring (byte-granular ring, hi|lo "mixed" records, a third slot with the
+// x tile parked in L2) -- all slower; the GEMM phases sit at the shared-memory bound of SS-mode operands
+// (profiles/r02b_ring_experiments.md).  Kept from that work: the pipelined TMEM loads of the hidden epilogues, the
+// LU fold (first conditioner GEMM issued together with the LU stage), the early log_q fetch, row maxima by shuffle.
 #include "nfb_kernels.h"
 #include "nfb_spline.cuh"
 
@@ -38,31 +43,26 @@ constexpr int kEpiWarps = 4 * kNG;             // 16 epilogue warps: 4 per SM su
 constexpr int kEpiThreads = 32 * kEpiWarps;    // 512
 constexpr int kFusedThreads = kEpiThreads + 64;  // + TMA producer warp + MMA issuer warp
 constexpr int kGC = 64 / kNG;                  // columns of a 64-column K-chunk handled per thread (16)
-constexpr uint32_t kTileA = 16384;    // one [128 x 64] bf16 SW128 tile
-constexpr uint32_t kSlotBytes = 32768;  // one record = up to [256 rows x 64 K] bf16
-#ifndef NFB_SLOTS
-#define NFB_SLOTS 2
-#endif
-constexpr int kSlots = NFB_SLOTS;  // (3 = timing experiment only: the third slot overlays the x tile)
+constexpr uint32_t kTileA = 16384;             // one [128 x 64] fp16 SW128 tile
+constexpr uint32_t kSlotBytes = 32768;         // one record = up to [256 rows x 64 K] fp16
+constexpr uint32_t kSlots = 2;                 // (a third slot was measured: no gain, profiles/r02b_ring_experiments.md)
 constexpr uint32_t kOffA = 0;
 constexpr uint32_t kOffW = 131072;
-constexpr uint32_t kOffX = kOffW + 2 * kSlotBytes;  // 196608
-constexpr uint32_t kOffSteps = kOffX + 32768;            // 229376
-constexpr uint32_t kMaxSteps = 256;
-constexpr uint32_t kOffBars = kOffSteps + kMaxSteps * 8;  // 231424
-constexpr uint32_t kNumBars = 24;
+constexpr uint32_t kOffX = kOffW + kSlots * kSlotBytes;  // 196608: x/y tile
+constexpr uint32_t kOffMisc = kOffX + 32768;             // 229376: log-det partials [kNG-1][128], row maxima [128]
+constexpr uint32_t kOffRowMax = kOffMisc + (kNG - 1) * 128 * 4;
+constexpr uint32_t kOffBars = kOffMisc + 2048;           // 231424
+constexpr uint32_t kNumBars = 18;
 constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;  // 231568
-constexpr uint32_t kOffLd = kOffSteps;                     // log-det partials [kNG-1][128] (the old step-table area)
 constexpr uint32_t kFusedSmem = kOffTmemPtr + 16;          // 231584 <= 232448
 static_assert(kFusedSmem <= 232448, "shared memory budget");
 
 // barrier indices
-constexpr int kBarWFull = 0, kBarWEmpty = 4, kBarAReady = 8 /* +kc, 4 barriers */, kBarAccFull = 12,
-              kBarCFull = 13, kBarCEmpty = 17;
+constexpr int kBarWFull = 0 /* +slot */, kBarWEmpty = 3 /* +slot */, kBarAReady = 6 /* +kc, 4 */, kBarAccFull = 10,
+              kBarCFull = 11 /* +b, 2 */, kBarCEmpty = 13 /* +b, 2 */, kBarLuFull = 15;
 // TMEM column of final-layer chunk buffer i
 // (both accumulator regions are dead once the last hidden epilogue has run: one buffer in each)
 __device__ __forceinline__ uint32_t chunk_col(int i) { return (uint32_t)i * 256u; }
-constexpr uint32_t kTmemAHi = 256;  // TS-mode A operand base (kept for experiments; unused by the table)
 
 __device__ __forceinline__ uint32_t xs_index(int r, int c) { return r * 64 + (c ^ (r & 31)); }
 
@@ -76,9 +76,17 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d)
                  : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() {  // the 256 epilogue threads only
+__device__ __forceinline__ void epi_bar_sync() {  // the 512 epilogue threads only
     asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
 }
+// tcgen05.wait::ld that also names the 16 destination registers of the load it completes, so that the compiler
+// cannot schedule arithmetic on them above the wait (the load's asm statement "returns" before the data has landed)
+#define NFB_TMEM_WAIT16(v)                                                                                     \
+    asm volatile("tcgen05.wait::ld.sync.aligned;"                                                              \
+                 : "+r"((v)[0]), "+r"((v)[1]), "+r"((v)[2]), "+r"((v)[3]), "+r"((v)[4]), "+r"((v)[5]),         \
+                   "+r"((v)[6]), "+r"((v)[7]), "+r"((v)[8]), "+r"((v)[9]), "+r"((v)[10]), "+r"((v)[11]),       \
+                   "+r"((v)[12]), "+r"((v)[13]), "+r"((v)[14]), "+r"((v)[15])                                  \
+                 :: "memory")
 
 // split 8 consecutive fp32 values (already in the GEMM's scaled units) into fp16 hi / lo chunks and store them at
 // the same chunk offset of the two A tiles.  hi + lo reproduces the value to ~2^-23 relative (11 + 11 bits + sign).
@@ -102,68 +110,51 @@ __device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t
 //   still "LU map, then spline block" -- the packer hands it the INVERSE LU map of the previous layer -- but the
 //   unconditional spline runs first and in its inverse branch, the conditioner sees its result, and the
 //   conditional spline is inverted (Coupling.inverse, neural_spline/coupling.py:100-128).
-// PAIR = true: launched as clusters of 2 CTAs.  A unit is (layer, PAIR of adjacent tiles): CTA r of the cluster owns tile
-//   2 tp + r (its own A tiles, x tile, TMEM accumulators and epilogue), streams bytes [r/2, (r+1)/2) of every weight
-//   record (rows [r N/2, (r+1) N/2) of the [N x 64] tile) into a 4 x 16 KB ring, and the LEADER's (rank 0) MMA warp issues
-//   tcgen05.mma.cta_group::2 (M = 256: rows 0..127 from CTA 0, 128..255 from CTA 1; each SM's tensor core reads both B
-//   halves) once both CTAs' operands are in.  Per SM this halves the weight bytes pulled from L2 and the B bytes the MMA
-//   reads from shared memory -- the two limits of the single-CTA schedule (profiles/r01c_fused_stack_ncu_summary.md).
-//   Synchronisation across the pair: epilogue warps of BOTH CTAs arrive (cluster scope) on the leader's a_ready /
-//   chunk_empty barriers; the peer's otherwise idle MMA warp relays "my half of the record has landed" to the leader's
-//   w_full barrier; tcgen05.commit multicasts slot-free / accumulator-ready to the barriers of both CTAs.
-template <bool SAMPLE, bool PAIR>
+// (The CTA-pair / cta_group::2 schedule of round 2a was measured 2-3 % slower and removed: profiles/r02_pair_vs_single.md;
+//  so were "mixed" hi|lo weight records and a byte-granular ring: profiles/r02b_ring_experiments.md.)
+template <bool SAMPLE>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* xs = reinterpret_cast<float*>(smem + kOffX);
     const uint32_t bars = sbase + kOffBars;
-    float* ldsum = reinterpret_cast<float*>(smem + kOffLd);
+    float* ldsum = reinterpret_cast<float*>(smem + kOffMisc);
+    float* rowmax = reinterpret_cast<float*>(smem + kOffRowMax);
     auto bar = [bars](int i) { return bars + 8u * i; };
 
     if ((sbase & 1023u) != 0) {
         if (threadIdx.x == 0 && p.err) atomicExch(p.err, 900);
         return;
     }
-    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
-    constexpr uint32_t kEpiArrivals = PAIR ? 2 * kEpiWarps : kEpiWarps;  // a_ready / chunk_empty count both CTAs' warps
     if (threadIdx.x == 0) {
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(bar(kBarWFull + i), (PAIR && rank == 0) ? 2 : 1);  // leader: own expect_tx + the peer's relay
+        for (int i = 0; i < (int)kSlots; ++i) {
+            mbar_init(bar(kBarWFull + i), 1);
             mbar_init(bar(kBarWEmpty + i), 1);
-            mbar_init(bar(kBarCFull + i), 1);
-            mbar_init(bar(kBarCEmpty + i), kEpiArrivals);
         }
-        for (int i = 0; i < 4; ++i) mbar_init(bar(kBarAReady + i), kEpiArrivals);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(bar(kBarCFull + i), 1);
+            mbar_init(bar(kBarCEmpty + i), kEpiWarps);
+        }
+        for (int i = 0; i < 4; ++i) mbar_init(bar(kBarAReady + i), kEpiWarps);
         mbar_init(bar(kBarAccFull), 1);
+        mbar_init(bar(kBarLuFull), 1);
         fence_mbar_init();
     }
-    if (PAIR) {
-        __syncthreads();
-        cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
-    }
     if (warp == kEpiWarps + 1) {
-        if (PAIR) { tmem_alloc2(sbase + kOffTmemPtr, 512); tmem_relinquish2(); }
-        else { tmem_alloc(sbase + kOffTmemPtr, 512); tmem_relinquish(); }
+        tmem_alloc(sbase + kOffTmemPtr, 512);
+        tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
-    if (PAIR) cluster_sync_all();
 
     const long long n_tiles = (p.rows + 127) / 128;
-    // work units, layer-major: (layer, tile) -- or (layer, pair of tiles) for CTA pairs; `tstride` tiles per unit
-    constexpr int tstride = PAIR ? 2 : 1;
-    const long long n_tu = (n_tiles + tstride - 1) / tstride;   // tile units per layer
-    const long long n_units = n_tu * p.n_layers;
-    const long long u_first = PAIR ? (long long)cluster_id_x() : (long long)blockIdx.x;
-    const long long u_step = PAIR ? (long long)cluster_nctaid_x() : (long long)gridDim.x;
-    // cluster-scope arrive on the LEADER's barrier (rank 0 maps onto itself)
-    auto arrive_leader = [&](uint32_t local_bar) {
-        if (PAIR) mbar_arrive_cluster(mapa_rank(local_bar, 0));
-        else mbar_arrive(local_bar);
-    };
+    // work units, layer-major: (layer, tile)
+    const long long n_units = n_tiles * p.n_layers;
+    const long long u_first = (long long)blockIdx.x;
+    const long long u_step = (long long)gridDim.x;
 
     // Warp roles: the SM arbiter favours high warp ids, so the two latency-critical single-lane roles
     // (TMA producer, MMA issuer) sit above the epilogue warps (0..kEpiWarps-1).
@@ -171,10 +162,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         // ------------------------------ weight producer -----------------------------------
         // whole warp walks the table (warp-uniform control flow); one elected lane issues the copy
         uint32_t slot = 0, par = 0;
-        constexpr uint32_t kRingSlots = PAIR ? 4 : kSlots;
-        constexpr uint32_t kRingBytes = PAIR ? kSlotBytes / 2 : kSlotBytes;
         for (long long u = u_first; u < n_units; u += u_step) {
-            const FusedLayer& L = p.layers[u / n_tu];
+            const FusedLayer& L = p.layers[u / n_tiles];
             const FusedStep* steps = L.steps;  // global (L2-resident); the producer only needs the size
             const int n_steps = L.n_steps;
             // autoregressive sampling (SAMPLE, ar_passes = D): the LU records are streamed once, the block's D times
@@ -192,16 +181,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 const uint32_t nbytes = i + 1 < total ? (uint32_t)__ldg(&steps[sn].bytes16) << 4 : 0u;
                 mbar_wait(bar(kBarWEmpty + slot), par ^ 1, p.err, 100 + slot);
                 if (elect_one_sync()) {
-                    const uint32_t nb = PAIR ? bytes >> 1 : bytes;   // this CTA's half: rows [rank N/2, (rank+1) N/2)
-                    mbar_expect_tx(bar(kBarWFull + slot), nb);
-                    bulk_g2s(sbase + kOffW + slot * kRingBytes, L.wstream + off + (PAIR ? rank * nb : 0u), nb,
-                             bar(kBarWFull + slot));
+                    mbar_expect_tx(bar(kBarWFull + slot), bytes);
+                    bulk_g2s(sbase + kOffW + slot * kSlotBytes, L.wstream + off, bytes, bar(kBarWFull + slot));
                 }
                 __syncwarp();
                 s = sn;
                 off = offn;
                 bytes = nbytes;
-                if (++slot == kRingSlots) { slot = 0; par ^= 1; }
+                if (++slot == kSlots) { slot = 0; par ^= 1; }
             }
         }
     } else if (warp == kEpiWarps + 1) {
@@ -211,11 +198,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         uint32_t slot = 0, wpar = 0, apar = 0, cebits = 0;
         const uint64_t adesc0 = umma_desc_sw128(sbase + kOffA);
         const uint64_t bdesc0 = umma_desc_sw128(sbase + kOffW);
-        constexpr uint32_t kIdesc0 = umma_idesc_f16(PAIR ? 256 : 128, 0);
-        constexpr uint32_t kRingSlots = PAIR ? 4 : kSlots;
-        constexpr uint32_t kRingBytes = PAIR ? kSlotBytes / 2 : kSlotBytes;
+        constexpr uint32_t kIdesc0 = umma_idesc_f16(128, 0);
         for (long long u = u_first; u < n_units; u += u_step) {
-            const FusedLayer& L = p.layers[u / n_tu];
+            const FusedLayer& L = p.layers[u / n_tiles];
             const uint2* steps = reinterpret_cast<const uint2*>(L.steps);  // 8-byte entries, L2-resident
             const int n_steps = L.n_steps;
             const int lu_steps = L.has_lu ? 2 : 0;
@@ -227,15 +212,6 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             for (int s = 0; s < total; ++s) {
                 sidx = sidx + 1 == n_steps ? lu_steps : sidx + 1;
                 nx.raw = __ldg(steps + sidx);  // prefetch one entry ahead (wraps to the block's first step)
-                if (PAIR && rank != 0) {
-                    // peer CTA: relay "my half of this record has landed" to the leader's w_full barrier
-                    mbar_wait(bar(kBarWFull + slot), wpar, p.err, 230 + slot);
-                    if (elect_one_sync()) mbar_arrive_cluster(mapa_rank(bar(kBarWFull + slot), 0));
-                    __syncwarp();
-                    if (++slot == kRingSlots) { slot = 0; wpar ^= 1; }
-                    cur.raw = nx.raw;
-                    continue;
-                }
                 const FusedStep st = cur.s;
                 const uint32_t ctl = st.ctl;
                 if (p.prof && u == 0 && s < 380 && lane == 0) p.prof[512 + s] = clock64();  // debug: step reached
@@ -257,49 +233,28 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 if (elect_one_sync()) {
                     const uint32_t d = tmem + (ctl & 511u);
                     const uint32_t idesc = kIdesc0 | ((uint32_t)st.n8 << 17);
-                    const uint64_t bd = bdesc0 + (uint64_t)(slot * (kRingBytes >> 4));
+                    const uint64_t bd = bdesc0 + (uint64_t)(slot * (kSlotBytes >> 4));
                     uint32_t accum = ((ctl >> 9) & 1u) ^ 1u;
-                    // A code: 0..7 = shared-memory tile; 0x80|t = tensor memory (final layer), t = split*4+kc
+                    // A tile t < 4: hi part of K-chunk t; 4 + t: lo part.  Four K=16 slabs per tile.
                     auto issue4 = [&](uint32_t code) {
-                        if (code & 0x80u) {
-                            const uint32_t at = tmem + kTmemAHi + (code & 7u) * 32u;
-                            umma_bf16_ts(d, at, bd, idesc, accum);
-                            umma_bf16_ts(d, at + 8, bd + 2, idesc, 1u);
-                            umma_bf16_ts(d, at + 16, bd + 4, idesc, 1u);
-                            umma_bf16_ts(d, at + 24, bd + 6, idesc, 1u);
-                        } else {
-                            const uint64_t ad = adesc0 + (uint64_t)(code * (kTileA >> 4));
-                            if (PAIR) {
-                                umma2_f16(d, ad, bd, idesc, accum);
-                                umma2_f16(d, ad + 2, bd + 2, idesc, 1u);
-                                umma2_f16(d, ad + 4, bd + 4, idesc, 1u);
-                                umma2_f16(d, ad + 6, bd + 6, idesc, 1u);
-                            } else {
-                                umma_bf16(d, ad, bd, idesc, accum);
-                                umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-                                umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-                                umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
-                            }
-                        }
+                        const uint64_t ad = adesc0 + (uint64_t)(code * (kTileA >> 4));
+                        umma_bf16(d, ad, bd, idesc, accum);
+                        umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
+                        umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
+                        umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
                         accum = 1u;
                     };
                     issue4(st.a0);
                     if (st.a1 != 0xFF) issue4(st.a1);
-                    if (st.a2 != 0xFF) issue4(st.a2);
                     if (p.prof && u == 0 && s < 380) p.prof[1280 + s] = clock64();  // debug: MMAs of this record issued
-                    if (PAIR) {
-                        umma2_commit_mc(bar(kBarWEmpty + slot));
-                        if (scode == 1) umma2_commit_mc(bar(kBarAccFull));
-                        else if (scode >= 2) umma2_commit_mc(bar(kBarCFull + (scode - 2)));
-                    } else {
-                        umma_commit(bar(kBarWEmpty + slot));
-                        if (scode == 1) umma_commit(bar(kBarAccFull));
-                        else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
-                    }
+                    umma_commit(bar(kBarWEmpty + slot));
+                    if (scode == 1) umma_commit(bar(kBarAccFull));
+                    else if (scode == 7) umma_commit(bar(kBarLuFull));
+                    else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
                     if (p.prof && u == 0 && s < 380) p.prof[1664 + s] = clock64();  // debug: commits issued
                 }
                 __syncwarp();
-                if (++slot == kRingSlots) { slot = 0; wpar ^= 1; }
+                if (++slot == kSlots) { slot = 0; wpar ^= 1; }
                 cur.raw = nx.raw;
             }
         }
@@ -311,7 +266,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const int r = q * 32 + lane;           // tile row owned by this thread
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t aA = sbase + kOffA;
-        uint32_t afpar = 0, cfbits = 0;
+        uint32_t afpar = 0, lupar = 0, cfbits = 0;
         // epilogue-side waits: every thread polls (default; measured 3-4 % faster than one polling lane per warp)
         auto ewait = [&](uint32_t b, uint32_t parity, int tag) {
             if (p.poll_all) mbar_wait(b, parity, p.err, tag);
@@ -322,9 +277,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 #define NFB_STAMP() do { if (prof && pi < 126) prof[pi++] = clock64(); } while (0)
 
         for (long long u = u_first; u < n_units; u += u_step) {
-            const int layer = (int)(u / n_tu);
-            const long long tile = (u - (long long)layer * n_tu) * tstride + rank;  // (may be one past the end: phantom)
-            const bool tile_live = tile < n_tiles;
+            const int layer = (int)(u / n_tiles);
+            const long long tile = u - (long long)layer * n_tiles;
             const FusedLayer& L = p.layers[layer];
             const int D = L.D, H = L.H;
             // layers >= 1 update z in place (z_stride = 0) or, for the training pass, every layer writes its own
@@ -332,31 +286,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             float* zdst = p.zout + (long long)layer * p.z_stride;
             const float* zsrc = layer == 0 ? p.zin : p.zout + (long long)(layer - 1) * p.z_stride;
             const long long row0 = tile * 128;
+            const long long grow = row0 + r;          // this thread's global row
+            const bool row_live = grow < p.rows;
             if (u != u_first) prof = nullptr;
             float ru = 1.f, ruinv = 1.f;  // this row's power-of-two unit (set after the tile load)
-            auto build_a = [&](bool lu_stage) {
-                // A[:, k] for k in [wh*kGC, (wh+1)*kGC): fp16 hi/lo split of xs[:, k] (LU stage, k < D) or of the
-                // conditioner input xs[:, in_idx[k]], in units of u * a_sc
-                const float sc = ru * (lu_stage ? L.a_sc[0] : L.a_sc[1]);
-    #pragma unroll
-                for (int g = 0; g < kGC / 8; ++g) {
-                    float v[8];
-    #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int k = wh * kGC + g * 8 + j;
-                        int c = lu_stage ? (k < D ? k : -1) : L.in_idx[k];
-                        v[j] = c >= 0 ? xs[xs_index(r, c)] * sc : 0.f;
-                    }
-                    split_store8(v, aA, aA + 4 * kTileA, a_chunk_off(r, wh * (kGC / 8) + g));
-                }
-                fence_proxy_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) arrive_leader(bar(kBarAReady + 0));
-            };
 
             // ---- layer-to-layer dependency: this tile's rows must have left layer-1 (any CTA) ----
-            if (layer > 0 && tile_live) {
+            if (layer > 0) {
                 if (lane == 0) {  // one lane per warp spins (keeps the warp converged for the .aligned ops below)
                     const int* flag = p.progress + tile;
                     int seen;
@@ -377,7 +313,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
             }
             // ---- host batch still in flight (nfb_api.cu start_h2d): layer-0 tiles wait for their rows ----
-            if (layer == 0 && p.in_ready && tile_live) {
+            if (layer == 0 && p.in_ready) {
                 const int need = (int)min(row0 + 128, p.rows);
                 if (lane == 0) {
                     int seen;
@@ -398,6 +334,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 }
             }
             NFB_STAMP();  // [0] tile start
+            // this row's running log_q (only this tile's units touch it): fetched now, used at the end of the unit
+            float lq_old = 0.f;
+            if (wh == 0 && row_live && (layer > 0 || p.accumulate)) lq_old = __ldcg(p.logq + grow);
             // ---- load z tile -> xs (coalesced global, swizzled shared) ----
             if (D == 64) {
                 float4 v[2048 / kEpiThreads];
@@ -415,6 +354,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     xs[xs_index(rr, c0 + 1)] = v[k].y;
                     xs[xs_index(rr, c0 + 2)] = v[k].z;
                     xs[xs_index(rr, c0 + 3)] = v[k].w;
+                    // max |z| of row rr: its 64 values sit in the 16 consecutive lanes of this half-warp
+                    float m = fmaxf(fmaxf(fabsf(v[k].x), fabsf(v[k].y)), fmaxf(fabsf(v[k].z), fabsf(v[k].w)));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+                    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                    if ((et & 15) == 0) rowmax[rr] = m;
                 }
             } else {
                 for (int i = et; i < 128 * D; i += kEpiThreads) {
@@ -428,35 +374,69 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 // row, so every fp16 operand of this unit stays inside the static bounds the packer derived
                 // (nfb_api.cu plan_scales) whatever the magnitude of the data; u = 1 for ordinary rows (|x| < 1 .. 2).
                 float zmax = 0.f;
-#pragma unroll 8
-                for (int c = 0; c < D; ++c) zmax = fmaxf(zmax, fabsf(xs[xs_index(r, c)]));
+                if (D == 64) zmax = rowmax[r];
+                else
+                    for (int c = 0; c < D; ++c) zmax = fmaxf(zmax, fabsf(xs[xs_index(r, c)]));
                 int e = (int)((__float_as_uint(zmax) >> 23) & 0xffu) - 126;
                 e = max(0, min(40, e));
                 ru = pow2i(-e);
                 ruinv = pow2i(e);
             }
             NFB_STAMP();  // [1] load done
+            auto get_x = [&](int c) -> float { return xs[xs_index(r, c)]; };
+            auto put_y = [&](int c, float y) { xs[xs_index(r, c)] = y; };
+            // A[:, k] for k in [wh*kGC, (wh+1)*kGC): fp16 hi/lo split of v[k], in units of u * a_sc
+            auto store_a = [&](const float* v) {
+    #pragma unroll
+                for (int g = 0; g < kGC / 8; ++g) split_store8(v + 8 * g, aA, aA + 4 * kTileA, a_chunk_off(r, wh * (kGC / 8) + g));
+                fence_proxy_async_smem();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar(kBarAReady + 0));
+            };
+            // conditioner input: column in_idx[k] of the (LU-transformed) row
+            auto build_a_net = [&]() {
+                const float sc = ru * L.a_sc[1];
+                float v[kGC];
+    #pragma unroll
+                for (int j = 0; j < kGC; ++j) {
+                    const int c = L.in_idx[wh * kGC + j];
+                    v[j] = c >= 0 ? get_x(c) * sc : 0.f;
+                }
+                store_a(v);
+            };
             float ladsum = 0.f;
+            // fold_lu (density direction): the packer multiplied the first conditioner matrix into the LU map, so the
+            // first hidden GEMM reads the SAME A operand as the LU stage (the split of z) and both are in flight at once;
+            // the LU result is only needed as spline input and is collected while hidden GEMM 0 runs.
+            const bool folded = !SAMPLE && L.has_lu && L.fold_lu;
             if (L.has_lu) {
-                build_a(true);
+                {
+                    const float sc = ru * L.a_sc[0];
+                    float v[kGC];
+    #pragma unroll
+                    for (int j = 0; j < kGC; ++j) v[j] = wh * kGC + j < D ? xs[xs_index(r, wh * kGC + j)] * sc : 0.f;
+                    store_a(v);
+                }
                 NFB_STAMP();  // build_a(lu) done
-                ewait(bar(kBarAccFull), afpar, 300);
+                ewait(bar(kBarLuFull), lupar, 300);
                 NFB_STAMP();  // LU gemm done
-                afpar ^= 1;
+                lupar ^= 1;
                 tc_fence_after();
                 // x' = acc + b  (64 columns at TMEM col 256; this thread: kGC of them)
                 uint32_t acc[kGC];
                 NFB_TMEM_LD16(tlane + 256 + wh * kGC, acc);
-                tc_wait_ld();
-                epi_bar_sync();  // every thread has built A from the old xs before it is overwritten
+                NFB_TMEM_WAIT16(acc);
+                // (this thread built the LU stage's A from exactly these elements of xs: no other reader to wait for)
 #pragma unroll
                 for (int j = 0; j < kGC; ++j) {
                     const int c = wh * kGC + j;
                     if (c < D) xs[xs_index(r, c)] = fmaf(__uint_as_float(acc[j]), L.a_inv[0] * ruinv, __ldg(L.bias_lu + c));
                 }
-                epi_bar_sync();
+                tc_fence_before();  // (folded: hidden GEMM 1 overwrites columns 256.. once every warp has passed epilogue 0)
+                epi_bar_sync();     // x' of the whole row is visible to the CTA
             }
-            auto store_tile = [&]() {
+            auto store_tile = [&]() {  // xs -> global, coalesced
                 if (D == 64) {
 #pragma unroll
                     for (int k = 0; k < 2048 / kEpiThreads; ++k) {
@@ -509,8 +489,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     const float* tb = L.uncond + i * 23;
                     auto acc = [tb](int k) { return __ldg(tb + k); };
                     float y, l;
-                    rqs_eval<8, SAMPLE>(xs[xs_index(r, c)], acc, L.tail, 1.0f, y, l);
-                    xs[xs_index(r, c)] = y;
+                    rqs_eval<8, SAMPLE>(get_x(c), acc, L.tail, 1.0f, y, l);
+                    put_y(c, y);
                     ladsum += l;
                 }
             };
@@ -518,10 +498,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 uncond();
                 epi_bar_sync();  // build_a reads this row's columns written by the other column groups
             }
-            build_a(false);
-            NFB_STAMP();  // net input A built
+            if (!folded) {
+                build_a_net();
+                NFB_STAMP();  // net input A built
+            }
             if (!SAMPLE && L.n_id > 0) {
-                epi_bar_sync();  // every warp has read the raw identity columns of this row into A
+                if (!folded) epi_bar_sync();  // every warp has read the raw identity columns of this row into A
                 uncond();
             }
 
@@ -535,34 +517,40 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 const bool relu = ph + 1 < L.n_hidden;
                 const float inv = L.a_inv[1 + ph] * ruinv;   // accumulator -> true value
                 const float sc = L.a_sc[2 + ph] * ru;       // true value -> the next GEMM's A units
-                // K-chunk order: both column halves convert the same 64 columns, then release that slice of
-                // the next A operand so the next GEMM's kc-step can start while the rest is converted
-                for (int kc = 0; kc < (H >> 6); ++kc) {
-                    const int c0 = kc * 64 + wh * kGC;
-                    uint32_t acc[kGC];
-                    NFB_TMEM_LD16(tlane + region + c0, acc);
-                    const float4* bf = reinterpret_cast<const float4*>(L.bias_h + ph * 256 + c0);  // warp-uniform
-                    float bv[kGC];
+                // K-chunk order: all column groups convert the same 64 columns, then release that slice of
+                // the next A operand so the next GEMM's kc-step can start while the rest is converted.
+                // The TMEM load of chunk kc + 1 is in flight while chunk kc is converted.
+                const int nkc = H >> 6;
+                uint32_t acc[2][kGC];
+                NFB_TMEM_LD16(tlane + region + wh * kGC, acc[0]);
 #pragma unroll
-                    for (int j = 0; j < kGC / 4; ++j) {
-                        const float4 q = __ldg(bf + j);
-                        bv[4 * j] = q.x; bv[4 * j + 1] = q.y; bv[4 * j + 2] = q.z; bv[4 * j + 3] = q.w;
+                for (int kc = 0; kc < 4; ++kc) {
+                    if (kc < nkc) {
+                        const int c0 = kc * 64 + wh * kGC;
+                        const float4* bf = reinterpret_cast<const float4*>(L.bias_h + ph * 256 + c0);  // warp-uniform
+                        float bv[kGC];
+#pragma unroll
+                        for (int j = 0; j < kGC / 4; ++j) {
+                            const float4 q4 = __ldg(bf + j);
+                            bv[4 * j] = q4.x; bv[4 * j + 1] = q4.y; bv[4 * j + 2] = q4.z; bv[4 * j + 3] = q4.w;
+                        }
+                        NFB_TMEM_WAIT16(acc[kc & 1]);
+                        if (kc + 1 < nkc) NFB_TMEM_LD16(tlane + region + c0 + 64, acc[(kc + 1) & 1]);
+                        float v[kGC];
+#pragma unroll
+                        for (int j = 0; j < kGC; ++j) {
+                            float t = fmaf(__uint_as_float(acc[kc & 1][j]), inv, bv[j]);
+                            v[j] = (relu ? fmaxf(t, 0.f) : t) * sc;
+                        }
+                        const uint32_t thi = aA + kc * kTileA, tlo = aA + (4 + kc) * kTileA;
+#pragma unroll
+                        for (int j = 0; j < kGC / 8; ++j)
+                            split_store8(v + 8 * j, thi, tlo, a_chunk_off(r, wh * (kGC / 8) + j));
+                        fence_proxy_async_smem();
+                        if (kc + 1 >= nkc) tc_fence_before();  // (the last TMEM read of this phase is complete)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar(kBarAReady + kc));
                     }
-                    tc_wait_ld();
-                    float v[kGC];
-#pragma unroll
-                    for (int j = 0; j < kGC; ++j) {
-                        float t = fmaf(__uint_as_float(acc[j]), inv, bv[j]);
-                        v[j] = (relu ? fmaxf(t, 0.f) : t) * sc;
-                    }
-                    const uint32_t thi = aA + kc * kTileA, tlo = aA + (4 + kc) * kTileA;
-#pragma unroll
-                    for (int j = 0; j < kGC / 8; ++j)
-                        split_store8(v + 8 * j, thi, tlo, a_chunk_off(r, wh * (kGC / 8) + j));
-                    fence_proxy_async_smem();
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) arrive_leader(bar(kBarAReady + kc));
                 }
                 NFB_STAMP();  // hidden epilogue ph done
             }
@@ -579,15 +567,18 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 // (= the epilogue has finished reading columns 0..255) before slot 1 overwrites buffer 0.
                 const int b = (ci + 1) & 1;
                 const int c = L.chunk_order[ci];
+                // rotate the deal by the chunk index: with F = 10 the groups get 3,3,2,2 features of a chunk, and
+                // a fixed deal would give groups 0/1 half as much work again as groups 2/3 over the tile
+                const int f0 = (wh + ci) & (kNG - 1);
                 ewait(bar(kBarCFull + b), (cfbits >> b) & 1u, 400 + b);
                 cfbits ^= 1u << b;
                 tc_fence_after();
                 NFB_STAMP();  // chunk c available
                 const uint32_t ta = tlane + chunk_col(b);
-                // rotate the deal by the chunk index: with F = 10 the groups get 3,3,2,2 features of a chunk, and
-                // a fixed deal would give groups 0/1 half as much work again as groups 2/3 over the tile
-                const int f0 = (wh + ci) & (kNG - 1);
-                for (int f = f0; f < L.F; f += kNG) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int f = f0 + j * kNG;
+                    if (f < L.F) {
                     const int t = c * L.F + f;
                     uint32_t pr[24];
                     NFB_TMEM_LD16(ta + f * 24, pr);
@@ -595,56 +586,53 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     const float4* bp = reinterpret_cast<const float4*>(L.bias_f + t * 24);  // warp-uniform
                     float bv[24];
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
-                        const float4 q = __ldg(bp + j);
-                        bv[4 * j] = q.x; bv[4 * j + 1] = q.y; bv[4 * j + 2] = q.z; bv[4 * j + 3] = q.w;
+                    for (int jj = 0; jj < 6; ++jj) {
+                        const float4 q4 = __ldg(bp + jj);
+                        bv[4 * jj] = q4.x; bv[4 * jj + 1] = q4.y; bv[4 * jj + 2] = q4.z; bv[4 * jj + 3] = q4.w;
                     }
                     tc_wait_ld();
                     if (f + kNG >= L.F) {  // all of this thread's columns are in registers: free the buffer
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) arrive_leader(bar(kBarCEmpty + b));
+                        if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
                     }
                     if (t < L.T) {
                         // the packer folded log2(e) (and the layer's 1/sqrt(H)) into the w/h columns and biases
                         float lw[8], lh[8], dd[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            lw[j] = fmaf(__uint_as_float(pr[j]), inv_f, bv[j]);
-                            lh[j] = fmaf(__uint_as_float(pr[8 + j]), inv_f, bv[8 + j]);
-                            dd[j] = fmaf(__uint_as_float(pr[16 + j]), inv_f, bv[16 + j]);
+                        for (int jj = 0; jj < 8; ++jj) {
+                            lw[jj] = fmaf(__uint_as_float(pr[jj]), inv_f, bv[jj]);
+                            lh[jj] = fmaf(__uint_as_float(pr[8 + jj]), inv_f, bv[8 + jj]);
+                            dd[jj] = fmaf(__uint_as_float(pr[16 + jj]), inv_f, bv[16 + jj]);
                         }
                         const int col = L.tr_idx[t];
                         float y, l;
-                        float xin = xs[xs_index(r, col)];
-                        if (arsamp) xin = row0 + r < p.rows ? __ldcg(zdst + (row0 + r) * D + col) : 0.f;
+                        float xin = get_x(col);
+                        if (arsamp) xin = row_live ? __ldcg(zdst + grow * D + col) : 0.f;
                         rqs_core<8, SAMPLE>(xin, lw, lh, [&dd](int k) { return dd[k]; }, L.tail, y, l);
-                        xs[xs_index(r, col)] = y;
+                        put_y(col, y);
                         ladsum += l;
+                    }
                     }
                 }
                 if (f0 >= L.F) {  // (F < kNG: this group had no feature in the chunk) still release the buffer
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) arrive_leader(bar(kBarCEmpty + b));
+                    if (lane == 0) mbar_arrive(bar(kBarCEmpty + b));
                 }
                 NFB_STAMP();  // chunk c consumed
             }
 
             }  // passes
             NFB_STAMP();  // last spline done
-            // ---- log-det reduction across the two column halves, then store ----
+            // ---- log-det reduction across the column groups, then store ----
             if (wh > 0) ldsum[(wh - 1) * 128 + r] = ladsum;
             epi_bar_sync();
-            if (wh == 0) {
-                const long long gr = row0 + r;
-                if (gr < p.rows) {
-                    float tot = ladsum + (L.lu_logdet ? __ldg(L.lu_logdet) : 0.f);
+            if (wh == 0 && row_live) {
+                float tot = ladsum + (L.lu_logdet ? __ldg(L.lu_logdet) : 0.f);
 #pragma unroll
-                    for (int g = 0; g < kNG - 1; ++g) tot += ldsum[g * 128 + r];
-                    if (layer > 0 || p.accumulate) tot += __ldcg(p.logq + gr);
-                    __stcg(p.logq + gr, tot);
-                }
+                for (int g = 0; g < kNG - 1; ++g) tot += ldsum[g * 128 + r];
+                __stcg(p.logq + grow, tot + lq_old);
             }
             store_tile();
             // publish this tile: each thread makes ITS OWN global stores visible device-wide, then the barrier,
@@ -652,7 +640,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             // warps still have in flight to L2)
             if (p.progress) __threadfence();
             epi_bar_sync();
-            if (p.progress && et == 0 && tile_live) {
+            if (p.progress && et == 0) {
                 __threadfence();
                 asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.progress + tile), "r"(layer + 1) : "memory");
             }
@@ -662,20 +650,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();  // the peer may still signal our barriers / the leader's MMAs read our B half
-    if (warp == kEpiWarps + 1) {
-        if (PAIR) tmem_dealloc2(tmem, 512);
-        else tmem_dealloc(tmem, 512);
-    }
+    if (warp == kEpiWarps + 1) tmem_dealloc(tmem, 512);
 }
 
 int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st) {
     static PerDevice per_dev;  // the opt-in shared-memory size is a per-device function attribute
     const int dev_sms = per_dev.ensure([] {
         cudaError_t e = cudaSuccess;
-        const void* fns[4] = {(const void*)fused_rqs_kernel<false, false>, (const void*)fused_rqs_kernel<true, false>,
-                              (const void*)fused_rqs_kernel<false, true>, (const void*)fused_rqs_kernel<true, true>};
-        for (int i = 0; i < 4 && e == cudaSuccess; ++i)
+        const void* fns[2] = {(const void*)fused_rqs_kernel<false>, (const void*)fused_rqs_kernel<true>};
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i)
             e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
         return e;
     });
@@ -684,39 +667,11 @@ int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_
     NFB_CHECK(p.n_layers >= 1 && (p.n_layers == 1 || p.progress), NFB_ERR_ARG, "fused rqs: bad layer list");
     const long long n_tiles = (p.rows + 127) / 128;
     if (n_tiles == 0) return NFB_OK;
-    // CTA pairs (cta_group::2): validated (all parity tests pass) but measured 2-3 % SLOWER than the single-CTA
-    // schedule on the flagship (profiles/r02_pair_vs_single.md: each SM's shared memory still serves its B half to
-    // both tensor cores, so the operand-fetch bandwidth that bounds the GEMM phases does not drop); kept behind
-    // NFB_PAIR=1 for measurement.
-    static const bool use_pair = getenv("NFB_PAIR") != nullptr;
-    if (n_tiles >= 2 && use_pair) {
-        const long long n_units = (n_tiles + 1) / 2 * p.n_layers;
-        cudaLaunchConfig_t cfg{};
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        cfg.blockDim = dim3(kFusedThreads); cfg.dynamicSmemBytes = kFusedSmem; cfg.stream = st;
-        cfg.gridDim = dim3(2 * (unsigned)(sm_count / 2));
-        // every cluster must be resident (units wait on flags published by other clusters)
-        int max_clusters = 0;
-        const void* fn = sample ? (const void*)fused_rqs_kernel<true, true> : (const void*)fused_rqs_kernel<false, true>;
-        NFB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, fn, &cfg));
-        NFB_CHECK(max_clusters >= 1, NFB_ERR_STATE, "fused rqs: no CTA pair fits on this device");
-        long long n_cl = sm_count / 2;
-        if (n_cl > max_clusters) n_cl = max_clusters;
-        if (n_cl > n_units) n_cl = n_units;
-        cfg.gridDim = dim3(2 * (unsigned)n_cl);
-        if (sample) NFB_CUDA(cudaLaunchKernelEx(&cfg, fused_rqs_kernel<true, true>, p));
-        else NFB_CUDA(cudaLaunchKernelEx(&cfg, fused_rqs_kernel<false, true>, p));
-        NFB_LAUNCH_CHECK();
-        return NFB_OK;
-    }
     const long long n_units = n_tiles * p.n_layers;
     // every CTA must be resident (units wait on flags published by other CTAs): grid <= #SMs, 1 CTA/SM
     const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
-    if (sample) fused_rqs_kernel<true, false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
-    else fused_rqs_kernel<false, false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    if (sample) fused_rqs_kernel<true><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    else fused_rqs_kernel<false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }
@@ -768,10 +723,10 @@ __global__ void swizzle_split_kernel(const float* __restrict__ E, int n_pad, int
     }
 }
 
-// one record: rows [row0, row0+nrows) x K-chunk kc of E (times the GEMM's power-of-two weight scale) -> fp16 hi and
+// one record pair: rows [row0, row0+nrows) x K-chunk kc of E (times the GEMM's power-of-two weight scale) -> fp16 hi and
 // lo swizzled tiles (nrows*128 B each)
 __global__ void pack_record_kernel(const float* __restrict__ E, int k_pad, int row0, int nrows, int kc, float scale,
-                                   uint8_t* __restrict__ out_hi, uint8_t* __restrict__ out_lo) {
+                                         uint8_t* __restrict__ out_hi, uint8_t* __restrict__ out_lo) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= nrows * 64) return;
     const int rr = idx >> 6, kk = idx & 63;
@@ -785,6 +740,30 @@ int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, f
                        uint8_t* out_lo, cudaStream_t st) {
     NFB_CHECK(nrows > 0 && nrows % 8 == 0, NFB_ERR_ARG, "pack_record: bad row count %d", nrows);
     pack_record_kernel<<<(nrows * 64 + 255) / 256, 256, 0, st>>>(E, k_pad, row0, nrows, kc, scale, out_hi, out_lo);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// LU fold: G[i, c] = gain * sum_k E0[i, k] Elu[in_idx[k], c],  delta[i] = sum_k E0[i, k] blu[in_idx[k]]
+// (E0: [H x 64] first conditioner matrix in sorted hidden order, column k <-> conditioner input k = x'[in_idx[k]];
+//  Elu: [64 x 64] with x' = Elu z + blu).  fp64 accumulation, one block per row i.
+__global__ void fold_lu_kernel(const float* __restrict__ E0, const float* __restrict__ Elu, const float* __restrict__ blu,
+                               const int* __restrict__ in_idx, int d, float gain, float* __restrict__ G,
+                               float* __restrict__ delta) {
+    const int i = blockIdx.x, c = threadIdx.x;
+    double acc = 0.0;
+    for (int k = 0; k < 64; ++k) {
+        const int src = in_idx[k];
+        if (src < 0 || src >= d) continue;
+        const double w = (double)E0[(size_t)i * 64 + k];
+        acc += w * (c < 64 ? (double)Elu[(size_t)src * 64 + c] : (double)blu[src]);
+    }
+    if (c < 64) G[(size_t)i * 64 + c] = (float)(acc * (double)gain);
+    else delta[i] = (float)acc;
+}
+int launch_fold_lu(const float* E0, const float* Elu, const float* blu, const int* in_idx, int H, int d, float gain,
+                   float* G, float* delta, cudaStream_t st) {
+    fold_lu_kernel<<<H, 65, 0, st>>>(E0, Elu, blu, in_idx, d, gain, G, delta);
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

@@ -121,17 +121,20 @@ int launch_affine_stack(const void* ops_dev, int n_ops, const float* zin, float*
 struct __align__(8) FusedStep {
     uint16_t bytes16;    // weight record size / 16
     uint8_t n8;          // MMA N / 8
-    uint8_t a0, a1, a2;  // A-operand tiles to multiply this record with (0xFF = none)
+    uint8_t a0, a1, a2;  // A-operand tiles to multiply this record with: a0 and (unless 0xFF) a1; tile t < 4 = hi part of
+                         //   K-chunk t, 4 + t = lo part; a2 unused (0xFF)
     uint16_t ctl;        // [0,9) TMEM column | [9] first (overwrite) | [10,13) wait | [13,16) signal
 };
 // wait codes : 0 none, 1 a_ready[kc], 2+i chunk_empty[i], 6 a_ready[kc] + chunk_empty[1]  (kc = a0 & 3)
-// signal codes: 0 none, 1 acc_full, 2+i chunk_full[i]
+// signal codes: 0 none, 1 acc_full, 2+i chunk_full[i] (i < 2), 7 lu_full
 
 // One fused [LULinearPermute +] spline block, packed.  Device-resident (uploaded at pack time): the kernel
 // reads it through a pointer so that ONE persistent launch can walk a whole stack of blocks.
 struct FusedLayer {
     int D, H, n_hidden, has_lu, T, F, n_chunks, n_id, n_steps;  // F = features per final-layer chunk
     int ar_passes;  // sampling direction of an autoregressive block: number of conditioner passes (= D), else 0
+    int fold_lu;    // density unit with an LU stage: the first conditioner GEMM was folded into the LU map (it reads the
+                    // split of z, like the LU stage), see nfb_api.cu repack_pair
     float tail;
     const uint8_t* wstream;
     const FusedStep* steps;
@@ -167,6 +170,8 @@ struct FusedParams {
     long long* prof;           // optional [128] clock64 stamps (debug)
 };
 int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_t st);
+int launch_fold_lu(const float* E0, const float* Elu, const float* blu, const int* in_idx, int H, int d, float gain,
+                   float* G, float* delta, cudaStream_t st);
 
 // general fp32 GEMM on the tensor core (csrc/nfb_gemm_tc.cu): training pass of the conditioners
 struct GemmTcArgs {
