@@ -116,6 +116,7 @@ struct FusedPack {
     DevBuf wstream, steps, uncond;
     std::vector<float> bias_h, bias_f;
     std::vector<int> in_idx, tr_idx, id_idx, chunk_order;
+    unsigned char blk_sig[7 * 4] = {};     // see FusedLayer::blk_sig
     struct Rec { int row0, nrows, kc; size_t off_hi, off_lo; };
     struct Gemm { DevBuf src_row, src_col, row_scale; const float* W; const float* M; int src_cols, n_pad, k_pad; std::vector<Rec> recs; };
     std::vector<int> hperm;  // sorted-by-degree order of the hidden units (identity for unmasked nets)
@@ -375,19 +376,30 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     }
 
     // ---- step table + record list (same order) ----
+    memset(F.blk_sig, 3, sizeof(F.blk_sig));
     std::vector<FusedStep> steps;
     size_t off = 0;
     auto add = [&](FusedPack::Gemm& g, int row0, int nrows, int kc, int col, int first, int wait_hi,
                    int signal_lo) {
         FusedStep s;
-        s.bytes16 = (uint16_t)(nrows * 8);
         s.n8 = (uint8_t)(nrows / 8);
-        s.a0 = (uint8_t)kc; s.a1 = (uint8_t)(4 + kc); s.a2 = 0xFF;
-        s.ctl = make_ctl(col, first, wait_hi, 0);
-        steps.push_back(s);  // W_hi x {A_hi, A_lo}
-        s.a1 = 0xFF;
-        s.ctl = make_ctl(col, 0, 0, signal_lo);
-        steps.push_back(s);  // W_lo x {A_hi}
+        static const bool no_merge = getenv("NFB_NO_MERGE") != nullptr;          // (A/B measurements)
+        if (nrows * 256 <= 32768 && !no_merge) {
+            // both tiles fit one ring slot: ONE record, 12 MMAs (the issuer's per-record sequence costs ~700 cycles
+            // whatever the record holds; the shrinking N of the block-triangular layers made it the bound)
+            s.bytes16 = (uint16_t)(nrows * 16);
+            s.a0 = (uint8_t)kc; s.a1 = (uint8_t)(4 + kc); s.a2 = (uint8_t)kc;
+            s.ctl = make_ctl(col, first, wait_hi, signal_lo);
+            steps.push_back(s);  // W_hi x {A_hi, A_lo}, W_lo x {A_hi}
+        } else {
+            s.bytes16 = (uint16_t)(nrows * 8);
+            s.a0 = (uint8_t)kc; s.a1 = (uint8_t)(4 + kc); s.a2 = 0xFF;
+            s.ctl = make_ctl(col, first, wait_hi, 0);
+            steps.push_back(s);  // W_hi x {A_hi, A_lo}
+            s.a1 = 0xFF;
+            s.ctl = make_ctl(col, 0, 0, signal_lo);
+            steps.push_back(s);  // W_lo x {A_hi}
+        }
         FusedPack::Rec r{row0, nrows, kc, off, off + (size_t)nrows * 128};
         off += (size_t)nrows * 256;
         g.recs.push_back(r);
@@ -398,12 +410,30 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         const int kcs = (ph == 0) ? 1 : kcs_h;
         FusedPack::Gemm& g = F.gemms[ph];
         int last = 0;
-        for (int kc = 0; kc < kcs; ++kc) if (ph == 0 || hidden_row0(kc) < H) last = kc;
+        std::vector<int> r0s(kcs, 0);
         for (int kc = 0; kc < kcs; ++kc) {
-            const int r0 = (ph == 0 || kc == 0) ? 0 : hidden_row0(kc);
+            r0s[kc] = (ph == 0 || kc == 0) ? 0 : hidden_row0(kc);
+            if (r0s[kc] < H) last = kc;
+        }
+        // Output chunk j (rows [64 j, 64 j + 64) of this GEMM = A K-chunk j of the next one) is final once the last
+        // K-chunk whose records reach those rows has been accumulated: fin(j).  Unmasked nets: the last K-chunk.
+        const int ochunks = H / 64;
+        std::vector<int> fin(ochunks, last);
+        for (int j = 0; j < ochunks; ++j) {
+            int fj = 0;
+            for (int kc = 0; kc <= last; ++kc) if (r0s[kc] < 64 * (j + 1)) fj = kc;
+            fin[j] = fj;
+            static const bool no_early = getenv("NFB_NO_EARLY_EPI") != nullptr;  // (A/B measurements)
+            F.blk_sig[ph * 4 + j] = (unsigned char)((fj >= last || fj > 2 || no_early) ? 3 : fj);
+        }
+        for (int kc = 0; kc < kcs; ++kc) {
+            const int r0 = r0s[kc];
             if (r0 >= H) continue;
+            int sig = kc == last ? 1 : 0;
+            if (kc < last && kc <= 2)
+                for (int j = 0; j < ochunks; ++j) if (F.blk_sig[ph * 4 + j] == kc) sig = 4 + kc;
             // every hi record is the first reader of A K-chunk kc in this phase: wait a_ready[kc]
-            add(g, r0, H - r0, kc, region + r0, (kc == 0 && !accum_onto) ? 1 : 0, 1, kc == last ? 1 : 0);
+            add(g, r0, H - r0, kc, region + r0, (kc == 0 && !accum_onto) ? 1 : 0, 1, sig);
         }
     }
     {
@@ -653,6 +683,7 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
         Lh.id_idx[k] = (unsigned char)(k < (int)F.id_idx.size() ? F.id_idx[k] : 0);
     }
     for (int k = 0; k < 16; ++k) Lh.chunk_order[k] = (unsigned char)(k < (int)F.chunk_order.size() ? F.chunk_order[k] : 0);
+    memcpy(Lh.blk_sig, F.blk_sig, sizeof(Lh.blk_sig));
     Lh.a_sc[0] = 1.f; Lh.a_inv[0] = 1.f;
     for (int gi = 0; gi < ng; ++gi) {
         Lh.a_sc[1 + gi] = pow2f(F.pa[gi]);
@@ -719,18 +750,18 @@ int build_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     std::vector<FusedStep> steps;
     auto mk = [&](int a0, int a1, int a2, int first, int wait, int signal) {
         FusedStep s;
-        s.bytes16 = 64 * 8; s.n8 = 8; s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
+        s.bytes16 = 64 * 16; s.n8 = 8; s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
         s.ctl = make_ctl(256, first, wait, signal);
         steps.push_back(s);
     };
-    mk(0, 4, 0xFF, 1, 1, 0);     // W_hi x {A_hi, A_lo}
-    mk(0, 4, 0xFF, 0, 0, 7);     // W_lo x {A_hi, A_lo}   (4 terms: the map transforms z itself, ~2^-22); signals lu_full
+    mk(0, 4, 0x80, 1, 1, 7);     // one record: W_hi x {A_hi, A_lo}, W_lo x {A_hi, A_lo}  (4 terms: the map transforms z
+                                 // itself, ~2^-22); signals lu_full
     steps.insert(steps.end(), F.steps_host.begin(), F.steps_host.end());
     F.pair_steps = (int)steps.size();
     NFB_TRY(F.pair_steps_dev.upload(steps));
     {   // folded variant: GEMM 0 of the block reads the LU stage's A operand (already waited for by the LU records)
         std::vector<FusedStep> sf = steps;
-        sf[2].ctl = (uint16_t)(sf[2].ctl & ~(7u << 10));
+        sf[1].ctl = (uint16_t)(sf[1].ctl & ~(7u << 10));
         NFB_TRY(F.pair_steps_fold_dev.upload(sf));
         NFB_TRY(F.in_idx_dev.upload(F.in_idx));
     }
@@ -798,12 +829,11 @@ int build_fwd_unit(nfb_flow* f, Layer& R, Layer* U) {
     std::vector<FusedStep> steps;
     auto mk = [&](int a0, int a1, int a2, int first, int wait, int signal) {
         FusedStep s;
-        s.bytes16 = 64 * 8; s.n8 = 8; s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
+        s.bytes16 = 64 * 16; s.n8 = 8; s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
         s.ctl = make_ctl(256, first, wait, signal);
         steps.push_back(s);
     };
-    mk(0, 4, 0xFF, 1, 1, 0);     // same 4-term schedule as the density pair (build_pair)
-    mk(0, 4, 0xFF, 0, 0, 7);
+    mk(0, 4, 0x80, 1, 1, 7);     // same 4-term record as the density pair (build_pair)
     steps.insert(steps.end(), F.steps_host.begin(), F.steps_host.end());
     NFB_TRY(F.fwd_steps_dev.upload(steps));
     NFB_TRY(F.fwd_wstream.reserve(2 * 8192 + F.rqs_bytes));
@@ -835,7 +865,7 @@ int repack_fwd_unit(nfb_flow* f, Layer& R, Layer* U, cudaStream_t st) {
     Lp.has_lu = 1;
     Lp.a_sc[0] = pow2f(14);
     Lp.a_inv[0] = pow2f(-(14 + pw_lu));
-    Lp.n_steps = F.n_steps + 2;
+    Lp.n_steps = F.n_steps + 1;
     Lp.wstream = F.fwd_wstream.as<uint8_t>();
     Lp.steps = F.fwd_steps_dev.as<FusedStep>();
     Lp.bias_lu = F.fwd_bias_lu.as<float>();

@@ -52,14 +52,14 @@ constexpr uint32_t kOffX = kOffW + kSlots * kSlotBytes;  // 196608: x/y tile
 constexpr uint32_t kOffMisc = kOffX + 32768;             // 229376: log-det partials [kNG-1][128], row maxima [128]
 constexpr uint32_t kOffRowMax = kOffMisc + (kNG - 1) * 128 * 4;
 constexpr uint32_t kOffBars = kOffMisc + 2048;           // 231424
-constexpr uint32_t kNumBars = 18;
-constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;  // 231568
-constexpr uint32_t kFusedSmem = kOffTmemPtr + 16;          // 231584 <= 232448
+constexpr uint32_t kNumBars = 20;
+constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;  // 231584
+constexpr uint32_t kFusedSmem = kOffTmemPtr + 16;          // 231600 <= 232448
 static_assert(kFusedSmem <= 232448, "shared memory budget");
 
 // barrier indices
 constexpr int kBarWFull = 0 /* +slot */, kBarWEmpty = 3 /* +slot */, kBarAReady = 6 /* +kc, 4 */, kBarAccFull = 10,
-              kBarCFull = 11 /* +b, 2 */, kBarCEmpty = 13 /* +b, 2 */, kBarLuFull = 15;
+              kBarCFull = 11 /* +b, 2 */, kBarCEmpty = 13 /* +b, 2 */, kBarLuFull = 15, kBarAccBlk = 16 /* +kc, 3 */;
 // TMEM column of final-layer chunk buffer i
 // (both accumulator regions are dead once the last hidden epilogue has run: one buffer in each)
 __device__ __forceinline__ uint32_t chunk_col(int i) { return (uint32_t)i * 256u; }
@@ -112,7 +112,9 @@ __device__ __forceinline__ float pow2i(int e) { return __uint_as_float((uint32_t
 //   conditional spline is inverted (Coupling.inverse, neural_spline/coupling.py:100-128).
 // (The CTA-pair / cta_group::2 schedule of round 2a was measured 2-3 % slower and removed: profiles/r02_pair_vs_single.md;
 //  so were "mixed" hi|lo weight records and a byte-granular ring: profiles/r02b_ring_experiments.md.)
-template <bool SAMPLE>
+// PROF = true: clock64 stamps of CTA 0's first unit (nfb_debug_profile); compiled out of the production instantiation --
+//   the MMA issuer's per-record sequence is on the critical path of every GEMM phase.
+template <bool SAMPLE, bool PROF>
 __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const FusedParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const uint32_t sbase = smem_u32(smem);
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         for (int i = 0; i < 4; ++i) mbar_init(bar(kBarAReady + i), kEpiWarps);
         mbar_init(bar(kBarAccFull), 1);
         mbar_init(bar(kBarLuFull), 1);
+        for (int i = 0; i < 3; ++i) mbar_init(bar(kBarAccBlk + i), 1);
         fence_mbar_init();
     }
     if (warp == kEpiWarps + 1) {
@@ -167,7 +170,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             const FusedStep* steps = L.steps;  // global (L2-resident); the producer only needs the size
             const int n_steps = L.n_steps;
             // autoregressive sampling (SAMPLE, ar_passes = D): the LU records are streamed once, the block's D times
-            const int lu_steps = L.has_lu ? 2 : 0;
+            const int lu_steps = L.has_lu ? 1 : 0;  // (hi and lo tile of the LU map travel as one record)
             const int reps = (SAMPLE && L.ar_passes > 0) ? L.ar_passes : 1;
             const int total = n_steps ? lu_steps + reps * (n_steps - lu_steps) : 0;
             const uint32_t lu_bytes = L.has_lu ? 2u * 8192u : 0u;
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             const FusedLayer& L = p.layers[u / n_tiles];
             const uint2* steps = reinterpret_cast<const uint2*>(L.steps);  // 8-byte entries, L2-resident
             const int n_steps = L.n_steps;
-            const int lu_steps = L.has_lu ? 2 : 0;
+            const int lu_steps = L.has_lu ? 1 : 0;  // (hi and lo tile of the LU map travel as one record)
             const int reps = (SAMPLE && L.ar_passes > 0) ? L.ar_passes : 1;
             const int total = n_steps ? lu_steps + reps * (n_steps - lu_steps) : 0;
             union { uint2 raw; FusedStep s; } cur, nx;
@@ -214,7 +217,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 nx.raw = __ldg(steps + sidx);  // prefetch one entry ahead (wraps to the block's first step)
                 const FusedStep st = cur.s;
                 const uint32_t ctl = st.ctl;
-                if (p.prof && u == 0 && s < 380 && lane == 0) p.prof[512 + s] = clock64();  // debug: step reached
+                if (PROF && p.prof && u == 0 && s < 380 && lane == 0) p.prof[512 + s] = clock64();  // debug: step reached
                 const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
                 if (wcode == 1 || wcode == 6) {  // first use of A-operand K-chunk kc in this phase
                     const uint32_t kc = st.a0 & 3u;
@@ -226,32 +229,38 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     mbar_wait(bar(kBarCEmpty + i), ((cebits >> i) & 1u) ^ 1u, p.err, 210 + i);
                     cebits ^= 1u << i;
                 }
-                if (p.prof && u == 0 && s < 380 && lane == 0) p.prof[896 + s] = clock64();  // debug: operands (A / chunk) ready
+                if (PROF && p.prof && u == 0 && s < 380 && lane == 0) p.prof[896 + s] = clock64();  // debug: operands (A / chunk) ready
                 mbar_wait(bar(kBarWFull + slot), wpar, p.err, 220 + slot);
                 tc_fence_after();
-                if (p.prof && u == 0 && s < 380 && lane == 0) p.prof[128 + s] = clock64();  // debug: issue time
+                if (PROF && p.prof && u == 0 && s < 380 && lane == 0) p.prof[128 + s] = clock64();  // debug: issue time
                 if (elect_one_sync()) {
                     const uint32_t d = tmem + (ctl & 511u);
                     const uint32_t idesc = kIdesc0 | ((uint32_t)st.n8 << 17);
                     const uint64_t bd = bdesc0 + (uint64_t)(slot * (kSlotBytes >> 4));
                     uint32_t accum = ((ctl >> 9) & 1u) ^ 1u;
                     // A tile t < 4: hi part of K-chunk t; 4 + t: lo part.  Four K=16 slabs per tile.
-                    auto issue4 = [&](uint32_t code) {
+                    auto issue4 = [&](uint32_t code, uint64_t b) {
                         const uint64_t ad = adesc0 + (uint64_t)(code * (kTileA >> 4));
-                        umma_bf16(d, ad, bd, idesc, accum);
-                        umma_bf16(d, ad + 2, bd + 2, idesc, 1u);
-                        umma_bf16(d, ad + 4, bd + 4, idesc, 1u);
-                        umma_bf16(d, ad + 6, bd + 6, idesc, 1u);
+                        umma_bf16(d, ad, b, idesc, accum);
+                        umma_bf16(d, ad + 2, b + 2, idesc, 1u);
+                        umma_bf16(d, ad + 4, b + 4, idesc, 1u);
+                        umma_bf16(d, ad + 6, b + 6, idesc, 1u);
                         accum = 1u;
                     };
-                    issue4(st.a0);
-                    if (st.a1 != 0xFF) issue4(st.a1);
-                    if (p.prof && u == 0 && s < 380) p.prof[1280 + s] = clock64();  // debug: MMAs of this record issued
+                    issue4(st.a0, bd);                       // W_hi tile x A tiles a0 (, a1)
+                    if (st.a1 != 0xFF) issue4(st.a1, bd);
+                    if (st.a2 != 0xFF) {                     // merged record: the W_lo tile follows the W_hi tile
+                        const uint64_t bd2 = bd + (uint64_t)st.n8 * 64u;   // n8 * 8 rows * 128 B, in 16-byte units
+                        issue4(st.a2 & 7u, bd2);
+                        if (st.a2 & 0x80u) issue4((st.a2 & 7u) + 4u, bd2);   // (LU map: all four terms)
+                    }
+                    if (PROF && p.prof && u == 0 && s < 380) p.prof[1280 + s] = clock64();  // debug: MMAs of this record issued
                     umma_commit(bar(kBarWEmpty + slot));
                     if (scode == 1) umma_commit(bar(kBarAccFull));
                     else if (scode == 7) umma_commit(bar(kBarLuFull));
+                    else if (scode >= 4) umma_commit(bar(kBarAccBlk + (scode - 4)));
                     else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
-                    if (p.prof && u == 0 && s < 380) p.prof[1664 + s] = clock64();  // debug: commits issued
+                    if (PROF && p.prof && u == 0 && s < 380) p.prof[1664 + s] = clock64();  // debug: commits issued
                 }
                 __syncwarp();
                 if (++slot == kSlots) { slot = 0; wpar ^= 1; }
@@ -266,15 +275,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const int r = q * 32 + lane;           // tile row owned by this thread
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
         const uint32_t aA = sbase + kOffA;
-        uint32_t afpar = 0, lupar = 0, cfbits = 0;
+        uint32_t afpar = 0, lupar = 0, cfbits = 0, blkpar = 0;
         // epilogue-side waits: every thread polls (default; measured 3-4 % faster than one polling lane per warp)
         auto ewait = [&](uint32_t b, uint32_t parity, int tag) {
             if (p.poll_all) mbar_wait(b, parity, p.err, tag);
             else mbar_wait_warp(b, parity, p.err, tag);
         };
-        long long* prof = (p.prof && blockIdx.x == 0 && et == 0) ? p.prof : nullptr;
+        long long* prof = (PROF && p.prof && blockIdx.x == 0 && et == 0) ? p.prof : nullptr;
         int pi = 0;
-#define NFB_STAMP() do { if (prof && pi < 126) prof[pi++] = clock64(); } while (0)
+#define NFB_STAMP() do { if (PROF && prof && pi < 126) prof[pi++] = clock64(); } while (0)
 
         for (long long u = u_first; u < n_units; u += u_step) {
             const int layer = (int)(u / n_tiles);
@@ -509,24 +518,35 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
 
             // ---- hidden layers ----
             for (int ph = 0; ph < L.n_hidden; ++ph) {
-                ewait(bar(kBarAccFull), afpar, 310 + ph);
-                afpar ^= 1;
-                tc_fence_after();
-                NFB_STAMP();  // hidden gemm ph done
                 const uint32_t region = (ph & 1) ? 256u : 0u;
                 const bool relu = ph + 1 < L.n_hidden;
                 const float inv = L.a_inv[1 + ph] * ruinv;   // accumulator -> true value
                 const float sc = L.a_sc[2 + ph] * ru;       // true value -> the next GEMM's A units
                 // K-chunk order: all column groups convert the same 64 columns, then release that slice of
                 // the next A operand so the next GEMM's kc-step can start while the rest is converted.
-                // The TMEM load of chunk kc + 1 is in flight while chunk kc is converted.
+                // Block-triangular (MADE) layers: output chunk j is FINAL as soon as the last K-chunk that reaches
+                // its rows has been accumulated (blk_sig: the barrier that says so; 3 = the whole GEMM), so the chunks
+                // are converted while the tensor core is still working on the later K-chunks of the same GEMM and the
+                // next GEMM follows without a gap.  The TMEM load of chunk kc + 1 is issued before chunk kc is
+                // converted whenever its barrier has already been passed.
                 const int nkc = H >> 6;
                 uint32_t acc[2][kGC];
-                NFB_TMEM_LD16(tlane + region + wh * kGC, acc[0]);
+                uint32_t waited = 0;
+                bool loading = false;
+                const uint32_t sig4 = *reinterpret_cast<const uint32_t*>(L.blk_sig + ph * 4);  // this phase's four entries
 #pragma unroll
                 for (int kc = 0; kc < 4; ++kc) {
                     if (kc < nkc) {
+                        const uint32_t sg = (sig4 >> (8 * kc)) & 3u;
+                        if (!((waited >> sg) & 1u)) {
+                            if (sg == 3u) { ewait(bar(kBarAccFull), afpar, 310 + ph); afpar ^= 1; }
+                            else { ewait(bar(kBarAccBlk + sg), (blkpar >> sg) & 1u, 320 + (int)sg); blkpar ^= 1u << sg; }
+                            tc_fence_after();
+                            waited |= 1u << sg;
+                            if (kc == 0) NFB_STAMP();  // first output chunk of hidden gemm ph available
+                        }
                         const int c0 = kc * 64 + wh * kGC;
+                        if (!loading) NFB_TMEM_LD16(tlane + region + c0, acc[kc & 1]);
                         const float4* bf = reinterpret_cast<const float4*>(L.bias_h + ph * 256 + c0);  // warp-uniform
                         float bv[kGC];
 #pragma unroll
@@ -535,7 +555,11 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                             bv[4 * j] = q4.x; bv[4 * j + 1] = q4.y; bv[4 * j + 2] = q4.z; bv[4 * j + 3] = q4.w;
                         }
                         NFB_TMEM_WAIT16(acc[kc & 1]);
-                        if (kc + 1 < nkc) NFB_TMEM_LD16(tlane + region + c0 + 64, acc[(kc + 1) & 1]);
+                        loading = false;
+                        if (kc + 1 < nkc && ((waited >> ((sig4 >> (8 * kc + 8)) & 3u)) & 1u)) {
+                            NFB_TMEM_LD16(tlane + region + c0 + 64, acc[(kc + 1) & 1]);
+                            loading = true;
+                        }
                         float v[kGC];
 #pragma unroll
                         for (int j = 0; j < kGC; ++j) {
@@ -645,7 +669,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p.progress + tile), "r"(layer + 1) : "memory");
             }
             NFB_STAMP();  // tile stored
-            if (prof) prof[127] = pi;
+            if (PROF && prof) prof[127] = pi;
         }
     }
     tc_fence_before();
@@ -657,8 +681,9 @@ int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_
     static PerDevice per_dev;  // the opt-in shared-memory size is a per-device function attribute
     const int dev_sms = per_dev.ensure([] {
         cudaError_t e = cudaSuccess;
-        const void* fns[2] = {(const void*)fused_rqs_kernel<false>, (const void*)fused_rqs_kernel<true>};
-        for (int i = 0; i < 2 && e == cudaSuccess; ++i)
+        const void* fns[4] = {(const void*)fused_rqs_kernel<false, false>, (const void*)fused_rqs_kernel<true, false>,
+                              (const void*)fused_rqs_kernel<false, true>, (const void*)fused_rqs_kernel<true, true>};
+        for (int i = 0; i < 4 && e == cudaSuccess; ++i)
             e = cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFusedSmem);
         return e;
     });
@@ -670,8 +695,13 @@ int launch_fused_rqs(const FusedParams& p, int sm_count, int sample, cudaStream_
     const long long n_units = n_tiles * p.n_layers;
     // every CTA must be resident (units wait on flags published by other CTAs): grid <= #SMs, 1 CTA/SM
     const unsigned grid = (unsigned)(n_units < sm_count ? n_units : sm_count);
-    if (sample) fused_rqs_kernel<true><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
-    else fused_rqs_kernel<false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    if (p.prof) {   // instrumented build (nfb_debug_profile)
+        if (sample) fused_rqs_kernel<true, true><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+        else fused_rqs_kernel<false, true><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    } else {
+        if (sample) fused_rqs_kernel<true, false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+        else fused_rqs_kernel<false, false><<<grid, kFusedThreads, kFusedSmem, st>>>(p);
+    }
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

@@ -121,12 +121,14 @@ int launch_affine_stack(const void* ops_dev, int n_ops, const float* zin, float*
 struct __align__(8) FusedStep {
     uint16_t bytes16;    // weight record size / 16
     uint8_t n8;          // MMA N / 8
-    uint8_t a0, a1, a2;  // A-operand tiles to multiply this record with: a0 and (unless 0xFF) a1; tile t < 4 = hi part of
-                         //   K-chunk t, 4 + t = lo part; a2 unused (0xFF)
+    uint8_t a0, a1, a2;  // A-operand tiles to multiply the record's (first) tile with: a0 and (unless 0xFF) a1; tile t < 4 =
+                         //   hi part of K-chunk t, 4 + t = lo part.  a2 != 0xFF: MERGED record -- a second [N x 64] tile (W_lo)
+                         //   follows the first (W_hi) and is multiplied with A tile a2 & 7 (and, bit 7 set, with its lo twin)
     uint16_t ctl;        // [0,9) TMEM column | [9] first (overwrite) | [10,13) wait | [13,16) signal
 };
 // wait codes : 0 none, 1 a_ready[kc], 2+i chunk_empty[i], 6 a_ready[kc] + chunk_empty[1]  (kc = a0 & 3)
-// signal codes: 0 none, 1 acc_full, 2+i chunk_full[i] (i < 2), 7 lu_full
+// signal codes: 0 none, 1 acc_full, 2+i chunk_full[i] (i < 2), 4+kc acc_blk[kc] (kc < 3: the output chunks whose last
+//               contributing K-chunk is kc are final), 7 lu_full
 
 // One fused [LULinearPermute +] spline block, packed.  Device-resident (uploaded at pack time): the kernel
 // reads it through a pointer so that ONE persistent launch can walk a whole stack of blocks.
@@ -145,6 +147,8 @@ struct FusedLayer {
     unsigned char tr_idx[64];  // transformed feature columns
     unsigned char id_idx[64];  // identity feature columns (coupled layer)
     unsigned char chunk_order[16];  // final-layer chunks in processing order (first one reads every K-chunk)
+    alignas(4) unsigned char blk_sig[7 * 4];   // [hidden phase][output chunk] -> barrier that announces the chunk: 0..2 = acc_blk[kc]
+                                    // (block-triangular MADE layer: final after K-chunk kc), 3 = acc_full (whole GEMM)
     // fp16 operand scaling (all powers of two; nfb_api.cu plan_scales): index 0 = LU stage, 1 + g = GEMM g of the
     // conditioner (g = n_hidden: final layer).  A operand = true value * u_row * a_sc; true value = acc * a_inv / u_row.
     float a_sc[10], a_inv[10];
