@@ -439,33 +439,46 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     {
         FusedPack::Gemm& g = F.gemms[n_hidden];
         bool a_waited[4] = {false, false, false, false};
-        // Which K-chunks does each chunk need (MADE masks)?  The chunk processed FIRST must read every K-chunk:
-        // its records carry all the a_ready[kc] waits, i.e. the MMA warp knows the last hidden epilogue has
-        // finished reading the residual stream (TMEM columns 0..255) before the chunk in processing slot 1
-        // overwrites those columns.  (A short first chunk there is a real race: found on hardware.)
+        // Which K-chunks does each chunk need (MADE masks)?  Processing slot 0 writes TMEM buffer 1 (columns 256..),
+        // slot 1 is the first writer of buffer 0 = the residual stream's columns, which the LAST hidden epilogue is
+        // still reading: before its first MMA the issuer must have passed a_ready[last K-chunk] (the epilogue converts
+        // the chunks in order, so that arrival means it has read everything).  (A short first chunk with nothing
+        // enforcing this is a real race: found on hardware in round 1.)  Round 2b: slot 0 takes the LIGHTEST chunk
+        // (features 0..F-1 of a MADE net need K-chunk 0 only) so that the spline evaluators start ~2 k cycles after the
+        // last hidden GEMM instead of waiting ~8 k for a dense chunk; the first record of slot 1 carries wait code 5 =
+        // a_ready[LAST K-chunk of the phase] + chunk buffer 0 free (its own K-chunk 0 was announced to slot 0 already).
+        // (K-chunks stay in ascending order: the accumulation order is part of the validated numerics.)
         std::vector<std::vector<int>> need_of(n_chunks);
         for (int c = 0; c < n_chunks; ++c)
             for (int kc = 0; kc < kcs_h; ++kc)
                 if (kc == 0 || c == n_chunks - 1 || final_needs(c, kc)) need_of[c].push_back(kc);
-        // heavy,light,heavy,light: the top chunk (all K-chunks) first, then alternate low/high chunks
+        // light, heavy, light, heavy, ...: chunk 0, the last chunk (every K-chunk), then alternate low / high chunks
         std::vector<int> order;
         for (int lo = 0, hi = n_chunks - 1; lo <= hi;) {
-            order.push_back(hi--);
-            if (lo <= hi) order.push_back(lo++);
+            order.push_back(lo++);
+            if (lo <= hi) order.push_back(hi--);
         }
         F.chunk_order = order;
         for (int ci = 0; ci < n_chunks; ++ci) {
             const int c = order[ci];
             const int b = (ci + 1) & 1;  // two TMEM chunk buffers (columns 0.. and 256..); slot 0 uses the second
             const std::vector<int>& need = need_of[c];
+            // live rows of the chunk: the last one usually holds fewer than F features -- no MMA work for the padding
+            const int live = std::min(fpc, T - fpc * c);
+            const int nrows = std::min(crow, (live * 24 + 15) / 16 * 16);
             for (size_t j = 0; j < need.size(); ++j) {
                 const int kc = need[j];
                 int wait = 0;
-                if (j == 0) wait = (ci == 0) ? 6 : 2 + b;          // chunk buffer free (+ a_ready[0] for slot 0)
-                else if (!a_waited[kc]) wait = 1;                     // first reader of this A K-chunk
-                if (j == 0 && ci > 0 && !a_waited[kc]) return NFB_OK; // cannot encode both waits: keep generic path
+                if (j == 0) {
+                    if (!a_waited[kc] && ci > 0) return NFB_OK;       // (slot 0 always reads K-chunk 0: cannot happen)
+                    if (ci == 0) wait = 6;                            // a_ready[kc] + chunk buffer 1 free
+                    else if (ci == 1 && !a_waited[kcs_h - 1]) {       // a_ready[last K-chunk] + chunk buffer 0 free
+                        wait = 5;
+                        a_waited[kcs_h - 1] = true;
+                    } else wait = 2 + b;                              // chunk buffer free
+                } else if (!a_waited[kc]) wait = 1;                   // first reader of this A K-chunk
                 a_waited[kc] = true;
-                add(g, c * crow, crow, kc, chunk_col_host(b), j == 0 ? 1 : 0, wait,
+                add(g, c * crow, nrows, kc, chunk_col_host(b), j == 0 ? 1 : 0, wait,
                     j + 1 == need.size() ? 2 + b : 0);
             }
         }

@@ -219,13 +219,14 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 const uint32_t ctl = st.ctl;
                 if (PROF && p.prof && u == 0 && s < 380 && lane == 0) p.prof[512 + s] = clock64();  // debug: step reached
                 const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
-                if (wcode == 1 || wcode == 6) {  // first use of A-operand K-chunk kc in this phase
-                    const uint32_t kc = st.a0 & 3u;
+                if (wcode == 1 || wcode == 5 || wcode == 6) {  // first use of A-operand K-chunk kc in this phase
+                    // (code 5: the LAST K-chunk of the final layer's A operand, whatever chunk the record itself reads)
+                    const uint32_t kc = wcode == 5 ? (uint32_t)(L.H >> 6) - 1u : st.a0 & 3u;
                     mbar_wait(bar(kBarAReady + kc), (apar >> kc) & 1u, p.err, 200 + kc);
                     apar ^= 1u << kc;
                 }
                 if (wcode >= 2) {
-                    const uint32_t i = wcode == 6 ? 1u : wcode - 2;  // chunk 0 lives in buffer 1
+                    const uint32_t i = wcode == 6 ? 1u : (wcode == 5 ? 0u : wcode - 2);  // processing slot 0 uses buffer 1
                     mbar_wait(bar(kBarCEmpty + i), ((cebits >> i) & 1u) ^ 1u, p.err, 210 + i);
                     cebits ^= 1u << i;
                 }
@@ -586,9 +587,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             const float inv_f = L.a_inv[1 + L.n_hidden] * ruinv;
             for (int ci = 0; ci < L.n_chunks; ++ci) {
                 // Processing slot 0 -> buffer 1 (columns 256..): the last hidden epilogue is still reading the
-                // residual stream (columns 0..255) when the first final-layer MMAs start.  The packer puts a
-                // chunk that reads EVERY A K-chunk into slot 0, so the MMA warp has consumed all a_ready[kc]
-                // (= the epilogue has finished reading columns 0..255) before slot 1 overwrites buffer 0.
+                // residual stream (columns 0..255) when the first final-layer MMAs start.  The packer makes the
+                // first record of slot 1 wait for a_ready[last K-chunk] (= the epilogue has finished reading
+                // columns 0..255) before it overwrites buffer 0 (nfb_api.cu build_fused).
                 const int b = (ci + 1) & 1;
                 const int c = L.chunk_order[ci];
                 // rotate the deal by the chunk index: with F = 10 the groups get 3,3,2,2 features of a chunk, and

@@ -126,7 +126,8 @@ struct __align__(8) FusedStep {
                          //   follows the first (W_hi) and is multiplied with A tile a2 & 7 (and, bit 7 set, with its lo twin)
     uint16_t ctl;        // [0,9) TMEM column | [9] first (overwrite) | [10,13) wait | [13,16) signal
 };
-// wait codes : 0 none, 1 a_ready[kc], 2+i chunk_empty[i], 6 a_ready[kc] + chunk_empty[1]  (kc = a0 & 3)
+// wait codes : 0 none, 1 a_ready[kc], 2+i chunk_empty[i], 5 a_ready[H/64 - 1] + chunk_empty[0],
+//              6 a_ready[kc] + chunk_empty[1]   (kc = a0 & 3)
 // signal codes: 0 none, 1 acc_full, 2+i chunk_full[i] (i < 2), 4+kc acc_blk[kc] (kc < 3: the output chunks whose last
 //               contributing K-chunk is kc are final), 7 lu_full
 

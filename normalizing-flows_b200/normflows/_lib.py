@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "libnfb200.so")
+# NFB200_LIB: another build of the SAME library (A/B measurements of kernel variants on one GPU box); default: in-tree
+LIB_PATH = os.environ.get("NFB200_LIB") or os.path.join(os.path.dirname(_HERE), "libnfb200.so")
 
 NFB_INVERSE, NFB_FORWARD = 0, 1
 _FP = C.POINTER(C.c_float)
