@@ -56,6 +56,22 @@ int nfb_rqs_spline(const float* x_dev, const float* params_dev, float* y_dev, fl
                    int64_t rows, int32_t feats, int32_t num_bins, float tail_bound, float wh_scale,
                    int32_t inverse, int32_t accumulate, void* stream);
 
+/* The same spline with PER-FEATURE tails (utils/splines.py:42-57; the circular NSF layers of
+ * flows/neural_spline/wrapper.py:88-183,247-311): params [rows, feats * (2K + num_derivatives)] with num_derivatives =
+ * K + 1 (tails given as a list: every knot has a parameter; linear features overwrite both ends with the constant of
+ * :35-38, circular features copy knot 0 into knot K; inputs outside a feature's interval come out as 0 with log-det 0 --
+ * the reference's list branch never copies them, :31,48-57) or K (tails="circular": identity outside, :46-47).  tail_bound_dev[feats], circular_dev[feats]
+ * (int32, != 0 = circular) live on the device. */
+int nfb_rqs_spline_tails(const float* x_dev, const float* params_dev, float* y_dev, float* log_det_dev, int64_t rows,
+                         int32_t feats, int32_t num_bins, int32_t num_derivatives, const float* tail_bound_dev,
+                         const int32_t* circular_dev, float wh_scale, int32_t inverse, int32_t accumulate, void* stream);
+
+/* utils/nn.py:64-130 PeriodicFeaturesElementwise.forward: y[r, j] = w[k,0] sin(scale[k] x) + w[k,1] cos(scale[k] x)
+ * (+ bias[k]) for the features with slot_dev[j] = k >= 0, y = x for slot -1.  weights_dev [n_periodic, 2],
+ * scale_dev / bias_dev [n_periodic] (bias may be NULL). */
+int nfb_periodic_features(const float* x_dev, float* y_dev, int64_t rows, int32_t dim, const int32_t* slot_dev,
+                          const float* weights_dev, const float* scale_dev, const float* bias_dev, void* stream);
+
 /* distributions/base.py:94-103 DiagGaussian.log_prob: log_q[r] (+)= log N(z_r; loc, exp(log_scale)) */
 int nfb_diag_gaussian_log_prob(const float* z_dev, const float* loc_dev, const float* log_scale_dev,
                                float* log_q_dev, int64_t rows, int32_t dim, int32_t accumulate,

@@ -304,6 +304,10 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         }
         // T = 64: 10 -> 70 slots beats 8 -> 64 because 120-cycle MMAs hide the per-record bubble
         if (T > 40 && fpc < 10) fpc = 10;
+        if (const char* e = getenv("NFB_FPC")) {   // (measurement override: features per final-layer chunk, even, 2..10)
+            const int v = atoi(e);
+            if (v >= 2 && v <= 10 && v % 2 == 0) fpc = v;
+        }
     }
     const int n_chunks = (T + fpc - 1) / fpc;
     const int kcs_h = H / 64;
@@ -603,6 +607,22 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
                                        g.n_pad, g.k_pad, acc_gain(3 * g.k_pad / 16), st));
         NFB_TRY(launch_matrix_norms(f->E.as<float>(), g.n_pad, g.k_pad, f->norms.as<float>() + 3 * gi, st));
     }
+    // LU fold, device part (before the one synchronisation of this function): G = gain * E0 E_lu[in_idx, :],
+    // delta = E0 b_lu[in_idx] (fp64 accumulation), norms of G
+    if (Ufold) {
+        auto& g0 = F.gemms[0];
+        const int Hf = n.H;
+        NFB_TRY(F.fold_lu.reserve(64 * 64 * 4));
+        NFB_TRY(F.fold_G.reserve((size_t)Hf * 64 * 4));
+        NFB_TRY(F.fold_delta.reserve((size_t)Hf * 4));
+        NFB_TRY(launch_build_effective(g0.W, g0.M, g0.src_cols, g0.src_row.as<int>(), g0.src_col.as<int>(), nullptr,
+                                       f->E.as<float>(), Hf, 64, 1.f, st));
+        NFB_TRY(launch_build_effective(Ufold->lu_Wd.as<float>(), nullptr, Ufold->D, F.lu_src_row.as<int>(),
+                                       F.lu_src_col.as<int>(), nullptr, F.fold_lu.as<float>(), 64, 64, 1.f, st));
+        NFB_TRY(launch_fold_lu(f->E.as<float>(), F.fold_lu.as<float>(), Ufold->lu.bias, F.in_idx_dev.as<int>(), Hf,
+                               Ufold->D, acc_gain(3 * 64 / 16), F.fold_G.as<float>(), F.fold_delta.as<float>(), st));
+        NFB_TRY(launch_matrix_norms(F.fold_G.as<float>(), Hf, 64, f->norms.as<float>() + 3 * ng, st));
+    }
     // biases (tiny; synchronous download is fine at pack time)
     NFB_CUDA(cudaStreamSynchronize(st));
     std::vector<float> nm;
@@ -626,22 +646,10 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
         for (int j = 0; j < H; ++j) bh[(size_t)(2 + 2 * b) * 256 + j] = cum[hp[j]];
     }
     F.bias_h = bh;
-    // LU fold: G = gain * E0 E_lu[in_idx, :], delta = E0 b_lu[in_idx] (fp64 accumulation), norms of G
+    // LU fold, host part: norms of G and the bias shift
     std::vector<float> fold_nm;
     float fold_bmax = 0.f;
     if (Ufold) {
-        auto& g0 = F.gemms[0];
-        NFB_TRY(F.fold_lu.reserve(64 * 64 * 4));
-        NFB_TRY(F.fold_G.reserve((size_t)H * 64 * 4));
-        NFB_TRY(F.fold_delta.reserve((size_t)H * 4));
-        NFB_TRY(launch_build_effective(g0.W, g0.M, g0.src_cols, g0.src_row.as<int>(), g0.src_col.as<int>(), nullptr,
-                                       f->E.as<float>(), H, 64, 1.f, st));
-        NFB_TRY(launch_build_effective(Ufold->lu_Wd.as<float>(), nullptr, Ufold->D, F.lu_src_row.as<int>(),
-                                       F.lu_src_col.as<int>(), nullptr, F.fold_lu.as<float>(), 64, 64, 1.f, st));
-        NFB_TRY(launch_fold_lu(f->E.as<float>(), F.fold_lu.as<float>(), Ufold->lu.bias, F.in_idx_dev.as<int>(), H,
-                               Ufold->D, acc_gain(3 * 64 / 16), F.fold_G.as<float>(), F.fold_delta.as<float>(), st));
-        NFB_TRY(launch_matrix_norms(F.fold_G.as<float>(), H, 64, f->norms.as<float>() + 3 * ng, st));
-        NFB_CUDA(cudaStreamSynchronize(st));
         NFB_TRY(download(f->norms.as<float>() + 3 * ng, 3, fold_nm));
         NFB_TRY(download(F.fold_delta.as<float>(), (size_t)H, F.fold_delta_host));
         for (int j = 0; j < H; ++j) fold_bmax = std::max(fold_bmax, std::fabs(bh[j] + F.fold_delta_host[j]));
@@ -815,8 +823,7 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     if (F.fold_ok) {
         // the block's first two records (GEMM 0, K-chunk 0, all H rows) are replaced by the folded matrix
         NFB_CUDA(cudaMemcpyAsync(F.pair_wstream.as<uint8_t>() + 2 * 8192, F.fold_recs.p, (size_t)F.H * 256,
-                                 cudaMemcpyDeviceToDevice, st));
-        NFB_CUDA(cudaStreamSynchronize(st));
+                                 cudaMemcpyDeviceToDevice, st));   // (stream-ordered after the copy of the block's records)
         Lp.fold_lu = 1;
         Lp.steps = F.pair_steps_fold_dev.as<FusedStep>();
         for (int ph = 0; ph < F.n_hidden; ph += 2)   // b0 (+ W0 b_lu) is part of every pre-summed residual bias
@@ -1101,6 +1108,22 @@ int nfb_rqs_spline(const float* x, const float* params, float* y, float* log_det
     if (log_det && !accumulate) NFB_TRY(launch_fill(log_det, rows, 0.f, S(stream)));
     return launch_rqs_rows(x, params, y, log_det, rows, feats, feats, nullptr, num_bins, tail_bound,
                            wh_scale, inverse, S(stream));
+}
+
+int nfb_rqs_spline_tails(const float* x, const float* params, float* y, float* log_det, int64_t rows, int32_t feats,
+                         int32_t num_bins, int32_t num_derivatives, const float* tail_bound, const int32_t* circular,
+                         float wh_scale, int32_t inverse, int32_t accumulate, void* stream) {
+    NFB_CHECK(x && params && y && tail_bound && circular, NFB_ERR_ARG, "nfb_rqs_spline_tails: null pointer");
+    NFB_CHECK(rows >= 0 && feats >= 0, NFB_ERR_ARG, "nfb_rqs_spline_tails: negative size");
+    if (log_det && !accumulate) NFB_TRY(launch_fill(log_det, rows, 0.f, S(stream)));
+    return launch_rqs_rows_tails(x, params, y, log_det, rows, feats, num_bins, num_derivatives, tail_bound, circular,
+                                 wh_scale, inverse, S(stream));
+}
+int nfb_periodic_features(const float* x, float* y, int64_t rows, int32_t dim, const int32_t* slot, const float* weights,
+                          const float* scale, const float* bias, void* stream) {
+    NFB_CHECK(x && y && slot && weights && scale, NFB_ERR_ARG, "nfb_periodic_features: null pointer");
+    NFB_CHECK(rows >= 0 && dim >= 0, NFB_ERR_ARG, "nfb_periodic_features: negative size");
+    return launch_periodic_features(x, y, rows, dim, slot, weights, scale, bias, S(stream));
 }
 
 int nfb_diag_gaussian_log_prob(const float* z, const float* loc, const float* log_scale, float* log_q,

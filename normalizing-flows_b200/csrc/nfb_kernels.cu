@@ -140,6 +140,82 @@ int launch_rqs_rows(const float* zin, const float* params, float* zout, float* l
     return NFB_OK;
 }
 
+// -----------------------------------------------------------------------------------------
+// stand-alone spline with PER-FEATURE tails (circular NSF layers, flows/neural_spline/wrapper.py:88-183,247-311;
+// utils/splines.py:42-57): nd derivative parameters per element (K + 1 for a tails list, K for all-circular),
+// circ[f] != 0 = circular feature, tail[f] = that feature's bound.  One thread per element, parameters read in place
+// (breadth path: the flagship shapes never come here).
+// -----------------------------------------------------------------------------------------
+template <bool INVERSE>
+__global__ void __launch_bounds__(256)
+rqs_rows_tails_kernel(const float* __restrict__ zin, const float* __restrict__ params, float* __restrict__ zout,
+                      float* __restrict__ logdet, long long rows, int feats, int K, int nd,
+                      const float* __restrict__ tail, const int* __restrict__ circ, float wh_scale) {
+    const long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+    const long long total = rows * (long long)feats;
+    float lad = 0.f;
+    long long row = -1;
+    if (e < total) {
+        row = e / feats;
+        const int f = (int)(e - row * feats);
+        const float* p = params + e * (long long)(2 * K + nd);
+        auto acc = [p](int i) { return __ldg(p + i); };
+        float y;
+        rqs_eval_dyn<INVERSE>(K, zin[e], acc, __ldg(tail + f), wh_scale, y, lad, nd, __ldg(circ + f) != 0);
+        zout[e] = y;
+    }
+    if (logdet) {
+        const unsigned lane = threadIdx.x & 31;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float v = __shfl_down_sync(0xffffffffu, lad, o);
+            const long long r = __shfl_down_sync(0xffffffffu, row, o);
+            if (lane + o < 32 && r == row) lad += v;
+        }
+        const long long prev = __shfl_up_sync(0xffffffffu, row, 1);
+        if (row >= 0 && (lane == 0 || prev != row)) atomicAdd(logdet + row, lad);
+    }
+}
+int launch_rqs_rows_tails(const float* zin, const float* params, float* zout, float* logdet, long long rows, int feats,
+                          int K, int nd, const float* tail, const int* circ, float wh_scale, int inverse,
+                          cudaStream_t st) {
+    NFB_CHECK(K >= 1 && K <= 32, NFB_ERR_ARG, "rqs: num_bins %d out of range [1,32]", K);
+    NFB_CHECK(nd == K || nd == K + 1, NFB_ERR_ARG, "rqs tails: %d derivative parameters for %d bins", nd, K);
+    if (rows == 0 || feats == 0) return NFB_OK;
+    const long long total = rows * (long long)feats;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (inverse) rqs_rows_tails_kernel<true><<<grid, 256, 0, st>>>(zin, params, zout, logdet, rows, feats, K, nd, tail, circ, wh_scale);
+    else rqs_rows_tails_kernel<false><<<grid, 256, 0, st>>>(zin, params, zout, logdet, rows, feats, K, nd, tail, circ, wh_scale);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
+// PeriodicFeaturesElementwise (utils/nn.py:64-130): y[r, j] = w[j,0] sin(s[j] x) + w[j,1] cos(s[j] x) (+ b[j]) where
+// kind[j] >= 0 is the feature's slot in the periodic parameter tables, y = x elsewhere.
+__global__ void periodic_features_kernel(const float* __restrict__ x, float* __restrict__ y, long long rows, int dim,
+                                         const int* __restrict__ slot, const float* __restrict__ w,
+                                         const float* __restrict__ scale, const float* __restrict__ bias) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * dim) return;
+    const int j = (int)(e % dim);
+    const int k = slot[j];
+    float v = x[e];
+    if (k >= 0) {
+        const float a = scale[k] * v;
+        v = w[2 * k] * sinf(a) + w[2 * k + 1] * cosf(a);
+        if (bias) v += bias[k];
+    }
+    y[e] = v;
+}
+int launch_periodic_features(const float* x, float* y, long long rows, int dim, const int* slot, const float* w,
+                             const float* scale, const float* bias, cudaStream_t st) {
+    if (rows == 0 || dim == 0) return NFB_OK;
+    const long long n = rows * dim;
+    periodic_features_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, y, rows, dim, slot, w, scale, bias);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
 int launch_rqs_shared(const float* zin, const float* table, float* zout, float* logdet,
                       long long rows, int feats, int ld, const int* fidx, int K, float tail,
                       int inverse, cudaStream_t st) {

@@ -42,6 +42,11 @@ struct PerDevice {
 int launch_rqs_rows(const float* zin, const float* params, float* zout, float* logdet,
                     long long rows, int feats, int ld, const int* fidx, int K, float tail,
                     float wh_scale, int inverse, cudaStream_t st);
+int launch_rqs_rows_tails(const float* zin, const float* params, float* zout, float* logdet, long long rows, int feats,
+                          int K, int nd, const float* tail, const int* circ, float wh_scale, int inverse,
+                          cudaStream_t st);
+int launch_periodic_features(const float* x, float* y, long long rows, int dim, const int* slot, const float* w,
+                             const float* scale, const float* bias, cudaStream_t st);
 int launch_rqs_shared(const float* zin, const float* table, float* zout, float* logdet,
                       long long rows, int feats, int ld, const int* fidx, int K, float tail,
                       int inverse, cudaStream_t st);

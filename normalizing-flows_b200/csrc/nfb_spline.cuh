@@ -86,9 +86,12 @@ __host__ __device__ __forceinline__ float softplus_f(float u) {
 // distance of a knot falls on is immaterial because the spline and its derivative are continuous there.
 // K = 8 (the reference default) locates the bin by bisection on the 9 knots: 3 compares + 30 selects
 // carrying {left, right} of both axes and the two derivative logits, instead of a 7-step scan.
+// ud_first / ud_last: raw derivative parameters of the two boundary knots.  Linear tails pin both to the constant that
+// makes the derivative exactly 1 (:35-38); circular tails (:42-45, :48-57) pass learned values (last = first).
 template <int K, bool INVERSE, typename PD>
 __host__ __device__ __forceinline__ void rqs_core(float x, const float (&lw)[K], const float (&lh)[K], PD pd,
-                                                  float tail, float& y, float& lad) {
+                                                  float tail, float& y, float& lad,
+                                                  float ud_first = NFB_BOUNDARY_UD, float ud_last = NFB_BOUNDARY_UD) {
     const bool inside = (x >= -tail) && (x <= tail);
     float mw = lw[0], mh = lh[0];
 #pragma unroll
@@ -109,7 +112,7 @@ __host__ __device__ __forceinline__ void rqs_core(float x, const float (&lw)[K],
     const float ah = (1.f - kMinBinHeight * K) * rcp_nr(sh);
     float kw[K + 1], kh[K + 1], ud[K + 1];
     kw[0] = 0.f; kh[0] = 0.f; kw[K] = 1.f; kh[K] = 1.f;
-    ud[0] = NFB_BOUNDARY_UD; ud[K] = NFB_BOUNDARY_UD;
+    ud[0] = ud_first; ud[K] = ud_last;
 #pragma unroll
     for (int i = 0; i < K - 1; ++i) {
         kw[i + 1] = fmaf(aw, cw[i], kMinBinWidth * (float)(i + 1));
@@ -200,9 +203,16 @@ __host__ __device__ __forceinline__ void rqs_eval(float x, P p, float tail, floa
 
 // Runtime-K version (K <= 32) reading parameters through the accessor twice; used by the
 // generic kernels for bin counts other than 8.
+// nd = number of derivative parameters per element: K - 1 (linear tails; boundaries pinned), K (circular: parameter
+// i is knot i, knot K repeats knot 0) or K + 1 (per-feature tails list: parameters 0..K are the knots; `circular`
+// says whether this feature copies knot 0 into knot K or pins both ends, utils/splines.py:48-57).
 template <bool INVERSE, typename P>
 __host__ __device__ __forceinline__ void rqs_eval_dyn(int K, float x, P p, float tail, float wh_scale,
-                                             float& y, float& lad) {
+                                             float& y, float& lad, int nd = -1, bool circular = false) {
+    if (nd < 0) nd = K - 1;
+    const int dshift = nd == K - 1 ? 1 : 0;                      // parameter index of knot i is i - dshift
+    const float ud_first = (nd == K - 1 || !circular) ? NFB_BOUNDARY_UD : p(2 * K);
+    const float ud_last = ud_first;
     const bool inside = (x >= -tail) && (x <= tail);
     const float s2 = wh_scale * kLog2e;
     float mw = -3.0e38f, mh = -3.0e38f;
@@ -220,7 +230,7 @@ __host__ __device__ __forceinline__ void rqs_eval_dyn(int K, float x, P p, float
     const float two_b = 2.f * tail;
     float cumw = 0.f, cumh = 0.f, left = -tail, bottom = -tail;
     float in_cw = -tail, in_w = 1.f, in_ch = -tail, in_h = 1.f;
-    float ud0 = NFB_BOUNDARY_UD, ud1 = NFB_BOUNDARY_UD;
+    float ud0 = ud_first, ud1 = ud_last;
     for (int i = 0; i < K; ++i) {
         cumw += kMinBinWidth + kw * fast_ex2(p(i) * s2 - mw);
         cumh += kMinBinHeight + kh * fast_ex2(p(K + i) * s2 - mh);
@@ -232,8 +242,8 @@ __host__ __device__ __forceinline__ void rqs_eval_dyn(int K, float x, P p, float
             in_w = right - left;
             in_ch = bottom;
             in_h = top - bottom;
-            ud0 = (i == 0) ? NFB_BOUNDARY_UD : p(2 * K + i - 1);
-            ud1 = (i == K - 1) ? NFB_BOUNDARY_UD : p(2 * K + i);
+            ud0 = (i == 0) ? ud_first : p(2 * K + i - dshift);
+            ud1 = (i == K - 1) ? ud_last : p(2 * K + i + 1 - dshift);
         }
         left = right;
         bottom = top;
@@ -265,7 +275,9 @@ __host__ __device__ __forceinline__ void rqs_eval_dyn(int K, float x, P p, float
     const float dnum = delta * delta * (d1 * theta * theta + 2.f * delta * tomt + d0 * omt * omt);
     float l = kLn2 * (fast_lg2(dnum) - 2.f * fast_lg2(den));
     if (INVERSE) l = -l;
-    y = inside ? out : x;
+    // (tails given as a LIST, nd = K + 1: the reference leaves out-of-interval outputs at their zero initialisation,
+    //  utils/splines.py:31,48-57 -- no identity copy in that branch; restated as is)
+    y = inside ? out : (nd == K + 1 ? 0.f : x);
     lad = inside ? l : 0.f;
 }
 

@@ -83,6 +83,8 @@ SYMBOLS = {
     "nfb_last_error": (C.c_char_p, []),
     "nfb_device_info": (C.c_int, [_I32P, _I32P, _I32P]),
     "nfb_rqs_spline": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _F, _F, _I32, _I32, _VP]),
+    "nfb_rqs_spline_tails": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _VP, _VP, _F, _I32, _I32, _VP]),
+    "nfb_periodic_features": (C.c_int, [_VP, _VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP]),
     "nfb_diag_gaussian_log_prob": (C.c_int, [_VP, _VP, _VP, _VP, _I64, _I32, _I32, _VP]),
     "nfb_swish": (C.c_int, [_VP, _F, _I64, _VP, _VP, _VP]),
     "nfb_mul_rows": (C.c_int, [_VP, _VP, _I64, _I32, _VP, _VP]),

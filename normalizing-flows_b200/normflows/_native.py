@@ -370,6 +370,33 @@ def rqs_spline(x, params, num_bins, tail_bound, wh_scale, inverse):
     return y, ld
 
 
+def rqs_spline_tails(x, params, num_bins, num_derivatives, tail_bound, circular, wh_scale, inverse):
+    """utils/splines.py:16-97 with per-feature tails (:42-57): tail_bound float32 [feats] and circular int32 [feats] on
+    the device, params [rows, feats * (2 K + num_derivatives)] (csrc/nfb_kernels.cu rqs_rows_tails_kernel)."""
+    x = require_cuda_f32(x)
+    params = params.contiguous()
+    y = torch.empty_like(x)
+    ld = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    if x.shape[0]:
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nfb_rqs_spline_tails(L.ptr(x), L.ptr(params), L.ptr(y), L.ptr(ld), x.shape[0], x.shape[1],
+                                                 num_bins, num_derivatives, L.ptr(tail_bound), L.ptr(circular),
+                                                 C.c_float(wh_scale), int(inverse), 0, L.stream_ptr()))
+    return y, ld
+
+
+def periodic_features(x, slot, weights, scale, bias=None):
+    """utils/nn.py:64-130 PeriodicFeaturesElementwise.forward on the device (csrc/nfb_kernels.cu)."""
+    x = require_cuda_f32(x)
+    y = torch.empty_like(x)
+    if x.numel():
+        with torch.cuda.device(x.device):
+            L.check(L.lib().nfb_periodic_features(L.ptr(x), L.ptr(y), x.shape[0], x.shape[1], L.ptr(slot),
+                                                  L.ptr(weights), L.ptr(scale), L.ptr(bias) if bias is not None else None,
+                                                  L.stream_ptr()))
+    return y
+
+
 def resnet_desc(net, masked):
     """Fill an nfb_resnet_desc_t from a ResidualNet / MADE shim; returns (desc, keepalive)."""
     nb = len(net.blocks)

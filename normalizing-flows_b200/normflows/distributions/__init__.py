@@ -1,2 +1,2 @@
-from .base import BaseDistribution, DiagGaussian, ClassCondDiagGaussian, ConditionalDiagGaussian
+from .base import BaseDistribution, DiagGaussian, ClassCondDiagGaussian, ConditionalDiagGaussian, GlowBase
 from .target import TwoMoons

@@ -145,3 +145,86 @@ class ConditionalDiagGaussian(BaseDistribution):
                 L.check(L.lib().nfb_diag_gaussian_log_prob(L.ptr(u), L.ptr(zeros), L.ptr(zeros), L.ptr(out), z.shape[0],
                                                            self.d, 0, L.stream_ptr()))
         return out - torch.sum(log_scale.reshape(z.shape[0], -1), dim=1)
+
+
+class GlowBase(BaseDistribution):
+    """Base distribution of the Glow model (reference: distributions/base.py:347-471): diagonal Gaussian with one mean
+    and one log-scale per CHANNEL (`loc * exp(loc_logs * f)`, `log_scale * exp(log_scale_logs * f)`), optionally shifted
+    per class (`loc_cc`, `log_scale_cc`).  The per-channel / per-class parameter tables are a few hundred numbers and are
+    assembled with torch on the device (parameter preparation, like the reference); the density of the batch is the CUDA
+    kernel (csrc/nfb_kernels.cu diag_gauss_kernel / csrc/nfb_glow.cu class-conditional twin)."""
+
+    def __init__(self, shape, num_classes=None, logscale_factor=3.0):
+        super().__init__()
+        if isinstance(shape, int):
+            shape = (shape,)
+        shape = tuple(shape)
+        self.shape, self.n_dim = shape, len(shape)
+        self.num_pix = int(np.prod(shape[1:]))
+        self.d = int(np.prod(shape))
+        self.num_classes = num_classes
+        self.class_cond = num_classes is not None
+        self.logscale_factor = logscale_factor
+        one = (1, shape[0]) + (1,) * (self.n_dim - 1)
+        self.loc = nn.Parameter(torch.zeros(*one))
+        self.loc_logs = nn.Parameter(torch.zeros(*one))
+        self.log_scale = nn.Parameter(torch.zeros(*one))
+        self.log_scale_logs = nn.Parameter(torch.zeros(*one))
+        if self.class_cond:
+            self.loc_cc = nn.Parameter(torch.zeros(num_classes, shape[0]))
+            self.log_scale_cc = nn.Parameter(torch.zeros(num_classes, shape[0]))
+        self.temperature = None
+
+    def _channel_params(self):
+        """([C] or [K, C]) mean and log-scale per channel (per class), base.py:397-424 / 438-461."""
+        with torch.no_grad():
+            loc = (self.loc * torch.exp(self.loc_logs * self.logscale_factor)).reshape(1, -1)
+            ls = (self.log_scale * torch.exp(self.log_scale_logs * self.logscale_factor)).reshape(1, -1)
+            if self.class_cond:
+                loc = loc + self.loc_cc
+                ls = ls + self.log_scale_cc
+            if self.temperature is not None:
+                ls = ls + np.log(self.temperature)
+        return loc, ls
+
+    @staticmethod
+    def _labels(y):
+        return y if y.dim() == 1 else torch.argmax(y, dim=1)   # one-hot rows select their class (base.py:403-411)
+
+    def forward(self, num_samples=1, y=None):
+        dev = self.loc.device
+        loc, ls = self._channel_params()
+        if self.class_cond:
+            if y is not None:
+                num_samples = len(y)
+                y = self._labels(y).to(device=dev, dtype=torch.int64)
+            else:
+                y = torch.randint(self.num_classes, (num_samples,), device=dev)
+            loc, ls = loc[y], ls[y]                                         # [B, C]
+        view = (-1, self.shape[0]) + (1,) * (self.n_dim - 1)
+        with torch.no_grad():
+            eps = torch.randn((num_samples,) + self.shape, dtype=self.loc.dtype, device=dev)
+            z = (loc.reshape(view) + torch.exp(ls.reshape(view)) * eps).contiguous()
+        return z, self.log_prob(z, y)
+
+    def log_prob(self, z, y=None):
+        z = require_cuda_f32(z)
+        loc, ls = self._channel_params()
+        out = torch.empty(z.shape[0], dtype=torch.float32, device=z.device)
+        if not z.shape[0]:
+            return out
+        with torch.cuda.device(z.device):
+            if self.class_cond:
+                y = self._labels(y).to(device=z.device, dtype=torch.int64).contiguous()
+                # [dim, K] tables: every pixel of channel c carries the channel's value
+                lt = loc.t().repeat_interleave(self.num_pix, dim=0).contiguous()
+                st = ls.t().repeat_interleave(self.num_pix, dim=0).contiguous()
+                L.check(L.lib().nfb_class_cond_diag_gaussian_log_prob(L.ptr(z), L.ptr(y), L.ptr(lt), L.ptr(st), L.ptr(out),
+                                                                      z.shape[0], self.d, self.num_classes, 0,
+                                                                      L.stream_ptr()))
+            else:
+                lt = loc.reshape(-1).repeat_interleave(self.num_pix).contiguous()
+                st = ls.reshape(-1).repeat_interleave(self.num_pix).contiguous()
+                L.check(L.lib().nfb_diag_gaussian_log_prob(L.ptr(z), L.ptr(lt), L.ptr(st), L.ptr(out), z.shape[0], self.d,
+                                                           0, L.stream_ptr()))
+        return out

@@ -62,8 +62,8 @@ class MADE(nn.Module):
         _check_plain(activation, dropout_probability, use_batch_norm, context_features)
         if not use_residual_blocks:
             raise NotImplementedError("feed-forward MADE blocks are not on the CUDA path")
-        if preprocessing is not None:
-            raise NotImplementedError("preprocessing is not on the CUDA path")
+        # (made.py:241-244: an elementwise module in front of the first masked layer, e.g. PeriodicFeaturesElementwise)
+        self.preprocessing = preprocessing
         in_deg = torch.arange(1, features + 1)
         if permute_mask:
             in_deg = in_deg[torch.randperm(features)]
@@ -81,4 +81,6 @@ class MADE(nn.Module):
     def forward(self, inputs, context=None):
         """nets/made.py:296-304, stand-alone call: masked weights, pre-activation residual blocks."""
         from .._native import resnet_forward
+        if self.preprocessing is not None:
+            inputs = self.preprocessing(inputs)
         return resnet_forward(self, inputs, masked=True, context=context)

@@ -37,10 +37,9 @@ class ResidualNet(nn.Module):
                  activation=F.relu, dropout_probability=0.0, use_batch_norm=False, preprocessing=None):
         super().__init__()
         _check_plain(activation, dropout_probability, use_batch_norm, context_features)
-        if preprocessing is not None:
-            raise NotImplementedError("preprocessing is not on the CUDA path")
         self.hidden_features = hidden_features
         self.context_features = context_features
+        self.preprocessing = preprocessing  # (a module, e.g. utils.nn.PeriodicFeaturesElementwise; resnet.py:71,93-96)
         self.initial_layer = nn.Linear(in_features + (context_features or 0), hidden_features)
         self.blocks = nn.ModuleList([ResidualBlock(hidden_features, context_features, activation) for _ in range(num_blocks)])
         self.final_layer = nn.Linear(hidden_features, out_features)
@@ -48,4 +47,6 @@ class ResidualNet(nn.Module):
     def forward(self, inputs, context=None):
         """nets/resnet.py:92-104, stand-alone call (inside a flow the net is part of the fused kernel)."""
         from .._native import resnet_forward
+        if self.preprocessing is not None:
+            inputs = self.preprocessing(inputs)
         return resnet_forward(self, inputs, masked=False, context=context)

@@ -71,9 +71,15 @@ def _knots(un, lo, hi, min_size):
     s = min_size + (1 - min_size * k) * s
     cum = np.cumsum(s, axis=-1, dtype=un.dtype)
     cum = np.concatenate([np.zeros_like(cum[..., :1]), cum], axis=-1)
-    cum = (hi - lo) * cum + lo
-    cum[..., 0] = lo
-    cum[..., -1] = hi
+    if np.ndim(lo) > 0:  # per-element bounds (:130-131, :145-148: the `lim_tensor` branch)
+        lo, hi = np.asarray(lo)[..., None], np.asarray(hi)[..., None]
+        cum = (hi - lo) * cum + lo
+        cum[..., 0] = lo[..., 0]
+        cum[..., -1] = hi[..., 0]
+    else:
+        cum = (hi - lo) * cum + lo
+        cum[..., 0] = lo
+        cum[..., -1] = hi
     size = cum[..., 1:] - cum[..., :-1]
     return cum.astype(un.dtype), size.astype(un.dtype)
 
@@ -301,6 +307,125 @@ def coupled_rqs(z, sd, p, L, direction):
     return out, ld
 
 
+def unconstrained_rqs_tails(x, uw, uh, ud, circular, inverse=False, tail_bound=1.0):
+    """utils/splines.py:16-97 with `tails` given as a list (:48-57): `ud` has K+1 entries per element; features with
+    linear tails overwrite entries 0 and K with the constant of :35-38, circular features copy entry 0 into entry K.
+    `circular`: bool [features]; `tail_bound`: scalar or [features] (broadcast_to, :61-66).  x: [B, features]."""
+    dt = x.dtype
+    tb = np.broadcast_to(np.asarray(tail_bound, dtype=dt), x.shape)
+    inside = (x >= -tb) & (x <= tb)
+    const = np.asarray(np.log(np.exp(1 - MIN_DERIVATIVE) - 1), dtype=dt)
+    udf = ud.astype(dt).copy()
+    circ = np.asarray(circular, dtype=bool)
+    udf[..., ~circ, 0] = const
+    udf[..., ~circ, -1] = const
+    udf[..., circ, -1] = udf[..., circ, 0]
+    xs = np.where(inside, x, np.zeros_like(x))
+    with np.errstate(all="ignore"):
+        y, lad = rational_quadratic_spline(xs, uw, uh, udf, inverse=inverse, left=-tb, right=tb, bottom=-tb, top=tb)
+    # NOTE (:48-57): the list branch never copies the out-of-interval inputs into `outputs`, which therefore keeps the
+    # zeros it was created with (:31) -- unlike the "linear" / "circular" string branches (:40-41, :46-47).  Restated as is.
+    return np.where(inside, y, np.zeros_like(x)).astype(dt), np.where(inside, lad, np.zeros_like(lad)).astype(dt)
+
+
+def periodic_features_elementwise(x, sd, p):
+    """utils/nn.py:120-130 PeriodicFeaturesElementwise.forward (no bias, identity activation): features `ind` become
+    w0 sin(scale f) + w1 cos(scale f), the rest pass through; order restored by inv_perm."""
+    ind = sd[p + "ind"].astype(np.int64)
+    ind_ = sd[p + "ind_"].astype(np.int64)
+    inv = sd[p + "inv_perm"].astype(np.int64)
+    w = sd[p + "weights"]
+    scale = sd[p + "scale"] if p + "scale" in sd else None
+    return ind, ind_, inv, w, scale
+
+
+def _periodic(x, sd, p, scale_default):
+    ind, ind_, inv, w, scale = periodic_features_elementwise(x, sd, p)
+    sc = np.asarray(scale_default if scale is None else scale, dtype=x.dtype)
+    a = sc * x[..., ind]
+    per = w[:, 0].astype(x.dtype) * np.sin(a) + w[:, 1].astype(x.dtype) * np.cos(a)
+    out = np.concatenate([per, x[..., ind_]], axis=-1)
+    return out[..., inv]
+
+
+def _tails_of(L, idx):
+    circ_all = np.zeros(L["features"], dtype=bool)
+    circ_all[np.asarray(L["ind_circ"], dtype=np.int64)] = True
+    return circ_all[idx]
+
+
+def circular_coupled_rqs(z, sd, p, L, direction):
+    """flows/neural_spline/wrapper.py:88-183 (CircularCoupledRationalQuadraticSpline) -> neural_spline/coupling.py:
+    71-128, 262-362 with tails as a per-feature list, PeriodicFeaturesElementwise in front of the ResidualNet
+    (wrapper.py:140-147) and the unconditional CDF with the identity features' tails (coupling.py:293-303)."""
+    k = L.get("num_bins", 8)
+    q = p + "prqct."
+    idf = sd[q + "identity_features"].astype(np.int64)
+    trf = sd[q + "transform_features"].astype(np.int64)
+    hidden = sd[q + "transform_net.initial_layer.weight"].shape[0]
+    bsz = z.shape[0]
+    tb_all = np.asarray(L.get("tail_bound", 3.0), dtype=np.float64)
+    tb_tr = tb_all[trf] if tb_all.ndim else tb_all
+    tb_id = tb_all[idf] if tb_all.ndim else tb_all
+    circ_tr, circ_id = _tails_of(L, trf), _tails_of(L, idf)
+    pre = q + "transform_net.preprocessing."
+    has_pre = (pre + "weights") in sd
+    # scale of the periodic features: pi / tail_bound of the circular identity features (wrapper.py:134-138)
+    ind_circ_id = [i for i, f in enumerate(idf) if f in set(L["ind_circ"])]
+    scale_pf = (np.pi / tb_all[idf][ind_circ_id]) if tb_all.ndim else np.pi / float(tb_all)
+
+    def net(v):
+        if has_pre:
+            v = _periodic(v, sd, pre, scale_pf)
+        return residual_net(v, sd, q + "transform_net.").reshape(bsz, len(trf), 3 * k + 1)
+
+    ident, trans = z[:, idf], z[:, trf]
+    u = q + "unconditional_transform."
+    bc = lambda a: np.broadcast_to(a[None], (bsz,) + a.shape).astype(z.dtype)
+    uuw, uuh, uud = bc(sd[u + "unnormalized_widths"]), bc(sd[u + "unnormalized_heights"]), \
+        bc(sd[u + "unnormalized_derivatives"])
+    if direction == "inverse":
+        uw, uh, ud = _split_params(net(ident), k, hidden)
+        yt, lad = unconstrained_rqs_tails(trans, uw, uh, ud, circ_tr, inverse=False, tail_bound=tb_tr)
+        yi, lad_i = unconstrained_rqs_tails(ident, uuw, uuh, uud, circ_id, inverse=False, tail_bound=tb_id)
+        ld = lad.sum(axis=1) + lad_i.sum(axis=1)
+    else:
+        yi, lad_i = unconstrained_rqs_tails(ident, uuw, uuh, uud, circ_id, inverse=True, tail_bound=tb_id)
+        uw, uh, ud = _split_params(net(yi), k, hidden)
+        yt, lad = unconstrained_rqs_tails(trans, uw, uh, ud, circ_tr, inverse=True, tail_bound=tb_tr)
+        ld = lad_i.sum(axis=1) + lad.sum(axis=1)
+    out = np.empty_like(z)
+    out[:, idf] = yi
+    out[:, trf] = yt
+    return out, ld
+
+
+def circular_ar_rqs(z, sd, p, L, direction):
+    """flows/neural_spline/wrapper.py:247-311 (CircularAutoregressiveRationalQuadraticSpline) ->
+    neural_spline/autoregressive.py:94-128 with tails as a per-feature list (3K+1 parameters per feature) and
+    PeriodicFeaturesElementwise in front of the MADE (autoregressive.py:44-53, nets/made.py:297)."""
+    k = L.get("num_bins", 8)
+    net = p + "mprqat.autoregressive_net."
+    bsz, d = z.shape
+    tb = np.asarray(L.get("tail_bound", 3.0), dtype=np.float64)
+    circ = _tails_of(L, np.arange(d))
+    scale_pf = (np.pi / tb[np.asarray(L["ind_circ"], dtype=np.int64)]) if tb.ndim else np.pi / float(tb)
+
+    def params_of(v):
+        v = _periodic(v, sd, net + "preprocessing.", scale_pf)
+        return _split_params(made(v, sd, net).reshape(bsz, d, 3 * k + 1), k, None)
+
+    if direction == "inverse":
+        uw, uh, ud = params_of(z)
+        y, lad = unconstrained_rqs_tails(z, uw, uh, ud, circ, inverse=False, tail_bound=tb)
+        return y, lad.sum(axis=1)
+    out, lad = np.zeros_like(z), None
+    for _ in range(d):
+        uw, uh, ud = params_of(out)
+        out, lad = unconstrained_rqs_tails(z, uw, uh, ud, circ, inverse=True, tail_bound=tb)
+    return out, lad.sum(axis=1)
+
+
 def lu_matrices(sd, p, dt):
     """flows/mixing.py:402-412 (_create_lower_upper), :514-516 (upper_diag, eps=1e-3)."""
     ud = sd[p + "linear.unconstrained_upper_diag"].astype(dt)
@@ -501,6 +626,8 @@ LAYERS = {
     "Invertible1x1Conv": inv1x1,
     "GlowBlock": glow_block,
     "Squeeze": squeeze,
+    "CircularCoupledRationalQuadraticSpline": circular_coupled_rqs,
+    "CircularAutoregressiveRationalQuadraticSpline": circular_ar_rqs,
 }
 
 
@@ -529,6 +656,27 @@ def class_cond_diag_gaussian_log_prob(z, y, sd, p):
 # --------------------------------------------------------------------------
 # drivers (core.py)
 # --------------------------------------------------------------------------
+def glow_base_log_prob(z, sd, p, y=None, logscale_factor=3.0, temperature=None):
+    """distributions/base.py:436-471 GlowBase.log_prob: per-channel mean / log-scale (times exp(*_logs * factor)), plus
+    the class rows of loc_cc / log_scale_cc, plus log(temperature); z: [B, C, ...]."""
+    dt = z.dtype
+    loc = sd[p + "loc"].astype(dt) * np.exp(sd[p + "loc_logs"].astype(dt) * logscale_factor)
+    ls = sd[p + "log_scale"].astype(dt) * np.exp(sd[p + "log_scale_logs"].astype(dt) * logscale_factor)
+    c = z.shape[1]
+    tail = (1,) * (z.ndim - 2)
+    if p + "loc_cc" in sd:
+        loc = loc + sd[p + "loc_cc"].astype(dt)[y].reshape((len(y), c) + tail)
+        ls = ls + sd[p + "log_scale_cc"].astype(dt)[y].reshape((len(y), c) + tail)
+    if temperature is not None:
+        ls = ls + np.log(temperature)
+    num_pix = int(np.prod(z.shape[2:]))
+    d = int(np.prod(z.shape[1:]))
+    axes = tuple(range(1, z.ndim))
+    ls_b = np.broadcast_to(ls, (z.shape[0],) + ls.shape[1:])
+    return (-0.5 * d * np.log(2 * np.pi) - num_pix * ls_b.sum(axis=axes)
+            - 0.5 * (((z - loc) / np.exp(ls)) ** 2).sum(axis=axes))
+
+
 def _cast(sd, dt):
     return {k: (v.astype(dt) if v.dtype.kind == "f" else v) for k, v in sd.items()}
 

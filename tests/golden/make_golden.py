@@ -564,3 +564,71 @@ def case_conditional():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "conditional":
     case_conditional()
+
+
+def case_circular():
+    """circular NSF layers (flows/neural_spline/wrapper.py:88-183, 247-311): per-feature tails list, periodic
+    features in front of the conditioner, scalar AND per-feature tail bounds; per-layer vectors in both directions.
+        python tests/golden/make_golden.py circular"""
+    torch.manual_seed(41)
+    g = torch.Generator().manual_seed(42)
+    out = {"torch_version": torch.__version__}
+    d = 6
+    tbt = torch.tensor([np.pi, 2.0, np.pi, 4.0, 3.0, np.pi])
+    cases = {
+        "cc_s": lambda: nf.flows.CircularCoupledRationalQuadraticSpline(d, 2, 32, [0, 2, 5], tail_bound=3.0),
+        "cc_t": lambda: nf.flows.CircularCoupledRationalQuadraticSpline(d, 1, 32, [0, 2, 5], tail_bound=tbt.clone(),
+                                                                         reverse_mask=True),
+        "ca_s": lambda: nf.flows.CircularAutoregressiveRationalQuadraticSpline(d, 2, 32, [1, 3], tail_bound=3.0),
+        "ca_t": lambda: nf.flows.CircularAutoregressiveRationalQuadraticSpline(d, 1, 32, [0, 2, 5], tail_bound=tbt.clone(),
+                                                                               permute_mask=False),
+    }
+    for tag, make in cases.items():
+        m = make()
+        perturb(m, 0.15, 43)
+        x = torch.randn(48, d, generator=g) * 1.6   # some coordinates beyond the smaller bounds -> identity branch
+        out[f"{tag}_x"] = x.numpy()
+        for k, v in m.state_dict().items():
+            out[f"{tag}__" + k] = v.detach().numpy()
+        md = m.double()
+        with torch.no_grad():
+            y, ld = md.forward(x.double())
+            xi, ldi = md.inverse(x.double())
+        out[f"{tag}_fwd_y"], out[f"{tag}_fwd_ld"] = y.numpy(), ld.numpy()
+        out[f"{tag}_inv_y"], out[f"{tag}_inv_ld"] = xi.numpy(), ldi.numpy()
+    out["tail_bound_tensor"] = tbt.numpy()
+    np.savez_compressed(os.path.join(HERE, "circular.npz"), **out)
+    print("wrote circular")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "circular":
+    case_circular()
+
+
+def case_glow_base():
+    """GlowBase (distributions/base.py:347-471): per-channel Gaussian, with and without class conditioning, with and
+    without temperature; log_prob in fp64.    python tests/golden/make_golden.py glow_base"""
+    g = torch.Generator().manual_seed(52)
+    out = {"torch_version": torch.__version__}
+    for tag, ncls in (("plain", None), ("cc", 5)):
+        torch.manual_seed(51)
+        q = nf.distributions.GlowBase((4, 3, 3), num_classes=ncls)
+        perturb(q, 0.3, 53)
+        z = torch.randn(20, 4, 3, 3, generator=g) * 1.3
+        y = torch.randint(5, (20,), generator=g) if ncls else None
+        out[f"{tag}_z"] = z.numpy()
+        if y is not None:
+            out[f"{tag}_y"] = y.numpy()
+        for k, v in q.state_dict().items():
+            out[f"{tag}__" + k] = v.detach().numpy()
+        qd = q.double()
+        with torch.no_grad():
+            out[f"{tag}_lp"] = (qd.log_prob(z.double(), y) if ncls else qd.log_prob(z.double())).numpy()
+            qd.temperature = 0.7
+            out[f"{tag}_lp_t07"] = (qd.log_prob(z.double(), y) if ncls else qd.log_prob(z.double())).numpy()
+    np.savez_compressed(os.path.join(HERE, "glow_base.npz"), **out)
+    print("wrote glow_base")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "glow_base":
+    case_glow_base()

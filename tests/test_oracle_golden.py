@@ -125,3 +125,40 @@ def test_gradient_oracle_matches_reference_autograd(kind):
     assert len(names) >= 48 and set(names) == set(grads)
     for n in names:
         np.testing.assert_allclose(grads[n], g["grad__" + n], rtol=1e-9, atol=1e-12, err_msg=n)
+
+
+_CIRC = {"cc_s": ("CircularCoupledRationalQuadraticSpline", [0, 2, 5], False),
+         "cc_t": ("CircularCoupledRationalQuadraticSpline", [0, 2, 5], True),
+         "ca_s": ("CircularAutoregressiveRationalQuadraticSpline", [1, 3], False),
+         "ca_t": ("CircularAutoregressiveRationalQuadraticSpline", [0, 2, 5], True)}
+
+
+@pytest.mark.parametrize("tag", sorted(_CIRC))
+def test_circular_spline_layers_fp64(tag):
+    """Circular NSF layers (per-feature tails, periodic features, scalar / per-feature bounds) against vectors minted
+    from the reference (tests/golden/make_golden.py circular): both directions, fp64, 1e-10."""
+    f = np.load("tests/golden/circular.npz")
+    kind, ind_circ, tensor_tb = _CIRC[tag]
+    sd = {"flows.0." + k[len(tag) + 2:]: np.asarray(f[k]) for k in f.files if k.startswith(tag + "__")}
+    L = {"type": kind, "features": 6, "ind_circ": ind_circ, "num_bins": 8,
+         "tail_bound": np.asarray(f["tail_bound_tensor"], dtype=np.float64) if tensor_tb else 3.0}
+    sd = {k: (v.astype(np.float64) if v.dtype.kind == "f" else v) for k, v in sd.items()}
+    x = np.asarray(f[f"{tag}_x"], dtype=np.float64)
+    fn = O.LAYERS[kind]
+    y, ld = fn(x, sd, "flows.0.", L, "forward")
+    np.testing.assert_allclose(y, f[f"{tag}_fwd_y"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(ld, f[f"{tag}_fwd_ld"], rtol=1e-10, atol=1e-10)
+    y, ld = fn(x, sd, "flows.0.", L, "inverse")
+    np.testing.assert_allclose(y, f[f"{tag}_inv_y"], rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(ld, f[f"{tag}_inv_ld"], rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("tag", ["plain", "cc"])
+def test_glow_base_log_prob_fp64(tag):
+    """GlowBase.log_prob (distributions/base.py:436-471) against reference-minted vectors, with and without temperature."""
+    f = np.load("tests/golden/glow_base.npz")
+    sd = {k[len(tag) + 2:]: np.asarray(f[k]).astype(np.float64) for k in f.files if k.startswith(tag + "__")}
+    z = np.asarray(f[f"{tag}_z"], dtype=np.float64)
+    y = np.asarray(f[f"{tag}_y"]) if tag == "cc" else None
+    np.testing.assert_allclose(O.glow_base_log_prob(z, sd, "", y), f[f"{tag}_lp"], rtol=1e-11, atol=1e-11)
+    np.testing.assert_allclose(O.glow_base_log_prob(z, sd, "", y, temperature=0.7), f[f"{tag}_lp_t07"], rtol=1e-11, atol=1e-11)
