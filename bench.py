@@ -457,9 +457,11 @@ def main():
                 "traffic": traffic, "kernel_ms": k_ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst; of measured)" if peaks else "fallback 1650 (of fallback)",
                 "note": "algorithmic = dense fp32-equivalent GEMM flops of the reference (1.327 MFLOP/sample/layer x 32 "
-                        "layers, SURVEY 8d).  The kernel runs every product as 3 bf16 tensor-core passes (split "
-                        "precision, needed for the rtol 1e-4 bar) so frac <= 1/3 by construction, and skips the "
-                        "all-zero blocks of the MADE masks (~31 % of the dense MMA work); ncu: tensor pipe 44 % active"}
+                        "layers, SURVEY 8d).  The kernel runs every product as 3 fp16 tensor-core passes (split "
+                        "precision with power-of-two operand scaling, needed for the rtol 1e-4 bar) so frac <= 1/3 by "
+                        "construction, and skips the all-zero blocks of the MADE masks (~31 % of the dense MMA work); "
+                        "ncu (profiles/r02b_fused_stack_ncu_summary.md): tensor pipe 42 % active, SM clock 1.81 GHz "
+                        "under this kernel's load"}
 
     # ---- training step (extra key; every rank takes part): forward_kld + native backward (tensor-core dgrad /
     # wgrad, analytic spline adjoint) + DDP-style bucketed gradient all-reduce (NCCL when world > 1) + Adam step.

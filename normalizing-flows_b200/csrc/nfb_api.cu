@@ -184,6 +184,7 @@ struct nfb_flow {
     const float* base_loc = nullptr;
     const float* base_log_scale = nullptr;
     // workspaces
+    DevBuf lu_args;                 // batched LU pack: one LuPackArgs per LULinearPermute layer
     DevBuf stack_layers, progress;  // whole-stack launch: FusedLayer[stack_n] in density order + tile flags
     int stack_n = 0;
     // sampling-direction plan: units (LU index or -1, spline index) in list order, optional trailing LU
@@ -724,14 +725,15 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
 }
 
 // LU layer pack (generic + the pieces the fused pair needs)
-int repack_lu(nfb_flow* f, Layer& L, cudaStream_t st) {
+int repack_lu(nfb_flow* f, Layer& L, cudaStream_t st, bool packed_already = false) {
     const int n = L.D;
     NFB_TRY(L.lu_Wd.reserve((size_t)n * n * 4));
     NFB_TRY(L.lu_Ws.reserve((size_t)n * n * 4));
     NFB_TRY(L.lu_logdet.reserve(4));
-    NFB_TRY(launch_lu_pack(L.lu.lower_entries, L.lu.upper_entries, L.lu.unconstrained_upper_diag,
-                           L.lu.eps, n, L.lu_Wd.as<float>(), L.lu_Ws.as<float>(),
-                           L.lu_logdet.as<float>(), st));
+    if (!packed_already)   // (nfb_flow_repack forms W, W^-1 and the log-det of ALL LU layers in one batched launch)
+        NFB_TRY(launch_lu_pack(L.lu.lower_entries, L.lu.upper_entries, L.lu.unconstrained_upper_diag,
+                               L.lu.eps, n, L.lu_Wd.as<float>(), L.lu_Ws.as<float>(),
+                               L.lu_logdet.as<float>(), st));
     // sampling direction: x = (z - b) Winv^T = z Winv^T + bs with bs = -Winv b (tiny; host side)
     NFB_CUDA(cudaStreamSynchronize(st));
     std::vector<float> winv, b, bs(n);
@@ -1388,8 +1390,27 @@ int nfb_flow_repack(nfb_flow_t* f, void* stream) {
     NFB_CHECK(f && f->finalized, NFB_ERR_STATE, "nfb_flow_repack: flow not finalized");
     cudaStream_t st = S(stream);
     // LU maps first: the fused blocks' fp16 scale plans need the norms of the maps in front of them
+    {
+        std::vector<LuPackArgs> args;
+        int n_max = 1;
+        for (auto& Lp : f->layers)
+            if (Lp->kind == L_LU) {
+                Layer& L = *Lp;
+                const int n = L.D;
+                NFB_TRY(L.lu_Wd.reserve((size_t)n * n * 4));
+                NFB_TRY(L.lu_Ws.reserve((size_t)n * n * 4));
+                NFB_TRY(L.lu_logdet.reserve(4));
+                args.push_back(LuPackArgs{L.lu.lower_entries, L.lu.upper_entries, L.lu.unconstrained_upper_diag, L.lu.eps, n,
+                                          L.lu_Wd.as<float>(), L.lu_Ws.as<float>(), L.lu_logdet.as<float>()});
+                n_max = std::max(n_max, n);
+            }
+        if (!args.empty()) {
+            NFB_TRY(f->lu_args.upload(args));
+            NFB_TRY(launch_lu_pack_batched(f->lu_args.as<LuPackArgs>(), (int)args.size(), n_max, st));
+        }
+    }
     for (auto& Lp : f->layers)
-        if (Lp->kind == L_LU) NFB_TRY(repack_lu(f, *Lp, st));
+        if (Lp->kind == L_LU) NFB_TRY(repack_lu(f, *Lp, st, true));
     for (auto& Lp : f->layers) {
         Layer& L = *Lp;
         // |input| u_row < 1.  Coupled block, sampling direction: the conditioner sees the inverse unconditional

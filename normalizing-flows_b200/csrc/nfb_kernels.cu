@@ -336,10 +336,10 @@ int launch_mask_mul(const float* w, const float* m, float* out, long long n, cud
 // _LULinear (flows/mixing.py:402-412,:514-532): builds W = L U  [n,n] (row-major, y = x W^T + b),
 // Winv = (L U)^-1 (for the sampling direction, :436-473), and logabsdet = sum log(softplus(d)+eps).
 // One block; n <= 64.  Triangular entries are packed row-major (np.tril_indices / np.triu_indices).
-__global__ void lu_pack_kernel(const float* __restrict__ lower_e, const float* __restrict__ upper_e,
-                               const float* __restrict__ udiag, float eps, int n,
-                               float* __restrict__ Wout, float* __restrict__ Winv,
-                               float* __restrict__ logabsdet) {
+__device__ __forceinline__ void lu_pack_block(const float* __restrict__ lower_e, const float* __restrict__ upper_e,
+                                              const float* __restrict__ udiag, float eps, int n,
+                                              float* __restrict__ Wout, float* __restrict__ Winv,
+                                              float* __restrict__ logabsdet) {
     extern __shared__ double sh[];
     double* L = sh;               // n*n
     double* U = sh + n * n;       // n*n
@@ -394,6 +394,26 @@ __global__ void lu_pack_kernel(const float* __restrict__ lower_e, const float* _
         for (int k = max(r, c); k < n; ++k) acc += Ui[r * n + k] * Li[k * n + c];
         Winv[i] = (float)acc;
     }
+}
+__global__ void lu_pack_kernel(const float* __restrict__ lower_e, const float* __restrict__ upper_e,
+                               const float* __restrict__ udiag, float eps, int n, float* __restrict__ Wout,
+                               float* __restrict__ Winv, float* __restrict__ logabsdet) {
+    lu_pack_block(lower_e, upper_e, udiag, eps, n, Wout, Winv, logabsdet);
+}
+// every LU layer of a flow in ONE launch, one block per layer (a 32-layer stack spent 3.9 ms per repack in 32 serialised
+// single-block launches: profiles/r02b_launches_bench_steps2.csv of the packing phase)
+__global__ void lu_pack_batched_kernel(const LuPackArgs* __restrict__ args) {
+    const LuPackArgs a = args[blockIdx.x];
+    lu_pack_block(a.lower_e, a.upper_e, a.udiag, a.eps, a.n, a.W, a.Winv, a.logabsdet);
+}
+int launch_lu_pack_batched(const LuPackArgs* args_dev, int count, int n_max, cudaStream_t st) {
+    if (count == 0) return NFB_OK;
+    NFB_CHECK(n_max >= 1 && n_max <= 64, NFB_ERR_UNSUPPORTED, "LULinearPermute: features %d > 64", n_max);
+    const size_t smem = (size_t)4 * n_max * n_max * sizeof(double);
+    NFB_CUDA(cudaFuncSetAttribute(lu_pack_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    lu_pack_batched_kernel<<<count, 256, smem, st>>>(args_dev);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
 }
 int launch_lu_pack(const float* lower_e, const float* upper_e, const float* udiag, float eps, int n,
                    float* W, float* Winv, float* logabsdet, cudaStream_t st) {

@@ -56,6 +56,11 @@ int launch_linear(const float* X, int ldx, const int* xidx, const float* W, cons
 int launch_maf_affine(const float* x, const float* params, float* y, float* logdet, long long rows, int d, int inverse,
                       int accumulate, cudaStream_t st);
 int launch_mask_mul(const float* w, const float* m, float* out, long long n, cudaStream_t st);
+struct LuPackArgs {
+    const float* lower_e; const float* upper_e; const float* udiag; float eps; int n;
+    float* W; float* Winv; float* logabsdet;
+};
+int launch_lu_pack_batched(const LuPackArgs* args_dev, int count, int n_max, cudaStream_t st);
 int launch_lu_pack(const float* lower_e, const float* upper_e, const float* udiag, float eps, int n,
                    float* W, float* Winv, float* logabsdet, cudaStream_t st);
 int launch_add_scalar(float* v, long long n, const float* c, float sign, cudaStream_t st);

@@ -24,3 +24,23 @@ for i in range(steps):
     torch.cuda.synchronize()
     t2 = time.perf_counter()
     print(f"step {i}: forward {1e3 * (t1 - t0):.2f} ms, backward {1e3 * (t2 - t1):.2f} ms, loss {float(loss):.4f}", flush=True)
+
+# host cost of re-packing the weights (every optimizer step triggers one): nfb_flow_repack alone
+from normflows._native import invalidate_packed_weights  # noqa: E402
+for i in range(3):
+    invalidate_packed_weights()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    model._stack().ensure(64, x.device)
+    torch.cuda.synchronize()
+    print(f"repack {i}: {1e3 * (time.perf_counter() - t0):.2f} ms", flush=True)
+opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+for i in range(3):
+    model.zero_grad(set_to_none=True)
+    loss = model.forward_kld(x)
+    loss.backward()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    opt.step()
+    torch.cuda.synchronize()
+    print(f"adam step {i}: {1e3 * (time.perf_counter() - t0):.2f} ms", flush=True)
