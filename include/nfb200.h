@@ -137,6 +137,15 @@ int nfb_glow_conditioner(const float* x_dev, int32_t x_channels, int32_t c0, int
                          const float* b1_dev, const float* w2_dev, const float* b2_dev, const float* w3_taps_dev,
                          float* y_taps_dev, int64_t batch, int32_t height, int32_t width, int32_t hidden, int32_t cout,
                          float leaky, void* stream);
+/* The same conditioner with its weights PRE-PACKED (bf16 hi | lo records in the kernel's swizzled layout): pack once per
+ * parameter version with nfb_glow_conditioner_pack into a device buffer of nfb_glow_conditioner_packed_bytes(...) bytes
+ * (-1: shape not supported), then call nfb_glow_conditioner_packed on every pass. */
+int64_t nfb_glow_conditioner_packed_bytes(int32_t cin, int32_t hidden, int32_t cout);
+int nfb_glow_conditioner_pack(const float* w1_dev, const float* w2_dev, const float* w3_taps_dev, int32_t cin,
+                              int32_t hidden, int32_t cout, void* packed_dev, void* stream);
+int nfb_glow_conditioner_packed(const float* x_dev, int32_t x_channels, int32_t c0, int32_t cin, const void* packed_dev,
+                                const float* b1_dev, const float* b2_dev, float* y_taps_dev, int64_t batch,
+                                int32_t height, int32_t width, int32_t hidden, int32_t cout, float leaky, void* stream);
 /* Second half of a k x k convolution computed as k*k stacked 1x1 products (the last, 256 -> few-channel layer of
  * ConvNet2d, nets/cnn.py:50-57): y_taps [B, k*k*cout, H, W] holds, for tap t = kh*k + kw, channel t*cout + n =
  * sum_c W[n, c, kh, kw] x[b, c]; out[b, n, y, x] = bias[n] + sum_t y_taps[b, t*cout + n, y + kh - k/2, x + kw - k/2]. */
@@ -162,6 +171,16 @@ int nfb_affine_coupling_image(float* z_dev, const float* param_dev, float* log_d
                               const float* logdet_const_dev, int64_t batch, int32_t channels, int32_t hw,
                               int32_t scale, int32_t scale_map, int32_t split_mode, int32_t direction,
                               int32_t accumulate, void* stream);
+/* The same coupling fed with the conditioner's output still in tap form (nfb_glow_conditioner*: y_taps [B, 9 * cout, H, W]
+ * with cout = (scale ? 2 : 1) * #transformed channels, bias [cout] or NULL): param[b, n, y, x] = bias[n] + sum over the
+ * nine taps of y_taps[b, t * cout + n, y + kh - 1, x + kw - 1] is formed on the fly from a shared-memory copy of the
+ * sample -- nfb_tap_shift_add and the summed parameter tensor are skipped.  ..._supported: 1 if one sample's taps
+ * (9 * cout * H * W floats) fit the kernel's shared memory (200 KB). */
+int nfb_affine_coupling_image_taps(float* z_dev, const float* y_taps_dev, const float* bias_dev, float* log_det_dev,
+                                   const float* logdet_const_dev, int64_t batch, int32_t channels, int32_t height,
+                                   int32_t width, int32_t scale, int32_t scale_map, int32_t split_mode, int32_t direction,
+                                   int32_t accumulate, void* stream);
+int32_t nfb_affine_coupling_image_taps_supported(int32_t channels, int32_t height, int32_t width, int32_t scale);
 /* flows/reshape.py:114-128 Squeeze; (channels,height,width) describe the high-resolution side;
  * NFB_INVERSE: [B,C,H,W] -> [B,4C,H/2,W/2], NFB_FORWARD the reverse. */
 int nfb_squeeze(const float* in_dev, float* out_dev, int64_t batch, int32_t channels, int32_t height,

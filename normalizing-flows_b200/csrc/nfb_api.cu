@@ -1140,17 +1140,47 @@ int nfb_conv2d(const float* x, int32_t x_channels, int32_t c0, const float* w, c
     NFB_CHECK(x && w && y, NFB_ERR_ARG, "nfb_conv2d: null pointer");
     return launch_conv2d(x, x_channels, c0, w, b, y, batch, cin, height, width, cout, ksize, leaky, S(stream));
 }
+static float glow_gain() {
+    static const float gain = [] { const char* e = getenv("NFB_ACC_COMP_STEP"); return e ? (float)atof(e) : nfb::kAccStepGain; }();
+    return gain;
+}
+static int glow_err_buf(int** out) {
+    static thread_local int* err_dev = nullptr;
+    if (!err_dev) { NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&err_dev), 16)); NFB_CUDA(cudaMemset(err_dev, 0, 16)); }
+    *out = err_dev;
+    return NFB_OK;
+}
 int nfb_glow_conditioner(const float* x, int32_t x_channels, int32_t c0, int32_t cin, const float* w1, const float* b1,
                          const float* w2, const float* b2, const float* w3_taps, float* y_taps, int64_t batch,
                          int32_t height, int32_t width, int32_t hidden, int32_t cout, float leaky, void* stream) {
     NFB_CHECK(x && w1 && b1 && w2 && b2 && w3_taps && y_taps, NFB_ERR_ARG, "nfb_glow_conditioner: null pointer");
     NFB_CHECK(glow_cond_supported(cin, hidden, cout, 3, 1, 3), NFB_ERR_UNSUPPORTED,
               "nfb_glow_conditioner: needs hidden %% 64 == 0 (<= 256), 9 cin <= 256, 9 cout <= 256");
-    static thread_local int* err_dev = nullptr;
-    if (!err_dev) { NFB_CUDA(cudaMalloc(reinterpret_cast<void**>(&err_dev), 16)); NFB_CUDA(cudaMemset(err_dev, 0, 16)); }
-    static const float gain = [] { const char* e = getenv("NFB_ACC_COMP_STEP"); return e ? (float)atof(e) : nfb::kAccStepGain; }();
-    return launch_glow_conditioner(x, x_channels, c0, cin, w1, b1, w2, b2, w3_taps, y_taps, batch, height, width, hidden,
-                                   cout, leaky, gain, err_dev, S(stream));
+    int* err_dev = nullptr;
+    NFB_TRY(glow_err_buf(&err_dev));
+    return launch_glow_conditioner(x, x_channels, c0, cin, w1, b1, w2, b2, w3_taps, nullptr, y_taps, batch, height, width,
+                                   hidden, cout, leaky, glow_gain(), err_dev, S(stream));
+}
+int64_t nfb_glow_conditioner_packed_bytes(int32_t cin, int32_t hidden, int32_t cout) {
+    if (!glow_cond_supported(cin, hidden, cout, 3, 1, 3)) return -1;
+    return (int64_t)glow_cond_packed_bytes(cin, hidden, cout);
+}
+int nfb_glow_conditioner_pack(const float* w1, const float* w2, const float* w3_taps, int32_t cin, int32_t hidden,
+                              int32_t cout, void* packed, void* stream) {
+    NFB_CHECK(w1 && w2 && w3_taps && packed, NFB_ERR_ARG, "nfb_glow_conditioner_pack: null pointer");
+    return launch_glow_cond_pack(w1, w2, w3_taps, cin, hidden, cout, glow_gain(), static_cast<uint8_t*>(packed), S(stream));
+}
+int nfb_glow_conditioner_packed(const float* x, int32_t x_channels, int32_t c0, int32_t cin, const void* packed,
+                                const float* b1, const float* b2, float* y_taps, int64_t batch, int32_t height,
+                                int32_t width, int32_t hidden, int32_t cout, float leaky, void* stream) {
+    NFB_CHECK(x && packed && b1 && b2 && y_taps, NFB_ERR_ARG, "nfb_glow_conditioner_packed: null pointer");
+    NFB_CHECK(glow_cond_supported(cin, hidden, cout, 3, 1, 3), NFB_ERR_UNSUPPORTED,
+              "nfb_glow_conditioner_packed: needs hidden %% 64 == 0 (<= 256), 9 cin <= 256, 9 cout <= 256");
+    int* err_dev = nullptr;
+    NFB_TRY(glow_err_buf(&err_dev));
+    return launch_glow_conditioner(x, x_channels, c0, cin, nullptr, b1, nullptr, b2, nullptr,
+                                   static_cast<const uint8_t*>(packed), y_taps, batch, height, width, hidden, cout, leaky,
+                                   glow_gain(), err_dev, S(stream));
 }
 int nfb_tap_shift_add(const float* y_taps, const float* bias, float* out, int64_t batch, int32_t cout, int32_t height,
                       int32_t width, int32_t ksize, void* stream) {
@@ -1185,6 +1215,19 @@ int nfb_affine_coupling_image(float* z, const float* param, float* log_det, cons
     NFB_CHECK(split_mode == 0 || split_mode == 1, NFB_ERR_UNSUPPORTED, "split mode is not implemented.");
     return launch_coupling_image(z, param, log_det, logdet_const, batch, channels, hw, scale, scale_map,
                                  split_mode, direction, accumulate, S(stream));
+}
+int nfb_affine_coupling_image_taps(float* z, const float* y_taps, const float* bias, float* log_det,
+                                   const float* logdet_const, int64_t batch, int32_t channels, int32_t height,
+                                   int32_t width, int32_t scale, int32_t scale_map, int32_t split_mode, int32_t direction,
+                                   int32_t accumulate, void* stream) {
+    NFB_CHECK(z && y_taps, NFB_ERR_ARG, "nfb_affine_coupling_image_taps: null pointer");
+    NFB_CHECK(scale_map >= 0 && scale_map <= 2, NFB_ERR_UNSUPPORTED, "This scale map is not implemented.");
+    NFB_CHECK(split_mode == 0 || split_mode == 1, NFB_ERR_UNSUPPORTED, "split mode is not implemented.");
+    return launch_coupling_taps(z, y_taps, bias, log_det, logdet_const, batch, channels, height, width, scale, scale_map,
+                                split_mode, direction, accumulate, S(stream));
+}
+int32_t nfb_affine_coupling_image_taps_supported(int32_t channels, int32_t height, int32_t width, int32_t scale) {
+    return coupling_taps_supported(channels, height, width, scale) ? 1 : 0;
 }
 int nfb_squeeze(const float* in, float* out, int64_t batch, int32_t channels, int32_t height, int32_t width,
                 int32_t direction, void* stream) {

@@ -318,6 +318,106 @@ int launch_coupling_image(float* z, const float* param, float* logdet, const flo
     return NFB_OK;
 }
 
+// The same coupling with its parameters still in "tap" form: the last 3x3 convolution of the conditioner leaves nine
+// stacked 1x1 products Y [B, 9 * cout, H, W] (csrc/nfb_glow_fused.cu; cout = np * n2), and param[b, n, y, x] = bias[n] +
+// sum_t Y[b, t * cout + n, y + kh - 1, x + kw - 1].  One block per sample stages that sample's Y (<= 200 KB) in shared
+// memory with coalesced 16-byte loads and forms the two parameters of every element on the fly: the summed parameter
+// tensor is never written, and the nine-fold read happens once, from shared memory (round 2a: tap_shift_add_kernel 55 us +
+// coupling_image_kernel 9 us per GlowBlock at C3's first level).
+__global__ void __launch_bounds__(256)
+coupling_taps_kernel(float* __restrict__ z, const float* __restrict__ Y, const float* __restrict__ bias,
+                     float* __restrict__ logdet, const float* __restrict__ logdet_const, int C, int H, int W, int scale,
+                     int smap, int inv_split, int direction, int accumulate) {
+    extern __shared__ __align__(16) float sy[];
+    const long long b = blockIdx.x;
+    const int HW = H * W;
+    const int h = (C + 1) / 2;
+    const int o2 = inv_split ? 0 : h, n2 = inv_split ? h : C - h;
+    const int np = scale ? 2 : 1, cout = np * n2;
+    const long long per = 9LL * cout * HW;
+    const float* src = Y + b * per;
+    if ((per & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        float4* d4 = reinterpret_cast<float4*>(sy);
+        for (int i = threadIdx.x; i < (int)(per >> 2); i += 256) d4[i] = __ldg(s4 + i);
+    } else {
+        for (int i = threadIdx.x; i < (int)per; i += 256) sy[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    auto param = [&](int n, int y, int x) {
+        float acc = bias ? __ldg(bias + n) : 0.f;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+            const int yy = y + kh - 1;
+            if (yy < 0 || yy >= H) continue;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int xx = x + kw - 1;
+                if (xx < 0 || xx >= W) continue;
+                acc += sy[((kh * 3 + kw) * cout + n) * HW + yy * W + xx];
+            }
+        }
+        return acc;
+    };
+    float ld = 0.f;
+    for (int i = threadIdx.x; i < n2 * HW; i += 256) {
+        const int c = i / HW, pix = i - c * HW;
+        const int y = pix / W, x = pix - y * W;
+        float& v = z[(b * C + o2 + c) * HW + pix];
+        if (!scale) {
+            const float pm = param(c, y, x);
+            v = direction ? v + pm : v - pm;
+            continue;
+        }
+        const float shift = param(2 * c, y, x);
+        const float sc = param(2 * c + 1, y, x);
+        if (smap == 0) {
+            if (direction) { v = v * expf(sc) + shift; ld += sc; }
+            else { v = (v - shift) * expf(-sc); ld -= sc; }
+        } else {
+            const float sg = 1.f / (1.f + expf(-(sc + 2.f)));
+            const float lsg = logf(sg);
+            const bool div = (smap == 1) == (direction != 0);
+            if (direction) v = div ? v / sg + shift : v * sg + shift;
+            else v = div ? (v - shift) / sg : (v - shift) * sg;
+            ld += div ? -lsg : lsg;
+        }
+    }
+    __shared__ float red[8];
+    ld = warp_sum(ld);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ld;
+    __syncthreads();
+    if (threadIdx.x == 0 && logdet) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        if (logdet_const) t += *logdet_const;
+        logdet[b] = accumulate ? logdet[b] + t : t;
+    }
+}
+bool coupling_taps_supported(int C, int H, int W, int scale) {
+    const int h = (C + 1) / 2;
+    const long long worst = 9LL * (scale ? 2 : 1) * h * H * W * 4;   // the larger of the two possible z2 chunks
+    return worst <= 200 * 1024;
+}
+int launch_coupling_taps(float* z, const float* Y, const float* bias, float* logdet, const float* logdet_const, long long B,
+                         int C, int H, int W, int scale, int smap, int inv_split, int direction, int accumulate,
+                         cudaStream_t st) {
+    if (B == 0) return NFB_OK;
+    NFB_CHECK(coupling_taps_supported(C, H, W, scale), NFB_ERR_UNSUPPORTED, "coupling_taps: sample too large for shared memory");
+    const int h = (C + 1) / 2;
+    const int n2 = inv_split ? h : C - h;
+    const size_t smem = (size_t)9 * (scale ? 2 : 1) * n2 * H * W * 4;
+    static PerDevice per_dev;
+    if (per_dev.ensure([] {
+            return cudaFuncSetAttribute(coupling_taps_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        }) < 0)
+        return NFB_ERR_CUDA;
+    coupling_taps_kernel<<<(unsigned)B, 256, smem, st>>>(z, Y, bias, logdet, logdet_const, C, H, W, scale, smap, inv_split,
+                                                         direction, accumulate);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+
 // Squeeze (flows/reshape.py:114-128).  direction 0 = inverse: [B,C,H,W] -> [B,4C,H/2,W/2]; 1 = forward.
 __global__ void squeeze_kernel(const float* __restrict__ in, float* __restrict__ out, long long B, int C, int H,
                                int W, int direction) {

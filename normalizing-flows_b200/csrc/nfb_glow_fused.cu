@@ -254,10 +254,33 @@ bool glow_cond_supported(int cin, int hid, int cout, int k1, int k2, int k3) {
            cout >= 1 && 9 * cout <= 256;
 }
 
+// packed weight image of one conditioner: GEMM 1 records, GEMM 2 records, GEMM 3 records (hi | lo pairs per K-chunk)
+size_t glow_cond_packed_bytes(int cin, int hid, int cout) {
+    const int k1c = (9 * cin + 63) / 64, kch = hid / 64;
+    const int n3 = (9 * cout + 15) / 16 * 16;
+    return (size_t)(k1c + kch) * hid * 256 + (size_t)kch * n3 * 256;
+}
 // w3t: the last convolution's weights rearranged to [9 * cout, hid] (row tap * cout + n = W3[n, :, kh, kw]).
+int launch_glow_cond_pack(const float* w1, const float* w2, const float* w3t, int cin, int hid, int cout,
+                          float gain_per_step, uint8_t* packed, cudaStream_t st) {
+    NFB_CHECK(glow_cond_supported(cin, hid, cout, 3, 1, 3), NFB_ERR_UNSUPPORTED, "glow conditioner: unsupported shape");
+    const int k1 = 9 * cin, k1c = (k1 + 63) / 64, kch = hid / 64;
+    const int n3_real = 9 * cout, n3 = (n3_real + 15) / 16 * 16;
+    auto pack = [&](const float* w, int rows, int kreal, int npad, int kcs, uint8_t* dst) {
+        const long long total = (long long)kcs * npad * 64;
+        const float gain = 1.f + gain_per_step * (float)(12 * kcs);
+        glow_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, rows, kreal, npad, kcs, gain, dst);
+    };
+    pack(w1, hid, k1, hid, k1c, packed);
+    pack(w2, hid, hid, hid, kch, packed + (size_t)k1c * hid * 256);
+    pack(w3t, n3_real, hid, n3, kch, packed + (size_t)(k1c + kch) * hid * 256);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
+}
+// packed != null: the caller keeps the packed image (one pack per parameter version); else packed per call
 int launch_glow_conditioner(const float* x, int ctot, int c0, int cin, const float* w1, const float* b1, const float* w2,
-                            const float* b2, const float* w3t, float* y_taps, long long B, int H, int W, int hid, int cout,
-                            float leaky, float gain_per_step, int* err, cudaStream_t st) {
+                            const float* b2, const float* w3t, const uint8_t* packed, float* y_taps, long long B, int H,
+                            int W, int hid, int cout, float leaky, float gain_per_step, int* err, cudaStream_t st) {
     static PerDevice per_dev;
     const int sm_count = per_dev.ensure([] {
         return cudaFuncSetAttribute(glow_cond_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGfSmem);
@@ -266,27 +289,23 @@ int launch_glow_conditioner(const float* x, int ctot, int c0, int cin, const flo
     NFB_CHECK(glow_cond_supported(cin, hid, cout, 3, 1, 3), NFB_ERR_UNSUPPORTED, "glow conditioner: unsupported shape");
     const long long M = B * H * W;
     if (M == 0) return NFB_OK;
-    const int k1 = 9 * cin, k1c = (k1 + 63) / 64, kch = hid / 64;
+    const int k1 = 9 * cin, k1c = (k1 + 63) / 64;
     const int n3_real = 9 * cout, n3 = (n3_real + 15) / 16 * 16;
-    const size_t bytes = (size_t)(k1c + kch) * hid * 256 + (size_t)kch * n3 * 256;
     uint8_t* scratch = nullptr;
-    NFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), bytes, st));
-    auto pack = [&](const float* w, int rows, int kreal, int npad, int kcs, uint8_t* dst) {
-        const long long total = (long long)kcs * npad * 64;
-        const float gain = 1.f + gain_per_step * (float)(12 * kcs);
-        glow_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, rows, kreal, npad, kcs, gain, dst);
-    };
-    pack(w1, hid, k1, hid, k1c, scratch);
-    pack(w2, hid, hid, hid, kch, scratch + (size_t)k1c * hid * 256);
-    pack(w3t, n3_real, hid, n3, kch, scratch + (size_t)(k1c + kch) * hid * 256);
+    if (!packed) {
+        NFB_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&scratch), glow_cond_packed_bytes(cin, hid, cout), st));
+        const int rc = launch_glow_cond_pack(w1, w2, w3t, cin, hid, cout, gain_per_step, scratch, st);
+        if (rc) { cudaFreeAsync(scratch, st); return rc; }
+        packed = scratch;
+    }
     GlowCondParams p{};
-    p.x = x; p.y = y_taps; p.b1 = b1; p.b2 = b2; p.wstream = scratch; p.M = M; p.ctot = ctot; p.c0 = c0; p.cin = cin;
+    p.x = x; p.y = y_taps; p.b1 = b1; p.b2 = b2; p.wstream = packed; p.M = M; p.ctot = ctot; p.c0 = c0; p.cin = cin;
     p.H = H; p.W = W; p.hid = hid; p.k1c = k1c; p.n3 = n3; p.n3_real = n3_real; p.leaky = leaky; p.err = err;
     const long long n_tiles = (M + 127) / 128;
     const unsigned grid = (unsigned)(n_tiles < sm_count ? n_tiles : sm_count);
     glow_cond_kernel<<<grid, kGfThreads, kGfSmem, st>>>(p);
     const cudaError_t e = cudaGetLastError();
-    cudaFreeAsync(scratch, st);
+    if (scratch) cudaFreeAsync(scratch, st);
     if (e != cudaSuccess) {
         nfb_set_error("glow_cond launch: %s", cudaGetErrorString(e));
         return NFB_ERR_CUDA;

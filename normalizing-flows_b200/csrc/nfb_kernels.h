@@ -88,9 +88,16 @@ int launch_glow_fold_fwd(const float* P, const float* L, const float* U, const f
 int launch_paste_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st);
 int launch_copy_channels(const float* in, float* out, long long B, int C, int c0, int n, int HW, cudaStream_t st);
 bool glow_cond_supported(int cin, int hid, int cout, int k1, int k2, int k3);
+size_t glow_cond_packed_bytes(int cin, int hid, int cout);
+int launch_glow_cond_pack(const float* w1, const float* w2, const float* w3t, int cin, int hid, int cout,
+                          float gain_per_step, uint8_t* packed, cudaStream_t st);
 int launch_glow_conditioner(const float* x, int ctot, int c0, int cin, const float* w1, const float* b1, const float* w2,
-                            const float* b2, const float* w3t, float* y_taps, long long B, int H, int W, int hid, int cout,
-                            float leaky, float gain_per_step, int* err, cudaStream_t st);
+                            const float* b2, const float* w3t, const uint8_t* packed, float* y_taps, long long B, int H,
+                            int W, int hid, int cout, float leaky, float gain_per_step, int* err, cudaStream_t st);
+bool coupling_taps_supported(int C, int H, int W, int scale);
+int launch_coupling_taps(float* z, const float* Y, const float* bias, float* logdet, const float* logdet_const, long long B,
+                         int C, int H, int W, int scale, int smap, int inv_split, int direction, int accumulate,
+                         cudaStream_t st);
 int launch_tap_shift_add(const float* Y, const float* bias, float* out, long long B, int cout, int H, int W, int ks,
                          cudaStream_t st);
 int launch_logit(const float* in, float* out, float* logdet, long long B, long long inner, float alpha, int direction,

@@ -194,6 +194,26 @@ class GlowBlock(Flow):
             self.__dict__[key] = cache
         return cache[1], cache[2], cache[3]
 
+    def _coupling(self, src, dst, c0, cin, ld, ldc, direction):
+        """Conditioner on src[:, c0:c0+cin], then the affine coupling in place on the other half of dst, log-det into ld.
+        Glow-shaped conditioners hand their output over in tap form (no summed parameter tensor); other shapes go
+        through apply_native + nfb_affine_coupling_image."""
+        lib = L.lib()
+        B, C, H, W = dst.shape
+        pm = self.flows[0].flows[1].param_map
+        args = (B, C)
+        tail = (int(bool(self.scale)), _MAPS[self.scale_map], 0 if self.split_mode == "channel" else 1, direction, 0,
+                L.stream_ptr())
+        taps = pm.apply_native_taps(src, c0, cin) if lib.nfb_affine_coupling_image_taps_supported(
+            C, H, W, int(bool(self.scale))) else None
+        if taps is not None:
+            yt, bias = taps
+            L.check(lib.nfb_affine_coupling_image_taps(L.ptr(dst), L.ptr(yt), L.ptr(bias), L.ptr(ld), L.ptr(ldc), *args,
+                                                       H, W, *tail))
+        else:
+            param = pm.apply_native(src, c0, cin)
+            L.check(lib.nfb_affine_coupling_image(L.ptr(dst), L.ptr(param), L.ptr(ld), L.ptr(ldc), *args, H * W, *tail))
+
     def forward(self, z):
         """Sampling direction (glow.py:72-77): coupling block, then Invertible1x1Conv.forward, then ActNorm.forward."""
         z = require_cuda_f32(z)
@@ -211,7 +231,8 @@ class GlowBlock(Flow):
         c0, cin = (0, h) if self.split_mode == "channel" else (h, C - h)
         mid = z.clone()  # the coupling kernel works in place on the transformed half
         with torch.cuda.device(dev):
-            param = self.flows[0].flows[1].param_map.apply_native(z, c0, cin)
+            # (initialised ActNorm: the conditioner's output stays in tap form and the coupling sums it on the fly)
+            param = self.flows[0].flows[1].param_map.apply_native(z, c0, cin) if not an._done() else None
             if not an._done():
                 # data-dependent init in the sampling direction sees the output of the 1x1 convolution
                 # (normalization.py:19-29); run the first two layers, initialise, then fold
@@ -226,10 +247,13 @@ class GlowBlock(Flow):
                                        L.stream_ptr()))
                 an._data_init(pre, "forward")
             w, b, ldc = self._folded("_nfb_fold_fwd", lib.nfb_glow_fold_conv1x1_actnorm_forward, H * W, dev)
-            L.check(lib.nfb_affine_coupling_image(
-                L.ptr(mid), L.ptr(param), L.ptr(ld), L.ptr(ldc), B, C, H * W, int(bool(self.scale)),
-                _MAPS[self.scale_map], 0 if self.split_mode == "channel" else 1, L.NFB_FORWARD, 0,
-                L.stream_ptr()))
+            if param is None:
+                self._coupling(z, mid, c0, cin, ld, ldc, L.NFB_FORWARD)
+            else:
+                L.check(lib.nfb_affine_coupling_image(
+                    L.ptr(mid), L.ptr(param), L.ptr(ld), L.ptr(ldc), B, C, H * W, int(bool(self.scale)),
+                    _MAPS[self.scale_map], 0 if self.split_mode == "channel" else 1, L.NFB_FORWARD, 0,
+                    L.stream_ptr()))
             L.check(lib.nfb_conv2d(L.ptr(mid), C, 0, L.ptr(w), L.ptr(b), L.ptr(out), B, C, H, W, C, 1, -1.0,
                                    L.stream_ptr()))
         return out, ld
@@ -254,9 +278,5 @@ class GlowBlock(Flow):
                                    L.stream_ptr()))
             h = (C + 1) // 2
             c0, cin = (0, h) if self.split_mode == "channel" else (h, C - h)
-            param = self.flows[0].flows[1].param_map.apply_native(out, c0, cin)
-            L.check(lib.nfb_affine_coupling_image(
-                L.ptr(out), L.ptr(param), L.ptr(ld), L.ptr(ldc), B, C, H * W, int(bool(self.scale)),
-                _MAPS[self.scale_map], 0 if self.split_mode == "channel" else 1, L.NFB_INVERSE, 0,
-                L.stream_ptr()))
+            self._coupling(out, out, c0, cin, ld, ldc, L.NFB_INVERSE)
         return out, ld

@@ -31,6 +31,31 @@ class ConvNet2d(nn.Module):
     def conv_layers(self):
         return [m for m in self.net if isinstance(m, nn.Conv2d)]
 
+    def _glow_shape(self, cin):
+        mods = list(self.net)
+        convs = self.conv_layers()
+        return (len(convs) == 3 and len(mods) == 5 and [cv.kernel_size[0] for cv in convs] == [3, 1, 3]
+                and convs[0].out_channels == convs[1].out_channels == convs[1].in_channels
+                and convs[0].out_channels % 64 == 0 and convs[0].out_channels <= 256
+                and 9 * cin <= 256 and 9 * convs[2].out_channels <= 256 and self.leaky >= 0.0)
+
+    def apply_native_taps(self, x, c0, cin):
+        """The Glow conditioner shape only: returns (y_taps [B, 9 * out, H, W], bias [out]) -- the last 3x3 convolution
+        left as nine stacked 1x1 products for nfb_affine_coupling_image_taps to sum on the fly -- or None."""
+        import torch
+        if not self._glow_shape(cin):
+            return None
+        B, ctot, H, W = x.shape
+        c1, c2, c3 = self.conv_layers()
+        cout, hid = c3.out_channels, c1.out_channels
+        yt = torch.empty(B, 9 * cout, H, W, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            packed = self._packed_conditioner(c1, c2, c3, cin, hid, cout)
+            L.check(L.lib().nfb_glow_conditioner_packed(L.ptr(x), ctot, c0, cin, L.ptr(packed), L.ptr(c1.bias),
+                                                        L.ptr(c2.bias), L.ptr(yt), B, H, W, hid, cout,
+                                                        float(self.leaky), L.stream_ptr()))
+        return yt, c3.bias
+
     def apply_native(self, x, c0, cin):
         """y = net(x[:, c0:c0+cin]) for a contiguous CUDA NCHW tensor x; returns [B, out, H, W]."""
         import torch
@@ -38,19 +63,17 @@ class ConvNet2d(nn.Module):
         from ..utils.nn import ActNorm
         mods = list(self.net)
         convs = self.conv_layers()
-        if (len(convs) == 3 and len(mods) == 5 and [cv.kernel_size[0] for cv in convs] == [3, 1, 3]
-                and convs[0].out_channels == convs[1].out_channels == convs[1].in_channels
-                and convs[0].out_channels % 64 == 0 and convs[0].out_channels <= 256
-                and 9 * cin <= 256 and 9 * convs[2].out_channels <= 256 and self.leaky >= 0.0):
+        if self._glow_shape(cin):
             # the Glow conditioner shape: ONE fused tensor-core kernel (csrc/nfb_glow_fused.cu) + the shifted tap sum
             c1, c2, c3 = convs
             cout, hid = c3.out_channels, c1.out_channels
             yt = torch.empty(B, 9 * cout, H, W, device=x.device, dtype=torch.float32)
             out = torch.empty(B, cout, H, W, device=x.device, dtype=torch.float32)
             with torch.cuda.device(x.device):
-                L.check(L.lib().nfb_glow_conditioner(L.ptr(x), ctot, c0, cin, L.ptr(c1.weight), L.ptr(c1.bias),
-                                                     L.ptr(c2.weight), L.ptr(c2.bias), L.ptr(self._tap_weights(c3)),
-                                                     L.ptr(yt), B, H, W, hid, cout, float(self.leaky), L.stream_ptr()))
+                packed = self._packed_conditioner(c1, c2, c3, cin, hid, cout)   # once per parameter version
+                L.check(L.lib().nfb_glow_conditioner_packed(L.ptr(x), ctot, c0, cin, L.ptr(packed), L.ptr(c1.bias),
+                                                            L.ptr(c2.bias), L.ptr(yt), B, H, W, hid, cout,
+                                                            float(self.leaky), L.stream_ptr()))
                 L.check(L.lib().nfb_tap_shift_add(L.ptr(yt), L.ptr(c3.bias), L.ptr(out), B, cout, H, W, 3, L.stream_ptr()))
             return out
         cur, cur_tot, cur_c0 = x, ctot, c0
@@ -92,6 +115,23 @@ class ConvNet2d(nn.Module):
                     run(w, b, -1.0 if last else float(self.leaky))
                 cur, cur_tot, cur_c0 = y, conv.out_channels, 0
         return cur
+
+    def _packed_conditioner(self, c1, c2, c3, cin, hid, cout):
+        """bf16 hi | lo records of the three convolutions in the fused kernel's layout (csrc/nfb_glow_fused.cu), cached per
+        parameter version (and packed-weight generation): round 2a re-packed them on every call (5.5 % of a Glow pass)."""
+        import torch
+        from .._native import generation
+        ws = (c1.weight, c2.weight, c3.weight)
+        sig = tuple((t.data_ptr(), t._version) for t in ws) + (generation(),)
+        cache = self.__dict__.get("_nfb_packed")
+        if cache is None or cache[0] != sig:
+            nbytes = int(L.lib().nfb_glow_conditioner_packed_bytes(cin, hid, cout))
+            buf = torch.empty(nbytes, dtype=torch.uint8, device=c1.weight.device)
+            L.check(L.lib().nfb_glow_conditioner_pack(L.ptr(c1.weight), L.ptr(c2.weight), L.ptr(self._tap_weights(c3)),
+                                                      cin, hid, cout, L.ptr(buf), L.stream_ptr()))
+            cache = (sig, buf)
+            self.__dict__["_nfb_packed"] = cache
+        return cache[1]
 
     def _tap_weights(self, conv):
         """[cout, cin, k, k] -> [k*k*cout, cin, 1, 1] with row (kh*k + kw)*cout + n = W[n, :, kh, kw]; cached per

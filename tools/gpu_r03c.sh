@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+T=r03c
+( python -m pytest tests -m gpu -q 2>&1 | tail -8 ) > gpurun_out/${T}_pytest.log 2>&1
+tail -4 gpurun_out/${T}_pytest.log
+python tools/bench_configs.py c3 2>&1 | tail -1
+python tools/bench_configs.py c3 2>&1 | tail -1
+python tools/train_step_probe.py 2>&1 | grep -E "repack|^step 2"
