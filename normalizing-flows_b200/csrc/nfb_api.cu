@@ -1155,7 +1155,7 @@ int nfb_glow_conditioner(const float* x, int32_t x_channels, int32_t c0, int32_t
                          int32_t height, int32_t width, int32_t hidden, int32_t cout, float leaky, void* stream) {
     NFB_CHECK(x && w1 && b1 && w2 && b2 && w3_taps && y_taps, NFB_ERR_ARG, "nfb_glow_conditioner: null pointer");
     NFB_CHECK(glow_cond_supported(cin, hidden, cout, 3, 1, 3), NFB_ERR_UNSUPPORTED,
-              "nfb_glow_conditioner: needs hidden %% 64 == 0 (<= 256), 9 cin <= 256, 9 cout <= 256");
+              "nfb_glow_conditioner: needs hidden %% 64 == 0 (<= 256), 9 cin <= 256, 9 cout <= 512");
     int* err_dev = nullptr;
     NFB_TRY(glow_err_buf(&err_dev));
     return launch_glow_conditioner(x, x_channels, c0, cin, w1, b1, w2, b2, w3_taps, nullptr, y_taps, batch, height, width,
@@ -1175,7 +1175,7 @@ int nfb_glow_conditioner_packed(const float* x, int32_t x_channels, int32_t c0, 
                                 int32_t width, int32_t hidden, int32_t cout, float leaky, void* stream) {
     NFB_CHECK(x && packed && b1 && b2 && y_taps, NFB_ERR_ARG, "nfb_glow_conditioner_packed: null pointer");
     NFB_CHECK(glow_cond_supported(cin, hidden, cout, 3, 1, 3), NFB_ERR_UNSUPPORTED,
-              "nfb_glow_conditioner_packed: needs hidden %% 64 == 0 (<= 256), 9 cin <= 256, 9 cout <= 256");
+              "nfb_glow_conditioner_packed: needs hidden %% 64 == 0 (<= 256), 9 cin <= 256, 9 cout <= 512");
     int* err_dev = nullptr;
     NFB_TRY(glow_err_buf(&err_dev));
     return launch_glow_conditioner(x, x_channels, c0, cin, nullptr, b1, nullptr, b2, nullptr,

@@ -83,8 +83,12 @@ __global__ void __launch_bounds__(kGfThreads, 1) glow_cond_kernel(const GlowCond
     const long long n_tiles = (p.M + 127) / 128;
     const int HID = p.hid, kch = HID >> 6;            // K chunks of the hidden GEMMs
     const uint32_t rec_h = (uint32_t)HID * 128u;       // one [hid x 64] bf16 record
-    const uint32_t rec_3 = (uint32_t)p.n3 * 128u;
-    const int n_rec = 2 * (p.k1c + kch + kch);
+    // GEMM 3 (N = n3 <= 512 output columns) runs as one or two N-halves: columns [0, n3a) into TMEM columns 0.., columns
+    // [256, n3) into TMEM columns 256.. (the second half starts after the first has passed every a_ready[kc], i.e. after
+    // the last hidden epilogue has finished reading the accumulator that lives there)
+    const int n3a = p.n3 > 256 ? 256 : p.n3, n3b = p.n3 - n3a;
+    const int halves3 = n3b > 0 ? 2 : 1;
+    const int n_rec = 2 * (p.k1c + kch + kch * halves3);
 
     if (warp == kGfEpiWarps) {
         // ------------------------------ weight producer -----------------------------------
@@ -92,7 +96,8 @@ __global__ void __launch_bounds__(kGfThreads, 1) glow_cond_kernel(const GlowCond
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             const uint8_t* src = p.wstream;
             for (int rix = 0; rix < n_rec; ++rix) {
-                const uint32_t bytes = rix < 2 * (p.k1c + kch) ? rec_h : rec_3;
+                const uint32_t bytes = rix < 2 * (p.k1c + kch) ? rec_h
+                                       : (rix < 2 * (p.k1c + 2 * kch) ? (uint32_t)n3a : (uint32_t)n3b) * 128u;
                 if (use > 0) mbar_wait(bar(GF_WEMPTY + slot), (use - 1) & 1u, p.err, 900 + slot);
                 if (elect_one_sync()) {
                     mbar_expect_tx(bar(GF_WFULL + slot), bytes);
@@ -108,14 +113,16 @@ __global__ void __launch_bounds__(kGfThreads, 1) glow_cond_kernel(const GlowCond
         uint32_t slot = 0, use = 0, apar = 0;
         const uint64_t adesc0 = umma_desc_sw128(sbase + kGfOffA), bdesc0 = umma_desc_sw128(sbase + kGfOffW);
         for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            for (int g = 0; g < 3; ++g) {
+            for (int g = 0; g < 2 + halves3; ++g) {   // GEMM 1, GEMM 2, GEMM 3 (first N-half), [GEMM 3 second N-half]
                 const int kcs = g == 0 ? p.k1c : kch;
-                const int N = g == 2 ? p.n3 : HID;
-                const uint32_t d = tmem + (g == 1 ? 256u : 0u);
+                const int N = g < 2 ? HID : (g == 2 ? n3a : n3b);
+                const uint32_t d = tmem + ((g == 1 || g == 3) ? 256u : 0u);
                 const uint32_t idesc = umma_idesc_bf16(128, (uint32_t)N);
                 for (int kc = 0; kc < kcs; ++kc) {
-                    mbar_wait(bar(GF_AREADY + kc), (apar >> kc) & 1u, p.err, 910 + kc);
-                    apar ^= 1u << kc;
+                    if (g < 3) {   // (the second half of GEMM 3 reads the A operand its first half already waited for)
+                        mbar_wait(bar(GF_AREADY + kc), (apar >> kc) & 1u, p.err, 910 + kc);
+                        apar ^= 1u << kc;
+                    }
                     for (int half = 0; half < 2; ++half) {  // hi record x {A_hi, A_lo}; lo record x {A_hi}
                         mbar_wait(bar(GF_WFULL + slot), use & 1u, p.err, 920 + slot);
                         tc_fence_after();
@@ -131,7 +138,8 @@ __global__ void __launch_bounds__(kGfThreads, 1) glow_cond_kernel(const GlowCond
                                 for (int j = 0; j < 4; ++j) umma_bf16(d, a_lo + 2 * j, bd + 2 * j, idesc, 1u);
                             }
                             umma_commit(bar(GF_WEMPTY + slot));
-                            if (kc == kcs - 1 && half == 1) umma_commit(bar(GF_ACCFULL));
+                            // accumulator-ready: after GEMM 1, GEMM 2 and the LAST part of GEMM 3
+                            if (kc == kcs - 1 && half == 1 && (g < 2 || g == 1 + halves3)) umma_commit(bar(GF_ACCFULL));
                         }
                         __syncwarp();
                         if (++slot == 2) { slot = 0; ++use; }
@@ -251,7 +259,7 @@ __global__ void glow_pack_kernel(const float* __restrict__ w, int rows_real, int
 
 bool glow_cond_supported(int cin, int hid, int cout, int k1, int k2, int k3) {
     return k1 == 3 && k2 == 1 && k3 == 3 && hid % 64 == 0 && hid >= 64 && hid <= 256 && cin >= 1 && 9 * cin <= 256 &&
-           cout >= 1 && 9 * cout <= 256;
+           cout >= 1 && 9 * cout <= 512;
 }
 
 // packed weight image of one conditioner: GEMM 1 records, GEMM 2 records, GEMM 3 records (hi | lo pairs per K-chunk)
@@ -273,7 +281,12 @@ int launch_glow_cond_pack(const float* w1, const float* w2, const float* w3t, in
     };
     pack(w1, hid, k1, hid, k1c, packed);
     pack(w2, hid, hid, hid, kch, packed + (size_t)k1c * hid * 256);
-    pack(w3t, n3_real, hid, n3, kch, packed + (size_t)(k1c + kch) * hid * 256);
+    {   // GEMM 3: rows [0, 256) and, when there are more than 256 output columns, rows [256, n3)
+        const int n3a = n3 > 256 ? 256 : n3, n3b = n3 - n3a;
+        uint8_t* dst = packed + (size_t)(k1c + kch) * hid * 256;
+        pack(w3t, n3_real < n3a ? n3_real : n3a, hid, n3a, kch, dst);
+        if (n3b > 0) pack(w3t + (size_t)n3a * hid, n3_real - n3a, hid, n3b, kch, dst + (size_t)kch * n3a * 256);
+    }
     NFB_LAUNCH_CHECK();
     return NFB_OK;
 }

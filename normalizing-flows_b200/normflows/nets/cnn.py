@@ -37,7 +37,7 @@ class ConvNet2d(nn.Module):
         return (len(convs) == 3 and len(mods) == 5 and [cv.kernel_size[0] for cv in convs] == [3, 1, 3]
                 and convs[0].out_channels == convs[1].out_channels == convs[1].in_channels
                 and convs[0].out_channels % 64 == 0 and convs[0].out_channels <= 256
-                and 9 * cin <= 256 and 9 * convs[2].out_channels <= 256 and self.leaky >= 0.0)
+                and 9 * cin <= 256 and 9 * convs[2].out_channels <= 512 and self.leaky >= 0.0)
 
     def apply_native_taps(self, x, c0, cin):
         """The Glow conditioner shape only: returns (y_taps [B, 9 * out, H, W], bias [out]) -- the last 3x3 convolution
