@@ -83,6 +83,34 @@ struct DevBuf {
     }
 };
 
+// A batch of small device->host reads through ONE pinned staging buffer and ONE stream synchronisation (every blocking
+// cudaMemcpy of a few hundred bytes costs ~15 us of host time and a device sync; the packer used to issue ~25 per layer
+// pair and optimizer step).  add() queues a copy, run() waits once, get() hands the floats out.
+struct StagedReads {
+    float* host = nullptr;   // pinned
+    size_t cap = 0, used = 0;
+    ~StagedReads() { if (host) cudaFreeHost(host); }
+    int reserve(size_t floats) {
+        if (floats <= cap) return NFB_OK;
+        if (host) cudaFreeHost(host);
+        host = nullptr; cap = 0;
+        NFB_CUDA(cudaMallocHost(reinterpret_cast<void**>(&host), floats * sizeof(float)));
+        cap = floats;
+        return NFB_OK;
+    }
+    void reset() { used = 0; }
+    // returns the offset of the queued block (floats); the buffer must have been reserved large enough
+    int add(const float* dev, size_t n, cudaStream_t st, size_t* off) {
+        NFB_CHECK(used + n <= cap, NFB_ERR_STATE, "staged reads: buffer too small (%zu + %zu > %zu)", used, n, cap);
+        *off = used;
+        if (n) NFB_CUDA(cudaMemcpyAsync(host + used, dev, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+        used += n;
+        return NFB_OK;
+    }
+    int run(cudaStream_t st) { NFB_CUDA(cudaStreamSynchronize(st)); return NFB_OK; }
+    void get(size_t off, size_t n, std::vector<float>& out) const { out.assign(host + off, host + off + n); }
+};
+
 template <typename T>
 int download(const T* dev, size_t n, std::vector<T>& out) {
     out.resize(n);
@@ -162,7 +190,7 @@ struct Layer {
     // fp16 operand planning: {inf-norm, max|w|} of W (density map) and W^-1 (sampling map), max |bias| of each
     float lu_norm_d = 1.f, lu_max_d = 1.f, lu_bmax_d = 0.f, lu_norm_s = 1.f, lu_max_s = 1.f, lu_bmax_s = 0.f;
     std::vector<int> perm_host, inv_perm_host;
-    std::vector<float> lu_bs_host;
+    std::vector<float> lu_bs_host, lu_bias_host;
     // affine family
     AffineOp op{};
     std::vector<int> perm_fwd, perm_inv;
@@ -184,6 +212,7 @@ struct nfb_flow {
     const float* base_loc = nullptr;
     const float* base_log_scale = nullptr;
     // workspaces
+    StagedReads reads;              // pinned staging for the packer's small device->host reads
     DevBuf lu_args;                 // batched LU pack: one LuPackArgs per LULinearPermute layer
     DevBuf stack_layers, progress;  // whole-stack launch: FusedLayer[stack_n] in density order + tile flags
     int stack_n = 0;
@@ -232,14 +261,16 @@ int copy_net(const nfb_resnet_desc_t& d, NetDesc& n) {
 }
 
 int pack_net_generic(const NetDesc& n, NetPack& p, cudaStream_t st) {
-    p.owned.clear(); p.wb.clear();
+    p.wb.clear();
+    size_t slot = 0;  // the masked-weight buffers are kept across repacks (a cudaFree + cudaMalloc pair per matrix and
+                      // optimizer step was most of the packer's host time: ADVICE r1, profiles/r02b_repack.md)
     auto eff = [&](const float* w, const float* m, size_t cnt, const float** out) -> int {
         if (!m) { *out = w; return NFB_OK; }
-        DevBuf b;
+        if (slot == p.owned.size()) p.owned.emplace_back();
+        DevBuf& b = p.owned[slot++];
         NFB_TRY(b.reserve(cnt * sizeof(float)));
         NFB_TRY(launch_mask_mul(w, m, b.as<float>(), (long long)cnt, st));
         *out = b.as<float>();
-        p.owned.push_back(std::move(b));
         return NFB_OK;
     };
     NFB_TRY(eff(n.w0, n.m0, (size_t)n.H * n.in, &p.w0));
@@ -624,13 +655,32 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
                                Ufold->D, acc_gain(3 * 64 / 16), F.fold_G.as<float>(), F.fold_delta.as<float>(), st));
         NFB_TRY(launch_matrix_norms(F.fold_G.as<float>(), Hf, 64, f->norms.as<float>() + 3 * ng, st));
     }
-    // biases (tiny; synchronous download is fine at pack time)
-    NFB_CUDA(cudaStreamSynchronize(st));
-    std::vector<float> nm;
-    NFB_TRY(download(f->norms.as<float>(), (size_t)ng * 3, nm));
+    // every small read of this layer (norms, biases, fold results, final-layer bias, unconditional spline tables) is
+    // queued into the pinned staging buffer and waited for ONCE
     const int H = n.H;
+    StagedReads& R = f->reads;
+    NFB_TRY(R.reserve((size_t)(ng + 1) * 3 + (size_t)(2 + 2 * n.nb) * H + (size_t)n.out + (size_t)L.n_id * 23 + 64));
+    R.reset();
+    size_t o_nm, o_b0, o_fnm = 0, o_fd = 0, o_bf, o_uw = 0, o_uh = 0, o_ud = 0;
+    std::vector<size_t> o_bb(2 * n.nb);
+    NFB_TRY(R.add(f->norms.as<float>(), (size_t)ng * 3, st, &o_nm));
+    NFB_TRY(R.add(n.b0, (size_t)H, st, &o_b0));
+    for (int i = 0; i < 2 * n.nb; ++i) NFB_TRY(R.add(n.bb[i], (size_t)H, st, &o_bb[i]));
+    if (Ufold) {
+        NFB_TRY(R.add(f->norms.as<float>() + 3 * ng, 3, st, &o_fnm));
+        NFB_TRY(R.add(F.fold_delta.as<float>(), (size_t)H, st, &o_fd));
+    }
+    NFB_TRY(R.add(n.bf, (size_t)n.out, st, &o_bf));
+    if (L.kind == L_COUPLED_RQS) {
+        NFB_TRY(R.add(L.uw, (size_t)L.n_id * 8, st, &o_uw));
+        NFB_TRY(R.add(L.uh, (size_t)L.n_id * 8, st, &o_uh));
+        NFB_TRY(R.add(L.ud, (size_t)L.n_id * 7, st, &o_ud));
+    }
+    NFB_TRY(R.run(st));
+    std::vector<float> nm;
+    R.get(o_nm, (size_t)ng * 3, nm);
     std::vector<float> bh((size_t)F.n_hidden * 256, 0.f), b0, tmp;
-    NFB_TRY(download(n.b0, (size_t)H, b0));
+    R.get(o_b0, (size_t)H, b0);
     std::vector<float> bmax(ng, 0.f);
     auto amax = [](const std::vector<float>& v) { float m = 0.f; for (float x : v) m = std::max(m, std::fabs(x)); return m; };
     bmax[0] = amax(b0);
@@ -638,10 +688,10 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
     std::vector<float> cum = b0;
     for (int j = 0; j < H; ++j) bh[j] = b0[hp[j]];
     for (int b = 0; b < n.nb; ++b) {
-        NFB_TRY(download(n.bb[2 * b], (size_t)H, tmp));
+        R.get(o_bb[2 * b], (size_t)H, tmp);
         bmax[1 + 2 * b] = amax(tmp);
         for (int j = 0; j < H; ++j) bh[(size_t)(1 + 2 * b) * 256 + j] = tmp[hp[j]];
-        NFB_TRY(download(n.bb[2 * b + 1], (size_t)H, tmp));
+        R.get(o_bb[2 * b + 1], (size_t)H, tmp);
         bmax[2 + 2 * b] = amax(tmp);
         for (int j = 0; j < H; ++j) cum[j] += tmp[j];
         for (int j = 0; j < H; ++j) bh[(size_t)(2 + 2 * b) * 256 + j] = cum[hp[j]];
@@ -651,8 +701,8 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
     std::vector<float> fold_nm;
     float fold_bmax = 0.f;
     if (Ufold) {
-        NFB_TRY(download(f->norms.as<float>() + 3 * ng, 3, fold_nm));
-        NFB_TRY(download(F.fold_delta.as<float>(), (size_t)H, F.fold_delta_host));
+        R.get(o_fnm, 3, fold_nm);
+        R.get(o_fd, (size_t)H, F.fold_delta_host);
         for (int j = 0; j < H; ++j) fold_bmax = std::max(fold_bmax, std::fabs(bh[j] + F.fold_delta_host[j]));
     }
     // pass 2: scale plan, then the fp16 records
@@ -676,7 +726,7 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
     }
     const int crow = F.F * 24;
     std::vector<float> bfin, bf((size_t)(F.n_chunks + 1) * crow, 0.f);  // +1 chunk: the bias prefetch runs one chunk ahead
-    NFB_TRY(download(n.bf, (size_t)n.out, bfin));
+    R.get(o_bf, (size_t)n.out, bfin);
     for (int i = 0; i < F.n_chunks * crow; ++i) {
         const int t = F.F * (i / crow) + (i % crow) / 24, q = (i % crow) % 24;
         if (t < F.T && q < 23) bf[i] = bfin[t * 23 + q] * ((q < 16) ? L.wh_scale * kLog2eHost : 1.f);
@@ -684,9 +734,9 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
     F.bias_f = bf;
     if (L.kind == L_COUPLED_RQS) {
         std::vector<float> w, h, d, tab((size_t)L.n_id * 23);
-        NFB_TRY(download(L.uw, (size_t)L.n_id * 8, w));
-        NFB_TRY(download(L.uh, (size_t)L.n_id * 8, h));
-        NFB_TRY(download(L.ud, (size_t)L.n_id * 7, d));
+        R.get(o_uw, (size_t)L.n_id * 8, w);
+        R.get(o_uh, (size_t)L.n_id * 8, h);
+        R.get(o_ud, (size_t)L.n_id * 7, d);
         for (int i = 0; i < L.n_id; ++i) {
             for (int k = 0; k < 8; ++k) { tab[i * 23 + k] = w[i * 8 + k]; tab[i * 23 + 8 + k] = h[i * 8 + k]; }
             for (int k = 0; k < 7; ++k) tab[i * 23 + 16 + k] = d[i * 7 + k];
@@ -734,11 +784,26 @@ int repack_lu(nfb_flow* f, Layer& L, cudaStream_t st, bool packed_already = fals
         NFB_TRY(launch_lu_pack(L.lu.lower_entries, L.lu.upper_entries, L.lu.unconstrained_upper_diag,
                                L.lu.eps, n, L.lu_Wd.as<float>(), L.lu_Ws.as<float>(),
                                L.lu_logdet.as<float>(), st));
-    // sampling direction: x = (z - b) Winv^T = z Winv^T + bs with bs = -Winv b (tiny; host side)
-    NFB_CUDA(cudaStreamSynchronize(st));
-    std::vector<float> winv, b, bs(n);
-    NFB_TRY(download(L.lu_Ws.as<float>(), (size_t)n * n, winv));
-    NFB_TRY(download(L.lu.bias, (size_t)n, b));
+    // sampling direction: x = (z - b) Winv^T = z Winv^T + bs with bs = -Winv b (tiny; host side).  The norms for the fp16
+    // scale plan of the fused units this map is part of (row/column permutations leave them unchanged) are launched
+    // first; everything the host needs comes back through the staged reads with ONE synchronisation.
+    NFB_TRY(f->norms.reserve(64));
+    NFB_TRY(launch_matrix_norms(L.lu_Wd.as<float>(), n, n, f->norms.as<float>(), st));
+    NFB_TRY(launch_matrix_norms(L.lu_Ws.as<float>(), n, n, f->norms.as<float>() + 4, st));
+    StagedReads& R = f->reads;
+    NFB_TRY(R.reserve((size_t)n * n + n + 16));
+    R.reset();
+    size_t o_w, o_b, o_nm, o_ld;
+    NFB_TRY(R.add(L.lu_Ws.as<float>(), (size_t)n * n, st, &o_w));
+    NFB_TRY(R.add(L.lu.bias, (size_t)n, st, &o_b));
+    NFB_TRY(R.add(f->norms.as<float>(), 8, st, &o_nm));
+    NFB_TRY(R.add(L.lu_logdet.as<float>(), 1, st, &o_ld));
+    NFB_TRY(R.run(st));
+    std::vector<float> winv, b, bs(n), nm, ld;
+    R.get(o_w, (size_t)n * n, winv);
+    R.get(o_b, (size_t)n, b);
+    R.get(o_nm, 8, nm);
+    R.get(o_ld, 1, ld);
     for (int i = 0; i < n; ++i) {
         double acc = 0.0;
         for (int k = 0; k < n; ++k) acc += (double)winv[(size_t)i * n + k] * b[k];
@@ -746,22 +811,12 @@ int repack_lu(nfb_flow* f, Layer& L, cudaStream_t st, bool packed_already = fals
     }
     NFB_TRY(L.lu_bs.upload(bs));
     L.lu_bs_host = bs;
-    {   // norms for the fp16 scale plan of the fused units this map is part of (row/column permutations leave them unchanged)
-        NFB_TRY(f->norms.reserve(64));
-        std::vector<float> nm;
-        NFB_TRY(launch_matrix_norms(L.lu_Wd.as<float>(), n, n, f->norms.as<float>(), st));
-        NFB_TRY(launch_matrix_norms(L.lu_Ws.as<float>(), n, n, f->norms.as<float>() + 4, st));
-        NFB_CUDA(cudaStreamSynchronize(st));
-        NFB_TRY(download(f->norms.as<float>(), 8, nm));
-        L.lu_norm_d = nm[0]; L.lu_max_d = nm[2]; L.lu_norm_s = nm[4]; L.lu_max_s = nm[6];
-        L.lu_bmax_d = 0.f; L.lu_bmax_s = 0.f;
-        for (int i = 0; i < n; ++i) { L.lu_bmax_d = std::max(L.lu_bmax_d, std::fabs(b[i])); L.lu_bmax_s = std::max(L.lu_bmax_s, std::fabs(bs[i])); }
-    }
-    std::vector<float> ld;
-    NFB_TRY(download(L.lu_logdet.as<float>(), 1, ld));
+    L.lu_norm_d = nm[0]; L.lu_max_d = nm[2]; L.lu_norm_s = nm[4]; L.lu_max_s = nm[6];
+    L.lu_bmax_d = 0.f; L.lu_bmax_s = 0.f;
+    for (int i = 0; i < n; ++i) { L.lu_bmax_d = std::max(L.lu_bmax_d, std::fabs(b[i])); L.lu_bmax_s = std::max(L.lu_bmax_s, std::fabs(bs[i])); }
+    L.lu_bias_host = b;
     ld[0] = -ld[0];
     NFB_TRY(L.lu_logdet_neg.upload(ld));
-    (void)f;
     return NFB_OK;
 }
 
@@ -809,10 +864,8 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     NFB_TRY(launch_swizzle_split(f->E.as<float>(), 64, 64, 64, 2, pow2f(pw_lu), F.pair_wstream.as<uint8_t>(), st));
     NFB_CUDA(cudaMemcpyAsync(F.pair_wstream.as<uint8_t>() + 2 * 8192, F.wstream.p, F.rqs_bytes,
                              cudaMemcpyDeviceToDevice, st));
-    std::vector<float> b, bl(64, 0.f);
-    NFB_CUDA(cudaStreamSynchronize(st));
-    NFB_TRY(download(U.lu.bias, (size_t)U.D, b));
-    for (int i = 0; i < U.D; ++i) bl[i] = b[i];
+    std::vector<float> bl(64, 0.f);
+    for (int i = 0; i < U.D; ++i) bl[i] = U.lu_bias_host[i];   // (read back by repack_lu in this same repack)
     NFB_TRY(F.bias_lu.upload(bl));
     FusedLayer& Lp = F.host_pair;
     Lp = F.host_layer;
