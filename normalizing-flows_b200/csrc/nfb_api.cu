@@ -146,7 +146,8 @@ struct FusedPack {
     std::vector<int> in_idx, tr_idx, id_idx, chunk_order;
     unsigned char blk_sig[7 * 4] = {};     // see FusedLayer::blk_sig
     struct Rec { int row0, nrows, kc; size_t off_hi, off_lo; };
-    struct Gemm { DevBuf src_row, src_col, row_scale; const float* W; const float* M; int src_cols, n_pad, k_pad; std::vector<Rec> recs; };
+    struct Gemm { DevBuf src_row, src_col, row_scale, recs_dev; const float* W; const float* M; int src_cols, n_pad, k_pad;
+                  int max_rows = 0; std::vector<Rec> recs; };
     std::vector<int> hperm;  // sorted-by-degree order of the hidden units (identity for unmasked nets)
     std::vector<Gemm> gemms;
     // LU + this block as one launch (built when the next layer in list order is an LU)
@@ -154,6 +155,8 @@ struct FusedPack {
     int pair_steps = 0;
     DevBuf pair_wstream, pair_steps_dev, lu_src_row, lu_src_col, bias_lu;
     // LU fold (density pair): first conditioner matrix times the LU map, packed as GEMM 0 of the pair (repack_fused)
+    bool images_dirty = true;              // per-layer device images (layer_dev, layer_fwd_dev, pair_dev) need a refresh
+    int ar_passes_fwd = 0;
     bool fold_ok = false;                  // decided per repack (scale plan permitting)
     DevBuf pair_steps_fold_dev, in_idx_dev, fold_lu, fold_G, fold_delta, fold_recs;
     std::vector<float> fold_delta_host;    // W0 b_lu in sorted hidden order
@@ -625,9 +628,17 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
     static const bool no_fold = getenv("NFB_NO_FOLD") != nullptr;
     if (no_fold || !F.pair_ok) Ufold = nullptr;
     const NetDesc& n = L.net;
-    size_t emax = 0;
-    for (auto& g : F.gemms) emax = std::max(emax, (size_t)g.n_pad * g.k_pad);
-    NFB_TRY(f->E.reserve(emax * sizeof(float)));
+    // every GEMM's effective matrix gets its own region of the scratch buffer: built once, normed, and (after the scale
+    // plan) packed from there -- the second build of round 2a is gone
+    size_t etot = 0, emax = 0;
+    std::vector<size_t> eoff;
+    for (auto& g : F.gemms) {
+        eoff.push_back(etot);
+        etot += (size_t)g.n_pad * g.k_pad;
+        emax = std::max(emax, (size_t)g.n_pad * g.k_pad);
+    }
+    NFB_TRY(f->E.reserve((etot + emax) * sizeof(float)));
+    float* const Escratch = f->E.as<float>() + etot;   // (fold: raw first matrix)
     const int ng = (int)F.gemms.size();
     NFB_CHECK(ng == F.n_hidden + 1 && ng <= 9, NFB_ERR_STATE, "fused pack: unexpected GEMM count %d", ng);
     // pass 1: norms of every effective matrix (for the fp16 scale plan)
@@ -635,9 +646,9 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
     for (int gi = 0; gi < ng; ++gi) {
         auto& g = F.gemms[gi];
         NFB_TRY(launch_build_effective(g.W, g.M, g.src_cols, g.src_row.as<int>(), g.src_col.as<int>(),
-                                       g.row_scale.p ? g.row_scale.as<float>() : nullptr, f->E.as<float>(),
+                                       g.row_scale.p ? g.row_scale.as<float>() : nullptr, f->E.as<float>() + eoff[gi],
                                        g.n_pad, g.k_pad, acc_gain(3 * g.k_pad / 16), st));
-        NFB_TRY(launch_matrix_norms(f->E.as<float>(), g.n_pad, g.k_pad, f->norms.as<float>() + 3 * gi, st));
+        NFB_TRY(launch_matrix_norms(f->E.as<float>() + eoff[gi], g.n_pad, g.k_pad, f->norms.as<float>() + 3 * gi, st));
     }
     // LU fold, device part (before the one synchronisation of this function): G = gain * E0 E_lu[in_idx, :],
     // delta = E0 b_lu[in_idx] (fp64 accumulation), norms of G
@@ -648,10 +659,10 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
         NFB_TRY(F.fold_G.reserve((size_t)Hf * 64 * 4));
         NFB_TRY(F.fold_delta.reserve((size_t)Hf * 4));
         NFB_TRY(launch_build_effective(g0.W, g0.M, g0.src_cols, g0.src_row.as<int>(), g0.src_col.as<int>(), nullptr,
-                                       f->E.as<float>(), Hf, 64, 1.f, st));
+                                       Escratch, Hf, 64, 1.f, st));
         NFB_TRY(launch_build_effective(Ufold->lu_Wd.as<float>(), nullptr, Ufold->D, F.lu_src_row.as<int>(),
                                        F.lu_src_col.as<int>(), nullptr, F.fold_lu.as<float>(), 64, 64, 1.f, st));
-        NFB_TRY(launch_fold_lu(f->E.as<float>(), F.fold_lu.as<float>(), Ufold->lu.bias, F.in_idx_dev.as<int>(), Hf,
+        NFB_TRY(launch_fold_lu(Escratch, F.fold_lu.as<float>(), Ufold->lu.bias, F.in_idx_dev.as<int>(), Hf,
                                Ufold->D, acc_gain(3 * 64 / 16), F.fold_G.as<float>(), F.fold_delta.as<float>(), st));
         NFB_TRY(launch_matrix_norms(F.fold_G.as<float>(), Hf, 64, f->norms.as<float>() + 3 * ng, st));
     }
@@ -717,12 +728,16 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
     }
     for (int gi = 0; gi < ng; ++gi) {
         auto& g = F.gemms[gi];
-        NFB_TRY(launch_build_effective(g.W, g.M, g.src_cols, g.src_row.as<int>(), g.src_col.as<int>(),
-                                       g.row_scale.p ? g.row_scale.as<float>() : nullptr, f->E.as<float>(),
-                                       g.n_pad, g.k_pad, acc_gain(3 * g.k_pad / 16), st));
-        for (auto& r : g.recs)
-            NFB_TRY(launch_pack_record(f->E.as<float>(), g.k_pad, r.row0, r.nrows, r.kc, pow2f(F.pw[gi]),
-                                       F.wstream.as<uint8_t>() + r.off_hi, F.wstream.as<uint8_t>() + r.off_lo, st));
+        if (g.recs_dev.p == nullptr && !g.recs.empty()) {   // the record table of a GEMM is static: uploaded once
+            std::vector<PackRec> tab;
+            for (auto& r : g.recs) {
+                tab.push_back(PackRec{r.row0, r.nrows, r.kc, 0, (unsigned long long)r.off_hi, (unsigned long long)r.off_lo});
+                g.max_rows = std::max(g.max_rows, r.nrows);
+            }
+            NFB_TRY(g.recs_dev.upload(tab));
+        }
+        NFB_TRY(launch_pack_records(f->E.as<float>() + eoff[gi], g.k_pad, g.recs_dev.as<PackRec>(), (int)g.recs.size(), g.max_rows,
+                                    pow2f(F.pw[gi]), F.wstream.as<uint8_t>(), st));
     }
     const int crow = F.F * 24;
     std::vector<float> bfin, bf((size_t)(F.n_chunks + 1) * crow, 0.f);  // +1 chunk: the bias prefetch runs one chunk ahead
@@ -763,14 +778,27 @@ int repack_fused(nfb_flow* f, Layer& L, cudaStream_t st, Layer* Ufold = nullptr)
     }
     memcpy(Lh.bias_h, F.bias_h.data(), std::min(sizeof(Lh.bias_h), F.bias_h.size() * sizeof(float)));
     memcpy(Lh.bias_f, F.bias_f.data(), std::min(sizeof(Lh.bias_f), F.bias_f.size() * sizeof(float)));
+    // The per-layer device images (layer alone, layer alone in the sampling direction, LU + layer pair) serve single-layer
+    // launches only; the whole-stack launches read the arrays nfb_flow_repack uploads.  They are refreshed on first use
+    // (upload_layer_images) instead of three blocking 18 KB copies per layer and optimizer step.
+    F.ar_passes_fwd = L.kind == L_AR_RQS ? L.D : 0;
+    F.images_dirty = true;
+    return NFB_OK;
+}
+
+int upload_layer_images(FusedPack& F) {
+    if (!F.images_dirty) return NFB_OK;
     NFB_TRY(F.layer_dev.reserve(sizeof(FusedLayer)));
-    NFB_CUDA(cudaMemcpy(F.layer_dev.p, &Lh, sizeof(FusedLayer), cudaMemcpyHostToDevice));
-    {   // sampling-direction image of the block alone: the autoregressive block iterates D conditioner passes
-        FusedLayer Lf = Lh;
-        Lf.ar_passes = L.kind == L_AR_RQS ? L.D : 0;
-        NFB_TRY(F.layer_fwd_dev.reserve(sizeof(FusedLayer)));
-        NFB_CUDA(cudaMemcpy(F.layer_fwd_dev.p, &Lf, sizeof(FusedLayer), cudaMemcpyHostToDevice));
+    NFB_CUDA(cudaMemcpy(F.layer_dev.p, &F.host_layer, sizeof(FusedLayer), cudaMemcpyHostToDevice));
+    FusedLayer Lf = F.host_layer;   // sampling-direction image of the block alone: the autoregressive block iterates D passes
+    Lf.ar_passes = F.ar_passes_fwd;
+    NFB_TRY(F.layer_fwd_dev.reserve(sizeof(FusedLayer)));
+    NFB_CUDA(cudaMemcpy(F.layer_fwd_dev.p, &Lf, sizeof(FusedLayer), cudaMemcpyHostToDevice));
+    if (F.pair_ok) {
+        NFB_TRY(F.pair_dev.reserve(sizeof(FusedLayer)));
+        NFB_CUDA(cudaMemcpy(F.pair_dev.p, &F.host_pair, sizeof(FusedLayer), cudaMemcpyHostToDevice));
     }
+    F.images_dirty = false;
     return NFB_OK;
 }
 
@@ -886,8 +914,7 @@ int repack_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     }
     Lp.bias_lu = F.bias_lu.as<float>();
     Lp.lu_logdet = U.lu_logdet.as<float>();
-    NFB_TRY(F.pair_dev.reserve(sizeof(FusedLayer)));
-    NFB_CUDA(cudaMemcpy(F.pair_dev.p, &Lp, sizeof(FusedLayer), cudaMemcpyHostToDevice));
+    F.images_dirty = true;   // (pair_dev is refreshed by upload_layer_images on first single-pair launch)
     return NFB_OK;
 }
 
@@ -951,6 +978,7 @@ int repack_fwd_unit(nfb_flow* f, Layer& R, Layer* U, cudaStream_t st) {
 int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float* zout, float* logq,
                        long long rows, int accumulate, cudaStream_t st, int sample = 0) {
     FusedPack& F = R.fused;
+    NFB_TRY(upload_layer_images(F));
     FusedParams p{};
     p.layers = U ? F.pair_dev.as<FusedLayer>() : (sample ? F.layer_fwd_dev.as<FusedLayer>() : F.layer_dev.as<FusedLayer>());
     p.n_layers = 1;
@@ -969,13 +997,14 @@ int launch_fused_layer(nfb_flow* f, Layer& R, Layer* U, const float* zin, float*
 int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, long long rows, cudaStream_t st,
                        int sample = 0, long long z_stride = 0) {
     const long long n_tiles = (rows + 127) / 128;
-    NFB_TRY(f->progress.reserve((size_t)n_tiles * sizeof(int)));
-    NFB_CUDA(cudaMemsetAsync(f->progress.p, 0, (size_t)n_tiles * sizeof(int), st));
+    NFB_TRY(f->progress.reserve((size_t)(n_tiles + 1) * sizeof(int)));   // + the unit ticket counter
+    NFB_CUDA(cudaMemsetAsync(f->progress.p, 0, (size_t)(n_tiles + 1) * sizeof(int), st));
     FusedParams p{};
     p.layers = sample ? f->fwd_layers.as<FusedLayer>() : f->stack_layers.as<FusedLayer>();
     p.n_layers = sample ? f->fwd_n : f->stack_n;
     p.zin = zin; p.zout = zout; p.logq = logq; p.rows = rows; p.accumulate = 1; p.z_stride = z_stride;
     p.progress = f->progress.as<int>();
+    p.ticket = getenv("NFB_STATIC_UNITS") ? nullptr : f->progress.as<int>() + n_tiles;
     p.in_ready = sample ? nullptr : f->cur_in_ready;
     f->cur_in_ready = nullptr;  // consumed (or not applicable): later launches must not wait on it
     p.err = f->err.as<int>();

@@ -52,14 +52,16 @@ constexpr uint32_t kOffX = kOffW + kSlots * kSlotBytes;  // 196608: x/y tile
 constexpr uint32_t kOffMisc = kOffX + 32768;             // 229376: log-det partials [kNG-1][128], row maxima [128]
 constexpr uint32_t kOffRowMax = kOffMisc + (kNG - 1) * 128 * 4;
 constexpr uint32_t kOffBars = kOffMisc + 2048;           // 231424
-constexpr uint32_t kNumBars = 20;
-constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;  // 231584
-constexpr uint32_t kFusedSmem = kOffTmemPtr + 16;          // 231600 <= 232448
+constexpr uint32_t kNumBars = 24;
+constexpr uint32_t kOffTmemPtr = kOffBars + kNumBars * 8;  // 231616
+constexpr uint32_t kOffUnitQ = kOffTmemPtr + 16;           // claimed work units, 4-deep (producer -> MMA issuer, epilogue)
+constexpr uint32_t kFusedSmem = kOffUnitQ + 16;            // 231648 <= 232448
 static_assert(kFusedSmem <= 232448, "shared memory budget");
 
 // barrier indices
 constexpr int kBarWFull = 0 /* +slot */, kBarWEmpty = 3 /* +slot */, kBarAReady = 6 /* +kc, 4 */, kBarAccFull = 10,
-              kBarCFull = 11 /* +b, 2 */, kBarCEmpty = 13 /* +b, 2 */, kBarLuFull = 15, kBarAccBlk = 16 /* +kc, 3 */;
+              kBarCFull = 11 /* +b, 2 */, kBarCEmpty = 13 /* +b, 2 */, kBarLuFull = 15, kBarAccBlk = 16 /* +kc, 3 */,
+              kBarUnit = 19 /* +slot, 4 */;
 // TMEM column of final-layer chunk buffer i
 // (both accumulator regions are dead once the last hidden epilogue has run: one buffer in each)
 __device__ __forceinline__ uint32_t chunk_col(int i) { return (uint32_t)i * 256u; }
@@ -142,6 +144,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         mbar_init(bar(kBarAccFull), 1);
         mbar_init(bar(kBarLuFull), 1);
         for (int i = 0; i < 3; ++i) mbar_init(bar(kBarAccBlk + i), 1);
+        for (int i = 0; i < 4; ++i) mbar_init(bar(kBarUnit + i), 1);
         fence_mbar_init();
     }
     if (warp == kEpiWarps + 1) {
@@ -156,8 +159,17 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     const long long n_tiles = (p.rows + 127) / 128;
     // work units, layer-major: (layer, tile)
     const long long n_units = n_tiles * p.n_layers;
-    const long long u_first = (long long)blockIdx.x;
-    const long long u_step = (long long)gridDim.x;
+    // Which unit a CTA works on next is decided by its producer warp and handed to the MMA issuer and the epilogue warps
+    // through a 4-deep queue in shared memory.  With a ticket counter (whole-stack launches) units are CLAIMED in
+    // increasing order from a global atomic: a unit's dependency (layer - 1, same tile) has a smaller index, so it was
+    // claimed earlier by a CTA that is running -- no co-residency of the whole grid is assumed (with the static
+    // b, b + grid, ... assignment a CTA that never gets scheduled would starve the others), and faster CTAs take more
+    // units.  Without a counter (single-layer launches: no dependencies) the static assignment is used.
+    volatile int* unit_q = reinterpret_cast<volatile int*>(smem + kOffUnitQ);
+    auto next_unit = [&](uint32_t i) -> long long {   // consumer side: the i-th unit of this CTA, -1 = no more
+        mbar_wait(bar(kBarUnit + (i & 3u)), (i >> 2) & 1u, p.err, 600 + (int)(i & 3u));
+        return (long long)unit_q[i & 3u];
+    };
 
     // Warp roles: the SM arbiter favours high warp ids, so the two latency-critical single-lane roles
     // (TMA producer, MMA issuer) sit above the epilogue warps (0..kEpiWarps-1).
@@ -165,7 +177,22 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         // ------------------------------ weight producer -----------------------------------
         // whole warp walks the table (warp-uniform control flow); one elected lane issues the copy
         uint32_t slot = 0, par = 0;
-        for (long long u = u_first; u < n_units; u += u_step) {
+        for (uint32_t ui = 0;; ++ui) {
+            long long u;
+            if (p.ticket) {
+                int t = 0;
+                if (lane == 0) t = atomicAdd(p.ticket, 1);
+                u = (long long)__shfl_sync(0xffffffffu, t, 0);
+            } else {
+                u = (long long)blockIdx.x + (long long)ui * gridDim.x;
+            }
+            const bool more = u < n_units;
+            if (lane == 0) {
+                unit_q[ui & 3u] = more ? (int)u : -1;
+                mbar_arrive(bar(kBarUnit + (ui & 3u)));   // (release: the queue entry is visible to whoever passes the wait)
+            }
+            __syncwarp();
+            if (!more) break;
             const FusedLayer& L = p.layers[u / n_tiles];
             const FusedStep* steps = L.steps;  // global (L2-resident); the producer only needs the size
             const int n_steps = L.n_steps;
@@ -202,7 +229,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const uint64_t adesc0 = umma_desc_sw128(sbase + kOffA);
         const uint64_t bdesc0 = umma_desc_sw128(sbase + kOffW);
         constexpr uint32_t kIdesc0 = umma_idesc_f16(128, 0);
-        for (long long u = u_first; u < n_units; u += u_step) {
+        for (uint32_t ui = 0;; ++ui) {
+            const long long u = next_unit(ui);
+            if (u < 0) break;
+            const bool prof_unit = PROF && p.prof && ui == 0 && blockIdx.x == 0;
             const FusedLayer& L = p.layers[u / n_tiles];
             const uint2* steps = reinterpret_cast<const uint2*>(L.steps);  // 8-byte entries, L2-resident
             const int n_steps = L.n_steps;
@@ -217,7 +247,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 nx.raw = __ldg(steps + sidx);  // prefetch one entry ahead (wraps to the block's first step)
                 const FusedStep st = cur.s;
                 const uint32_t ctl = st.ctl;
-                if (PROF && p.prof && u == 0 && s < 380 && lane == 0) p.prof[512 + s] = clock64();  // debug: step reached
+                if (prof_unit && s < 380 && lane == 0) p.prof[512 + s] = clock64();  // debug: step reached
                 const uint32_t wcode = (ctl >> 10) & 7u, scode = (ctl >> 13) & 7u;
                 if (wcode == 1 || wcode == 5 || wcode == 6) {  // first use of A-operand K-chunk kc in this phase
                     // (code 5: the LAST K-chunk of the final layer's A operand, whatever chunk the record itself reads)
@@ -230,10 +260,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     mbar_wait(bar(kBarCEmpty + i), ((cebits >> i) & 1u) ^ 1u, p.err, 210 + i);
                     cebits ^= 1u << i;
                 }
-                if (PROF && p.prof && u == 0 && s < 380 && lane == 0) p.prof[896 + s] = clock64();  // debug: operands (A / chunk) ready
+                if (prof_unit && s < 380 && lane == 0) p.prof[896 + s] = clock64();  // debug: operands (A / chunk) ready
                 mbar_wait(bar(kBarWFull + slot), wpar, p.err, 220 + slot);
                 tc_fence_after();
-                if (PROF && p.prof && u == 0 && s < 380 && lane == 0) p.prof[128 + s] = clock64();  // debug: issue time
+                if (prof_unit && s < 380 && lane == 0) p.prof[128 + s] = clock64();  // debug: issue time
                 if (elect_one_sync()) {
                     const uint32_t d = tmem + (ctl & 511u);
                     const uint32_t idesc = kIdesc0 | ((uint32_t)st.n8 << 17);
@@ -255,13 +285,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                         issue4(st.a2 & 7u, bd2);
                         if (st.a2 & 0x80u) issue4((st.a2 & 7u) + 4u, bd2);   // (LU map: all four terms)
                     }
-                    if (PROF && p.prof && u == 0 && s < 380) p.prof[1280 + s] = clock64();  // debug: MMAs of this record issued
+                    if (prof_unit && s < 380) p.prof[1280 + s] = clock64();  // debug: MMAs of this record issued
                     umma_commit(bar(kBarWEmpty + slot));
                     if (scode == 1) umma_commit(bar(kBarAccFull));
                     else if (scode == 7) umma_commit(bar(kBarLuFull));
                     else if (scode >= 4) umma_commit(bar(kBarAccBlk + (scode - 4)));
                     else if (scode >= 2) umma_commit(bar(kBarCFull + (scode - 2)));
-                    if (PROF && p.prof && u == 0 && s < 380) p.prof[1664 + s] = clock64();  // debug: commits issued
+                    if (prof_unit && s < 380) p.prof[1664 + s] = clock64();  // debug: commits issued
                 }
                 __syncwarp();
                 if (++slot == kSlots) { slot = 0; wpar ^= 1; }
@@ -286,7 +316,9 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         int pi = 0;
 #define NFB_STAMP() do { if (PROF && prof && pi < 126) prof[pi++] = clock64(); } while (0)
 
-        for (long long u = u_first; u < n_units; u += u_step) {
+        for (uint32_t ui = 0;; ++ui) {
+            const long long u = next_unit(ui);
+            if (u < 0) break;
             const int layer = (int)(u / n_tiles);
             const long long tile = u - (long long)layer * n_tiles;
             const FusedLayer& L = p.layers[layer];
@@ -298,7 +330,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             const long long row0 = tile * 128;
             const long long grow = row0 + r;          // this thread's global row
             const bool row_live = grow < p.rows;
-            if (u != u_first) prof = nullptr;
+            if (ui != 0) prof = nullptr;
             float ru = 1.f, ruinv = 1.f;  // this row's power-of-two unit (set after the tile load)
 
             // ---- layer-to-layer dependency: this tile's rows must have left layer-1 (any CTA) ----
@@ -766,6 +798,28 @@ __global__ void pack_record_kernel(const float* __restrict__ E, int k_pad, int r
     const __half h = __float2half_rn(v);
     *reinterpret_cast<__half*>(out_hi + off) = h;
     *reinterpret_cast<__half*>(out_lo + off) = __float2half_rn(v - __half2float(h));
+}
+// all records of one GEMM in ONE launch: blockIdx.y = record (table entry), blockIdx.x = 256-element slice of it
+__global__ void pack_records_kernel(const float* __restrict__ E, int k_pad, const PackRec* __restrict__ recs, float scale,
+                                    uint8_t* __restrict__ base) {
+    const PackRec r = recs[blockIdx.y];
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= r.nrows * 64) return;
+    const int rr = idx >> 6, kk = idx & 63;
+    const float v = E[(size_t)(r.row0 + rr) * k_pad + r.kc * 64 + kk] * scale;
+    const size_t off = (size_t)(rr >> 3) * 1024 + (rr & 7) * 128 + (((kk >> 3) ^ (rr & 7)) << 4) + (kk & 7) * 2;
+    const __half h = __float2half_rn(v);
+    *reinterpret_cast<__half*>(base + r.off_hi + off) = h;
+    *reinterpret_cast<__half*>(base + r.off_lo + off) = __float2half_rn(v - __half2float(h));
+}
+int launch_pack_records(const float* E, int k_pad, const PackRec* recs_dev, int n_recs, int max_rows, float scale,
+                        uint8_t* base, cudaStream_t st) {
+    if (n_recs == 0) return NFB_OK;
+    NFB_CHECK(max_rows > 0 && max_rows % 8 == 0, NFB_ERR_ARG, "pack_records: bad row count %d", max_rows);
+    const dim3 grid((unsigned)((max_rows * 64 + 255) / 256), (unsigned)n_recs);
+    pack_records_kernel<<<grid, 256, 0, st>>>(E, k_pad, recs_dev, scale, base);
+    NFB_LAUNCH_CHECK();
+    return NFB_OK;
 }
 int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, float scale, uint8_t* out_hi,
                        uint8_t* out_lo, cudaStream_t st) {

@@ -185,6 +185,8 @@ struct FusedParams {
     long long rows;
     int accumulate;            // layer 0: logq += (1) or = (0); later layers always accumulate
     int* progress;             // [n_tiles] zero-initialised, or null when n_layers == 1
+    int* ticket;               // zero-initialised unit counter (units are claimed in increasing order), or null: static
+                               // assignment CTA b -> units b, b + grid, ... (single-layer launches)
     const int* in_ready;       // optional: number of rows of `zin` that have landed (chunked H2D in flight, written
                                // by the copy engine); layer-0 tiles wait for their rows.  null = all resident
     int* err;
@@ -245,6 +247,9 @@ int launch_conv2d_tc(const float* x, int ctot, int c0, const float* w, const flo
 int launch_build_effective(const float* W, const float* M, int src_cols, const int* src_row,
                            const int* src_col, const float* row_scale, float* E, int n_pad,
                            int k_pad, float gain, cudaStream_t st);
+struct PackRec { int row0, nrows, kc, pad_; unsigned long long off_hi, off_lo; };  // one weight record of a GEMM
+int launch_pack_records(const float* E, int k_pad, const PackRec* recs_dev, int n_recs, int max_rows, float scale,
+                        uint8_t* base, cudaStream_t st);
 int launch_pack_record(const float* E, int k_pad, int row0, int nrows, int kc, float scale, uint8_t* out_hi,
                        uint8_t* out_lo, cudaStream_t st);
 int launch_swizzle_split(const float* E, int n_pad, int k_pad, int rows_per_rec, int nsplit, float scale,
