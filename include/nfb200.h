@@ -146,6 +146,18 @@ int nfb_glow_conditioner_pack(const float* w1_dev, const float* w2_dev, const fl
 int nfb_glow_conditioner_packed(const float* x_dev, int32_t x_channels, int32_t c0, int32_t cin, const void* packed_dev,
                                 const float* b1_dev, const float* b2_dev, float* y_taps_dev, int64_t batch,
                                 int32_t height, int32_t width, int32_t hidden, int32_t cout, float leaky, void* stream);
+/* flows/affine/glow.py:72-84 GlowBlock.forward / .inverse as ONE call: [AffineCouplingBlock(ConvNet2d (3,1,3)),
+ * Invertible1x1Conv, ActNorm] with the parameter preparation done once per parameter version by the caller --
+ * w1x1 [C, C], b1x1 [C], logdet_const (device scalar): the folded 1x1 convolution of nfb_glow_fold_actnorm_conv1x1
+ * (density) / nfb_glow_fold_conv1x1_actnorm_forward (sampling); cond_packed: nfb_glow_conditioner_pack; cond_b1/b2/b3:
+ * the three convolution biases.  z_in, z_out: [B, C, H, W] (distinct); y_taps: work space [B, 9 * cout, H, W] with
+ * cout = (scale ? 2 : 1) * #transformed channels; scratch: [B, C, H, W], sampling direction only; log_det [B] is
+ * overwritten.  NFB_ERR_UNSUPPORTED when the conditioner shape is outside the fused kernels. */
+int nfb_glow_block(const float* z_in_dev, float* z_out_dev, float* scratch_dev, float* y_taps_dev, float* log_det_dev,
+                   const float* w1x1_dev, const float* b1x1_dev, const float* logdet_const_dev, const void* cond_packed_dev,
+                   const float* cond_b1_dev, const float* cond_b2_dev, const float* cond_b3_dev, int64_t batch,
+                   int32_t channels, int32_t height, int32_t width, int32_t hidden, int32_t scale, int32_t scale_map,
+                   int32_t split_mode, float leaky, int32_t direction, void* stream);
 /* Second half of a k x k convolution computed as k*k stacked 1x1 products (the last, 256 -> few-channel layer of
  * ConvNet2d, nets/cnn.py:50-57): y_taps [B, k*k*cout, H, W] holds, for tap t = kh*k + kw, channel t*cout + n =
  * sum_c W[n, c, kh, kw] x[b, c]; out[b, n, y, x] = bias[n] + sum_t y_taps[b, t*cout + n, y + kh - k/2, x + kw - k/2]. */

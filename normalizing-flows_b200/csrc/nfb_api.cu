@@ -1264,6 +1264,43 @@ int nfb_glow_conditioner_packed(const float* x, int32_t x_channels, int32_t c0, 
                                    static_cast<const uint8_t*>(packed), y_taps, batch, height, width, hidden, cout, leaky,
                                    glow_gain(), err_dev, S(stream));
 }
+// One GlowBlock in one call (flows/affine/glow.py:72-84), parameters prepared by the caller once per parameter version:
+//   density  (NFB_INVERSE): z_out = conv1x1(z_in; w, b)   [ActNorm.inverse folded into Invertible1x1Conv.inverse], then the
+//                            affine coupling in place on z_out, conditioner reading z_out's other half;
+//   sampling (NFB_FORWARD): coupling on a copy of z_in (conditioner reads z_in), then z_out = conv1x1(copy; w, b).
+int nfb_glow_block(const float* z_in, float* z_out, float* scratch, float* y_taps, float* log_det, const float* w1x1,
+                   const float* b1x1, const float* logdet_const, const void* cond_packed, const float* cond_b1,
+                   const float* cond_b2, const float* cond_b3, int64_t batch, int32_t channels, int32_t height,
+                   int32_t width, int32_t hidden, int32_t scale, int32_t scale_map, int32_t split_mode, float leaky,
+                   int32_t direction, void* stream) {
+    NFB_CHECK(z_in && z_out && y_taps && log_det && w1x1 && b1x1 && cond_packed && cond_b1 && cond_b2, NFB_ERR_ARG,
+              "nfb_glow_block: null pointer");
+    NFB_CHECK(direction == NFB_INVERSE || scratch, NFB_ERR_ARG, "nfb_glow_block: the sampling direction needs a scratch tensor");
+    NFB_CHECK(scale_map >= 0 && scale_map <= 2, NFB_ERR_UNSUPPORTED, "This scale map is not implemented.");
+    NFB_CHECK(split_mode == 0 || split_mode == 1, NFB_ERR_UNSUPPORTED, "split mode is not implemented.");
+    const int C = channels, h = (C + 1) / 2;
+    const int c0 = split_mode == 0 ? 0 : h, cin = split_mode == 0 ? h : C - h;   // conditioner input chunk
+    const int n2 = C - cin, cout = (scale ? 2 : 1) * n2;
+    NFB_CHECK(glow_cond_supported(cin, hidden, cout, 3, 1, 3) && coupling_taps_supported(C, height, width, scale),
+              NFB_ERR_UNSUPPORTED, "nfb_glow_block: conditioner shape outside the fused kernels");
+    cudaStream_t st = S(stream);
+    int* err_dev = nullptr;
+    NFB_TRY(glow_err_buf(&err_dev));
+    const uint8_t* packed = static_cast<const uint8_t*>(cond_packed);
+    if (direction == NFB_INVERSE) {
+        NFB_TRY(launch_conv2d(z_in, C, 0, w1x1, b1x1, z_out, batch, C, height, width, C, 1, -1.f, st));
+        NFB_TRY(launch_glow_conditioner(z_out, C, c0, cin, nullptr, cond_b1, nullptr, cond_b2, nullptr, packed, y_taps, batch,
+                                        height, width, hidden, cout, leaky, glow_gain(), err_dev, st));
+        return launch_coupling_taps(z_out, y_taps, cond_b3, log_det, logdet_const, batch, C, height, width, scale, scale_map,
+                                    split_mode, direction, 0, st);
+    }
+    NFB_CUDA(cudaMemcpyAsync(scratch, z_in, (size_t)batch * C * height * width * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    NFB_TRY(launch_glow_conditioner(z_in, C, c0, cin, nullptr, cond_b1, nullptr, cond_b2, nullptr, packed, y_taps, batch,
+                                    height, width, hidden, cout, leaky, glow_gain(), err_dev, st));
+    NFB_TRY(launch_coupling_taps(scratch, y_taps, cond_b3, log_det, logdet_const, batch, C, height, width, scale, scale_map,
+                                 split_mode, direction, 0, st));
+    return launch_conv2d(scratch, C, 0, w1x1, b1x1, z_out, batch, C, height, width, C, 1, -1.f, st);
+}
 int nfb_tap_shift_add(const float* y_taps, const float* bias, float* out, int64_t batch, int32_t cout, int32_t height,
                       int32_t width, int32_t ksize, void* stream) {
     NFB_CHECK(y_taps && out, NFB_ERR_ARG, "nfb_tap_shift_add: null pointer");

@@ -102,6 +102,7 @@ SYMBOLS = {
     "nfb_glow_conditioner_packed": (C.c_int, [_VP, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _F, _VP]),
     "nfb_affine_coupling_image_taps": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _VP]),
     "nfb_affine_coupling_image_taps_supported": (C.c_int32, [_I32, _I32, _I32, _I32]),
+    "nfb_glow_block": (C.c_int, [_VP] * 12 + [_I64, _I32, _I32, _I32, _I32, _I32, _I32, _I32, _F, _I32, _VP]),
     "nfb_tap_shift_add": (C.c_int, [_VP, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _VP]),
     "nfb_glow_fold_actnorm_conv1x1": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),
     "nfb_glow_fold_conv1x1_actnorm_forward": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I32, _I32, _VP, _VP, _VP, _VP]),

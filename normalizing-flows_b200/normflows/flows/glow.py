@@ -194,6 +194,28 @@ class GlowBlock(Flow):
             self.__dict__[key] = cache
         return cache[1], cache[2], cache[3]
 
+    def _one_call(self, z, out, scratch, ld, w, b, ldc, direction):
+        """The whole block through nfb_glow_block (one C-ABI call: folded 1x1 convolution, fused conditioner, tap-form
+        coupling) when the conditioner has the Glow shape; False = not applicable, the caller takes the step-by-step path."""
+        lib = L.lib()
+        B, C, H, W = z.shape
+        pm = self.flows[0].flows[1].param_map
+        h = (C + 1) // 2
+        cin = h if self.split_mode == "channel" else C - h
+        if not (pm._glow_shape(cin) and lib.nfb_affine_coupling_image_taps_supported(C, H, W, int(bool(self.scale)))):
+            return False
+        c1, c2, c3 = pm.conv_layers()
+        cout, hid = c3.out_channels, c1.out_channels
+        with torch.cuda.device(z.device):
+            packed = pm._packed_conditioner(c1, c2, c3, cin, hid, cout)
+            yt = torch.empty(B, 9 * cout, H, W, device=z.device, dtype=torch.float32)
+            L.check(lib.nfb_glow_block(L.ptr(z), L.ptr(out), L.ptr(scratch) if scratch is not None else None, L.ptr(yt),
+                                       L.ptr(ld), L.ptr(w), L.ptr(b), L.ptr(ldc), L.ptr(packed), L.ptr(c1.bias),
+                                       L.ptr(c2.bias), L.ptr(c3.bias), B, C, H, W, hid, int(bool(self.scale)),
+                                       _MAPS[self.scale_map], 0 if self.split_mode == "channel" else 1,
+                                       float(pm.leaky), direction, L.stream_ptr()))
+        return True
+
     def _coupling(self, src, dst, c0, cin, ld, ldc, direction):
         """Conditioner on src[:, c0:c0+cin], then the affine coupling in place on the other half of dst, log-det into ld.
         Glow-shaped conditioners hand their output over in tap form (no summed parameter tensor); other shapes go
@@ -229,6 +251,10 @@ class GlowBlock(Flow):
             return out, ld
         h = (C + 1) // 2
         c0, cin = (0, h) if self.split_mode == "channel" else (h, C - h)
+        if an._done():
+            w, b, ldc = self._folded("_nfb_fold_fwd", lib.nfb_glow_fold_conv1x1_actnorm_forward, H * W, dev)
+            if self._one_call(z, out, torch.empty_like(z), ld, w, b, ldc, L.NFB_FORWARD):
+                return out, ld
         mid = z.clone()  # the coupling kernel works in place on the transformed half
         with torch.cuda.device(dev):
             # (initialised ActNorm: the conditioner's output stays in tap form and the coupling sums it on the fly)
@@ -273,6 +299,8 @@ class GlowBlock(Flow):
         if B == 0:
             return out, ld
         w, b, ldc = self._folded("_nfb_fold", lib.nfb_glow_fold_actnorm_conv1x1, H * W, dev)
+        if self._one_call(z, out, None, ld, w, b, ldc, L.NFB_INVERSE):
+            return out, ld
         with torch.cuda.device(dev):
             L.check(lib.nfb_conv2d(L.ptr(z), C, 0, L.ptr(w), L.ptr(b), L.ptr(out), B, C, H, W, C, 1, -1.0,
                                    L.stream_ptr()))
