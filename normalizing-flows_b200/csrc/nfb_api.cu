@@ -384,6 +384,21 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
         return false;
     };
 
+    // first row (multiple of 16) of final-layer chunk c that has a non-zero in K-chunk kc: the features of a chunk are in
+    // ascending order and a feature sees the hidden units of smaller degree only, so the rows that need a LATE K-chunk are
+    // the chunk's last ones -- the MMA runs on rows [r0, nrows) only, like the shrinking N of the hidden layers
+    auto final_row0 = [&](int c, int kc, int nrows) -> int {
+        static const bool no_shrink = getenv("NFB_NO_FINAL_SHRINK") != nullptr;   // (A/B measurements)
+        if (!masked || kc == 0 || no_shrink) return 0;
+        for (int i = 0; i < nrows; ++i) {
+            const int t = fpc * c + i / 24, q = i % 24;
+            if (t >= T || q >= 23) continue;
+            for (int k = kc * 64; k < kc * 64 + 64; ++k)
+                if (m_fin[(size_t)(t * 23 + q) * H + perm[k]] != 0.f) return i & ~15;
+        }
+        return nrows - 16;   // (a K-chunk this chunk reads only for the ordering rule below: smallest legal record)
+    };
+
     // ---- GEMM source tables (effective matrices are built in sorted hidden order) ----
     F.gemms.clear();
     auto add_gemm = [&](const float* W, const float* M, int src_cols, int n_pad, int k_pad,
@@ -517,7 +532,8 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
                     } else wait = 2 + b;                              // chunk buffer free
                 } else if (!a_waited[kc]) wait = 1;                   // first reader of this A K-chunk
                 a_waited[kc] = true;
-                add(g, c * crow, nrows, kc, chunk_col_host(b), j == 0 ? 1 : 0, wait,
+                const int r0 = j == 0 ? 0 : final_row0(c, kc, nrows);   // (the first record initialises every column)
+                add(g, c * crow + r0, nrows - r0, kc, chunk_col_host(b) + r0, j == 0 ? 1 : 0, wait,
                     j + 1 == need.size() ? 2 + b : 0);
             }
         }
