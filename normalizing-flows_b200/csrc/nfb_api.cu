@@ -372,6 +372,14 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
                 if (m_hid[(size_t)perm[i] * H + perm[k]] != 0.f) return i & ~15;
         return H;  // no row uses this K-chunk at all
     };
+    // the same per K=16 slab s of K-chunk kc (-1: no row reaches the slab)
+    auto hidden_row0_slab = [&](int kc, int s) -> int {
+        if (!masked || m_hid.empty()) return 0;
+        for (int i = 0; i < H; ++i)
+            for (int k = kc * 64 + 16 * s; k < kc * 64 + 16 * s + 16; ++k)
+                if (m_hid[(size_t)perm[i] * H + perm[k]] != 0.f) return i & ~15;
+        return -1;
+    };
     // does chunk c of the final layer have a non-zero in K-chunk kc?
     auto final_needs = [&](int c, int kc) -> bool {
         if (!masked) return true;
@@ -387,6 +395,16 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     // first row (multiple of 16) of final-layer chunk c that has a non-zero in K-chunk kc: the features of a chunk are in
     // ascending order and a feature sees the hidden units of smaller degree only, so the rows that need a LATE K-chunk are
     // the chunk's last ones -- the MMA runs on rows [r0, nrows) only, like the shrinking N of the hidden layers
+    auto final_row0_slab = [&](int c, int kc, int s, int nrows) -> int {   // (relative to the chunk; -1: no row)
+        if (!masked) return 0;
+        for (int i = 0; i < nrows; ++i) {
+            const int t = fpc * c + i / 24, q = i % 24;
+            if (t >= T || q >= 23) continue;
+            for (int k = kc * 64 + 16 * s; k < kc * 64 + 16 * s + 16; ++k)
+                if (m_fin[(size_t)(t * 23 + q) * H + perm[k]] != 0.f) return i & ~15;
+        }
+        return -1;
+    };
     auto final_row0 = [&](int c, int kc, int nrows) -> int {
         static const bool no_shrink = getenv("NFB_NO_FINAL_SHRINK") != nullptr;   // (A/B measurements)
         if (!masked || kc == 0 || no_shrink) return 0;
@@ -433,10 +451,20 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
     memset(F.blk_sig, 3, sizeof(F.blk_sig));
     std::vector<FusedStep> steps;
     size_t off = 0;
+    // slab_r0[s]: first row (absolute, multiple of 16, >= row0; -1 = no row) the K=16 slab s of this K-chunk reaches
     auto add = [&](FusedPack::Gemm& g, int row0, int nrows, int kc, int col, int first, int wait_hi,
-                   int signal_lo) {
-        FusedStep s;
+                   int signal_lo, const int* slab_r0 = nullptr) {
+        FusedStep s{};
         s.n8 = (uint8_t)(nrows / 8);
+        static const bool no_slab = getenv("NFB_NO_SLAB_SHRINK") != nullptr;   // (A/B measurements)
+        for (int j = 0; j < 4; ++j) {
+            int r = (slab_r0 && !no_slab) ? slab_r0[j] : row0;
+            if (r >= 0 && r < row0) r = row0;
+            if (first && j == 0) r = row0;                       // the overwriting MMA initialises every column
+            s.dr[j] = r < 0 ? 0xFF : (uint8_t)((r - row0) / 8);
+            if (r >= 0 && nrows - (r - row0) < 16) s.dr[j] = (uint8_t)((nrows - 16) / 8);
+        }
+        if (s.dr[0] == 0xFF && s.dr[1] == 0xFF && s.dr[2] == 0xFF && s.dr[3] == 0xFF) s.dr[0] = (uint8_t)((nrows - 16) / 8);
         static const bool no_merge = getenv("NFB_NO_MERGE") != nullptr;          // (A/B measurements)
         if (nrows * 256 <= 32768 && !no_merge) {
             // both tiles fit one ring slot: ONE record, 12 MMAs (the issuer's per-record sequence costs ~700 cycles
@@ -487,7 +515,9 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
             if (kc < last && kc <= 2)
                 for (int j = 0; j < ochunks; ++j) if (F.blk_sig[ph * 4 + j] == kc) sig = 4 + kc;
             // every hi record is the first reader of A K-chunk kc in this phase: wait a_ready[kc]
-            add(g, r0, H - r0, kc, region + r0, (kc == 0 && !accum_onto) ? 1 : 0, 1, sig);
+            int sr[4] = {r0, r0, r0, r0};
+            if (ph > 0) for (int s4 = 0; s4 < 4; ++s4) sr[s4] = hidden_row0_slab(kc, s4);
+            add(g, r0, H - r0, kc, region + r0, (kc == 0 && !accum_onto) ? 1 : 0, 1, sig, sr);
         }
     }
     {
@@ -533,8 +563,13 @@ int build_fused(nfb_flow* f, Layer& L, cudaStream_t st) {
                 } else if (!a_waited[kc]) wait = 1;                   // first reader of this A K-chunk
                 a_waited[kc] = true;
                 const int r0 = j == 0 ? 0 : final_row0(c, kc, nrows);   // (the first record initialises every column)
+                int sr[4];
+                for (int s4 = 0; s4 < 4; ++s4) {
+                    const int rs = final_row0_slab(c, kc, s4, nrows);
+                    sr[s4] = rs < 0 ? -1 : c * crow + rs;
+                }
                 add(g, c * crow + r0, nrows - r0, kc, chunk_col_host(b) + r0, j == 0 ? 1 : 0, wait,
-                    j + 1 == need.size() ? 2 + b : 0);
+                    j + 1 == need.size() ? 2 + b : 0, sr);
             }
         }
     }
@@ -871,7 +906,7 @@ int build_pair(nfb_flow* f, Layer& R, Layer& U, cudaStream_t st) {
     if (F.n_steps + 2 > 256) return NFB_OK;
     std::vector<FusedStep> steps;
     auto mk = [&](int a0, int a1, int a2, int first, int wait, int signal) {
-        FusedStep s;
+        FusedStep s{};
         s.bytes16 = 64 * 16; s.n8 = 8; s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
         s.ctl = make_ctl(256, first, wait, signal);
         steps.push_back(s);
@@ -946,7 +981,7 @@ int build_fwd_unit(nfb_flow* f, Layer& R, Layer* U) {
     if (U->D != R.D || U->D > 64 || F.n_steps + 2 > 256) return NFB_OK;
     std::vector<FusedStep> steps;
     auto mk = [&](int a0, int a1, int a2, int first, int wait, int signal) {
-        FusedStep s;
+        FusedStep s{};
         s.bytes16 = 64 * 16; s.n8 = 8; s.a0 = (uint8_t)a0; s.a1 = (uint8_t)a1; s.a2 = (uint8_t)a2;
         s.ctl = make_ctl(256, first, wait, signal);
         steps.push_back(s);

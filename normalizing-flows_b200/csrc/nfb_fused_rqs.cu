@@ -234,12 +234,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             if (u < 0) break;
             const bool prof_unit = PROF && p.prof && ui == 0 && blockIdx.x == 0;
             const FusedLayer& L = p.layers[u / n_tiles];
-            const uint2* steps = reinterpret_cast<const uint2*>(L.steps);  // 8-byte entries, L2-resident
+            const uint4* steps = reinterpret_cast<const uint4*>(L.steps);  // 16-byte entries, L2-resident
             const int n_steps = L.n_steps;
             const int lu_steps = L.has_lu ? 1 : 0;  // (hi and lo tile of the LU map travel as one record)
             const int reps = (SAMPLE && L.ar_passes > 0) ? L.ar_passes : 1;
             const int total = n_steps ? lu_steps + reps * (n_steps - lu_steps) : 0;
-            union { uint2 raw; FusedStep s; } cur, nx;
+            union { uint4 raw; FusedStep s; } cur, nx;
             cur.raw = __ldg(steps);
             int sidx = 0;
             for (int s = 0; s < total; ++s) {
@@ -266,17 +266,29 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                 if (prof_unit && s < 380 && lane == 0) p.prof[128 + s] = clock64();  // debug: issue time
                 if (elect_one_sync()) {
                     const uint32_t d = tmem + (ctl & 511u);
-                    const uint32_t idesc = kIdesc0 | ((uint32_t)st.n8 << 17);
                     const uint64_t bd = bdesc0 + (uint64_t)(slot * (kSlotBytes >> 4));
                     uint32_t accum = ((ctl >> 9) & 1u) ^ 1u;
+                    // Per K=16 slab s the record's rows [8 dr[s], 8 n8) are multiplied (block-triangular MADE matrices: a
+                    // later slab reaches fewer rows; dr = 0xFF: no row at all): D columns, B rows and the MMA's N shift
+                    // together.  (Unmasked nets: dr = 0 everywhere.)
+                    uint32_t dcol[4], nsl[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t dr = st.dr[j];
+                        dcol[j] = dr == 0xFFu ? 0xFFFFFFFFu : dr * 8u;
+                        nsl[j] = kIdesc0 | (((uint32_t)st.n8 - (dr == 0xFFu ? 0u : dr)) << 17);
+                    }
                     // A tile t < 4: hi part of K-chunk t; 4 + t: lo part.  Four K=16 slabs per tile.
                     auto issue4 = [&](uint32_t code, uint64_t b) {
                         const uint64_t ad = adesc0 + (uint64_t)(code * (kTileA >> 4));
-                        umma_bf16(d, ad, b, idesc, accum);
-                        umma_bf16(d, ad + 2, b + 2, idesc, 1u);
-                        umma_bf16(d, ad + 4, b + 4, idesc, 1u);
-                        umma_bf16(d, ad + 6, b + 6, idesc, 1u);
-                        accum = 1u;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            if (dcol[j] != 0xFFFFFFFFu) {
+                                // 8 dr rows of the [N x 64] SW128 tile = dr KB = 64 dr descriptor units
+                                umma_bf16(d + dcol[j], ad + 2 * j, b + 2 * j + (uint64_t)(dcol[j] * 8u), nsl[j], accum);
+                                accum = 1u;
+                            }
+                        }
                     };
                     issue4(st.a0, bd);                       // W_hi tile x A tiles a0 (, a1)
                     if (st.a1 != 0xFF) issue4(st.a1, bd);

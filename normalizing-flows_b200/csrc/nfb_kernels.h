@@ -135,13 +135,15 @@ int launch_affine_stack(const void* ops_dev, int n_ops, const float* zin, float*
                         long long rows, int d, int accumulate, int direction, cudaStream_t st);
 
 // ---- fused tcgen05 neural-spline block (nfb_fused_rqs.cu) ----
-struct __align__(8) FusedStep {
+struct __align__(16) FusedStep {
     uint16_t bytes16;    // weight record size / 16
-    uint8_t n8;          // MMA N / 8
+    uint8_t n8;          // MMA N / 8 (rows of the record's tile(s))
     uint8_t a0, a1, a2;  // A-operand tiles to multiply the record's (first) tile with: a0 and (unless 0xFF) a1; tile t < 4 =
                          //   hi part of K-chunk t, 4 + t = lo part.  a2 != 0xFF: MERGED record -- a second [N x 64] tile (W_lo)
                          //   follows the first (W_hi) and is multiplied with A tile a2 & 7 (and, bit 7 set, with its lo twin)
     uint16_t ctl;        // [0,9) TMEM column | [9] first (overwrite) | [10,13) wait | [13,16) signal
+    uint8_t dr[4];       // per K=16 slab: the slab reaches the tile's rows [8 dr, 8 n8) only (dr even; 0xFF: none)
+    uint8_t pad_[4];
 };
 // wait codes : 0 none, 1 a_ready[kc], 2+i chunk_empty[i], 5 a_ready[H/64 - 1] + chunk_empty[0],
 //              6 a_ready[kc] + chunk_empty[1]   (kc = a0 & 3)
