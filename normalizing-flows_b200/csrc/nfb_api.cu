@@ -234,6 +234,7 @@ struct nfb_flow {
     DevBuf tr_store, tr_h, tr_P, tr_gP, tr_ga, tr_gb, tr_xp, tr_gxp, tr_zp, tr_gzp, tr_in, tr_gin, tr_g0, tr_g1, tr_small,
         tr_glq, tr_t0, tr_t1, tr_wpack;
     const int* cur_in_ready = nullptr;
+    int64_t h2d_rows_seen = -1;      // batch size of the previous host-buffer pass (see nfb_flow_forward_kld_host)
     ~nfb_flow() {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_reset) cudaEventDestroy(ev_reset);
@@ -1910,7 +1911,12 @@ constexpr int kH2dChunks = 16;
 // counter (FusedParams::in_ready), so the transfer overlaps the first layers; any other execution plan simply
 // waits for the last piece (event).  Copy engines do not need SMs, so a resident spinning kernel cannot starve
 // them.  Returns with *gated = 1 if the kernel-side gate is armed.
-int start_h2d(nfb_flow* f, const float* x_host, float* xd, int64_t rows, int* gated) {
+// Host batch -> device in kH2dChunks pieces on a copy stream; after every piece a 4-byte copy publishes the number of
+// resident rows, and the whole-stack kernel's layer-0 tiles wait for their rows (fused_rqs_kernel, in_ready).
+// Two halves so that the COMPUTE launches can be enqueued between them: h2d_prepare resets the counter and decides
+// whether the pass is gated; h2d_copies enqueues the pieces.  Gated passes enqueue the kernels first -- the ~34 async-copy
+// calls cost the host ~100 us, during which the (already resident) kernel would otherwise not even have been launched.
+int h2d_prepare(nfb_flow* f, int64_t rows, int* gated) {
     if (!f->copy_stream) {
         NFB_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
         NFB_CUDA(cudaEventCreateWithFlags(&f->ev_reset, cudaEventDisableTiming));
@@ -1922,6 +1928,11 @@ int start_h2d(nfb_flow* f, const float* x_host, float* xd, int64_t rows, int* ga
     NFB_CUDA(cudaMemsetAsync(f->in_ready.p, 0, 4, 0));
     NFB_CUDA(cudaEventRecord(f->ev_reset, 0));
     NFB_CUDA(cudaStreamWaitEvent(f->copy_stream, f->ev_reset, 0));  // previous pass has finished with xd / the counter
+    if (gate) f->cur_in_ready = f->in_ready.as<int>();
+    *gated = gate ? 1 : 0;
+    return NFB_OK;
+}
+int h2d_copies(nfb_flow* f, const float* x_host, float* xd, int64_t rows, int gate) {
     const int64_t per = ((rows + kH2dChunks - 1) / kH2dChunks + 127) / 128 * 128;  // whole tiles per chunk
     int64_t done = 0;
     for (int c = 0; c < kH2dChunks && done < rows; ++c) {
@@ -1935,9 +1946,7 @@ int start_h2d(nfb_flow* f, const float* x_host, float* xd, int64_t rows, int* ga
         }
     }
     NFB_CUDA(cudaEventRecord(f->ev_copied, f->copy_stream));
-    if (gate) f->cur_in_ready = f->in_ready.as<int>();
-    else NFB_CUDA(cudaStreamWaitEvent(0, f->ev_copied, 0));
-    *gated = gate ? 1 : 0;
+    if (!gate) NFB_CUDA(cudaStreamWaitEvent(0, f->ev_copied, 0));
     return NFB_OK;
 }
 }  // namespace
@@ -1950,9 +1959,15 @@ int nfb_flow_log_prob_host(nfb_flow_t* f, const float* x_host, float* log_q_host
     float* xd = f->host_x.as<float>();
     float* lq = xd + (size_t)rows * f->D;
     int gated = 0;
-    NFB_TRY(start_h2d(f, x_host, xd, rows, &gated));
+    NFB_TRY(h2d_prepare(f, rows, &gated));
+    // Kernels before copies only when this exact batch size has run before: a first pass may still grow work buffers
+    // (cudaFree synchronises the device -- with the kernel resident and its copies not yet enqueued that would wait forever).
+    const bool kernels_first = gated && f->h2d_rows_seen == rows;
+    f->h2d_rows_seen = rows;
+    if (!kernels_first) NFB_TRY(h2d_copies(f, x_host, xd, rows, gated));
     const int rc = nfb_flow_log_prob(f, xd, lq, rows, nullptr);
     f->cur_in_ready = nullptr;
+    if (kernels_first) NFB_TRY(h2d_copies(f, x_host, xd, rows, 1));   // (even after a failed launch: nothing may wait forever)
     if (rc) return rc;
     NFB_CUDA(cudaMemcpyAsync(log_q_host, lq, (size_t)rows * 4, cudaMemcpyDeviceToHost, 0));
     NFB_CUDA(cudaStreamSynchronize(0));
@@ -1967,9 +1982,15 @@ int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, 
     NFB_TRY(f->loss.reserve(16 + (size_t)rows * 4));
     float* xd = f->host_x.as<float>();
     int gated = 0;
-    NFB_TRY(start_h2d(f, x_host, xd, rows, &gated));
+    NFB_TRY(h2d_prepare(f, rows, &gated));
+    // Kernels before copies only when this exact batch size has run before: a first pass may still grow work buffers
+    // (cudaFree synchronises the device -- with the kernel resident and its copies not yet enqueued that would wait forever).
+    const bool kernels_first = gated && f->h2d_rows_seen == rows;
+    f->h2d_rows_seen = rows;
+    if (!kernels_first) NFB_TRY(h2d_copies(f, x_host, xd, rows, gated));
     const int rc = nfb_flow_forward_kld(f, xd, rows, f->loss.as<float>(), nullptr, nullptr);
     f->cur_in_ready = nullptr;
+    if (kernels_first) NFB_TRY(h2d_copies(f, x_host, xd, rows, 1));
     if (rc) return rc;
     NFB_CUDA(cudaMemcpyAsync(loss_host, f->loss.p, 4, cudaMemcpyDeviceToHost, 0));
     NFB_CUDA(cudaStreamSynchronize(0));

@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
                     if (seen < layer) { if (p.err) atomicExch(p.err, 501); asm volatile("trap;"); }
                 }
             }
-            // ---- host batch still in flight (nfb_api.cu start_h2d): layer-0 tiles wait for their rows ----
+            // ---- host batch still in flight (nfb_api.cu h2d_prepare / h2d_copies): layer-0 tiles wait for their rows ----
             if (layer == 0 && p.in_ready) {
                 const int need = (int)min(row0 + 128, p.rows);
                 if (lane == 0) {

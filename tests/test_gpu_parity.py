@@ -1042,3 +1042,22 @@ def test_glow_base_distribution(tag):
     assert zs.shape == (16, 4, 3, 3) and lps.shape == (16,)
     again = q.log_prob(zs, y[:16]) if tag == "cc" else q.log_prob(zs)
     np.testing.assert_allclose(lps.cpu().numpy(), again.cpu().numpy(), rtol=1e-6, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_host_batch_in_flight_repeated_calls():
+    """Host-buffer entry points at a batch large enough for the in-flight path (chunked H2D gating the layer-0 tiles of the
+    whole-stack kernel): the first call of a batch size enqueues the copies first, repeated calls enqueue the kernels
+    first (nfb_api.cu h2d_prepare / h2d_copies) -- every call must reproduce the device-resident result, also when the
+    batch size changes in between and for a ragged last tile."""
+    import bench
+    model = bench.build_model("ar", layers=4).cuda()
+    g = torch.Generator().manual_seed(7)
+    for rows in (16384 + 37, 16384 + 37, 24576, 16384 + 37, 16384 + 37):
+        x = (torch.randn(rows, bench.D, generator=g) * 1.5)
+        xh = x.pin_memory()
+        ref_lp = model.log_prob(x.cuda()).cpu().numpy()
+        ref_kld = float(model.forward_kld(x.cuda()))
+        for _ in range(2):
+            assert model.forward_kld_host(xh) == pytest.approx(ref_kld, rel=1e-6)
+            np.testing.assert_array_equal(model.log_prob_host(xh).numpy(), ref_lp)
