@@ -216,6 +216,9 @@ struct nfb_flow {
     const float* base_log_scale = nullptr;
     // workspaces
     StagedReads reads;              // pinned staging for the packer's small device->host reads
+    DevBuf wave_order;              // diagonal unit order of gated host passes (launch_fused_stack)
+    int wave_layers = 0;
+    long long wave_tiles = 0;
     DevBuf lu_args;                 // batched LU pack: one LuPackArgs per LULinearPermute layer
     DevBuf stack_layers, progress;  // whole-stack launch: FusedLayer[stack_n] in density order + tile flags
     int stack_n = 0;
@@ -1059,6 +1062,30 @@ int launch_fused_stack(nfb_flow* f, const float* zin, float* zout, float* logq, 
     p.ticket = getenv("NFB_STATIC_UNITS") ? nullptr : f->progress.as<int>() + n_tiles;
     p.in_ready = sample ? nullptr : f->cur_in_ready;
     f->cur_in_ready = nullptr;  // consumed (or not applicable): later launches must not wait on it
+    if (p.in_ready && p.ticket && p.n_layers > 1 && p.n_layers <= 255 && n_tiles >= 64 && z_stride == 0 &&
+        getenv("NFB_NO_WAVE_ORDER") == nullptr) {
+        // host batch in flight: diagonal (layer, tile group) order, groups in arrival order (fused_rqs_kernel `decode`)
+        const int tpg = (int)((n_tiles + 7) / 8);
+        const int G = (int)((n_tiles + tpg - 1) / tpg);   // (<= 8 groups, the last one possibly short, none empty)
+        if (f->wave_layers != p.n_layers || f->wave_tiles != n_tiles) {
+            std::vector<unsigned int> tab;
+            unsigned int start = 0;
+            for (int d = 0; d < p.n_layers + G - 1; ++d)
+                for (int g = 0; g < G; ++g) {
+                    const int l = d - g;
+                    if (l < 0 || l >= p.n_layers) continue;
+                    tab.push_back((unsigned int)(l | (g << 8)));
+                    tab.push_back(start);
+                    start += (unsigned int)std::min<long long>(tpg, n_tiles - (long long)g * tpg);
+                }
+            NFB_TRY(f->wave_order.upload(tab));
+            f->wave_layers = p.n_layers;
+            f->wave_tiles = n_tiles;
+        }
+        p.wave_order = f->wave_order.as<unsigned int>();
+        p.wave_elems = p.n_layers * G;
+        p.wave_tpg = tpg;
+    }
     p.err = f->err.as<int>();
     p.poll_all = getenv("NFB_POLL_LANE0") == nullptr;
     p.prof = f->prof.p ? f->prof.as<long long>() : nullptr;

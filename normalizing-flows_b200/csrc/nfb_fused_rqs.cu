@@ -157,8 +157,24 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
     const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(smem + kOffTmemPtr);
 
     const long long n_tiles = (p.rows + 127) / 128;
-    // work units, layer-major: (layer, tile)
+    // Unit index -> (layer, tile).  Default: layer-major.  Host batch in flight (wave_order): the tiles are split into
+    // groups in arrival order and the (layer, group) elements are walked DIAGONALLY -- (l, g) sorted by l + g, then g -- so
+    // that the first groups move through the layers while the later groups' rows are still on the PCIe bus; every element
+    // still comes after (l - 1, g), so claiming in increasing order stays deadlock-free.  wave_order[2 e] = layer |
+    // group << 8, wave_order[2 e + 1] = first unit index of element e; each role walks it with its own cursor (the units
+    // a role sees are increasing).  Every unit is a real tile -- an empty unit would let the producer lap the unit queue.
     const long long n_units = n_tiles * p.n_layers;
+    auto decode = [&](long long u, int& cursor, int& layer, long long& tile) {
+        if (!p.wave_order) {
+            layer = (int)(u / n_tiles);
+            tile = u - (long long)layer * n_tiles;
+            return;
+        }
+        while (cursor + 1 < p.wave_elems && u >= (long long)__ldg(p.wave_order + 2 * (cursor + 1) + 1)) ++cursor;
+        const uint32_t w = __ldg(p.wave_order + 2 * cursor);
+        layer = (int)(w & 0xffu);
+        tile = (long long)(w >> 8) * p.wave_tpg + (u - (long long)__ldg(p.wave_order + 2 * cursor + 1));
+    };
     // Which unit a CTA works on next is decided by its producer warp and handed to the MMA issuer and the epilogue warps
     // through a 4-deep queue in shared memory.  With a ticket counter (whole-stack launches) units are CLAIMED in
     // increasing order from a global atomic: a unit's dependency (layer - 1, same tile) has a smaller index, so it was
@@ -177,6 +193,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         // ------------------------------ weight producer -----------------------------------
         // whole warp walks the table (warp-uniform control flow); one elected lane issues the copy
         uint32_t slot = 0, par = 0;
+        int wcur = 0;
         for (uint32_t ui = 0;; ++ui) {
             long long u;
             if (p.ticket) {
@@ -193,7 +210,10 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
             }
             __syncwarp();
             if (!more) break;
-            const FusedLayer& L = p.layers[u / n_tiles];
+            int ulayer;
+            long long utile;
+            decode(u, wcur, ulayer, utile);
+            const FusedLayer& L = p.layers[ulayer];
             const FusedStep* steps = L.steps;  // global (L2-resident); the producer only needs the size
             const int n_steps = L.n_steps;
             // autoregressive sampling (SAMPLE, ar_passes = D): the LU records are streamed once, the block's D times
@@ -229,11 +249,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         const uint64_t adesc0 = umma_desc_sw128(sbase + kOffA);
         const uint64_t bdesc0 = umma_desc_sw128(sbase + kOffW);
         constexpr uint32_t kIdesc0 = umma_idesc_f16(128, 0);
+        int wcur = 0;
         for (uint32_t ui = 0;; ++ui) {
             const long long u = next_unit(ui);
             if (u < 0) break;
             const bool prof_unit = PROF && p.prof && ui == 0 && blockIdx.x == 0;
-            const FusedLayer& L = p.layers[u / n_tiles];
+            int ulayer;
+            long long utile;
+            decode(u, wcur, ulayer, utile);
+            const FusedLayer& L = p.layers[ulayer];
             const uint4* steps = reinterpret_cast<const uint4*>(L.steps);  // 16-byte entries, L2-resident
             const int n_steps = L.n_steps;
             const int lu_steps = L.has_lu ? 1 : 0;  // (hi and lo tile of the LU map travel as one record)
@@ -328,11 +352,13 @@ __global__ void __launch_bounds__(kFusedThreads, 1) fused_rqs_kernel(const Fused
         int pi = 0;
 #define NFB_STAMP() do { if (PROF && prof && pi < 126) prof[pi++] = clock64(); } while (0)
 
+        int wcur = 0;
         for (uint32_t ui = 0;; ++ui) {
             const long long u = next_unit(ui);
             if (u < 0) break;
-            const int layer = (int)(u / n_tiles);
-            const long long tile = u - (long long)layer * n_tiles;
+            int layer;
+            long long tile;
+            decode(u, wcur, layer, tile);
             const FusedLayer& L = p.layers[layer];
             const int D = L.D, H = L.H;
             // layers >= 1 update z in place (z_stride = 0) or, for the training pass, every layer writes its own

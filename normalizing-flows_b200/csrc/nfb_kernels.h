@@ -189,6 +189,8 @@ struct FusedParams {
     int* progress;             // [n_tiles] zero-initialised, or null when n_layers == 1
     int* ticket;               // zero-initialised unit counter (units are claimed in increasing order), or null: static
                                // assignment CTA b -> units b, b + grid, ... (single-layer launches)
+    const unsigned int* wave_order;    // optional (with in_ready): diagonal (layer, tile group) order, two words per element:
+    int wave_elems, wave_tpg;          //   layer | group << 8, first unit index; tiles per group (last group may be short)
     const int* in_ready;       // optional: number of rows of `zin` that have landed (chunked H2D in flight, written
                                // by the copy engine); layer-0 tiles wait for their rows.  null = all resident
     int* err;
