@@ -237,7 +237,6 @@ struct nfb_flow {
     DevBuf tr_store, tr_h, tr_P, tr_gP, tr_ga, tr_gb, tr_xp, tr_gxp, tr_zp, tr_gzp, tr_in, tr_gin, tr_g0, tr_g1, tr_small,
         tr_glq, tr_t0, tr_t1, tr_wpack;
     const int* cur_in_ready = nullptr;
-    int64_t h2d_rows_seen = -1;      // batch size of the previous host-buffer pass (see nfb_flow_forward_kld_host)
     ~nfb_flow() {
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (ev_reset) cudaEventDestroy(ev_reset);
@@ -1940,9 +1939,7 @@ constexpr int kH2dChunks = 16;
 // them.  Returns with *gated = 1 if the kernel-side gate is armed.
 // Host batch -> device in kH2dChunks pieces on a copy stream; after every piece a 4-byte copy publishes the number of
 // resident rows, and the whole-stack kernel's layer-0 tiles wait for their rows (fused_rqs_kernel, in_ready).
-// Two halves so that the COMPUTE launches can be enqueued between them: h2d_prepare resets the counter and decides
-// whether the pass is gated; h2d_copies enqueues the pieces.  Gated passes enqueue the kernels first -- the ~34 async-copy
-// calls cost the host ~100 us, during which the (already resident) kernel would otherwise not even have been launched.
+// h2d_prepare resets the counter and decides whether the pass is gated; h2d_copies enqueues the pieces.
 int h2d_prepare(nfb_flow* f, int64_t rows, int* gated) {
     if (!f->copy_stream) {
         NFB_CUDA(cudaStreamCreateWithFlags(&f->copy_stream, cudaStreamNonBlocking));
@@ -1987,14 +1984,12 @@ int nfb_flow_log_prob_host(nfb_flow_t* f, const float* x_host, float* log_q_host
     float* lq = xd + (size_t)rows * f->D;
     int gated = 0;
     NFB_TRY(h2d_prepare(f, rows, &gated));
-    // Kernels before copies only when this exact batch size has run before: a first pass may still grow work buffers
-    // (cudaFree synchronises the device -- with the kernel resident and its copies not yet enqueued that would wait forever).
-    const bool kernels_first = gated && f->h2d_rows_seen == rows;
-    f->h2d_rows_seen = rows;
-    if (!kernels_first) NFB_TRY(h2d_copies(f, x_host, xd, rows, gated));
+    // Copies are enqueued BEFORE the compute launches: a launch that blocks the host until the kernel has finished
+    // (CUDA_LAUNCH_BLOCKING, ncu, compute-sanitizer) must find its input already on its way -- the kernel waits for it.
+    // (Kernels-first was measured: no e2e gain; the gap to the device-resident pass is PCIe time, not enqueue time.)
+    NFB_TRY(h2d_copies(f, x_host, xd, rows, gated));
     const int rc = nfb_flow_log_prob(f, xd, lq, rows, nullptr);
     f->cur_in_ready = nullptr;
-    if (kernels_first) NFB_TRY(h2d_copies(f, x_host, xd, rows, 1));   // (even after a failed launch: nothing may wait forever)
     if (rc) return rc;
     NFB_CUDA(cudaMemcpyAsync(log_q_host, lq, (size_t)rows * 4, cudaMemcpyDeviceToHost, 0));
     NFB_CUDA(cudaStreamSynchronize(0));
@@ -2010,14 +2005,12 @@ int nfb_flow_forward_kld_host(nfb_flow_t* f, const float* x_host, int64_t rows, 
     float* xd = f->host_x.as<float>();
     int gated = 0;
     NFB_TRY(h2d_prepare(f, rows, &gated));
-    // Kernels before copies only when this exact batch size has run before: a first pass may still grow work buffers
-    // (cudaFree synchronises the device -- with the kernel resident and its copies not yet enqueued that would wait forever).
-    const bool kernels_first = gated && f->h2d_rows_seen == rows;
-    f->h2d_rows_seen = rows;
-    if (!kernels_first) NFB_TRY(h2d_copies(f, x_host, xd, rows, gated));
+    // Copies are enqueued BEFORE the compute launches: a launch that blocks the host until the kernel has finished
+    // (CUDA_LAUNCH_BLOCKING, ncu, compute-sanitizer) must find its input already on its way -- the kernel waits for it.
+    // (Kernels-first was measured: no e2e gain; the gap to the device-resident pass is PCIe time, not enqueue time.)
+    NFB_TRY(h2d_copies(f, x_host, xd, rows, gated));
     const int rc = nfb_flow_forward_kld(f, xd, rows, f->loss.as<float>(), nullptr, nullptr);
     f->cur_in_ready = nullptr;
-    if (kernels_first) NFB_TRY(h2d_copies(f, x_host, xd, rows, 1));
     if (rc) return rc;
     NFB_CUDA(cudaMemcpyAsync(loss_host, f->loss.p, 4, cudaMemcpyDeviceToHost, 0));
     NFB_CUDA(cudaStreamSynchronize(0));
