@@ -460,8 +460,8 @@ def main():
                         "layers, SURVEY 8d).  The kernel runs every product as 3 fp16 tensor-core passes (split "
                         "precision with power-of-two operand scaling, needed for the rtol 1e-4 bar) so frac <= 1/3 by "
                         "construction, and skips the all-zero blocks of the MADE masks (~31 % of the dense MMA work); "
-                        "ncu (profiles/r02b_fused_stack_ncu_summary.md): tensor pipe 42 % active, SM clock 1.81 GHz "
-                        "under this kernel's load"}
+                        "ncu (profiles/r02b_fused_stack_ncu_summary.md): tensor pipe 29 % active after the zero-block "
+                        "skipping of round 2b (42 % before it), SM clock 1.81 GHz under this kernel's load"}
 
     # ---- training step (extra key; every rank takes part): forward_kld + native backward (tensor-core dgrad /
     # wgrad, analytic spline adjoint) + DDP-style bucketed gradient all-reduce (NCCL when world > 1) + Adam step.
