@@ -19,3 +19,18 @@ void spline_host_check(const float* x, const float* params, int n, int K, float 
         }
     }
 }
+
+// per-feature tails (circular NSF layers): nd derivative parameters per element, circular flag and tail bound per feature
+extern "C" __attribute__((visibility("default")))
+void spline_host_check_tails(const float* x, const float* params, int rows, int feats, int K, int nd, const float* tail,
+                             const int* circ, float wh_scale, int inverse, float* y, float* lad) {
+    const int P = 2 * K + nd;
+    for (int r = 0; r < rows; ++r)
+        for (int f = 0; f < feats; ++f) {
+            const size_t e = (size_t)r * feats + f;
+            const float* p = params + e * P;
+            auto acc = [p](int k) { return p[k]; };
+            if (inverse) nfb::rqs_eval_dyn<true>(K, x[e], acc, tail[f], wh_scale, y[e], lad[e], nd, circ[f] != 0);
+            else nfb::rqs_eval_dyn<false>(K, x[e], acc, tail[f], wh_scale, y[e], lad[e], nd, circ[f] != 0);
+        }
+}

@@ -148,3 +148,33 @@ def test_spline_backward_matches_finite_differences(bwdlib):
                 args_m[i] = arr - d
                 fd = (pick(fwd(*args_p)) - pick(fwd(*args_m))) / (2 * eps)
                 assert (np.abs(fd - g[:, k]) < 1e-5 * (1 + np.abs(g[:, k]))).mean() > 0.98, (which, i, k)
+
+
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_spline_tails_list_vs_oracle(hostlib, inverse):
+    """The per-feature-tails evaluator the circular NSF layers use (csrc/nfb_spline.cuh rqs_eval_dyn with nd = K + 1,
+    csrc/nfb_kernels.cu rqs_rows_tails_kernel), compiled for the host, against the oracle's restatement of
+    utils/splines.py:48-57 (itself pinned to reference-minted vectors): circular and linear features, per-feature
+    bounds, inputs outside a feature's interval (the reference's list branch returns 0 for those)."""
+    from oracle import nf_oracle as O
+    rng = np.random.default_rng(3)
+    rows, feats, K = 600, 5, 8
+    circ = np.array([1, 0, 1, 0, 1], dtype=np.int32)
+    tail = np.array([np.pi, 2.0, np.pi, 4.0, 3.0], dtype=np.float32)
+    uw, uh = rng.normal(size=(rows, feats, K)) * 1.5, rng.normal(size=(rows, feats, K)) * 1.5
+    ud = rng.normal(size=(rows, feats, K + 1)) * 1.5
+    x = rng.normal(size=(rows, feats)) * 2.0
+    params = np.ascontiguousarray(np.concatenate([uw, uh, ud], axis=2).astype(np.float32))
+    xf = np.ascontiguousarray(x.astype(np.float32))
+    y, lad = np.empty((rows, feats), np.float32), np.empty((rows, feats), np.float32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    hostlib.spline_host_check_tails(vp(xf), vp(params), rows, feats, K, K + 1, vp(tail), vp(circ), C.c_float(1.0),
+                                    int(inverse), vp(y), vp(lad))
+    yr, lr = O.unconstrained_rqs_tails(xf.astype(np.float64), params[..., :K].astype(np.float64),
+                                       params[..., K:2 * K].astype(np.float64), params[..., 2 * K:].astype(np.float64),
+                                       circ.astype(bool), inverse=bool(inverse), tail_bound=tail.astype(np.float64))
+    outside = np.abs(xf) > tail[None, :]
+    assert outside.any() and (y[outside] == 0).all() and (lad[outside] == 0).all()
+    ok = ~outside
+    np.testing.assert_allclose(y[ok], yr[ok], rtol=2e-5, atol=3e-5)
+    np.testing.assert_allclose(lad[ok], lr[ok], rtol=2e-4, atol=1e-3)
