@@ -632,3 +632,26 @@ def case_glow_base():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "glow_base":
     case_glow_base()
+
+
+def case_spline_circular():
+    """utils/splines.py:42-47 tails="circular" (K derivative parameters, knot K repeats knot 0; identity outside):
+    element-wise vectors for the nd = K mode of nfb_rqs_spline_tails.    python tests/golden/make_golden.py spline_circular"""
+    from normflows.utils import splines
+    g = torch.Generator().manual_seed(61)
+    n, K = 500, 8
+    x = torch.randn(n, generator=g, dtype=torch.float64) * 2.2
+    uw = torch.randn(n, K, generator=g, dtype=torch.float64) * 1.5
+    uh = torch.randn(n, K, generator=g, dtype=torch.float64) * 1.5
+    ud = torch.randn(n, K, generator=g, dtype=torch.float64) * 1.5
+    out = {"torch_version": torch.__version__, "x": x.numpy(), "uw": uw.numpy(), "uh": uh.numpy(), "ud": ud.numpy()}
+    for inv in (0, 1):
+        y, lad = splines.unconstrained_rational_quadratic_spline(x, uw.clone(), uh.clone(), ud.clone(), inverse=bool(inv),
+                                                                 tails="circular", tail_bound=3.0)
+        out[f"y_{inv}"], out[f"lad_{inv}"] = y.numpy(), lad.numpy()
+    np.savez_compressed(os.path.join(HERE, "spline_circular.npz"), **out)
+    print("wrote spline_circular")
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "spline_circular":
+    case_spline_circular()

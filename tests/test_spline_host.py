@@ -178,3 +178,25 @@ def test_spline_tails_list_vs_oracle(hostlib, inverse):
     ok = ~outside
     np.testing.assert_allclose(y[ok], yr[ok], rtol=2e-5, atol=3e-5)
     np.testing.assert_allclose(lad[ok], lr[ok], rtol=2e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_spline_all_circular_vs_reference_golden(hostlib, inverse):
+    """tails="circular" (utils/splines.py:42-47: K derivative parameters, the last knot repeats the first, identity
+    outside the interval) = the nd = K mode of nfb_rqs_spline_tails: the host build of the device evaluator against vectors
+    minted from the reference (tests/golden/make_golden.py spline_circular)."""
+    f = np.load(os.path.join(ROOT, "tests/golden/spline_circular.npz"))
+    K = 8
+    n = f["x"].shape[0]
+    params = np.ascontiguousarray(np.concatenate([f["uw"], f["uh"], f["ud"]], axis=1).astype(np.float32))
+    xf = np.ascontiguousarray(f["x"].astype(np.float32))
+    y, lad = np.empty(n, np.float32), np.empty(n, np.float32)
+    tail, circ = np.array([3.0], np.float32), np.array([1], np.int32)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    # one "feature" per row: rows = n, feats = 1
+    hostlib.spline_host_check_tails(vp(xf), vp(params), n, 1, K, K, vp(tail), vp(circ), C.c_float(1.0), int(inverse),
+                                    vp(y), vp(lad))
+    outside = np.abs(xf) > 3.0
+    assert outside.any() and (y[outside] == xf[outside]).all() and (lad[outside] == 0).all()   # identity, not zero
+    np.testing.assert_allclose(y, f[f"y_{inverse}"], rtol=2e-5, atol=3e-5)
+    np.testing.assert_allclose(lad, f[f"lad_{inverse}"], rtol=2e-4, atol=1e-3)
