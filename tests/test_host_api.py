@@ -148,3 +148,37 @@ def test_flow_handle_tensor_slots_follow_module_state():
     for _ in range(256):
         ts = h._tensors()
     assert same(ts, h._tensors_slow())
+
+
+@pytest.mark.parametrize("tag", ["cc_s", "cc_t", "ca_s", "ca_t", "gb_plain", "gb_cc"])
+def test_round2b_modules_match_reference_state_dicts(tag):
+    """Circular NSF layers and GlowBase: parameter / buffer names and shapes equal the reference's (the goldens hold the
+    reference `state_dict()`), reference checkpoints load strict=True, and -- without CUDA -- the layers refuse to run
+    (no CPU fallback)."""
+    if tag.startswith("gb"):
+        f = np.load(os.path.join(ROOT, "tests/golden/glow_base.npz"))
+        pre = tag[3:] + "__"
+        m = nf.distributions.GlowBase((4, 3, 3), num_classes=5 if tag == "gb_cc" else None)
+    else:
+        f = np.load(os.path.join(ROOT, "tests/golden/circular.npz"))
+        pre = tag + "__"
+        tbt = torch.from_numpy(np.asarray(f["tail_bound_tensor"]))
+        m = {"cc_s": lambda: nf.flows.CircularCoupledRationalQuadraticSpline(6, 2, 32, [0, 2, 5], tail_bound=3.0),
+             "cc_t": lambda: nf.flows.CircularCoupledRationalQuadraticSpline(6, 1, 32, [0, 2, 5], tail_bound=tbt.clone(),
+                                                                              reverse_mask=True),
+             "ca_s": lambda: nf.flows.CircularAutoregressiveRationalQuadraticSpline(6, 2, 32, [1, 3], tail_bound=3.0),
+             "ca_t": lambda: nf.flows.CircularAutoregressiveRationalQuadraticSpline(6, 1, 32, [0, 2, 5], tail_bound=tbt.clone(),
+                                                                                    permute_mask=False)}[tag]()
+    ref = {k[len(pre):]: np.asarray(f[k]) for k in f.files if k.startswith(pre)}
+    ours = m.state_dict()
+    assert set(ours.keys()) == set(ref.keys())
+    for k, v in ref.items():
+        assert tuple(ours[k].shape) == tuple(v.shape), k
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in ref.items()}, strict=True)
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            if tag.startswith("gb"):
+                m.log_prob(torch.zeros(2, 4, 3, 3), torch.zeros(2, dtype=torch.long)) if tag == "gb_cc" \
+                    else m.log_prob(torch.zeros(2, 4, 3, 3))
+            else:
+                m.inverse(torch.zeros(3, 6))
